@@ -1,0 +1,239 @@
+/*
+ * bq2_gpu.h -- C ABI of the B200-native alias-model lerp + stencil-shadow-volume path.
+ *
+ * This is the drop-in boundary for ONE hot path of Berserker@Quake2 (reference citations are
+ * file:line under the reference tree; "M:" = main.c):
+ *
+ *   R_CalcAliasFrameLerp          M:63510-63583   MD2 keyframe lerp (+ shell push-out)
+ *   R_CalcAliasFrameLerpShadow    M:63586-63631   extrusion + triangle normal + light-facing
+ *   R_CalcAliasFrameShadowVolume  M:63634-63710   silhouette edges + caps  -> vertex stream
+ *   R_DrawAliasShadowVolume       M:63713-63797   light -> model space, drives the two above
+ *   R_DrawMD3AliasShadowVolume    M:63800-64038   the same, fused, per MD3 mesh
+ *   GL_DrawAliasFrameLerpLightARB_vp  M:65140-65267 / GL_DrawMD3...ARB_vp M:65671-65828  N/T/B lerp
+ *   GL_DrawAliasFrameLerpLightARB     M:64889-65017 / GL_DrawMD3...ARB    M:65839-65898  LightP / tsH
+ *
+ * The reference has no plugin layer: those functions talk through file-scope globals
+ * (currententity, currentmodel, currentshadowlight, tempVertexArray, extrudedVerts, viss,
+ * TrisVerts, TrisCounter; data.h:624, 2626, 2709, 2731-2736, 2827).  The replacement is a batched
+ * API: the renderer's per-light / per-entity loops (R_DrawEntsShadowVolumes M:64041-64133) collect
+ * (entity, light) pairs, the trigonometry stays on the host in C (bq2_host_* below restate the
+ * reference's own host lines so libm's sincosf is the same code on both sides), and one CUDA
+ * launch does every pair.  berserkerquake2_b200/csrc/bq2_dropin.c shows the five reference
+ * signatures re-implemented on top of this header (batch of one).
+ *
+ * Plain C, plain pointers and sizes; no torch / C++ types.  All functions return BQ2_OK (0) or a
+ * negative bq2_status; bq2_last_error() gives text.  Nothing here ever longjmps or aborts and
+ * there is NO CPU fallback: without a CUDA device bq2_create() fails with BQ2_E_NODEVICE.
+ * A ctx is bound to one device and one stream and is not thread-safe; multi-GPU = one ctx per
+ * device (one process per GPU under torch.distributed, or one host thread per ctx).
+ */
+#ifndef BQ2_GPU_H
+#define BQ2_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BQ2_ABI_VERSION 1
+
+typedef enum bq2_status {
+    BQ2_OK          = 0,
+    BQ2_E_INVALID   = -1,   /* bad argument / malformed model blob                                  */
+    BQ2_E_CUDA      = -2,   /* CUDA runtime error, text in bq2_last_error                           */
+    BQ2_E_NOMEM     = -3,   /* host or device allocation failed                                     */
+    BQ2_E_LIMIT     = -4,   /* exceeds a reference limit (MAX_VERTS 2048, MAX_TRIANGLES 4096, ...)   */
+    BQ2_E_OVERFLOW  = -5,   /* some pair produced more indices than index_stride holds              */
+    BQ2_E_NODEVICE  = -6    /* no usable CUDA device: there is no CPU path                          */
+} bq2_status;
+
+/* Reference limits (defs.h:3455-3456 MD2; defs.h:560-565 MD3 per mesh). */
+#define BQ2_MD2_MAX_VERTS      2048
+#define BQ2_MD2_MAX_TRIANGLES  4096
+#define BQ2_MD3_MAX_VERTS      4096
+#define BQ2_MD3_MAX_TRIANGLES  8192
+#define BQ2_MD3_MAX_MESHES     32
+#define BQ2_NUM_ANORMS         162
+
+/* Entity render flags that matter on this path (values as in the reference's defs.h RF_* set). */
+#define BQ2_RF_VIEWERMODEL   0x00000002u
+#define BQ2_RF_WEAPONMODEL   0x00000004u
+#define BQ2_RF_FULLBRIGHT    0x00000008u
+#define BQ2_RF_TRANSLUCENT   0x00000020u
+#define BQ2_RF_BEAM          0x00000080u
+#define BQ2_RF_SHELL_RED     0x00000400u
+#define BQ2_RF_SHELL_GREEN   0x00000800u
+#define BQ2_RF_SHELL_BLUE    0x00001000u
+
+/* bq2_entity.flags (ours) */
+#define BQ2_ENT_SHELL        0x1u   /* add anorm[cur.lightnormalindex]*shell_scale  (M:63565-63572) */
+
+/* model flags */
+#define BQ2_MODEL_SMOOTHVECS 0x1u   /* RF_SMOOTHVECS: tangent/binormal bytes are per vertex (M:51661)
+                                       otherwise per triangle, plus per-triangle normal bytes (M:51747) */
+
+typedef struct bq2_ctx bq2_ctx;
+
+/* One entity for one frame.  move/frontv/backv are the reference's host-side lerp constants
+ * (M:63531-63553 for MD2, M:63825-63856 for MD3 where frontv = frontlerp, backv = backlerp in all
+ * three lanes); fill them with bq2_host_entity_md2 / bq2_host_entity_md3.  64 bytes. */
+typedef struct bq2_entity {
+    int32_t  model;        /* id returned by bq2_upload_md2 / bq2_upload_md3        */
+    int32_t  frame;        /* currententity->frame                                   */
+    int32_t  oldframe;     /* currententity->oldframe                                */
+    uint32_t flags;        /* BQ2_ENT_*                                              */
+    float    backlerp;     /* currententity->backlerp                                */
+    float    frontlerp;    /* (float)(1.0 - backlerp), computed as the reference does */
+    float    move[3];
+    float    frontv[3];
+    float    backv[3];
+    float    shell_scale;  /* POWERSUIT_SCALE(_WEAPON) when BQ2_ENT_SHELL            */
+} bq2_entity;
+
+/* One (entity, light) pair.  light[] is the light origin ALREADY in the entity's model space
+ * (M:63733-63745; bq2_host_light_to_model), scale = 32 * light radius (M:63597), view[] is
+ * r_origin in model space (M:66689-66715), only read when BQ2_WANT_TSLIGHT.  32 bytes. */
+typedef struct bq2_pair {
+    int32_t entity;        /* index into the frame's entity array */
+    float   light[3];
+    float   scale;
+    float   view[3];
+} bq2_pair;
+
+/* What one bq2_frame call computes. */
+#define BQ2_WANT_SHADOW   0x1u  /* extruded verts, facing bits, canonical index buffer per pair   */
+#define BQ2_WANT_NTB      0x2u  /* lerped normal / tangent / binormal per entity (a10)            */
+#define BQ2_WANT_TSLIGHT  0x4u  /* tangent-space light vector LightP and half vector tsH per pair */
+#define BQ2_WANT_NOLERPOUT 0x8u /* do not write lerped[] to memory (shadow-only callers)          */
+
+typedef struct bq2_frame_desc {
+    const bq2_entity *ents;    int32_t n_ents;
+    const bq2_pair   *pairs;   int32_t n_pairs;   /* may be 0 / NULL: lerp only                    */
+    uint32_t want;                                 /* BQ2_WANT_*; lerped positions always computed  */
+    uint32_t index_stride;                         /* u32 words reserved per pair (per mesh-pair for
+                                                      MD3); 0 = 12 * max triangles of any model used,
+                                                      the reference's own TrisVerts ratio
+                                                      (data.h:2736: 36*8192 floats = 12 verts/tri)   */
+} bq2_frame_desc;
+
+/* Where the results of the last frame live.  All pointers are DEVICE pointers owned by the ctx,
+ * valid until the next bq2_frame*(ctx) or bq2_destroy.  "Slots": MD2 entities/pairs occupy one
+ * slot; an MD3 entity/pair occupies one slot per mesh (the reference draws per mesh, M:63858).
+ *   ent_slot_first[e]  .. +n meshes : slots of entity e        (n_ents + 1 entries, host array)
+ *   pair_slot_first[p] .. +n meshes : slots of pair p          (n_pairs + 1 entries, host array)
+ * Vertex rows are padded to a multiple of 4 vertices so every row starts 16-byte aligned. */
+typedef struct bq2_frame_out {
+    int32_t  n_ent_slots, n_pair_slots;
+    const int32_t  *ent_slot_first;     /* HOST, n_ents+1                                            */
+    const int32_t  *pair_slot_first;    /* HOST, n_pairs+1                                           */
+    const uint32_t *ent_vert_offset;    /* HOST, n_ent_slots+1 : first vertex of the slot's row      */
+    const uint32_t *pair_vert_offset;   /* HOST, n_pair_slots+1                                      */
+    const uint32_t *pair_bits_offset;   /* HOST, n_pair_slots+1 : first u32 word of the facing bits  */
+    const uint32_t *ent_tb_offset;      /* HOST, n_ent_slots+1 : first row of N/T/B (verts or tris)  */
+    /* device */
+    float    *lerped;          /* [ent verts][3]   tempVertexArray                                    */
+    float    *extruded;        /* [pair verts][3]  extrudedVerts                                      */
+    uint32_t *facing_bits;     /* viss[] packed, bit (t&31) of word t>>5                              */
+    uint32_t *indices;         /* [n_pair_slots][index_stride] canonical index form, see DESIGN.md    */
+    uint32_t *index_count;     /* [n_pair_slots]   == TrisCounter                                     */
+    float    *normals, *tangents, *binormals;   /* [ent rows][3]  (BQ2_WANT_NTB)                      */
+    float    *lightp, *tsh;                     /* [pair verts][3] (BQ2_WANT_TSLIGHT, smooth models)  */
+    uint32_t index_stride;
+    /* totals, valid after bq2_frame / bq2_frame_wait */
+    uint64_t total_lerped_verts;   /* sum of V over entity slots                                      */
+    uint64_t total_indices;        /* sum of index_count                                              */
+    uint64_t total_pairs;          /* pair slots processed                                            */
+    int32_t  overflow_pairs;       /* pair slots whose true count exceeded index_stride (count is the
+                                      true count; only the first index_stride words were written)     */
+} bq2_frame_out;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int          bq2_abi_version(void);
+bq2_status   bq2_create(int device, bq2_ctx **out);
+void         bq2_destroy(bq2_ctx *ctx);
+const char  *bq2_last_error(const bq2_ctx *ctx);          /* ctx may be NULL: last create error   */
+void        *bq2_stream(bq2_ctx *ctx);                     /* cudaStream_t the ctx launches on     */
+int          bq2_device(const bq2_ctx *ctx);
+uint64_t     bq2_kernel_launches(const bq2_ctx *ctx);      /* kernels launched by this ctx so far  */
+
+/* ---- model upload (replaces what Mod_LoadAliasModel M:51216 / Mod_LoadAliasMD3Model M:50584
+ *      leave in model_t for this path) ------------------------------------------------------- */
+/* dmdl_blob: MD2 image in memory exactly as the reference holds it after load (dmdl_t header,
+ * frames at ofs_frames with scale/translate already multiplied by the load scale, dtriangle_t at
+ * ofs_tris; defs.h:3682-3726).  neighbours: int[num_tris][3] (model_t.triangles, defs.h:3486).
+ * tangents/binormals(/normals): model_t.tangents/binormals/normals bytes, [frames][num_xyz] when
+ * BQ2_MODEL_SMOOTHVECS else [frames][num_tris]; may be NULL when N/T/B is never requested. */
+bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *dmdl_blob, size_t blob_bytes,
+                          const int32_t *neighbours, const uint8_t *tangents,
+                          const uint8_t *binormals, const uint8_t *normals,
+                          uint32_t model_flags, int32_t *model_id);
+
+/* One MD3 mesh as the reference keeps it in memory (maliasmesh_t, defs.h:4426-4461). */
+typedef struct bq2_md3_mesh {
+    int32_t num_verts, num_tris;
+    const void     *vertexes;   /* maliasvertex_t[num_frames*num_verts]: float point[3];
+                                   u8 normal, tangent, binormal, pad  (16 bytes, defs.h:4401-4407) */
+    const uint16_t *indexes;    /* WORD[3*num_tris]                                                 */
+    const int32_t  *neighbours; /* neighbours_t[num_tris]                                           */
+    int32_t casts_shadow;       /* 0 = the per-mesh skin filter M:63862-63880 rejects this mesh     */
+} bq2_md3_mesh;
+
+bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t num_frames, const float *frame_translate /*[F][3]*/,
+                          const bq2_md3_mesh *meshes, int32_t num_meshes, int32_t *model_id);
+
+bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
+                          int32_t *num_frames, int32_t *num_meshes,
+                          int32_t *num_verts /*[meshes]*/, int32_t *num_tris /*[meshes]*/);
+
+/* ---- per frame ------------------------------------------------------------------------------ */
+/* Host records in, one fused launch per model family, per-slot counts back.  Equivalent to
+ * bq2_frame_submit + bq2_frame_wait. */
+bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *desc, bq2_frame_out *out);
+bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *desc);   /* async on bq2_stream   */
+bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out);             /* sync + counts readback */
+/* Re-run the kernels of the last submitted frame on the records already resident in HBM
+ * (no host->device or device->host traffic, no sync): the "inputs resident" measurement leg. */
+bq2_status bq2_frame_replay(bq2_ctx *ctx);
+
+/* ---- result download helpers (tests, the drop-in shim) --------------------------------------- */
+/* Copies `count` 32-bit words starting at word offset `first` of a device result array to host. */
+typedef enum bq2_array {
+    BQ2_A_LERPED = 0, BQ2_A_EXTRUDED, BQ2_A_FACING_BITS, BQ2_A_INDICES, BQ2_A_INDEX_COUNT,
+    BQ2_A_NORMALS, BQ2_A_TANGENTS, BQ2_A_BINORMALS, BQ2_A_LIGHTP, BQ2_A_TSH
+} bq2_array;
+bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host);
+const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx);  /* pinned host copy, n_pair_slots      */
+
+/* Expand one pair slot into the reference's non-indexed stream: TrisVerts[3*k..] =
+ * pool[indices[k]] with pool = lerped ++ extruded (M:63661-63708).  Host-side, for the shim. */
+bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t pair_slot, float *tris_verts,
+                                int32_t max_verts, int32_t *tris_counter);
+
+/* ---- host-side C that stays on the CPU (libm trig must be the reference's) ------------------- */
+/* AngleVectors (M:37566-37620). */
+void bq2_host_angle_vectors(const float angles[3], float forward[3], float right[3], float up[3]);
+/* M:63531-63553: move / frontv / backv of an MD2 entity from the two frame headers. */
+void bq2_host_entity_md2(const void *dmdl_blob, int32_t frame, int32_t oldframe, float backlerp,
+                         const float origin[3], const float oldorigin[3], const float angles[3],
+                         uint32_t rf_flags, bq2_entity *out);
+/* M:63825-63856 (also M:66802-66839): the MD3 flavour. */
+void bq2_host_entity_md3(const float frame_translate[3], const float oldframe_translate[3],
+                         int32_t frame, int32_t oldframe, float backlerp,
+                         const float origin[3], const float oldorigin[3], const float angles[3],
+                         bq2_entity *out);
+/* M:63733-63745: world-space point (light origin, or r_origin per M:66689-66715) -> model space. */
+void bq2_host_point_to_model(const float world[3], const float origin[3], const float angles[3],
+                             float out[3]);
+/* Flag filter of R_DrawAliasShadowVolume M:63722-63727 (+ M:64089): 1 = entity casts a volume. */
+int  bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow, float r_shadows);
+
+/* ---- multi-GPU plan (entity-major sharding) ---------------------------------------- */
+/* Rank r of n owns entities [first, first+count).  Pairs follow their entity. */
+void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *first, int32_t *count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BQ2_GPU_H */

@@ -1,0 +1,374 @@
+/*
+ * ref_driver.c -- thin C driver linked in FRONT of the unmodified reference objects
+ * (main.o, unpak.o) to expose the reference's own hot-path functions to tests through ctypes.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT.  Compiled only by oracle/ref/build_ref.sh into
+ * oracle/_ref/libbq2ref.so; includes the reference's defs.h FROM the reference tree (never
+ * copied).  Every bq2ref_* function sets the reference's file-scope globals exactly as the
+ * engine would, calls the reference function, and copies the result globals out.
+ * No arithmetic of the path is restated here.
+ */
+#include "defs.h"          /* reference types: entity_t, model_t, shadowlight_t, dmdl_t, ... */
+#include <string.h>
+#include <math.h>
+
+/* ---- reference globals / functions we touch (data.h) --------------------------------------- */
+extern entity_t       *currententity;                   /* data.h:624  */
+extern model_t        *currentmodel;                    /* data.h:2626 */
+extern shadowlight_t  *currentshadowlight;              /* data.h:2709 */
+extern vec3_t          r_origin;                        /* data.h:766  */
+extern vec3_t          tempVertexArray[MD3_MAX_VERTS];  /* data.h:2827 */
+extern vec3_t          extrudedVerts[MD3_MAX_VERTS];    /* data.h:2731 */
+extern vec3_t          trinormals[MD3_MAX_TRIANGLES];
+extern byte            viss[MD3_MAX_TRIANGLES];
+extern int             TrisCounter;
+extern float           TrisVerts[36 * MD3_MAX_TRIANGLES];
+extern float           smooth_cosine;                   /* data.h:2927 */
+extern bool            r_mirror;
+extern float         (*Sqrt)(float);                    /* data.h:2964 */
+extern cvar_t         *r_faststencil, *r_shadows, *r_playershadow;
+extern glconfig_t      gl_config;
+extern glstate_t       gl_state;
+extern image_t        *r_notexture;
+extern float           r_avertexnormals[162][3];
+extern PFNGLACTIVETEXTUREARBPROC        pglActiveTextureARB;
+extern PFNGLCLIENTACTIVETEXTUREARBPROC  pglClientActiveTextureARB;
+
+void  BuildSqrtTable(void);
+void  R_CalcAliasFrameLerp(dmdl_t *);
+void  R_CalcAliasFrameLerpShadow(dmdl_t *);
+void  R_CalcAliasFrameShadowVolume(dmdl_t *);
+void  R_DrawAliasShadowVolume(void);
+void  R_DrawMD3AliasShadowVolume(void);
+void  GL_DrawAliasFrameLerpLightARB(dmdl_t *, int);
+void  GL_DrawAliasFrameLerpLightARB_vp(dmdl_t *, int);
+void  GL_DrawMD3AliasFrameLerpLightARB(maliasmesh_t *, int, int);
+void  GL_DrawMD3AliasFrameLerpLightARB_vp(maliasmesh_t *, int, maliasmodel_t *, int);
+int   findneighbour(int, int, int, neighbours_t *, dtriangle_t *);
+void  R_BuildTriangleNeighbors(neighbours_t *, WORD *, int);
+void  VecsForTris(float *, float *, float *, float *, float *, float *, vec3_t, vec3_t);
+void  TangentForTrimd3(WORD *, maliasvertex_t *, maliascoord_t *, vec3_t, vec3_t);
+byte  Normal2Index(const vec3_t);
+float VectorNormalize(vec3_t);
+void  AngleVectors(vec3_t, vec3_t, vec3_t, vec3_t);
+
+#define SHADER_ARB6_VALUE 6     /* data.h:2143 (enum shadertype) */
+
+/* ---- GL capture: the light-lerp family hands its stack arrays to glTexCoordPointer --------- */
+#define CAP_TMUS 8
+static int          cap_tmu;
+static const float *cap_ptr[CAP_TMUS];
+static int          cap_size[CAP_TMUS];
+static const float *cap_vertex_ptr;
+static float       *cap_out[CAP_TMUS];          /* destination for each TMU's array, or NULL  */
+static float       *cap_vertex_out;
+static int          cap_count;                  /* vertices of the last glDrawArrays          */
+static int          cap_mesh_hook;              /* MD3: per-mesh readback inside glDrawArrays */
+
+static void APIENTRY cap_active(GLenum t)        { (void)t; }
+static void APIENTRY cap_client_active(GLenum t) { cap_tmu = (int)(t - GL_TEXTURE0); }
+void glTexCoordPointer(GLint size, GLenum type, GLsizei stride, const GLvoid *p)
+{ (void)type; (void)stride; if (cap_tmu >= 0 && cap_tmu < CAP_TMUS) { cap_ptr[cap_tmu] = p; cap_size[cap_tmu] = size; } }
+void glVertexPointer(GLint size, GLenum type, GLsizei stride, const GLvoid *p)
+{ (void)size; (void)type; (void)stride; cap_vertex_ptr = p; }
+
+/* MD3 per-mesh results (the reference overwrites its globals for every mesh, M:63919) */
+typedef struct {
+    float *lerped, *extruded, *tris_verts; uint8_t *viss; int *tris_counter;
+    const int *vert_off, *tri_off, *tv_off; int n; int drawn;
+} md3_sink_t;
+static md3_sink_t md3_sink;
+static int md3_mesh_nverts[MD3_MAX_MESHES], md3_mesh_ntris[MD3_MAX_MESHES], md3_mesh_order[MD3_MAX_MESHES], md3_nmesh_cast;
+
+void glDrawArrays(GLenum mode, GLint first, GLsizei count)
+{
+    (void)mode; (void)first;
+    cap_count = count;
+    for (int t = 0; t < CAP_TMUS; t++)
+        if (cap_out[t] && cap_ptr[t]) memcpy(cap_out[t], cap_ptr[t], sizeof(float) * cap_size[t] * count);
+    if (cap_vertex_out && cap_vertex_ptr) memcpy(cap_vertex_out, cap_vertex_ptr, sizeof(float) * 3 * count);
+    if (cap_mesh_hook && md3_sink.drawn < md3_nmesh_cast) {
+        int m = md3_mesh_order[md3_sink.drawn++];
+        int V = md3_mesh_nverts[m], T = md3_mesh_ntris[m];
+        memcpy(md3_sink.lerped + 3 * md3_sink.vert_off[m], tempVertexArray, sizeof(float) * 3 * V);
+        memcpy(md3_sink.extruded + 3 * md3_sink.vert_off[m], extrudedVerts, sizeof(float) * 3 * V);
+        memcpy(md3_sink.viss + md3_sink.tri_off[m], viss, T);
+        memcpy(md3_sink.tris_verts + 3 * md3_sink.tv_off[m], TrisVerts, sizeof(float) * 3 * TrisCounter);
+        md3_sink.tris_counter[m] = TrisCounter;
+    }
+}
+
+static int cap_elems_nverts;                    /* MD3 light family draws indexed: copy this many rows */
+void glDrawElements(GLenum mode, GLsizei count, GLenum type, const GLvoid *indices)
+{
+    (void)mode; (void)count; (void)type; (void)indices;
+    for (int t = 0; t < CAP_TMUS; t++)
+        if (cap_out[t] && cap_ptr[t]) memcpy(cap_out[t], cap_ptr[t], sizeof(float) * cap_size[t] * cap_elems_nverts);
+}
+/* R_RotateForEntity (M:26670) is called right after the light went to model space (M:63747):
+   snapshot what the compute functions will see. */
+static float snap_light[3], snap_view[3];
+void glTranslatef(GLfloat x, GLfloat y, GLfloat z)
+{
+    (void)x; (void)y; (void)z;
+    if (currentshadowlight) for (int k = 0; k < 3; k++) snap_light[k] = currentshadowlight->origin[k];
+    for (int k = 0; k < 3; k++) snap_view[k] = r_origin[k];
+}
+
+/* ---- set-up ---------------------------------------------------------------------------------- */
+static cvar_t cv_faststencil, cv_shadows, cv_playershadow;
+static entity_t      ent;          /* 9 KB each: static, zeroed */
+static model_t       mdl;
+static shadowlight_t light;
+static image_t       skin_img;
+static int           inited;
+
+int bq2ref_init(void)
+{
+    if (inited) return 0;
+    BuildSqrtTable();
+    Sqrt = sqrtf;                                   /* the reference's default (M:79665-79669, 97006-97010) */
+    smooth_cosine = cos(45.0 * M_PI / 180.0);       /* r_smoothangle 45 (M:4427-4435) */
+    memset(&cv_faststencil, 0, sizeof cv_faststencil);
+    memset(&cv_shadows, 0, sizeof cv_shadows);      cv_shadows.value = 2;       /* r_shadows "2" */
+    memset(&cv_playershadow, 0, sizeof cv_playershadow);
+    r_faststencil = &cv_faststencil; r_shadows = &cv_shadows; r_playershadow = &cv_playershadow;
+    r_mirror = false;
+    memset(&gl_config, 0, sizeof gl_config);        /* vbo = 0: the non-VBO branches compute everything */
+    pglActiveTextureARB = cap_active;
+    pglClientActiveTextureARB = cap_client_active;
+    inited = 1;
+    return 0;
+}
+float bq2ref_smooth_cosine(void) { bq2ref_init(); return smooth_cosine; }
+const float *bq2ref_anorms(void) { return &r_avertexnormals[0][0]; }
+
+static void set_entity(int frame, int oldframe, float backlerp, const float *origin,
+                       const float *oldorigin, const float *angles, int flags)
+{
+    memset(&ent, 0, sizeof ent);
+    ent.model = &mdl; ent.frame = frame; ent.oldframe = oldframe; ent.backlerp = backlerp; ent.flags = flags;
+    for (int k = 0; k < 3; k++) { ent.origin[k] = origin[k]; ent.oldorigin[k] = oldorigin[k]; ent.angles[k] = angles[k]; }
+    currententity = &ent;
+}
+static void set_light(const float *org, float radius)
+{
+    memset(&light, 0, sizeof light);
+    for (int k = 0; k < 3; k++) light.origin[k] = org[k];
+    light.radius = radius;
+    currentshadowlight = &light;
+}
+
+/* ---- MD2 ------------------------------------------------------------------------------------- */
+/* R_CalcAliasFrameLerp alone (M:63510). flags may carry RF_SHELL_* / RF_WEAPONMODEL. */
+int bq2ref_md2_lerp(void *blob, int frame, int oldframe, float backlerp, const float *origin,
+                    const float *oldorigin, const float *angles, int flags, float *lerped)
+{
+    bq2ref_init();
+    dmdl_t *h = (dmdl_t *)blob;
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blob; currentmodel = &mdl;
+    set_entity(frame, oldframe, backlerp, origin, oldorigin, angles, flags);
+    R_CalcAliasFrameLerp(h);
+    memcpy(lerped, tempVertexArray, sizeof(float) * 3 * h->num_xyz);
+    return h->num_xyz;
+}
+
+/* The whole R_DrawAliasShadowVolume (M:63713): world-space light in, every intermediate out.
+ * light_local receives currentshadowlight->origin as seen by the compute functions. */
+int bq2ref_md2_shadow(void *blob, const int32_t *neighbours, int frame, int oldframe, float backlerp,
+                      const float *origin, const float *oldorigin, const float *angles, int flags,
+                      const float *light_world, float radius,
+                      float *lerped, float *extruded, float *trinorm, uint8_t *viss_out,
+                      float *tris_verts, float *light_local)
+{
+    bq2ref_init();
+    dmdl_t *h = (dmdl_t *)blob;
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blob;
+    mdl.triangles = (neighbours_t *)neighbours;
+    set_entity(frame, oldframe, backlerp, origin, oldorigin, angles, flags);
+    set_light(light_world, radius);
+    /* poison outputs so "not written" is visible */
+    memset(extrudedVerts, 0xff, sizeof(float) * 3 * h->num_xyz);
+    TrisCounter = -1;
+    R_DrawAliasShadowVolume();
+    if (TrisCounter < 0) return -1;                   /* early-out by flags (M:63722-63727) */
+    if (lerped)     memcpy(lerped, tempVertexArray, sizeof(float) * 3 * h->num_xyz);
+    if (extruded)   memcpy(extruded, extrudedVerts, sizeof(float) * 3 * h->num_xyz);
+    if (trinorm)    memcpy(trinorm, trinormals, sizeof(float) * 3 * h->num_tris);
+    if (viss_out)   memcpy(viss_out, viss, h->num_tris);
+    if (tris_verts) memcpy(tris_verts, TrisVerts, sizeof(float) * 3 * TrisCounter);
+    if (light_local) for (int k = 0; k < 3; k++) light_local[k] = snap_light[k];
+    return TrisCounter;
+}
+
+/* The two compute functions with a light that is ALREADY in model space (M:63586, 63634). */
+int bq2ref_md2_shadow_local(void *blob, const int32_t *neighbours, int frame, int oldframe, float backlerp,
+                            const float *origin, const float *oldorigin, const float *angles,
+                            const float *light_model, float radius,
+                            float *lerped, float *extruded, float *trinorm, uint8_t *viss_out, float *tris_verts)
+{
+    bq2ref_init();
+    dmdl_t *h = (dmdl_t *)blob;
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blob;
+    mdl.triangles = (neighbours_t *)neighbours; currentmodel = &mdl;
+    set_entity(frame, oldframe, backlerp, origin, oldorigin, angles, 0);
+    set_light(light_model, radius);
+    memset(extrudedVerts, 0xff, sizeof(float) * 3 * h->num_xyz);
+    R_CalcAliasFrameLerpShadow(h);
+    R_CalcAliasFrameShadowVolume(h);
+    if (lerped)     memcpy(lerped, tempVertexArray, sizeof(float) * 3 * h->num_xyz);
+    if (extruded)   memcpy(extruded, extrudedVerts, sizeof(float) * 3 * h->num_xyz);
+    if (trinorm)    memcpy(trinorm, trinormals, sizeof(float) * 3 * h->num_tris);
+    if (viss_out)   memcpy(viss_out, viss, h->num_tris);
+    if (tris_verts) memcpy(tris_verts, TrisVerts, sizeof(float) * 3 * TrisCounter);
+    return TrisCounter;
+}
+
+/* Timing loop for the CPU baseline: n pairs over one model, entity/light lists supplied.
+ * Returns the sum of TrisCounter (so the work cannot be optimised away). */
+long long bq2ref_md2_bench(void *blob, const int32_t *neighbours, int n_pairs,
+                           const int32_t *frames, const int32_t *oldframes, const float *backlerps,
+                           const float *lights_model /*[n][3]*/, float radius)
+{
+    bq2ref_init();
+    dmdl_t *h = (dmdl_t *)blob;
+    static const float zero[3] = {0, 0, 0};
+    long long total = 0;
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blob;
+    mdl.triangles = (neighbours_t *)neighbours; currentmodel = &mdl;
+    for (int p = 0; p < n_pairs; p++) {
+        set_entity(frames[p], oldframes[p], backlerps[p], zero, zero, zero, 0);
+        set_light(lights_model + 3 * p, radius);
+        R_CalcAliasFrameLerpShadow(h);
+        R_CalcAliasFrameShadowVolume(h);
+        total += TrisCounter;
+    }
+    return total;
+}
+
+/* MD2 light-lerp family.  which: 0 = ..LightARB (LightP on TMU1, tsH on TMU3, expanded verts on
+ * TMU2), 1 = ..LightARB_vp (tangent TMU1? see below).  We record every TMU; callers pick. */
+int bq2ref_md2_light(void *blob, const uint8_t *tangents, const uint8_t *binormals, const uint8_t *normals,
+                     int smooth, int frame, int oldframe, float backlerp,
+                     const float *origin, const float *oldorigin, const float *angles,
+                     const float *light_model, const float *view_model, int vp,
+                     float *tmu_out /*[CAP_TMUS][3*3*T]*/, float *vertex_out, int *sizes /*[CAP_TMUS]*/)
+{
+    bq2ref_init();
+    dmdl_t *h = (dmdl_t *)blob;
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blob;
+    mdl.tangents = (byte *)tangents; mdl.binormals = (byte *)binormals; mdl.normals = (byte *)normals;
+    mdl.flags = smooth ? RF_SMOOTHVECS : 0; currentmodel = &mdl;
+    set_entity(frame, oldframe, backlerp, origin, oldorigin, angles, 0);
+    set_light(light_model, 300.0f);
+    for (int k = 0; k < 3; k++) r_origin[k] = view_model[k];
+    memset(cap_ptr, 0, sizeof cap_ptr); memset(cap_size, 0, sizeof cap_size); cap_vertex_ptr = 0;
+    gl_state.currenttmu = -1; cap_tmu = 0;
+    cap_out[0] = 0;
+    for (int t = 1; t < CAP_TMUS; t++) cap_out[t] = tmu_out + (size_t)t * 9 * h->num_tris;
+    cap_vertex_out = vertex_out;
+    if (vp) GL_DrawAliasFrameLerpLightARB_vp(h, SHADER_ARB6_VALUE);
+    else    GL_DrawAliasFrameLerpLightARB(h, SHADER_ARB6_VALUE);
+    for (int t = 0; t < CAP_TMUS; t++) { cap_out[t] = 0; if (sizes) sizes[t] = cap_ptr[t] ? cap_size[t] : 0; }
+    cap_vertex_out = 0;
+    return cap_count;
+}
+
+/* ---- MD3 ------------------------------------------------------------------------------------- */
+/* Build a maliasmodel_t around caller arrays and run R_DrawMD3AliasShadowVolume (M:63800) whole.
+ * mesh_verts[m] : maliasvertex_t[num_frames*V_m]; results are gathered per mesh from inside the
+ * (stubbed) glDrawArrays the function issues after each mesh. */
+int bq2ref_md3_shadow(int num_frames, const float *frame_translate, int num_meshes,
+                      const int *num_verts, const int *num_tris, void *const *mesh_verts,
+                      void *const *mesh_indexes, void *const *mesh_neighbours, const int *casts,
+                      int frame, int oldframe, float backlerp,
+                      const float *origin, const float *oldorigin, const float *angles, int flags,
+                      const float *light_world, float radius,
+                      const int *vert_off, const int *tri_off, const int *tv_off,
+                      float *lerped, float *extruded, uint8_t *viss_out, float *tris_verts, int *tris_counter)
+{
+    static maliasmodel_t mm; static maliasmesh_t meshes[MD3_MAX_MESHES]; static maliasframe_t frames[MD3_MAX_FRAMES];
+    static image_t noshadow_img;
+    bq2ref_init();
+    if (num_meshes > MD3_MAX_MESHES || num_frames > MD3_MAX_FRAMES) return -2;
+    memset(&mm, 0, sizeof mm); memset(meshes, 0, sizeof meshes);
+    memset(&skin_img, 0, sizeof skin_img); skin_img.CastShadow = true;
+    memset(&noshadow_img, 0, sizeof noshadow_img); noshadow_img.AlphaTest = true;   /* rejected by M:63878-63880 */
+    for (int f = 0; f < num_frames; f++) for (int k = 0; k < 3; k++) frames[f].translate[k] = frame_translate[3*f+k];
+    mm.num_frames = num_frames; mm.frames = frames; mm.num_meshes = num_meshes; mm.meshes = meshes;
+    md3_nmesh_cast = 0;
+    for (int m = 0; m < num_meshes; m++) {
+        meshes[m].num_verts = num_verts[m]; meshes[m].num_tris = num_tris[m];
+        meshes[m].vertexes = (maliasvertex_t *)mesh_verts[m];
+        meshes[m].indexes = (WORD *)mesh_indexes[m];
+        meshes[m].triangles = (neighbours_t *)mesh_neighbours[m];
+        meshes[m].num_skins = 1;
+        meshes[m].img_skins[0] = casts[m] ? &skin_img : &noshadow_img;
+        md3_mesh_nverts[m] = num_verts[m]; md3_mesh_ntris[m] = num_tris[m];
+        tris_counter[m] = -1;
+        if (casts[m]) md3_mesh_order[md3_nmesh_cast++] = m;
+    }
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias_md3; mdl.extradata = &mm;
+    set_entity(frame, oldframe, backlerp, origin, oldorigin, angles, flags);
+    set_light(light_world, radius);
+    md3_sink.lerped = lerped; md3_sink.extruded = extruded; md3_sink.viss = viss_out;
+    md3_sink.tris_verts = tris_verts; md3_sink.tris_counter = tris_counter;
+    md3_sink.vert_off = vert_off; md3_sink.tri_off = tri_off; md3_sink.tv_off = tv_off; md3_sink.drawn = 0;
+    cap_mesh_hook = 1;
+    R_DrawMD3AliasShadowVolume();
+    cap_mesh_hook = 0;
+    return md3_sink.drawn;
+}
+
+/* MD3 light family, one mesh.  The reference lerps the mesh's verts in R_DrawMD3AliasObjectLight
+ * (M:66892-66896) before calling these; callers pass the lerped verts they want used.
+ * vp=0: TMU1 = LightP, TMU3 = tsH (M:65839).  vp=1: TMU1 = binormal, TMU2 = normal, TMU3 = tangent
+ * (M:65671).  tmu_out = [CAP_TMUS][3*V]. */
+int bq2ref_md3_light(void *mesh_verts, int num_verts, int frame, int oldframe, float backlerp,
+                     const float *lerped_in, const float *light_model, const float *view_model, int vp,
+                     float *tmu_out, int *sizes)
+{
+    static maliasmodel_t mm; static maliasmesh_t mesh;
+    static const float zero[3] = {0, 0, 0};
+    bq2ref_init();
+    memset(&mm, 0, sizeof mm); memset(&mesh, 0, sizeof mesh);
+    mesh.num_verts = num_verts; mesh.vertexes = (maliasvertex_t *)mesh_verts; mesh.num_tris = 0;
+    mm.num_meshes = 1; mm.meshes = &mesh;
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias_md3; mdl.extradata = &mm; currentmodel = &mdl;
+    set_entity(frame, oldframe, backlerp, zero, zero, zero, 0);
+    set_light(light_model, 300.0f);
+    for (int k = 0; k < 3; k++) r_origin[k] = view_model[k];
+    memcpy(tempVertexArray, lerped_in, sizeof(float) * 3 * num_verts);
+    memset(cap_ptr, 0, sizeof cap_ptr); memset(cap_size, 0, sizeof cap_size);
+    gl_state.currenttmu = -1; cap_tmu = 0;
+    cap_out[0] = 0;
+    for (int t = 1; t < CAP_TMUS; t++) cap_out[t] = tmu_out + (size_t)t * 3 * num_verts;
+    cap_elems_nverts = num_verts;
+    if (vp) GL_DrawMD3AliasFrameLerpLightARB_vp(&mesh, SHADER_ARB6_VALUE, &mm, 0);
+    else    GL_DrawMD3AliasFrameLerpLightARB(&mesh, SHADER_ARB6_VALUE, 0);
+    for (int t = 0; t < CAP_TMUS; t++) { cap_out[t] = 0; if (sizes) sizes[t] = cap_ptr[t] ? cap_size[t] : 0; }
+    return num_verts;
+}
+
+/* ---- precompute ------------------------------------------------------------------------------ */
+/* M:51643-51653 restated as a CALL sequence around the reference's findneighbour. */
+void bq2ref_md2_neighbours(void *blob, int32_t *out)
+{
+    dmdl_t *h = (dmdl_t *)blob;
+    dtriangle_t *tris = (dtriangle_t *)((byte *)h + h->ofs_tris);
+    neighbours_t *nb = (neighbours_t *)out;
+    for (int i = 0; i < h->num_tris; i++) for (int j = 0; j < 3; j++) nb[i].neighbours[j] = -1;
+    for (int i = 0; i < h->num_tris; i++)
+        for (int j = 0; j < 3; j++)
+            if (nb[i].neighbours[j] == -1)
+                nb[i].neighbours[j] = findneighbour(i, j, h->num_tris, nb, tris);
+}
+void bq2ref_md3_neighbours(uint16_t *indexes, int num_tris, int32_t *out)
+{ R_BuildTriangleNeighbors((neighbours_t *)out, (WORD *)indexes, num_tris); }
+int  bq2ref_normal2index(const float *v) { vec3_t t = { v[0], v[1], v[2] }; return Normal2Index(t); }
+void bq2ref_vecs_for_tris(float *v0, float *v1, float *v2, float *st0, float *st1, float *st2, float *tan, float *bin)
+{ VecsForTris(v0, v1, v2, st0, st1, st2, tan, bin); }
+void bq2ref_tangent_for_tri_md3(uint16_t *index, void *verts, float *st, float *tan, float *bin)
+{ TangentForTrimd3((WORD *)index, (maliasvertex_t *)verts, (maliascoord_t *)st, tan, bin); }
+void bq2ref_angle_vectors(float *angles, float *f, float *r, float *u) { AngleVectors(angles, f, r, u); }
+float bq2ref_vector_normalize(float *v) { return VectorNormalize(v); }
