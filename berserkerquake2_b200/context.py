@@ -1,0 +1,181 @@
+"""Context / FrameResult: the Python face of ``bq2_ctx`` (include/bq2_gpu.h).
+
+One Context per GPU (one process per GPU under torch.distributed).  Inputs are numpy structured
+arrays with the C record layouts; results stay in HBM and are fetched on demand with
+``FrameResult.lerped(slot)`` etc. (tests) or consumed in place through the device pointers in
+``FrameResult.out`` (a renderer).  Nothing here computes: no numpy arithmetic stands in for a kernel.
+"""
+import ctypes as C
+import numpy as np
+from . import _capi as c
+
+
+class Context:
+    def __init__(self, device=0):
+        h = C.c_void_p()
+        st = c.lib.bq2_create(int(device), C.byref(h))
+        if st != c.OK:
+            raise c.Bq2Error(st, (c.lib.bq2_last_error(None) or b"").decode())
+        self._h = h
+        self.device = int(device)
+        self._keep = []          # host arrays borrowed by the C side for the duration of a call
+
+    # -- lifetime ------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            c.lib.bq2_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st, allow=()):
+        if st != c.OK and st not in allow:
+            raise c.Bq2Error(st, (c.lib.bq2_last_error(self._h) or b"").decode())
+        return st
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) all work of this context is launched on."""
+        return c.lib.bq2_stream(self._h) or 0
+
+    @property
+    def kernel_launches(self):
+        return int(c.lib.bq2_kernel_launches(self._h))
+
+    # -- models --------------------------------------------------------------------------------------
+    def upload_md2(self, blob, neighbours, tangents=None, binormals=None, normals=None, smooth=True):
+        """blob: uint8 MD2 image as the reference holds it after Mod_LoadAliasModel (main.c:51216);
+        neighbours: int32 [T][3] (model_t.triangles)."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        nb = None if neighbours is None else np.ascontiguousarray(neighbours, np.int32)
+        tb = [None if a is None else np.ascontiguousarray(a, np.uint8) for a in (tangents, binormals, normals)]
+        mid = C.c_int32(-1)
+        self._check(c.lib.bq2_upload_md2(self._h, c.ptr(blob), blob.nbytes, c.ptr(nb), c.ptr(tb[0]), c.ptr(tb[1]),
+                                         c.ptr(tb[2]), c.MODEL_SMOOTHVECS if smooth else 0, C.byref(mid)))
+        return mid.value
+
+    def upload_md3(self, frame_translate, meshes):
+        """meshes: list of dicts {verts: MD3_VERTEX [F][V], indexes: uint16 [T][3], neighbours: int32 [T][3],
+        casts_shadow: bool}."""
+        ft = np.ascontiguousarray(frame_translate, np.float32)
+        arr = (c.Md3Mesh * len(meshes))()
+        keep = []
+        for i, m in enumerate(meshes):
+            v = np.ascontiguousarray(m["verts"]); ix = np.ascontiguousarray(m["indexes"], np.uint16)
+            nb = None if m.get("neighbours") is None else np.ascontiguousarray(m["neighbours"], np.int32)
+            keep += [v, ix, nb]
+            assert v.shape[0] == ft.shape[0]
+            arr[i].num_verts = v.shape[1]; arr[i].num_tris = ix.shape[0]
+            arr[i].vertexes = v.ctypes.data; arr[i].indexes = ix.ctypes.data
+            arr[i].neighbours = None if nb is None else nb.ctypes.data
+            arr[i].casts_shadow = 1 if m.get("casts_shadow", True) else 0
+        mid = C.c_int32(-1)
+        self._check(c.lib.bq2_upload_md3(self._h, ft.shape[0], c.ptr(ft), arr, len(meshes), C.byref(mid)))
+        return mid.value
+
+    # -- per frame -----------------------------------------------------------------------------------
+    def build_records(self, world_ents, world_lights, pair_ent, pair_light, view_world=None):
+        """The renderer's (light x entity) loop nest flattened into bq2_entity / bq2_pair records, on the
+        host in C (bq2_build_records)."""
+        we = np.ascontiguousarray(world_ents, c.WORLD_ENTITY_DTYPE)
+        wl = np.ascontiguousarray(world_lights, c.WORLD_LIGHT_DTYPE)
+        pe = np.ascontiguousarray(pair_ent, np.int32); pl = np.ascontiguousarray(pair_light, np.int32)
+        vw = None if view_world is None else np.ascontiguousarray(view_world, np.float32)
+        ents = np.zeros(len(we), c.ENTITY_DTYPE); pairs = np.zeros(len(pe), c.PAIR_DTYPE)
+        kept = C.c_int32(0)
+        self._check(c.lib.bq2_build_records(self._h, c.ptr(we), len(we), c.ptr(wl), len(wl), c.ptr(pe), c.ptr(pl),
+                                            len(pe), c.ptr(vw), c.ptr(ents), c.ptr(pairs), C.byref(kept)))
+        return ents, pairs[:kept.value]
+
+    def _desc(self, ents, pairs, want, index_stride):
+        ents = np.ascontiguousarray(ents, c.ENTITY_DTYPE)
+        pairs = np.zeros(0, c.PAIR_DTYPE) if pairs is None else np.ascontiguousarray(pairs, c.PAIR_DTYPE)
+        self._keep = [ents, pairs]
+        d = c.FrameDesc()
+        d.ents = ents.ctypes.data if len(ents) else None; d.n_ents = len(ents)
+        d.pairs = pairs.ctypes.data if len(pairs) else None; d.n_pairs = len(pairs)
+        d.want = int(want); d.index_stride = int(index_stride)
+        return d
+
+    def frame(self, ents, pairs=None, want=c.WANT_SHADOW, index_stride=0, allow_overflow=False):
+        d = self._desc(ents, pairs, want, index_stride)
+        out = c.FrameOut()
+        st = self._check(c.lib.bq2_frame(self._h, C.byref(d), C.byref(out)),
+                         allow=(c.E_OVERFLOW,) if allow_overflow else ())
+        return FrameResult(self, out, st)
+
+    def submit(self, ents, pairs=None, want=c.WANT_SHADOW, index_stride=0):
+        d = self._desc(ents, pairs, want, index_stride)
+        self._check(c.lib.bq2_frame_submit(self._h, C.byref(d)))
+
+    def wait(self, allow_overflow=False):
+        out = c.FrameOut()
+        st = self._check(c.lib.bq2_frame_wait(self._h, C.byref(out)), allow=(c.E_OVERFLOW,) if allow_overflow else ())
+        return FrameResult(self, out, st)
+
+    def replay(self):
+        """Re-launch the last frame's kernel on the records already in HBM (no copies, no sync)."""
+        self._check(c.lib.bq2_frame_replay(self._h))
+
+    def download(self, which, first, count, dtype):
+        buf = np.zeros(int(count), dtype)
+        assert buf.itemsize == 4
+        if count:
+            self._check(c.lib.bq2_download(self._h, which, int(first), int(count), c.ptr(buf)))
+        return buf
+
+
+class FrameResult:
+    """Where one frame's results live (device) plus host-side slot tables."""
+
+    def __init__(self, ctx, out, status):
+        self.ctx, self.out, self.status = ctx, out, status
+        nes, nps = out.n_ent_slots, out.n_pair_slots
+        self.n_ent_slots, self.n_pair_slots = nes, nps
+        self.ent_vert_offset = np.ctypeslib.as_array(out.ent_vert_offset, (nes + 1,)).copy()
+        self.ent_tb_offset = np.ctypeslib.as_array(out.ent_tb_offset, (nes + 1,)).copy()
+        self.pair_vert_offset = np.ctypeslib.as_array(out.pair_vert_offset, (nps + 1,)).copy()
+        self.pair_bits_offset = np.ctypeslib.as_array(out.pair_bits_offset, (nps + 1,)).copy()
+        self.index_stride = out.index_stride
+        self.total_lerped_verts = out.total_lerped_verts
+        self.total_indices = out.total_indices
+        self.overflow_pairs = out.overflow_pairs
+        hc = c.lib.bq2_host_index_counts(ctx._h)
+        self.index_counts = np.ctypeslib.as_array(hc, (nps,)).copy() if nps else np.zeros(0, np.uint32)
+
+    # rows are padded to 4 vertices; callers pass the true V / T
+    def lerped(self, ent_slot, V):
+        return self.ctx.download(c.A_LERPED, 3 * int(self.ent_vert_offset[ent_slot]), 3 * V, np.float32).reshape(V, 3)
+
+    def extruded(self, pair_slot, V):
+        return self.ctx.download(c.A_EXTRUDED, 3 * int(self.pair_vert_offset[pair_slot]), 3 * V, np.float32).reshape(V, 3)
+
+    def facing(self, pair_slot, T):
+        w = self.ctx.download(c.A_FACING_BITS, int(self.pair_bits_offset[pair_slot]), (T + 31) // 32, np.uint32)
+        return ((w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & 1).astype(np.uint8).reshape(-1)[:T]
+
+    def indices(self, pair_slot):
+        n = min(int(self.index_counts[pair_slot]), int(self.index_stride))
+        return self.ctx.download(c.A_INDICES, int(pair_slot) * int(self.index_stride), n, np.uint32)
+
+    def ntb(self, ent_slot, rows):
+        o = 3 * int(self.ent_tb_offset[ent_slot])
+        return tuple(self.ctx.download(w, o, 3 * rows, np.float32).reshape(rows, 3)
+                     for w in (c.A_NORMALS, c.A_TANGENTS, c.A_BINORMALS))
+
+    def tslight(self, pair_slot, V):
+        o = 3 * int(self.pair_vert_offset[pair_slot])
+        return tuple(self.ctx.download(w, o, 3 * V, np.float32).reshape(V, 3) for w in (c.A_LIGHTP, c.A_TSH))
+
+    def trisverts(self, pair_slot, max_verts=36 * 8192 // 3):
+        """The reference's expanded stream (TrisVerts, TrisCounter) for one pair slot."""
+        buf = np.zeros((max_verts, 3), np.float32)
+        n = C.c_int32(0)
+        self.ctx._check(c.lib.bq2_expand_trisverts(self.ctx._h, int(pair_slot), c.ptr(buf), max_verts, C.byref(n)))
+        return buf[:n.value].copy()

@@ -1,0 +1,629 @@
+/*
+ * bq2_api.cu -- host side of the C ABI in include/bq2_gpu.h: context, model residency in HBM,
+ * per-frame record packing, launch, read-back.  C++ inside, extern "C" outside.
+ *
+ * What lives in HBM (bq2_internal.h has the exact layouts): per mesh the vertex frames, the
+ * 12-byte/triangle index+neighbour table and the tangent-space byte arrays, allocated from
+ * 64 MiB slabs; per frame one packed record buffer (entity slots then pair slots, one H2D copy)
+ * and the output arrays, grown geometrically and reused across frames.
+ *
+ * There is no CPU fallback anywhere in this file: every entry point either runs the CUDA path or
+ * returns an error.
+ */
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "bq2_gpu.h"
+#include "bq2_internal.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct Slab { unsigned char *base; size_t size, used; };
+
+struct Model {
+    bool md3 = false;
+    int  F = 0;
+    int  first_mesh = 0, n_mesh = 0;
+    uint32_t flags = 0;
+    std::vector<int> V, T, casts;
+    std::vector<float> hdr;      /* MD2: F x {scale[3], translate[3]} (daliasframe_t header);
+                                    MD3: F x translate[3] (maliasframe_t.translate)            */
+};
+
+template <typename T> struct DevBuf {
+    T *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = std::max(n, cap + cap / 2);
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {
+    unsigned char *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        size_t want = std::max(n, cap + cap / 2);
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMallocHost((void **)&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+} // namespace
+
+struct bq2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    std::vector<Slab> slabs;
+    std::vector<Model> models;
+    std::vector<bq2_dev_mesh> meshes;           /* host mirror of the device mesh table */
+    DevBuf<bq2_dev_mesh> d_meshes;
+    bool meshes_dirty = false;
+
+    /* frame state */
+    std::vector<int32_t>  ent_slot_first, pair_slot_first;
+    std::vector<uint32_t> ent_vert_off, pair_vert_off, pair_bits_off, ent_tb_off;
+    std::vector<uint32_t> pair_slot_ent, cursor;                 /* scratch for the counting sort */
+    std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
+    std::vector<int32_t>  pair_slot_entslot;
+    PinBuf h_records, h_counts;
+    DevBuf<unsigned char> d_records;
+    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
+    DevBuf<uint32_t> facing_bits, indices, index_count;
+    bq2_launch launch{};
+    int max_V = 0, max_T = 0, any_md2 = 0;
+    int32_t n_ent_slots = 0, n_pair_slots = 0, n_ents = 0, n_pairs = 0;
+    uint64_t total_verts = 0;
+    bool submitted = false;
+    bq2_frame_out out{};
+};
+
+namespace {
+
+bq2_status fail(bq2_ctx *c, bq2_status s, const char *what)
+{ if (c) c->err = what; else g_create_error = what; return s; }
+bq2_status fail_cuda(bq2_ctx *c, cudaError_t e, const char *where)
+{
+    std::string m = std::string(where) + ": " + cudaGetErrorString(e);
+    if (c) c->err = m; else g_create_error = m;
+    return BQ2_E_CUDA;
+}
+#define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, where); } while (0)
+
+/* bump allocation out of 64 MiB slabs; 256-byte aligned so every array is TMA/128-bit friendly */
+bq2_status arena_alloc(bq2_ctx *ctx, size_t bytes, unsigned char **out)
+{
+    const size_t kSlab = 64u << 20;
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (!ctx->slabs.empty()) {
+        Slab &s = ctx->slabs.back();
+        if (s.used + bytes <= s.size) { *out = s.base + s.used; s.used += bytes; return BQ2_OK; }
+    }
+    Slab s; s.size = std::max(kSlab, bytes); s.used = bytes;
+    CK(cudaMalloc((void **)&s.base, s.size), "cudaMalloc(model slab)");
+    ctx->slabs.push_back(s);
+    *out = s.base;
+    return BQ2_OK;
+}
+
+struct md2_header {
+    int32_t ident, version, skinwidth, skinheight, framesize;
+    int32_t num_skins, num_xyz, num_st, num_tris, num_glcmds, num_frames;
+    int32_t ofs_skins, ofs_st, ofs_tris, ofs_frames, ofs_glcmds, ofs_end;
+};
+
+inline uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
+
+/* index + neighbour table -> six s16 arrays of Tp entries */
+void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t *nb /*[T][3] or null*/, int16_t *dst)
+{
+    memset(dst, 0, sizeof(int16_t) * 6 * (size_t)Tp);
+    for (int t = 0; t < T; t++)
+        for (int k = 0; k < 3; k++) {
+            dst[(size_t)k * Tp + t] = (int16_t)idx[3 * t + k];
+            dst[(size_t)(3 + k) * Tp + t] = (int16_t)(nb ? nb[3 * t + k] : -1);
+        }
+    for (int t = T; t < Tp; t++) for (int k = 0; k < 3; k++) dst[(size_t)(3 + k) * Tp + t] = -1;
+}
+
+} // namespace
+
+extern "C" {
+
+int bq2_abi_version(void) { return BQ2_ABI_VERSION; }
+
+bq2_status bq2_create(int device, bq2_ctx **out)
+{
+    if (!out) return fail(nullptr, BQ2_E_INVALID, "bq2_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("bq2_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path";
+        return BQ2_E_NODEVICE;
+    }
+    if (device < 0 || device >= n) return fail(nullptr, BQ2_E_INVALID, "bq2_create: device index out of range");
+    bq2_ctx *ctx = new (std::nothrow) bq2_ctx();
+    if (!ctx) return fail(nullptr, BQ2_E_NOMEM, "bq2_create: out of host memory");
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaSetDevice"); delete ctx; return BQ2_E_CUDA; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaGetDeviceProperties"); delete ctx; return BQ2_E_CUDA; }
+    if (prop.major != 10) {
+        g_create_error = "bq2_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        delete ctx; return BQ2_E_NODEVICE;
+    }
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaStreamCreate"); delete ctx; return BQ2_E_CUDA; }
+    if ((e = (cudaError_t)bq2_kernel_prepare()) != cudaSuccess) { fail_cuda(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)"); cudaStreamDestroy(ctx->stream); delete ctx; return BQ2_E_CUDA; }
+    *out = ctx;
+    return BQ2_OK;
+}
+
+void bq2_destroy(bq2_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (Slab &s : ctx->slabs) cudaFree(s.base);
+    ctx->d_meshes.release(); ctx->d_records.release();
+    ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
+    ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release();
+    ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
+    ctx->h_records.release(); ctx->h_counts.release();
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *bq2_last_error(const bq2_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+void *bq2_stream(bq2_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int bq2_device(const bq2_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t bq2_kernel_launches(const bq2_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, const int32_t *neighbours,
+                          const uint8_t *tangents, const uint8_t *binormals, const uint8_t *normals,
+                          uint32_t model_flags, int32_t *model_id)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!blob || !model_id || blob_bytes < sizeof(md2_header)) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: bad arguments");
+    const md2_header *h = (const md2_header *)blob;
+    const int V = h->num_xyz, T = h->num_tris, F = h->num_frames;
+    /* the reference's load-time checks, M:51247-51264 */
+    if (h->version != 8) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: wrong version number");
+    if (V <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: model has no vertices");
+    if (V > BQ2_MD2_MAX_VERTS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md2: model has too many vertices");
+    if (T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: model has no triangles");
+    if (T > BQ2_MD2_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md2: model has too many triangles");
+    if (F <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: model has no frames");
+    if (h->framesize < 40 + 4 * V || h->ofs_tris < 0 || h->ofs_frames < 0 ||
+        (size_t)h->ofs_tris + 12u * (size_t)T > blob_bytes ||
+        (size_t)h->ofs_frames + (size_t)F * (size_t)h->framesize > blob_bytes)
+        return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: offsets run past the blob");
+    const unsigned char *base = (const unsigned char *)blob;
+    const int16_t *tri = (const int16_t *)(base + h->ofs_tris);
+    std::vector<int32_t> idx(3 * (size_t)T);
+    for (int t = 0; t < T; t++)
+        for (int k = 0; k < 3; k++) {
+            int v = tri[6 * t + k];
+            if (v < 0 || v >= V) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: triangle index out of range");
+            idx[3 * t + k] = v;
+        }
+    if (neighbours)
+        for (size_t i = 0; i < 3 * (size_t)T; i++)
+            if (neighbours[i] < -1 || neighbours[i] >= T) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: neighbour out of range");
+
+    const bool smooth = model_flags & BQ2_MODEL_SMOOTHVECS;
+    const bool has_tb = tangents && binormals && (smooth || normals);
+    const int Tp = (T + 7) & ~7;
+    const uint32_t vstride = up16(4u * (uint32_t)V);
+    const uint32_t rows = smooth ? (uint32_t)V : (uint32_t)T, tbstride = up16(rows);
+    const size_t off_tri = (size_t)F * vstride;
+    const size_t off_tb = off_tri + up16(12u * (uint32_t)Tp);
+    const size_t n_tb = has_tb ? (smooth ? 2u : 3u) : 0u;
+    const size_t total = off_tb + n_tb * (size_t)F * tbstride;
+    std::vector<unsigned char> img(total, 0);
+    for (int f = 0; f < F; f++)
+        memcpy(&img[(size_t)f * vstride], base + h->ofs_frames + (size_t)f * h->framesize + 40, 4u * (size_t)V);
+    pack_tri_table(T, Tp, idx.data(), neighbours, (int16_t *)&img[off_tri]);
+    if (has_tb)
+        for (int f = 0; f < F; f++) {
+            memcpy(&img[off_tb + (size_t)f * tbstride], tangents + (size_t)f * rows, rows);
+            memcpy(&img[off_tb + ((size_t)F + f) * tbstride], binormals + (size_t)f * rows, rows);
+            if (!smooth) memcpy(&img[off_tb + (2 * (size_t)F + f) * tbstride], normals + (size_t)f * rows, rows);
+        }
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    unsigned char *d = nullptr;
+    bq2_status s = arena_alloc(ctx, total, &d);
+    if (s != BQ2_OK) return s;
+    CK(cudaMemcpyAsync(d, img.data(), total, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(model)");
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(model)");
+
+    bq2_dev_mesh m{};
+    m.verts = d; m.tri = (const int16_t *)(d + off_tri);
+    m.tb = has_tb ? d + off_tb : nullptr;
+    m.bn = has_tb ? d + off_tb + (size_t)F * tbstride : nullptr;
+    m.nm = (has_tb && !smooth) ? d + off_tb + 2 * (size_t)F * tbstride : nullptr;
+    m.V = V; m.T = T; m.F = F; m.Tp = Tp; m.vstride = vstride; m.tbstride = tbstride;
+    m.flags = (smooth ? BQ2_MESH_SMOOTH : 0u) | (has_tb ? BQ2_MESH_HAS_TB : 0u);
+    Model mo; mo.md3 = false; mo.F = F; mo.first_mesh = (int)ctx->meshes.size(); mo.n_mesh = 1; mo.flags = model_flags;
+    mo.V.push_back(V); mo.T.push_back(T); mo.casts.push_back(1);
+    mo.hdr.resize(6 * (size_t)F);
+    for (int f = 0; f < F; f++) memcpy(&mo.hdr[6 * (size_t)f], base + h->ofs_frames + (size_t)f * h->framesize, 24);
+    ctx->meshes.push_back(m); ctx->models.push_back(mo); ctx->meshes_dirty = true;
+    *model_id = (int32_t)ctx->models.size() - 1;
+    return BQ2_OK;
+}
+
+bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate, const bq2_md3_mesh *meshes,
+                          int32_t num_meshes, int32_t *model_id)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!meshes || !model_id || !frame_translate || F <= 0 || num_meshes <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md3: bad arguments");
+    if (num_meshes > BQ2_MD3_MAX_MESHES) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: too many meshes");
+    if (F > 1024) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: too many frames");
+    for (int m = 0; m < num_meshes; m++) {
+        const bq2_md3_mesh &me = meshes[m];
+        if (me.num_verts <= 0 || me.num_tris <= 0 || !me.vertexes || !me.indexes)
+            return fail(ctx, BQ2_E_INVALID, "bq2_upload_md3: empty mesh");
+        if (me.num_verts > BQ2_MD3_MAX_VERTS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: mesh has too many vertices");
+        if (me.num_tris > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: mesh has too many triangles");
+        for (int i = 0; i < 3 * me.num_tris; i++) {
+            if (me.indexes[i] >= me.num_verts) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md3: index out of range");
+            if (me.neighbours && (me.neighbours[i] < -1 || me.neighbours[i] >= me.num_tris))
+                return fail(ctx, BQ2_E_INVALID, "bq2_upload_md3: neighbour out of range");
+        }
+    }
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    Model mo; mo.md3 = true; mo.F = F; mo.first_mesh = (int)ctx->meshes.size(); mo.n_mesh = num_meshes; mo.flags = BQ2_MODEL_SMOOTHVECS;
+    mo.hdr.assign(frame_translate, frame_translate + 3 * (size_t)F);   /* host-only: folded into bq2_entity.move */
+    for (int mi = 0; mi < num_meshes; mi++) {
+        const bq2_md3_mesh &me = meshes[mi];
+        const int V = me.num_verts, T = me.num_tris, Tp = (T + 7) & ~7;
+        const uint32_t vstride = 16u * (uint32_t)V;
+        const size_t off_tri = (size_t)F * vstride, total = off_tri + up16(12u * (uint32_t)Tp);
+        std::vector<int32_t> idx(3 * (size_t)T);
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = me.indexes[i];
+        std::vector<int16_t> tab(6 * (size_t)Tp);
+        pack_tri_table(T, Tp, idx.data(), me.neighbours, tab.data());
+        unsigned char *d = nullptr;
+        bq2_status s = arena_alloc(ctx, total, &d);
+        if (s != BQ2_OK) return s;
+        CK(cudaMemcpyAsync(d, me.vertexes, off_tri, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(md3 verts)");
+        CK(cudaMemcpyAsync(d + off_tri, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(md3 tris)");
+        CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(md3)");
+        bq2_dev_mesh m{};
+        m.verts = d; m.tri = (const int16_t *)(d + off_tri);
+        m.V = V; m.T = T; m.F = F; m.Tp = Tp; m.vstride = vstride; m.tbstride = 0;
+        m.flags = BQ2_MESH_MD3 | BQ2_MESH_SMOOTH | BQ2_MESH_HAS_TB;
+        ctx->meshes.push_back(m);
+        mo.V.push_back(V); mo.T.push_back(T); mo.casts.push_back(me.casts_shadow ? 1 : 0);
+    }
+    ctx->models.push_back(mo); ctx->meshes_dirty = true;
+    *model_id = (int32_t)ctx->models.size() - 1;
+    return BQ2_OK;
+}
+
+bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t id, int32_t *is_md3, int32_t *num_frames,
+                          int32_t *num_meshes, int32_t *num_verts, int32_t *num_tris)
+{
+    if (!ctx || id < 0 || id >= (int32_t)ctx->models.size()) return BQ2_E_INVALID;
+    const Model &m = ctx->models[id];
+    if (is_md3) *is_md3 = m.md3; if (num_frames) *num_frames = m.F; if (num_meshes) *num_meshes = m.n_mesh;
+    for (int i = 0; i < m.n_mesh; i++) { if (num_verts) num_verts[i] = m.V[i]; if (num_tris) num_tris[i] = m.T[i]; }
+    return BQ2_OK;
+}
+
+bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
+                             const bq2_world_light *lights, int32_t n_lights,
+                             const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
+                             const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
+                             int32_t *n_pairs_out)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (n_ents < 0 || n_pairs < 0 || (n_ents && (!ents || !out_ents)) ||
+        (n_pairs && (!lights || !pair_ent || !pair_light || !out_pairs)) || !n_pairs_out)
+        return fail(ctx, BQ2_E_INVALID, "bq2_build_records: bad arguments");
+    const int nModels = (int)ctx->models.size();
+    for (int e = 0; e < n_ents; e++) {
+        const bq2_world_entity &W = ents[e];
+        if (W.model < 0 || W.model >= nModels) return fail(ctx, BQ2_E_INVALID, "bq2_build_records: unknown model");
+        const Model &mo = ctx->models[W.model];
+        if (W.frame < 0 || W.frame >= mo.F || W.oldframe < 0 || W.oldframe >= mo.F)
+            return fail(ctx, BQ2_E_INVALID, "bq2_build_records: frame out of range");
+        if (mo.md3)
+            bq2_host_entity_md3(&mo.hdr[3 * (size_t)W.frame], &mo.hdr[3 * (size_t)W.oldframe], W.frame, W.oldframe,
+                                W.backlerp, W.origin, W.oldorigin, W.angles, &out_ents[e]);
+        else
+            bq2_host_entity_md2_hdr(&mo.hdr[6 * (size_t)W.frame], &mo.hdr[6 * (size_t)W.oldframe], W.frame, W.oldframe,
+                                    W.backlerp, W.origin, W.oldorigin, W.angles, W.rf_flags, &out_ents[e]);
+        out_ents[e].model = W.model;
+    }
+    int kept = 0;
+    for (int k = 0; k < n_pairs; k++) {
+        int e = pair_ent[k], l = pair_light[k];
+        if (e < 0 || e >= n_ents || l < 0 || l >= n_lights) return fail(ctx, BQ2_E_INVALID, "bq2_build_records: pair out of range");
+        const bq2_world_entity &W = ents[e];
+        if (!bq2_host_casts_shadow(W.rf_flags, 0, 0.0f, 2.0f)) continue;
+        if (W.rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT)) continue;          /* M:64089 */
+        bq2_pair &P = out_pairs[kept++];
+        P.entity = e;
+        bq2_host_point_to_model(lights[l].origin, W.origin, W.angles, P.light);
+        P.scale = 32 * lights[l].radius;                                            /* M:63597 */
+        if (view_world) bq2_host_point_to_model(view_world, W.origin, W.angles, P.view);
+        else P.view[0] = P.view[1] = P.view[2] = 0.0f;
+    }
+    *n_pairs_out = kept;
+    return BQ2_OK;
+}
+
+bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!fd || fd->n_ents < 0 || fd->n_pairs < 0 || (fd->n_ents > 0 && !fd->ents) || (fd->n_pairs > 0 && !fd->pairs))
+        return fail(ctx, BQ2_E_INVALID, "bq2_frame: bad descriptor");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const int nE = fd->n_ents, nP = fd->n_pairs;
+    const int nModels = (int)ctx->models.size();
+    const uint32_t want = fd->want;
+
+    /* ---- entity slots ------------------------------------------------------------------------- */
+    ctx->ent_slot_first.resize((size_t)nE + 1);
+    int nES = 0, maxV = 0, maxT = 0, anyMd2 = 0;
+    for (int e = 0; e < nE; e++) {
+        int mid = fd->ents[e].model;
+        if (mid < 0 || mid >= nModels) return fail(ctx, BQ2_E_INVALID, "bq2_frame: entity refers to an unknown model");
+        const Model &mo = ctx->models[mid];
+        if (fd->ents[e].frame < 0 || fd->ents[e].frame >= mo.F || fd->ents[e].oldframe < 0 || fd->ents[e].oldframe >= mo.F)
+            return fail(ctx, BQ2_E_INVALID, "bq2_frame: frame out of range");
+        ctx->ent_slot_first[e] = nES; nES += mo.n_mesh;
+    }
+    ctx->ent_slot_first[nE] = nES;
+    ctx->ent_vert_off.resize((size_t)nES + 1); ctx->ent_tb_off.resize((size_t)nES + 1);
+    ctx->cursor.assign((size_t)nES + 1, 0u);                    /* pair-slot count per entity slot */
+
+    /* ---- pair slots ---------------------------------------------------------------------------- */
+    ctx->pair_slot_first.resize((size_t)nP + 1);
+    int nPS = 0;
+    for (int p = 0; p < nP; p++) {
+        int e = fd->pairs[p].entity;
+        if (e < 0 || e >= nE) return fail(ctx, BQ2_E_INVALID, "bq2_frame: pair refers to an unknown entity");
+        ctx->pair_slot_first[p] = nPS; nPS += ctx->models[fd->ents[e].model].n_mesh;
+    }
+    ctx->pair_slot_first[nP] = nPS;
+    ctx->pair_vert_off.resize((size_t)nPS + 1); ctx->pair_bits_off.resize((size_t)nPS + 1);
+    ctx->slot_mesh_V.resize((size_t)nPS); ctx->slot_mesh_T.resize((size_t)nPS); ctx->pair_slot_entslot.resize((size_t)nPS);
+
+    size_t rec_bytes = (size_t)nES * sizeof(bq2_dev_ent) + (size_t)nPS * sizeof(bq2_dev_pair);
+    CK(ctx->h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
+    CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
+    bq2_dev_ent  *he = (bq2_dev_ent *)ctx->h_records.p;
+    bq2_dev_pair *hp = (bq2_dev_pair *)(ctx->h_records.p + (size_t)nES * sizeof(bq2_dev_ent));
+
+    uint32_t voff = 0, tboff = 0;
+    uint64_t total_verts = 0;
+    for (int e = 0; e < nE; e++) {
+        const bq2_entity &E = fd->ents[e];
+        const Model &mo = ctx->models[E.model];
+        for (int m = 0; m < mo.n_mesh; m++) {
+            int s = ctx->ent_slot_first[e] + m;
+            const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
+            if ((want & BQ2_WANT_NTB) && !(me.flags & BQ2_MESH_HAS_TB))
+                return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_NTB but the model was uploaded without tangent/binormal bytes");
+            bq2_dev_ent &d = he[s];
+            d.mesh = mo.first_mesh + m; d.frame = E.frame; d.oldframe = E.oldframe; d.flags = E.flags;
+            d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
+            for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
+            d.shell_scale = E.shell_scale;
+            d.vert_off = voff; d.tb_off = tboff; d.pair_begin = 0; d.pair_count = 0;
+            ctx->ent_vert_off[s] = voff; ctx->ent_tb_off[s] = tboff;
+            voff += (uint32_t)(me.V + 3) & ~3u;
+            tboff += (uint32_t)(((me.flags & BQ2_MESH_SMOOTH) ? me.V : me.T) + 3) & ~3u;
+            total_verts += (uint64_t)me.V;
+            maxV = std::max(maxV, me.V); maxT = std::max(maxT, me.T);
+            if (!(me.flags & BQ2_MESH_MD3)) anyMd2 = 1;
+        }
+    }
+    ctx->ent_vert_off[nES] = voff; ctx->ent_tb_off[nES] = tboff;
+    const uint32_t ent_verts = voff, tb_rows = tboff;
+
+    /* pair slots: offsets in caller order, then a counting sort by entity slot for the kernel */
+    uint32_t pvoff = 0, pboff = 0;
+    for (int p = 0; p < nP; p++) {
+        int e = fd->pairs[p].entity;
+        const Model &mo = ctx->models[fd->ents[e].model];
+        for (int m = 0; m < mo.n_mesh; m++) {
+            int ps = ctx->pair_slot_first[p] + m, es = ctx->ent_slot_first[e] + m;
+            const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
+            ctx->pair_vert_off[ps] = pvoff; ctx->pair_bits_off[ps] = pboff;
+            ctx->slot_mesh_V[ps] = me.V; ctx->slot_mesh_T[ps] = me.T; ctx->pair_slot_entslot[ps] = es;
+            pvoff += (uint32_t)(me.V + 3) & ~3u;
+            pboff += (uint32_t)(me.T + 31) >> 5;
+            if (mo.casts[m]) ctx->cursor[es]++;
+        }
+    }
+    ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff;
+    {
+        uint32_t run = 0;
+        for (int s = 0; s < nES; s++) { uint32_t c = ctx->cursor[s]; he[s].pair_begin = run; he[s].pair_count = c; ctx->cursor[s] = run; run += c; }
+    }
+    for (int p = 0; p < nP; p++) {
+        const bq2_pair &P = fd->pairs[p];
+        const Model &mo = ctx->models[fd->ents[P.entity].model];
+        for (int m = 0; m < mo.n_mesh; m++) {
+            if (!mo.casts[m]) continue;
+            int ps = ctx->pair_slot_first[p] + m, es = ctx->ent_slot_first[P.entity] + m;
+            bq2_dev_pair &d = hp[ctx->cursor[es]++];
+            for (int k = 0; k < 3; k++) { d.light[k] = P.light[k]; d.view[k] = P.view[k]; }
+            d.scale = P.scale; d.vert_off = ctx->pair_vert_off[ps]; d.bits_off = ctx->pair_bits_off[ps];
+            d.slot = (uint32_t)ps; d.pad[0] = d.pad[1] = 0;
+        }
+    }
+
+    uint32_t stride = fd->index_stride ? fd->index_stride : 12u * (uint32_t)maxT;
+    stride = (stride + 3u) & ~3u;
+
+    /* ---- output capacity ------------------------------------------------------------------------ */
+    CK(ctx->lerped.ensure(3 * (size_t)ent_verts + 4), "cudaMalloc(lerped)");
+    if (want & BQ2_WANT_SHADOW) {
+        CK(ctx->extruded.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(extruded)");
+        CK(ctx->facing_bits.ensure((size_t)pboff + 1), "cudaMalloc(facing_bits)");
+        CK(ctx->indices.ensure((size_t)nPS * stride + 4), "cudaMalloc(indices)");
+    }
+    CK(ctx->index_count.ensure((size_t)nPS + 1), "cudaMalloc(index_count)");
+    if (want & BQ2_WANT_NTB) {
+        CK(ctx->normals.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(normals)");
+        CK(ctx->tangents.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(tangents)");
+        CK(ctx->binormals.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(binormals)");
+    }
+    if (want & BQ2_WANT_TSLIGHT) {
+        if (!(want & BQ2_WANT_NTB)) return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_TSLIGHT needs BQ2_WANT_NTB");
+        CK(ctx->lightp.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(lightp)");
+        CK(ctx->tsh.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(tsh)");
+    }
+    CK(ctx->h_counts.ensure(sizeof(uint32_t) * ((size_t)nPS + 1)), "cudaMallocHost(counts)");
+    if (ctx->meshes_dirty) {
+        CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
+        CK(cudaMemcpyAsync(ctx->d_meshes.p, ctx->meshes.data(), ctx->meshes.size() * sizeof(bq2_dev_mesh),
+                           cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(mesh table)");
+        CK(cudaStreamSynchronize(ctx->stream), "sync(mesh table)");   /* source is pageable */
+        ctx->meshes_dirty = false;
+    }
+    if (bq2_kernel_smem_bytes(maxV, maxT, anyMd2) > 227u * 1024u)
+        return fail(ctx, BQ2_E_LIMIT, "bq2_frame: mesh too large for one CTA's shared memory");
+
+    /* ---- go -------------------------------------------------------------------------------------- */
+    if (rec_bytes)
+        CK(cudaMemcpyAsync(ctx->d_records.p, ctx->h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(records)");
+    if (nPS) CK(cudaMemsetAsync(ctx->index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, ctx->stream), "cudaMemset(index_count)");
+
+    bq2_launch &L = ctx->launch;
+    L.meshes = ctx->d_meshes.p;
+    L.ents = (const bq2_dev_ent *)ctx->d_records.p;
+    L.pairs = (const bq2_dev_pair *)(ctx->d_records.p + (size_t)nES * sizeof(bq2_dev_ent));
+    L.n_ent_slots = nES; L.want = want; L.index_stride = stride;
+    L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
+    L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
+    L.normals = ctx->normals.p; L.tangents = ctx->tangents.p; L.binormals = ctx->binormals.p;
+    L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p;
+    ctx->max_V = maxV; ctx->max_T = maxT; ctx->any_md2 = anyMd2;
+    ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
+    ctx->total_verts = total_verts;
+    if (nES) {
+        CK((cudaError_t)bq2_launch_frame(&L, maxV, maxT, anyMd2, ctx->stream), "launch(bq2_frame_kernel)");
+        ctx->launches++;
+    }
+    if (nPS) CK(cudaMemcpyAsync(ctx->h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nPS,
+                                cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
+    ctx->submitted = true;
+    return BQ2_OK;
+}
+
+bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_frame_wait: nothing submitted");
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(frame)");
+    bq2_frame_out &o = ctx->out;
+    o.n_ent_slots = ctx->n_ent_slots; o.n_pair_slots = ctx->n_pair_slots;
+    o.ent_slot_first = ctx->ent_slot_first.data(); o.pair_slot_first = ctx->pair_slot_first.data();
+    o.ent_vert_offset = ctx->ent_vert_off.data(); o.pair_vert_offset = ctx->pair_vert_off.data();
+    o.pair_bits_offset = ctx->pair_bits_off.data(); o.ent_tb_offset = ctx->ent_tb_off.data();
+    o.lerped = ctx->lerped.p; o.extruded = ctx->extruded.p; o.facing_bits = ctx->facing_bits.p;
+    o.indices = ctx->indices.p; o.index_count = ctx->index_count.p;
+    o.normals = ctx->normals.p; o.tangents = ctx->tangents.p; o.binormals = ctx->binormals.p;
+    o.lightp = ctx->lightp.p; o.tsh = ctx->tsh.p;
+    o.index_stride = ctx->launch.index_stride;
+    o.total_lerped_verts = ctx->total_verts;
+    o.total_pairs = 0; o.total_indices = 0; o.overflow_pairs = 0;
+    const uint32_t *cnt = (const uint32_t *)ctx->h_counts.p;
+    for (int i = 0; i < ctx->n_pair_slots; i++) {
+        o.total_indices += cnt[i];
+        if (cnt[i] > o.index_stride) o.overflow_pairs++;
+    }
+    o.total_pairs = (uint64_t)ctx->n_pair_slots;
+    if (out) *out = o;
+    if (o.overflow_pairs) return fail(ctx, BQ2_E_OVERFLOW, "bq2_frame: index_stride too small for at least one pair (counts are exact, indices truncated)");
+    return BQ2_OK;
+}
+
+bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
+{
+    bq2_status s = bq2_frame_submit(ctx, fd);
+    if (s != BQ2_OK) return s;
+    return bq2_frame_wait(ctx, out);
+}
+
+bq2_status bq2_frame_replay(bq2_ctx *ctx)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!ctx->submitted || !ctx->n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
+    CK((cudaError_t)bq2_launch_frame(&ctx->launch, ctx->max_V, ctx->max_T, ctx->any_md2, ctx->stream), "launch(bq2_frame_kernel)");
+    ctx->launches++;
+    return BQ2_OK;
+}
+
+const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->h_counts.p : nullptr; }
+
+bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host)
+{
+    if (!ctx || !host) return BQ2_E_INVALID;
+    const void *src = nullptr; size_t cap = 0;
+    switch (which) {
+    case BQ2_A_LERPED:      src = ctx->lerped.p;      cap = ctx->lerped.cap; break;
+    case BQ2_A_EXTRUDED:    src = ctx->extruded.p;    cap = ctx->extruded.cap; break;
+    case BQ2_A_FACING_BITS: src = ctx->facing_bits.p; cap = ctx->facing_bits.cap; break;
+    case BQ2_A_INDICES:     src = ctx->indices.p;     cap = ctx->indices.cap; break;
+    case BQ2_A_INDEX_COUNT: src = ctx->index_count.p; cap = ctx->index_count.cap; break;
+    case BQ2_A_NORMALS:     src = ctx->normals.p;     cap = ctx->normals.cap; break;
+    case BQ2_A_TANGENTS:    src = ctx->tangents.p;    cap = ctx->tangents.cap; break;
+    case BQ2_A_BINORMALS:   src = ctx->binormals.p;   cap = ctx->binormals.cap; break;
+    case BQ2_A_LIGHTP:      src = ctx->lightp.p;      cap = ctx->lightp.cap; break;
+    case BQ2_A_TSH:         src = ctx->tsh.p;         cap = ctx->tsh.cap; break;
+    default: return fail(ctx, BQ2_E_INVALID, "bq2_download: unknown array");
+    }
+    if (!src || first + count > cap) return fail(ctx, BQ2_E_INVALID, "bq2_download: range outside the array");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaMemcpyAsync(host, (const uint32_t *)src + first, count * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(download)");
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(download)");
+    return BQ2_OK;
+}
+
+bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t ps, float *tris_verts, int32_t max_verts, int32_t *tris_counter)
+{
+    if (!ctx || !tris_verts || !tris_counter) return BQ2_E_INVALID;
+    if (!ctx->submitted || ps < 0 || ps >= ctx->n_pair_slots) return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: bad pair slot");
+    const int V = ctx->slot_mesh_V[ps];
+    const uint32_t stride = ctx->launch.index_stride;
+    uint32_t cnt = 0;
+    bq2_status s = bq2_download(ctx, BQ2_A_INDEX_COUNT, (uint64_t)ps, 1, &cnt);
+    if (s != BQ2_OK) return s;
+    if (cnt > stride || (int32_t)cnt > max_verts) return fail(ctx, BQ2_E_OVERFLOW, "bq2_expand_trisverts: output too small");
+    std::vector<float> pool(6 * (size_t)V);
+    std::vector<uint32_t> idx(cnt);
+    s = bq2_download(ctx, BQ2_A_LERPED, 3ull * ctx->ent_vert_off[ctx->pair_slot_entslot[ps]], 3ull * V, pool.data());
+    if (s != BQ2_OK) return s;
+    s = bq2_download(ctx, BQ2_A_EXTRUDED, 3ull * ctx->pair_vert_off[ps], 3ull * V, pool.data() + 3 * (size_t)V);
+    if (s != BQ2_OK) return s;
+    if (cnt) { s = bq2_download(ctx, BQ2_A_INDICES, (uint64_t)ps * stride, cnt, idx.data()); if (s != BQ2_OK) return s; }
+    for (uint32_t k = 0; k < cnt; k++) memcpy(tris_verts + 3 * (size_t)k, &pool[3 * (size_t)idx[k]], 12);
+    *tris_counter = (int32_t)cnt;
+    return BQ2_OK;
+}
+
+} // extern "C"

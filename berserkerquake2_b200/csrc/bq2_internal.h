@@ -1,0 +1,86 @@
+/*
+ * bq2_internal.h -- records shared by the host API (bq2_api.cu) and the kernels (bq2_kernels.cu).
+ * Not part of the public ABI.
+ *
+ * HBM layout of one model "mesh" (an MD2 model is one mesh; an MD3 model is one per maliasmesh_t):
+ *
+ *   verts   MD2: frames x vstride bytes; a frame row is V x {u8 x, y, z, lightnormalindex}
+ *                (dtrivertx_t, defs.h:3714-3718) padded to 16 B.  The 40-byte frame header
+ *                (scale/translate/name) is NOT resident: the host folds it into move/frontv/backv.
+ *           MD3: frames x V x 16 B maliasvertex_t rows (defs.h:4401-4407), already 16-byte records.
+ *   tri     six s16 arrays of Tp = round_up(T, 8) entries each, back to back:
+ *                i0[Tp] i1[Tp] i2[Tp]   index_xyz[0..2]   (dtriangle_t / WORD indexes)
+ *                n0[Tp] n1[Tp] n2[Tp]   neighbours[0..2]  (neighbours_t, -1 = open; T <= 8192 fits)
+ *           12 bytes per triangle instead of the reference's 12 + 12, one 16-byte-aligned block so a
+ *           single TMA bulk copy stages it.
+ *   tb/bn/nm  tangent / binormal (/ flat normal) anorm-index bytes, frames x tbstride (MD2 only;
+ *           MD3 carries them inside the vertex rows).
+ */
+#ifndef BQ2_INTERNAL_H
+#define BQ2_INTERNAL_H
+#include <stdint.h>
+
+#define BQ2_THREADS 256
+
+#define BQ2_MESH_MD3     0x1u
+#define BQ2_MESH_SMOOTH  0x2u   /* N/T/B rows are per vertex (MD3 always; MD2 with RF_SMOOTHVECS) */
+#define BQ2_MESH_HAS_TB  0x4u
+
+typedef struct bq2_dev_mesh {
+    const uint8_t *verts;
+    const int16_t *tri;
+    const uint8_t *tb, *bn, *nm;
+    int32_t  V, T, F, Tp;
+    uint32_t vstride;       /* bytes per frame of verts                          */
+    uint32_t tbstride;      /* bytes per frame of each tangent-space byte array  */
+    uint32_t flags;
+    uint32_t pad;
+} bq2_dev_mesh;             /* 72 bytes */
+
+/* one entity slot = (entity, mesh) */
+typedef struct bq2_dev_ent {
+    int32_t  mesh;          /* index into the device mesh table */
+    int32_t  frame, oldframe;
+    uint32_t flags;         /* BQ2_ENT_* */
+    float    backlerp, frontlerp;
+    float    move[3], frontv[3], backv[3];
+    float    shell_scale;
+    uint32_t vert_off;      /* first vertex row of this slot in lerped[]            */
+    uint32_t pair_begin;    /* first entry of this slot in the sorted pair-slot list */
+    uint32_t pair_count;
+    uint32_t tb_off;        /* first row in normals/tangents/binormals              */
+} bq2_dev_ent;              /* 80 bytes */
+
+typedef struct bq2_dev_pair {
+    float    light[3];
+    float    scale;
+    float    view[3];
+    uint32_t vert_off;      /* first vertex row in extruded[] / lightp[] / tsh[] */
+    uint32_t bits_off;      /* first u32 word in facing_bits[]                   */
+    uint32_t slot;          /* pair slot in caller order: indices + slot*stride  */
+    uint32_t pad[2];
+} bq2_dev_pair;             /* 48 bytes */
+
+typedef struct bq2_launch {
+    const bq2_dev_mesh *meshes;
+    const bq2_dev_ent  *ents;
+    const bq2_dev_pair *pairs;
+    int32_t  n_ent_slots;
+    uint32_t want;
+    uint32_t index_stride;
+    float    *lerped, *extruded;
+    uint32_t *facing_bits, *indices, *index_count;
+    float    *normals, *tangents, *binormals, *lightp, *tsh;
+} bq2_launch;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+/* returns cudaError_t as int; smem_bytes = dynamic shared memory for the largest mesh in the batch */
+int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);
+int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
+size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -178,12 +178,12 @@ int bq2_synth_md3_mesh(int32_t S, int32_t R, int32_t F, uint32_t phase_seed, con
 }
 
 void bq2_synth_scene(int32_t n_ents, int32_t L, int32_t num_frames, int32_t n_models,
-                     uint32_t seed, uint32_t step, bq2_scene_entity *ents, float *lights)
+                     uint32_t seed, uint32_t step, bq2_world_entity *ents, float *lights)
 {
     uint32_t x = seed;
     int32_t side = 1; while ((int64_t)side * side < n_ents) side++;
     for (int32_t e = 0; e < n_ents; e++) {
-        bq2_scene_entity *E = &ents[e];
+        bq2_world_entity *E = &ents[e];
         x = 1664525u * x + 1013904223u;
         E->model = n_models > 0 ? e % n_models : 0;
         E->frame = (int32_t)(((x >> 8) + step) % (uint32_t)num_frames);

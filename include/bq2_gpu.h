@@ -66,6 +66,8 @@ typedef enum bq2_status {
 #define BQ2_RF_SHELL_RED     0x00000400u
 #define BQ2_RF_SHELL_GREEN   0x00000800u
 #define BQ2_RF_SHELL_BLUE    0x00001000u
+#define BQ2_RF_NOCASTSHADOW  0x00080000u   /* filtered by the caller loop, M:64089 */
+#define BQ2_RF_DISTORT       0x10000000u
 
 /* bq2_entity.flags (ours) */
 #define BQ2_ENT_SHELL        0x1u   /* add anorm[cur.lightnormalindex]*shell_scale  (M:63565-63572) */
@@ -218,6 +220,11 @@ void bq2_host_angle_vectors(const float angles[3], float forward[3], float right
 void bq2_host_entity_md2(const void *dmdl_blob, int32_t frame, int32_t oldframe, float backlerp,
                          const float origin[3], const float oldorigin[3], const float angles[3],
                          uint32_t rf_flags, bq2_entity *out);
+/* The same from the two {scale[3], translate[3]} frame headers alone (24 bytes each). */
+void bq2_host_entity_md2_hdr(const float *frame_hdr, const float *oldframe_hdr, int32_t frame,
+                             int32_t oldframe, float backlerp, const float origin[3],
+                             const float oldorigin[3], const float angles[3], uint32_t rf_flags,
+                             bq2_entity *out);
 /* M:63825-63856 (also M:66802-66839): the MD3 flavour. */
 void bq2_host_entity_md3(const float frame_translate[3], const float oldframe_translate[3],
                          int32_t frame, int32_t oldframe, float backlerp,
@@ -228,6 +235,25 @@ void bq2_host_point_to_model(const float world[3], const float origin[3], const 
                              float out[3]);
 /* Flag filter of R_DrawAliasShadowVolume M:63722-63727 (+ M:64089): 1 = entity casts a volume. */
 int  bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow, float r_shadows);
+
+/* ---- the renderer's loop nest, flattened (host, C) -------------------------------------------- */
+/* The fields of entity_t (defs.h:573-618) and shadowlight_t (defs.h:3927-3973) this path reads. */
+typedef struct bq2_world_entity {
+    int32_t model, frame, oldframe; uint32_t rf_flags;
+    float backlerp; float origin[3]; float oldorigin[3]; float angles[3];
+} bq2_world_entity;                                     /* 56 bytes */
+typedef struct bq2_world_light { float origin[3]; float radius; } bq2_world_light;
+
+/* For k < n_pairs: entity pair_ent[k] is lit by light pair_light[k] (what the per-light loop
+ * M:72113-72280 + R_DrawEntsShadowVolumes M:64062 enumerate).  Fills out_ents[n_ents] (lerp constants,
+ * M:63531-63553 / M:63825-63856) and out_pairs (light and view_world moved to model space,
+ * M:63733-63745 / M:66689-66715; scale = 32*radius M:63597), dropping pairs whose entity fails the
+ * flag filter M:63722-63727.  *n_pairs_out = pairs kept.  Uses the frame headers kept at upload. */
+bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
+                             const bq2_world_light *lights, int32_t n_lights,
+                             const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
+                             const float *view_world /* [3] or NULL */,
+                             bq2_entity *out_ents, bq2_pair *out_pairs, int32_t *n_pairs_out);
 
 /* ---- multi-GPU plan (entity-major sharding) ---------------------------------------- */
 /* Rank r of n owns entities [first, first+count).  Pairs follow their entity. */

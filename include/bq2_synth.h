@@ -11,6 +11,7 @@
 #define BQ2_SYNTH_H
 #include <stddef.h>
 #include <stdint.h>
+#include "bq2_gpu.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -40,13 +41,10 @@ uint8_t bq2_host_normal2index(const float v[3]);
 const float *bq2_host_anorms(void);    /* [162][4] x,y,z,0 */
 
 /* Scene generator (SURVEY 8d "Entities"/"Lights"): LCG x <- 1664525x + 1013904223. */
-typedef struct bq2_scene_entity {
-    int32_t model, frame, oldframe; uint32_t rf_flags;
-    float backlerp; float origin[3]; float oldorigin[3]; float angles[3];
-} bq2_scene_entity;   /* 56 bytes */
+/* Writes entity_t-style world entities and lights_per_ent world-space light origins per entity. */
 void bq2_synth_scene(int32_t n_ents, int32_t lights_per_ent, int32_t num_frames, int32_t n_models,
                      uint32_t seed, uint32_t step,
-                     bq2_scene_entity *ents, float *lights_world /*[n_ents*lights_per_ent][3]*/);
+                     bq2_world_entity *ents, float *lights_world /*[n_ents*lights_per_ent][3]*/);
 
 #ifdef __cplusplus
 }
