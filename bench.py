@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path (MD2 keyframe lerp -> light-facing -> silhouette / cap / extrusion index
+buffers) on BASELINE.json's configs[1]: 1,024 synthetic MD2 entities x 4 lights per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU)
+  python bench.py --impl reference [...]                          the reference's own CPU code, all host cores
+
+One "step" = one pass of the path over the whole batch = ONE launch of the fused kernel.
+  value     shadow-volume triangles/s (sum index_count / 3 / time), inputs resident in HBM, L2 flushed
+            between steps, CUDA events on the launching stream, max over ranks
+  e2e       the same metric through the C ABI with HOST records in: bq2_build_records (host trig) +
+            bq2_frame (pack, H2D, kernel, D2H of the per-pair counts), wall clock around K calls
+  roofline  SURVEY.md 8(d) algorithmic bytes per launch / mean kernel time, vs MEASURED_PEAKS.json
+  cpu_baseline  oracle/_ref (the unmodified reference, compiled headless) on the host cores, N=1 only
+
+The oracle (oracle/) is loaded ONLY by the cpu_baseline / --impl reference legs below, as the thing that
+is reported beside the GPU number -- never by the measured GPU path.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (entities per GPU, lights per entity, description)
+    "c2": (1024, 4, "BASELINE configs[1]: 1,024 synthetic MD2 entities (V=258,T=512,198 frames) x 4 lights"),
+    "c3shard": (8192, 8, "one GPU's share of BASELINE configs[2]: 8,192 entities x 8 lights"),
+}
+SLICES, RINGS, FRAMES = 16, 17, 198
+RADIUS = 300.0
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(n_ents, n_pairs, V, T, total_indices):
+    """per entity read 2(40+4V)+36, write 12V; per pair read 6T+12T+16, write
+    12V + 4*ceil(T/32) + 4*I + 4 (I = measured index count)."""
+    per_ent = 2 * (40 + 4 * V) + 36 + 12 * V
+    per_pair = 18 * T + 16 + 12 * V + 4 * ((T + 31) // 32) + 4
+    return n_ents * per_ent + n_pairs * per_pair + 4 * total_indices
+
+
+def min_traffic_bytes(n_ents, n_pairs, V, T, total_indices):
+    """What THIS layout has to move at minimum: per entity two 4V-byte frames + an 80-byte record + the
+    12T-byte index/neighbour table (read once per entity, not per pair) + 12V out; per pair a 48-byte
+    record in, 12V + 4*ceil(T/32) + 4 + 4*I out."""
+    per_ent = 2 * 4 * V + 80 + 12 * T + 12 * V
+    per_pair = 48 + 12 * V + 4 * ((T + 31) // 32) + 4
+    return n_ents * per_ent + n_pairs * per_pair + 4 * total_indices
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 7:
+                continue
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except ValueError:
+                continue
+            for k, n in enumerate(names):
+                if r[3 + k].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def make_scene(n_ents, lights, first_global_ent=0, total_ents=None, step=0):
+    """World entities / lights of this rank's shard of the global entity list (entity-major sharding)."""
+    from berserkerquake2_b200 import synth
+    import berserkerquake2_b200 as bq2
+    total = total_ents or n_ents
+    we, lw = synth.scene(total, lights, FRAMES, total, 12345, step)       # one distinct model per entity
+    we, lw = we[first_global_ent:first_global_ent + n_ents].copy(), \
+        lw[first_global_ent * lights:(first_global_ent + n_ents) * lights].copy()
+    wl = np.zeros(len(lw), bq2.WORLD_LIGHT_DTYPE)
+    wl["origin"] = lw
+    wl["radius"] = RADIUS
+    pe = np.repeat(np.arange(n_ents, dtype=np.int32), lights)
+    pl = np.arange(n_ents * lights, dtype=np.int32)
+    return we, wl, pe, pl
+
+
+def run_gpu(args):
+    import torch
+    import berserkerquake2_b200 as bq2
+    from berserkerquake2_b200 import synth, host, _capi as c
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n_ents, lights, desc = WORKLOADS[args.workload]
+    first, _ = host.shard_entities(n_ents * world, rank, world)           # weak scaling: n_ents per GPU
+    ctx = bq2.Context(local)
+    t0 = time.time()
+    V, T = synth.sphere_dims(SLICES, RINGS)
+    nb = None
+    mids = np.zeros(n_ents, np.int32)
+    model_bytes = 0
+    for e in range(n_ents):
+        blob = synth.md2(SLICES, RINGS, FRAMES, first + e)
+        if nb is None:
+            nb = host.md2_neighbours(blob)                                 # same topology for every sphere
+        mids[e] = ctx.upload_md2(blob, nb)
+        model_bytes += FRAMES * 4 * V + 12 * T
+    we, wl, pe, pl = make_scene(n_ents, lights, first, n_ents * world)
+    we["model"] = mids
+    setup_s = time.time() - t0
+
+    ents, pairs = ctx.build_records(we, wl, pe, pl)
+    res = ctx.frame(ents, pairs, want=bq2.WANT_SHADOW)                     # records now resident
+    n_pairs = len(pairs)
+    total_indices = int(res.total_indices)
+    assert res.overflow_pairs == 0 and total_indices > 0
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident(ev0=None, ev1=None):
+        with torch.cuda.stream(stream):
+            flush.zero_()                                                  # evict the previous step from L2
+            if ev0 is not None:
+                ev0.record(stream)
+            ctx.replay()                                                   # ONE fused launch on ctx.stream
+            if ev1 is not None:
+                ev1.record(stream)
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    barrier()
+    launches0 = ctx.kernel_launches
+    clocks = ClockSampler(local) if rank == 0 else None
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        step_resident(a, b)
+    barrier()
+    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    launches = ctx.kernel_launches - launches0
+    ms_total = float(sum(kernel_ms))
+
+    # ---- e2e: HOST records in through the C ABI, counts back, wall clock -----------------------------
+    we_c = np.ascontiguousarray(we); wl_c = np.ascontiguousarray(wl)
+    ents_h = np.zeros(n_ents, c.ENTITY_DTYPE); pairs_h = np.zeros(n_pairs, c.PAIR_DTYPE)
+    kept = C.c_int32(0)
+    fd = c.FrameDesc(); fo = c.FrameOut()
+
+    def step_e2e():
+        st = c.lib.bq2_build_records(ctx._h, c.ptr(we_c), n_ents, c.ptr(wl_c), len(wl_c), c.ptr(pe), c.ptr(pl), n_pairs,
+                                     None, c.ptr(ents_h), c.ptr(pairs_h), C.byref(kept))
+        fd.ents = ents_h.ctypes.data; fd.n_ents = n_ents; fd.pairs = pairs_h.ctypes.data; fd.n_pairs = kept.value
+        fd.want = bq2.WANT_SHADOW; fd.index_stride = 0
+        st |= c.lib.bq2_frame(ctx._h, C.byref(fd), C.byref(fo))
+        if st != 0:
+            raise RuntimeError(c.lib.bq2_last_error(ctx._h))
+        return fo.total_indices
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_indices = 0
+    for _ in range(args.steps):
+        e2e_indices += step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clock_info = clocks.stop() if clocks else None
+
+    # ---- reduce: max time over ranks; NCCL all_gather of the per-shard counters (the only collective) --
+    counters = torch.tensor([n_pairs, n_ents * V, total_indices // 3, total_indices, e2e_indices // 3],
+                            dtype=torch.int64, device=f"cuda:{local}")
+    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        gathered = [torch.zeros_like(counters) for _ in range(world)]
+        dist.all_gather(gathered, counters)
+        counters = torch.stack(gathered).sum(0)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    g_pairs, g_verts, g_tris, g_indices, g_e2e_tris = [int(x) for x in counters.tolist()]
+    ms_total_max, e2e_ms_max = times.tolist()
+
+    if rank == 0:
+        ms_per_step = ms_total_max / args.steps
+        peak, peak_src = peaks()
+        alg = algorithmic_bytes(n_ents, n_pairs, V, T, total_indices)       # per launch (this rank's)
+        mint = min_traffic_bytes(n_ents, n_pairs, V, T, total_indices)
+        k_ms = float(np.mean(kernel_ms))
+        out = {
+            "metric": "shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/extrusion index "
+                      "generation); lerped verts/s alongside",
+            "value": g_tris / (ms_per_step * 1e-3), "unit": "tris/s",
+            "lerped_verts_per_s": g_verts / (ms_per_step * 1e-3),
+            "pairs_per_s": g_pairs / (ms_per_step * 1e-3),
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc + " per GPU; one distinct model per entity; entity-major sharding, "
+                                          "no data-path collective",
+                       "entities_per_gpu": n_ents, "lights_per_entity": lights, "pairs_per_gpu": n_pairs,
+                       "verts": V, "tris": T, "frames": FRAMES, "model_bytes_in_hbm_per_gpu": model_bytes,
+                       "mean_indices_per_pair": total_indices / n_pairs,
+                       "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset on the same stream, untimed)",
+                       "timing": "CUDA events around each launch on the ctx stream, summed over K steps, max over ranks"},
+            "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
+                    "ms_per_step": e2e_ms_max / args.steps,
+                    "h2d_bytes_per_step": n_ents * 80 + n_pairs * 48, "d2h_bytes_per_step": 4 * n_pairs,
+                    "what": "bq2_build_records (host C trig) + bq2_frame: host records -> pinned pack -> H2D -> "
+                            "kernel -> D2H of per-pair index counts; vertex/index buffers stay in HBM for the draw"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                         "kernel": "bq2_frame_kernel", "kernel_ms": k_ms,
+                         "min_traffic_bytes_per_launch": mint,
+                         "achieved_min_traffic": mint / (k_ms * 1e-3) / 1e9,
+                         "frac_min_traffic": mint / (k_ms * 1e-3) / 1e9 / peak},
+            "clocks": clock_info,
+            "setup_s": setup_s,
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            try:
+                with open(prof) as f:
+                    out["roofline"]["traffic"] = json.load(f).get(args.workload)
+            except (OSError, ValueError):
+                pass
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_arm(WORKLOADS["c2"][0], WORKLOADS["c2"][1], steps=None, warmup=1,
+                                          budget_s=args.cpu_seconds)
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own code (oracle/_ref/libbq2ref.so) or, failing that, the oracle port.
+# The reference is single-threaded and keeps its state in globals, so "all host cores" = one worker
+# PROCESS per core, each owning a contiguous slice of the pair list.
+def cpu_worker(args):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from berserkerquake2_b200 import synth, host
+    n_ents, lights = args.cpu_ents, args.cpu_lights
+    lo, hi = args.cpu_lo, args.cpu_hi                                      # pair range of this worker
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libbq2ref.so")
+    if os.path.exists(ref_so):
+        lib = C.CDLL(ref_so); fn = lib.bq2ref_md2_world_bench; lib.bq2ref_init()
+    else:
+        lib = C.CDLL(os.path.join(ROOT, "oracle", "liboracle.so")); fn = lib.bq2o_md2_world_bench
+    fn.restype = C.c_longlong
+    fn.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 8
+    we, wl, pe, pl = make_scene(n_ents, lights)
+    pe, pl = pe[lo:hi], pl[lo:hi]
+    n = hi - lo
+    blobs, nb = {}, None
+    for e in np.unique(pe):
+        blobs[int(e)] = synth.md2(SLICES, RINGS, FRAMES, int(e))
+        if nb is None:
+            nb = host.md2_neighbours(blobs[int(e)])
+    bp = (C.c_void_p * n)(*[blobs[int(e)].ctypes.data for e in pe])
+    np_ = (C.c_void_p * n)(*[nb.ctypes.data] * n)
+    a = dict(frames=we["frame"][pe].astype(np.int32), oldframes=we["oldframe"][pe].astype(np.int32),
+             backlerps=we["backlerp"][pe].astype(np.float32), origins=np.ascontiguousarray(we["origin"][pe]),
+             oldorigins=np.ascontiguousarray(we["oldorigin"][pe]), angles=np.ascontiguousarray(we["angles"][pe]),
+             lights=np.ascontiguousarray(wl["origin"][pl]), radii=np.ascontiguousarray(wl["radius"][pl]))
+    P = lambda x: x.ctypes.data_as(C.c_void_p)
+    print("ready", flush=True)
+    for line in sys.stdin:
+        if line.strip() != "go":
+            break
+        t0 = time.perf_counter()
+        tot = fn(bp, np_, n, P(a["frames"]), P(a["oldframes"]), P(a["backlerps"]), P(a["origins"]),
+                 P(a["oldorigins"]), P(a["angles"]), P(a["lights"]), P(a["radii"]))
+        print(json.dumps({"indices": int(tot), "s": time.perf_counter() - t0}), flush=True)
+
+
+def cpu_arm(n_ents, lights, steps, warmup, budget_s=12.0, cores=None):
+    """Each step = the whole batch (n_ents x lights pairs) once, split over one process per core."""
+    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    n_pairs = n_ents * lights
+    cores = max(1, min(cores, n_pairs))
+    kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libbq2ref.so")) else "port"
+    procs = []
+    for w in range(cores):
+        lo, hi = n_pairs * w // cores, n_pairs * (w + 1) // cores
+        procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--_cpu_worker", "--cpu-ents", str(n_ents),
+                                       "--cpu-lights", str(lights), "--cpu-lo", str(lo), "--cpu-hi", str(hi)],
+                                      stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1))
+    for p in procs:
+        assert p.stdout.readline().strip() == "ready"
+
+    def one_step():
+        t0 = time.perf_counter()
+        for p in procs:
+            p.stdin.write("go\n"); p.stdin.flush()
+        tot = sum(json.loads(p.stdout.readline())["indices"] for p in procs)
+        return time.perf_counter() - t0, tot
+
+    for _ in range(warmup):
+        one_step()
+    times, tot = [], 0
+    t_begin = time.perf_counter()
+    k = 0
+    while (steps is not None and k < steps) or (steps is None and time.perf_counter() - t_begin < budget_s and k < 1000):
+        dt, tot = one_step()
+        times.append(dt); k += 1
+    for p in procs:
+        p.stdin.write("quit\n"); p.stdin.flush(); p.wait(timeout=10)
+    s_per_step = float(np.mean(times))
+    V, T = 258, 512
+    return {"value": tot / 3 / s_per_step, "unit": "tris/s", "cores": cores, "kind": kind,
+            "lerped_verts_per_s": n_pairs * V / s_per_step, "pairs_per_s": n_pairs / s_per_step,
+            "ms_per_step": s_per_step * 1e3, "steps": k,
+            "sample": f"{k} passes over the whole {n_ents} x {lights} batch ({n_pairs} pairs, {tot // 3} tris per pass), "
+                      f"one process per core, each looping the reference's R_DrawAliasShadowVolume over its slice"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_ents, lights, desc = WORKLOADS["c2"]
+    r = cpu_arm(n_ents, lights, steps=args.steps, warmup=max(args.warmup, 1))
+    out = {"impl": "reference", "metric": "shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/"
+                                          "extrusion index generation); lerped verts/s alongside",
+           "value": r["value"], "unit": "tris/s", "lerped_verts_per_s": r["lerped_verts_per_s"],
+           "pairs_per_s": r["pairs_per_s"], "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": desc + "; the reference's CPU path (R_DrawAliasShadowVolume per pair) on the host "
+                                         "cores; the reference lerps once per PAIR, so lerped verts/s counts V per pair",
+                      "entities": n_ents, "lights_per_entity": lights},
+           "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "e2e": {"value": r["value"], "unit": "tris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--_cpu_worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-ents", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-lights", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-lo", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-hi", type=int, default=0, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args._cpu_worker:
+        return cpu_worker(args)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

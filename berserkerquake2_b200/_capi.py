@@ -97,6 +97,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_host_point_to_model", None, vp, vp, vp, vp),
     _sig("bq2_host_casts_shadow", C.c_int, u32, C.c_int, f32, f32),
     _sig("bq2_build_records", C.c_int, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, C.POINTER(i32)),
+    _sig("bq2_host_md2_neighbours", C.c_int, vp, i32, vp),
+    _sig("bq2_host_md3_neighbours", C.c_int, vp, i32, vp),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),
 ]
 EXPORTS_SYNTH_H = [

@@ -163,3 +163,100 @@ void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *fi
     *first = rank * base + (rank < rem ? rank : rem);
     *count = base + (rank < rem ? 1 : 0);
 }
+
+/* ---- load-time neighbour tables, host C ------------------------------------- */
+/* Both reference builders scan every triangle for every edge (O(T^2): M:61782-61824, M:68646-68676).
+ * These produce the same tables from one sorted edge list; every order-dependent rule of the reference
+ * (first match wins, a second match poisons the edge, MD2 writes the back-pointer of the match, MD3 counts
+ * each triangle once with the forward test taking precedence) is kept. */
+#include <stdlib.h>
+
+typedef struct { uint32_t key, slot; } edge_rec;        /* slot = 3*tri + edge */
+static int edge_cmp(const void *a, const void *b)
+{
+    const edge_rec *x = (const edge_rec *)a, *y = (const edge_rec *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->slot < y->slot ? -1 : (x->slot > y->slot);
+}
+static size_t edge_lower_bound(const edge_rec *e, size_t n, uint32_t key)
+{
+    size_t lo = 0, hi = n;
+    while (lo < hi) { size_t mid = (lo + hi) >> 1; if (e[mid].key < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+/* MD2: findneighbour (M:61782-61824) driven by the loader loop M:51643-51653.  dtriangles = dtriangle_t[T]
+ * (index_xyz[3], index_st[3]).  Returns 0, or -1 when out of memory. */
+int bq2_host_md2_neighbours(const int16_t *dtriangles, int32_t num_tris, int32_t *out)
+{
+    size_t n = 3 * (size_t)num_tris, s;
+    edge_rec *e = (edge_rec *)malloc(sizeof(edge_rec) * (n ? n : 1));
+    if (!e) return -1;
+    for (s = 0; s < n; s++) {
+        size_t t = s / 3, j = s % 3;
+        uint32_t a = (uint16_t)dtriangles[6 * t + j], b = (uint16_t)dtriangles[6 * t + (j + 1) % 3];
+        e[s].key = a < b ? (a << 16 | b) : (b << 16 | a);      /* the match is undirected */
+        e[s].slot = (uint32_t)s;
+        out[s] = -1;
+    }
+    qsort(e, n, sizeof *e, edge_cmp);
+    for (s = 0; s < n; s++) {
+        size_t t = s / 3, j = s % 3, k;
+        uint32_t a, b, key;
+        int32_t found = -1, foundj = 0, dup = 0;
+        if (out[s] != -1) continue;                             /* "none found yet", M:51652 */
+        a = (uint16_t)dtriangles[6 * t + j]; b = (uint16_t)dtriangles[6 * t + (j + 1) % 3];
+        key = a < b ? (a << 16 | b) : (b << 16 | a);
+        for (k = edge_lower_bound(e, n, key); k < n && e[k].key == key; k++) {
+            uint32_t ot = e[k].slot / 3;
+            if (ot == t) continue;                              /* i == index is skipped whole */
+            if (found == -1) { found = (int32_t)ot; foundj = (int32_t)(e[k].slot % 3); }
+            else { dup = 1; break; }
+        }
+        if (!dup && found != -1) { out[3 * found + foundj] = (int32_t)t; out[s] = found; }
+    }
+    free(e);
+    return 0;
+}
+
+/* MD3: R_BuildTriangleNeighbors / R_FindTriangleWithEdge (M:68646-68696). */
+int bq2_host_md3_neighbours(const uint16_t *indexes, int32_t num_tris, int32_t *out)
+{
+    size_t n = 3 * (size_t)num_tris, s;
+    edge_rec *e = (edge_rec *)malloc(sizeof(edge_rec) * (n ? n : 1));
+    if (!e) return -1;
+    for (s = 0; s < n; s++) {
+        size_t t = s / 3, j = s % 3;
+        e[s].key = (uint32_t)indexes[3 * t + j] << 16 | indexes[3 * t + (j + 1) % 3];   /* directed */
+        e[s].slot = (uint32_t)s;
+    }
+    qsort(e, n, sizeof *e, edge_cmp);
+    for (s = 0; s < n; s++) {
+        size_t t = s / 3, j = s % 3, k;
+        /* edge j of the triangle runs idx[j] -> idx[j+1]; the query is its reverse (M:68691-68693) */
+        uint32_t start = indexes[3 * t + (j + 1) % 3], end = indexes[3 * t + j];
+        uint32_t fkey = start << 16 | end, bkey = end << 16 | start, last = 0xffffffffu;
+        int32_t match = -1, count = 0;
+        for (k = edge_lower_bound(e, n, fkey); k < n && e[k].key == fkey; k++) {
+            uint32_t ot = e[k].slot / 3;
+            if (ot == last) continue;                           /* one triangle counts once */
+            last = ot;
+            if (ot != t) match = (int32_t)ot;                   /* ascending: the last one wins */
+            count++;
+        }
+        last = 0xffffffffu;
+        for (k = edge_lower_bound(e, n, bkey); k < n && e[k].key == bkey; k++) {
+            uint32_t ot = e[k].slot / 3;
+            const uint16_t *ix = indexes + 3 * ot;
+            if (ot == last) continue;
+            last = ot;
+            if ((ix[0] == start && ix[1] == end) || (ix[1] == start && ix[2] == end) || (ix[2] == start && ix[0] == end))
+                continue;                                       /* already counted by the forward branch */
+            count++;
+        }
+        if (count > 2) match = -1;                              /* edge shared by three triangles: a seam */
+        out[s] = match;
+    }
+    free(e);
+    return 0;
+}

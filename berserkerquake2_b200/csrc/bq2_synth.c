@@ -107,6 +107,12 @@ int bq2_synth_md2(int32_t S, int32_t R, int32_t F, uint32_t phase_seed, void *bl
         for (int k = 0; k < 3; k++) { tri[6*t+k] = (int16_t)ix[k]; tri[6*t+3+k] = (int16_t)ix[k]; }
     }
     double phase = (double)(hash32(phase_seed * 2654435761u + 17u) & 0xffff) / 65536.0 * 2.0 * PI_D;
+    uint8_t lni[2048];                              /* the direction, hence the anorm, is per vertex */
+    for (int32_t v = 0; v < V; v++) {
+        double th, ph; sphere_dir(S, R, v, &th, &ph);
+        float df[3] = { (float)(sin(th) * cos(ph)), (float)(sin(th) * sin(ph)), (float)cos(th) };
+        lni[v] = bq2_host_normal2index(df);
+    }
     for (int32_t f = 0; f < F; f++) {
         uint8_t *fr = base + h->ofs_frames + (size_t)f * h->framesize;
         float *sc = (float *)fr, *tr = sc + 3;
@@ -125,8 +131,7 @@ int bq2_synth_md2(int32_t S, int32_t R, int32_t F, uint32_t phase_seed, void *bl
                 double x = floor(128.0 + rho * d[k] + 0.5);
                 vb[4*v+k] = (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x));
             }
-            float df[3] = { (float)d[0], (float)d[1], (float)d[2] };
-            vb[4*v+3] = bq2_host_normal2index(df);
+            vb[4*v+3] = lni[v];
         }
     }
     return 0;
@@ -159,6 +164,12 @@ int bq2_synth_md3_mesh(int32_t S, int32_t R, int32_t F, uint32_t phase_seed, con
         for (int k = 0; k < 3; k++) indexes[3*t+k] = (uint16_t)ix[k];
     }
     double phase = (double)(hash32(phase_seed * 2654435761u + 29u) & 0xffff) / 65536.0 * 2.0 * PI_D;
+    uint8_t lni[4096];
+    for (int32_t v = 0; v < V; v++) {
+        double th, ph; sphere_dir(S, R, v, &th, &ph);
+        float df[3] = { (float)(sin(th) * cos(ph)), (float)(sin(th) * sin(ph)), (float)cos(th) };
+        lni[v] = bq2_host_normal2index(df);
+    }
     for (int32_t f = 0; f < F; f++)
         for (int32_t v = 0; v < V; v++) {
             double th, ph; sphere_dir(S, R, v, &th, &ph);
@@ -170,8 +181,7 @@ int bq2_synth_md3_mesh(int32_t S, int32_t R, int32_t F, uint32_t phase_seed, con
                 int16_t q = (int16_t)floor((centre[k] + rho * d[k]) * 64.0 + 0.5);
                 o->point[k] = (float)q * (1.0f / 64.0f);
             }
-            float df[3] = { (float)d[0], (float)d[1], (float)d[2] };
-            o->normal = bq2_host_normal2index(df); o->tangent = 0; o->binormal = 0; o->pad = 0;
+            o->normal = lni[v]; o->tangent = 0; o->binormal = 0; o->pad = 0;
             if (st && f == 0) { st[2*v] = (float)(ph / (2.0 * PI_D)); st[2*v+1] = (float)(th / PI_D); }
         }
     return 0;

@@ -46,3 +46,24 @@ def shard_entities(n_ents, rank, world):
     first, count = C.c_int32(), C.c_int32()
     c.lib.bq2_shard_entities(n_ents, rank, world, C.byref(first), C.byref(count))
     return first.value, count.value
+
+
+def md2_neighbours(blob):
+    """model_t.triangles for an in-memory MD2 image (findneighbour rules, main.c:61782-61824, 51643-51653)."""
+    h = blob[:68].view("<i4")
+    T, o = int(h[8]), int(h[13])
+    tris = np.ascontiguousarray(blob[o:o + 12 * T]).view(np.int16)
+    out = np.zeros((T, 3), np.int32)
+    if c.lib.bq2_host_md2_neighbours(c.ptr(tris), T, c.ptr(out)) != 0:
+        raise MemoryError("bq2_host_md2_neighbours")
+    return out
+
+
+def md3_neighbours(indexes):
+    """maliasmesh_t.triangles (R_BuildTriangleNeighbors, main.c:68646-68696)."""
+    ix = np.ascontiguousarray(indexes, np.uint16)
+    T = ix.size // 3
+    out = np.zeros((T, 3), np.int32)
+    if c.lib.bq2_host_md3_neighbours(c.ptr(ix), T, c.ptr(out)) != 0:
+        raise MemoryError("bq2_host_md3_neighbours")
+    return out

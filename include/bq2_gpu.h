@@ -236,6 +236,13 @@ void bq2_host_point_to_model(const float world[3], const float origin[3], const 
 /* Flag filter of R_DrawAliasShadowVolume M:63722-63727 (+ M:64089): 1 = entity casts a volume. */
 int  bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow, float r_shadows);
 
+/* Load-time neighbour tables with the reference's exact rules, from one sorted edge list instead of the
+ * reference's O(T^2) scans: MD2 findneighbour M:61782-61824 under the loader loop M:51643-51653
+ * (dtriangles = dtriangle_t[T]); MD3 R_BuildTriangleNeighbors M:68646-68696.  out = int[T][3].
+ * Return 0, or -1 when out of memory. */
+int  bq2_host_md2_neighbours(const int16_t *dtriangles, int32_t num_tris, int32_t *out);
+int  bq2_host_md3_neighbours(const uint16_t *indexes, int32_t num_tris, int32_t *out);
+
 /* ---- the renderer's loop nest, flattened (host, C) -------------------------------------------- */
 /* The fields of entity_t (defs.h:573-618) and shadowlight_t (defs.h:3927-3973) this path reads. */
 typedef struct bq2_world_entity {

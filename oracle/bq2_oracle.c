@@ -268,6 +268,33 @@ int bq2o_shadow_volume(const float *lerped, const float *extruded, int num_verts
     return counter;
 }
 
+/* CPU-baseline loop ("port" kind, used only when the compiled reference is unavailable): the restated
+ * R_DrawAliasShadowVolume per world-space pair, writing the same arrays the reference writes. */
+long long bq2o_md2_world_bench(void *const *blobs, void *const *neighbours, int n_pairs,
+                               const int32_t *frames, const int32_t *oldframes, const float *backlerps,
+                               const float *origins, const float *oldorigins, const float *angles,
+                               const float *lights_world, const float *radii)
+{
+    static float lerped[3 * 4096], extruded[3 * 4096], trin[3 * 8192], tris_verts[36 * 8192];
+    static uint8_t viss[8192];
+    static int32_t idx[3 * 4096];
+    long long total = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        const o_md2_header *h = (const o_md2_header *)blobs[p];
+        const o_md2_tri *tris = (const o_md2_tri *)((const uint8_t *)blobs[p] + h->ofs_tris);
+        float move[3], frontv[3], backv[3], fl, light[3];
+        bq2o_md2_lerp_consts(blobs[p], frames[p], oldframes[p], backlerps[p], origins + 3 * p, oldorigins + 3 * p,
+                             angles + 3 * p, move, frontv, backv, &fl);
+        bq2o_point_to_model(lights_world + 3 * p, origins + 3 * p, angles + 3 * p, light);
+        bq2o_md2_lerp(blobs[p], frames[p], oldframes[p], move, frontv, backv, 0, 0.0f, lerped);
+        for (int t = 0; t < h->num_tris; t++) for (int k = 0; k < 3; k++) idx[3 * t + k] = tris[t].index_xyz[k];
+        bq2o_facing(lerped, idx, h->num_tris, light, 32 * radii[p], extruded, trin, viss);
+        total += bq2o_shadow_volume(lerped, extruded, h->num_xyz, idx, (const int32_t *)neighbours[p], viss,
+                                    h->num_tris, tris_verts, NULL);
+    }
+    return total;
+}
+
 /* a10.  MD2 writes old*backlerp + cur*frontlerp (M:65220), MD3 cur*frontlerp + old*backlerp
  * (M:65714); IEEE addition commutes, the two are bit-identical. */
 void bq2o_ntb(const uint8_t *n_cur, const uint8_t *n_old, int n_stride,

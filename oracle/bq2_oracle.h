@@ -73,6 +73,12 @@ void bq2o_tslight(const float *lerped, const float *normals, const float *tangen
                   const float *binormals, int rows, const float light[3], const float view[3],
                   float *lightp, float *tsh);
 
+/* CPU-baseline loop over world-space pairs, one model per pair (bench.py cpu_baseline "port" kind). */
+long long bq2o_md2_world_bench(void *const *blobs, void *const *neighbours, int n_pairs,
+                               const int32_t *frames, const int32_t *oldframes, const float *backlerps,
+                               const float *origins, const float *oldorigins, const float *angles,
+                               const float *lights_world, const float *radii);
+
 /* precompute (SURVEY 8f "next" rows 1-2) */
 uint8_t bq2o_normal2index(const float v[3]);                                  /* M:25206-25223 */
 void bq2o_md2_neighbours(const int16_t *tris /*dtriangle_t[T]*/, int num_tris, int32_t *out); /* M:51643-51653 + 61782-61824 */

@@ -246,6 +246,29 @@ long long bq2ref_md2_bench(void *blob, const int32_t *neighbours, int n_pairs,
     return total;
 }
 
+/* CPU-baseline loop over a world-space pair list with one model per pair: the WHOLE of
+ * R_DrawAliasShadowVolume (M:63713: flag filter, light -> model space, lerp, facing, silhouette + caps,
+ * the (stubbed) GL submit) per pair, exactly what R_DrawEntsShadowVolumes (M:64062) does per marked entity.
+ * Returns the sum of TrisCounter. */
+long long bq2ref_md2_world_bench(void *const *blobs, void *const *neighbours, int n_pairs,
+                                 const int32_t *frames, const int32_t *oldframes, const float *backlerps,
+                                 const float *origins, const float *oldorigins, const float *angles,
+                                 const float *lights_world, const float *radii)
+{
+    bq2ref_init();
+    long long total = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blobs[p];
+        mdl.triangles = (neighbours_t *)neighbours[p];
+        set_entity(frames[p], oldframes[p], backlerps[p], origins + 3 * p, oldorigins + 3 * p, angles + 3 * p, 0);
+        set_light(lights_world + 3 * p, radii[p]);
+        TrisCounter = 0;
+        R_DrawAliasShadowVolume();
+        total += TrisCounter;
+    }
+    return total;
+}
+
 /* MD2 light-lerp family.  which: 0 = ..LightARB (LightP on TMU1, tsH on TMU3, expanded verts on
  * TMU2), 1 = ..LightARB_vp (tangent TMU1? see below).  We record every TMU; callers pick. */
 int bq2ref_md2_light(void *blob, const uint8_t *tangents, const uint8_t *binormals, const uint8_t *normals,

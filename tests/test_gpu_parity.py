@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path, called through the C ABI (libbq2gpu.so), against the CPU oracle on the
+same seeded inputs.  Bit-exact everywhere (the kernels use the reference's operation order with
+round-to-nearest, no FMA), which is stronger than north_star's 1e-5 relative for positions."""
+import numpy as np
+import pytest
+
+import berserkerquake2_b200 as bq2
+from scenes import Md2Model, Md3Model, world_scene, bits
+
+pytestmark = pytest.mark.gpu
+
+
+def check_md2_pairs(ctx, o, models, mids, we, wl, pe, pl, which=None):
+    ents, pairs = ctx.build_records(we, wl, pe, pl)
+    assert len(pairs) == len(pe)
+    res = ctx.frame(ents, pairs)
+    assert res.overflow_pairs == 0
+    sel = range(len(pe)) if which is None else which
+    total = 0
+    for p in sel:
+        e = int(pe[p]); W = we[e]; m = models[mids.index(int(W["model"]))]
+        w = o.md2_pair(m.blob, m.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                       W["oldorigin"], W["angles"], wl["origin"][pl[p]], float(wl["radius"][pl[p]]), idx=m.idx)
+        assert np.array_equal(bits(res.lerped(e, m.V)), bits(w["lerped"])), f"lerped pair {p}"
+        used = np.unique(m.idx)               # the reference only writes extrudedVerts of referenced verts
+        assert np.array_equal(bits(res.extruded(p, m.V))[used], bits(w["extruded"])[used]), f"extruded pair {p}"
+        assert np.array_equal(res.facing(p, m.T), w["viss"]), f"facing pair {p}"
+        assert int(res.index_counts[p]) == len(w["indices"]), f"TrisCounter pair {p}"
+        assert np.array_equal(res.indices(p), w["indices"]), f"indices pair {p}"
+        total += len(w["indices"])
+    return res, total
+
+
+def test_c1_single_md2_one_light(gpu_ctx, oracle):
+    """BASELINE config 1: one MD2 (V=258, T=512, 198 frames) x 1 point light."""
+    m = Md2Model(oracle)
+    mid = m.upload(gpu_ctx)
+    for step in range(4):
+        we, wl, pe, pl = world_scene(1, 1, m.F, step=step * 37)
+        we["model"] = mid
+        res, _ = check_md2_pairs(gpu_ctx, oracle, [m], [mid], we, wl, pe, pl)
+        w = oracle.md2_pair(m.blob, m.nb, int(we["frame"][0]), int(we["oldframe"][0]), float(we["backlerp"][0]),
+                            we["origin"][0], we["oldorigin"][0], we["angles"][0], wl["origin"][0], 300.0)
+        assert np.array_equal(bits(res.trisverts(0)), bits(w["tris_verts"]))      # TrisVerts stream itself
+
+
+def test_md2_batch_many_models(gpu_ctx, oracle):
+    """64 entities x 4 lights over 8 distinct models, rotated entities included."""
+    models = [Md2Model(oracle, frames=12, seed=s) for s in range(8)]
+    mids = [m.upload(gpu_ctx) for m in models]
+    we, wl, pe, pl = world_scene(64, 4, 12, n_models=8, seed=777)
+    we["model"] = np.array(mids)[we["model"]]
+    assert (we["angles"][:, 1] != 0).any()
+    res, total = check_md2_pairs(gpu_ctx, oracle, models, mids, we, wl, pe, pl)
+    assert int(res.total_indices) == total
+    assert int(res.total_lerped_verts) == 64 * models[0].V
+
+
+def test_md2_mixed_sizes_and_pair_order(gpu_ctx, oracle):
+    """Different V/T in one launch, pairs given in light-major (the renderer's) order, entities
+    with zero lights, and one light shared by many entities."""
+    shapes = [(8, 5), (16, 17), (24, 13), (64, 33), (3, 2)]
+    models = [Md2Model(oracle, s, r, frames=6, seed=10 + i) for i, (s, r) in enumerate(shapes)]
+    assert models[3].T == 4096 and models[4].T == 6            # MAX_TRIANGLES and a tiny double tetra-ish
+    mids = [m.upload(gpu_ctx) for m in models]
+    n = 20
+    we, wl, _, _ = world_scene(n, 3, 6, n_models=len(models), seed=4242)
+    we["model"] = np.array(mids)[we["model"]]
+    pe, pl = [], []
+    for l in range(3):                          # light-major, entity 7 and 13 unlit, light 0 hits everyone
+        for e in range(n):
+            if e in (7, 13):
+                continue
+            pe.append(e); pl.append(0 if l == 0 else e * 3 + l)
+    pe, pl = np.array(pe, np.int32), np.array(pl, np.int32)
+    res, _ = check_md2_pairs(gpu_ctx, oracle, models, mids, we, wl, pe, pl)
+    # unlit entities are still lerped
+    for e in (7, 13):
+        m = models[mids.index(int(we["model"][e]))]
+        w = oracle.md2_lerp(m.blob, int(we["frame"][e]), int(we["oldframe"][e]), float(we["backlerp"][e]),
+                            we["origin"][e], we["oldorigin"][e], we["angles"][e])
+        assert np.array_equal(bits(res.lerped(e, m.V)), bits(w))
+
+
+def test_md2_open_mesh_and_degenerate(gpu_ctx, oracle):
+    """Open edges (neighbour -1), an ambiguous 3-triangle edge (dup rule) and a zero-area triangle whose
+    NaN normal must count as facing (M:63620-63626)."""
+    m = Md2Model(oracle, 8, 5, frames=3, seed=5)
+    from berserkerquake2_b200 import synth
+    tris = synth.md2_tris(m.blob)
+    tris[3, 0:3] = tris[3, [0, 0, 2]]           # degenerate: repeated vertex -> zero normal -> NaN
+    tris[10, 0:3] = tris[11, 0:3]               # duplicate triangle -> edges shared by 3 tris
+    tris[20, 0:3] = (0, 1, 1)
+    m.idx = __import__("oracle_lib").md2_idx(m.blob)
+    m.nb = oracle.md2_neighbours(m.blob)
+    assert (m.nb == -1).any()
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(6, 2, 3, seed=99)
+    we["model"] = mid
+    res, _ = check_md2_pairs(gpu_ctx, oracle, [m], [mid], we, wl, pe, pl)
+    assert res.facing(0, m.T)[3] == 1
+
+
+def test_md2_shell_lerp(gpu_ctx, oracle):
+    """RF_SHELL_* push-out along the current frame's anorm (M:63565-63572); shells cast no volume
+    (M:63725), so only the lerp is compared and the pair is filtered on the host."""
+    m = Md2Model(oracle, frames=5, seed=2)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(4, 1, 5, seed=5)
+    we["model"] = mid
+    we["rf_flags"][1] = 0x400                        # RF_SHELL_RED
+    we["rf_flags"][2] = 0x800 | 0x4                  # RF_SHELL_GREEN | RF_WEAPONMODEL -> half scale
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    assert len(pairs) == 2 and list(pairs["entity"]) == [0, 3]
+    res = gpu_ctx.frame(ents, pairs)
+    for e in range(4):
+        shell = bool(we["rf_flags"][e] & 0x1c00)
+        scale = 0.5 if we["rf_flags"][e] & 4 else 1.0
+        move, fv, bv, _ = oracle.md2_lerp_consts(m.blob, int(we["frame"][e]), int(we["oldframe"][e]),
+                                                 float(we["backlerp"][e]), we["origin"][e], we["oldorigin"][e],
+                                                 we["angles"][e])
+        w = np.zeros((m.V, 3), np.float32)
+        import oracle_lib as ol
+        oracle.lib.bq2o_md2_lerp(ol.P(m.blob), int(we["frame"][e]), int(we["oldframe"][e]), ol.P(move), ol.P(fv),
+                                 ol.P(bv), int(shell), scale if shell else 0.0, ol.P(w))
+        assert np.array_equal(bits(res.lerped(e, m.V)), bits(w)), f"entity {e}"
+
+
+def test_md2_lerp_only(gpu_ctx, oracle):
+    """R_CalcAliasFrameLerp alone (ambient pass, M:50303): no pairs."""
+    m = Md2Model(oracle, frames=7, seed=8)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(9, 1, 7, seed=31)
+    we["model"] = mid
+    ents, _ = gpu_ctx.build_records(we, wl, pe[:0], pl[:0])
+    res = gpu_ctx.frame(ents, None)
+    assert res.n_pair_slots == 0
+    for e in range(9):
+        w = oracle.md2_lerp(m.blob, int(we["frame"][e]), int(we["oldframe"][e]), float(we["backlerp"][e]),
+                            we["origin"][e], we["oldorigin"][e], we["angles"][e])
+        assert np.array_equal(bits(res.lerped(e, m.V)), bits(w))
+
+
+def test_index_stride_overflow_reports_exact_count(gpu_ctx, oracle):
+    m = Md2Model(oracle, frames=3, seed=1)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(2, 1, 3, seed=3)
+    we["model"] = mid
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    full = gpu_ctx.frame(ents, pairs)
+    small = gpu_ctx.frame(ents, pairs, index_stride=600, allow_overflow=True)
+    assert small.status == -5 and small.overflow_pairs == 2
+    assert np.array_equal(small.index_counts, full.index_counts)          # counts stay exact
+    for p in range(2):
+        assert np.array_equal(small.indices(p), full.indices(p)[:600])   # prefix written, nothing beyond
+
+
+def test_empty_frame_and_bad_arguments(gpu_ctx, oracle):
+    res = gpu_ctx.frame(np.zeros(0, bq2.ENTITY_DTYPE), None)
+    assert res.n_ent_slots == 0 and res.total_indices == 0
+    e = np.zeros(1, bq2.ENTITY_DTYPE); e["model"] = 10 ** 6
+    with pytest.raises(bq2.Bq2Error):
+        gpu_ctx.frame(e, None)
+    with pytest.raises(bq2.Bq2Error):
+        gpu_ctx.upload_md2(np.zeros(100, np.uint8), None)
+
+
+def test_c4_md3_multisurface(gpu_ctx, oracle):
+    """BASELINE config 4: MD3, 4 surfaces x (V=1026, T=2048) = 8192 tris, one surface's skin casts no
+    shadow (M:63862-63880)."""
+    md3 = Md3Model(oracle, 32, 33, frames=6, num_meshes=4, seed=1, casts=[1, 1, 0, 1])
+    mid = md3.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(3, 2, 6, seed=2024)
+    we["model"] = mid
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    res = gpu_ctx.frame(ents, pairs)
+    assert res.n_ent_slots == 12 and res.n_pair_slots == 24
+    for p in range(len(pe)):
+        e = int(pe[p]); W = we[e]
+        for k, mesh in enumerate(md3.meshes):
+            es, ps = 4 * e + k, 4 * p + k
+            V, T = mesh["verts"].shape[1], len(mesh["indexes"])
+            w = oracle.md3_mesh_pair(mesh["verts"], mesh["indexes"], mesh["neighbours"], md3.frame_translate,
+                                     int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                                     W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0)
+            assert np.array_equal(bits(res.lerped(es, V)), bits(w["lerped"])), (p, k)
+            if not mesh["casts_shadow"]:
+                assert int(res.index_counts[ps]) == 0
+                continue
+            assert np.array_equal(bits(res.extruded(ps, V)), bits(w["extruded"])), (p, k)
+            assert np.array_equal(res.facing(ps, T), w["viss"]), (p, k)
+            assert np.array_equal(res.indices(ps), w["indices"]), (p, k)
+            assert np.array_equal(bits(res.trisverts(ps)), bits(w["tris_verts"])), (p, k)
+
+
+@pytest.mark.parametrize("smooth", [True, False])
+def test_md2_tangent_space_basis(gpu_ctx, oracle, smooth):
+    """a10/a11: lerped N/T/B (per vertex when RF_SMOOTHVECS, else per triangle) and LightP / tsH."""
+    m = Md2Model(oracle, 12, 9, frames=5, seed=4, tangent_space=True, smooth=smooth)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(5, 2, 5, seed=11)
+    we["model"] = mid
+    view = np.array([100.0, -50.0, 80.0], np.float32)
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl, view_world=view)
+    want = bq2.WANT_SHADOW | bq2.WANT_NTB | (bq2.WANT_TSLIGHT if smooth else 0)
+    res = gpu_ctx.frame(ents, pairs, want=want)
+    from berserkerquake2_b200 import synth
+    for e in range(5):
+        f, of = int(we["frame"][e]), int(we["oldframe"][e])
+        bl = float(we["backlerp"][e]); fl = float(ents["frontlerp"][e])
+        if smooth:
+            nc, no = synth.md2_frame_verts(m.blob, f)[:, 3], synth.md2_frame_verts(m.blob, of)[:, 3]
+            rows = m.V
+        else:
+            nc, no = m.normals[f], m.normals[of]
+            rows = m.T
+        N, T_, B = oracle.ntb_rows(nc, no, m.tangents[f], m.tangents[of], m.binormals[f], m.binormals[of], bl, fl)
+        gN, gT, gB = res.ntb(e, rows)
+        assert np.array_equal(bits(gN), bits(N)) and np.array_equal(bits(gT), bits(T_)) and np.array_equal(bits(gB), bits(B))
+        if smooth:
+            P = oracle.md2_lerp(m.blob, f, of, bl, we["origin"][e], we["oldorigin"][e], we["angles"][e])
+            for l in range(2):
+                p = 2 * e + l
+                lp, ts = oracle.tslight(P, N, T_, B, pairs["light"][p], pairs["view"][p])
+                gl, gt = res.tslight(p, m.V)
+                assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
+
+
+def test_md3_tangent_space_basis(gpu_ctx, oracle):
+    md3 = Md3Model(oracle, 16, 9, frames=4, num_meshes=2, seed=3)
+    mid = md3.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(2, 1, 4, seed=8)
+    we["model"] = mid
+    view = np.array([10.0, 20.0, 30.0], np.float32)
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl, view_world=view)
+    res = gpu_ctx.frame(ents, pairs, want=bq2.WANT_SHADOW | bq2.WANT_NTB | bq2.WANT_TSLIGHT)
+    for e in range(2):
+        f, of = int(we["frame"][e]), int(we["oldframe"][e])
+        bl = float(we["backlerp"][e]); fl = float(ents["frontlerp"][e])
+        for k, mesh in enumerate(md3.meshes):
+            v = mesh["verts"]; V = v.shape[1]
+            N, T_, B = oracle.ntb_rows(v["normal"][f], v["normal"][of], v["tangent"][f], v["tangent"][of],
+                                       v["binormal"][f], v["binormal"][of], bl, fl)
+            gN, gT, gB = res.ntb(2 * e + k, V)
+            assert np.array_equal(bits(gN), bits(N)) and np.array_equal(bits(gT), bits(T_)) and np.array_equal(bits(gB), bits(B))
+            P = res.lerped(2 * e + k, V)
+            lp, ts = oracle.tslight(P, N, T_, B, pairs["light"][e], pairs["view"][e])
+            gl, gt = res.tslight(2 * e + k, V)
+            assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
+
+
+def test_c2_full_size_properties(gpu_ctx, oracle):
+    """BASELINE config 2 at full size (1,024 entities x 4 lights, one distinct model per 16 entities):
+    size-independent properties + oracle spot checks on a sample of pairs."""
+    n_models = 64
+    models = [Md2Model(oracle, frames=16, seed=100 + s) for s in range(n_models)]
+    mids = [m.upload(gpu_ctx) for m in models]
+    we, wl, pe, pl = world_scene(1024, 4, 16, n_models=n_models, seed=12345)
+    we["model"] = np.array(mids)[we["model"]]
+    sample = list(range(0, 4096, 97))
+    res, _ = check_md2_pairs(gpu_ctx, oracle, models, mids, we, wl, pe, pl, which=sample)
+    cnt = res.index_counts
+    assert (cnt % 6 == 0).all() and (cnt > 0).all()
+    assert int(res.total_indices) == int(cnt.sum())
+    # closed 2-manifold: every silhouette edge borders exactly one facing tri, so the silhouette is a set of
+    # closed loops; caps = 6 * facing, sides = 6 * silhouette edges
+    T, V = models[0].T, models[0].V
+    for p in sample[:8]:
+        f = res.facing(p, T)
+        ind = res.indices(p)
+        nf = int(f.sum())
+        sides = (len(ind) - 6 * nf) // 6
+        quads = ind[:6 * sides].reshape(-1, 6)
+        assert (quads[:, 1] == quads[:, 0] + V).all() and (quads[:, 5] == quads[:, 0]).all()
+        assert (quads[:, 2] == quads[:, 3]).all() and (quads[:, 3] == quads[:, 4] + V).all()
+        starts, ends = np.sort(quads[:, 0]), np.sort(quads[:, 4])
+        assert np.array_equal(starts, ends)                       # loops: each vertex entered once, left once
+        caps = ind[6 * sides:].reshape(-1, 6)
+        assert (caps[:, 3:] == caps[:, 2::-1] + V).all()
+    # replay (inputs resident) is idempotent
+    before = res.indices(sample[3]).copy()
+    gpu_ctx.replay()
+    gpu_ctx.wait()
+    from berserkerquake2_b200 import _capi
+    cnt2 = gpu_ctx.download(_capi.A_INDEX_COUNT, 0, len(cnt), np.uint32)
+    assert np.array_equal(cnt2, cnt) and np.array_equal(res.indices(sample[3]), before)
