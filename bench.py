@@ -72,7 +72,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.start, self.frozen = [], None, 0, False
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -84,7 +84,17 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            if not self.frozen:
+                self.rows.append([x.strip() for x in line.split(",")])
+
+    def mark(self):
+        self.start = len(self.rows)
+
+    def since_mark(self):
+        return len(self.rows) - self.start
+
+    def freeze(self):
+        self.frozen = True
 
     def stop(self):
         if not self.proc:
@@ -97,7 +107,7 @@ class ClockSampler:
         self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.start:]:
             if len(r) < 7:
                 continue
             try:
@@ -108,7 +118,9 @@ class ClockSampler:
                 if r[3 + k].lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "how": "nvidia-smi -lms 100 from the start of the timed region, the same step kept running until "
+                       "at least 4 samples were seen"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -188,17 +200,29 @@ def run_gpu(args):
             if ev1 is not None:
                 ev1.record(stream)
 
+    clocks = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    t_spin = time.perf_counter()                       # idle GPUs sit at ~120 MHz: keep stepping until the
+    while time.perf_counter() - t_spin < args.spinup:  # clocks have ramped, then start the timed region
+        step_resident()
+        torch.cuda.synchronize()
     barrier()
+    if clocks:
+        clocks.mark()
     launches0 = ctx.kernel_launches
-    clocks = ClockSampler(local) if rank == 0 else None
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evs:
         step_resident(a, b)
     barrier()
     kernel_ms = [a.elapsed_time(b) for a, b in evs]
     launches = ctx.kernel_launches - launches0
+    if clocks:                                         # the timed region can be shorter than nvidia-smi's
+        t_more = time.perf_counter()                   # period: keep the SAME step running until it has
+        while clocks.since_mark() < 4 and time.perf_counter() - t_more < 3.0:   # seen a few samples
+            step_resident()
+            torch.cuda.synchronize()
+        clocks.freeze()
     ms_total = float(sum(kernel_ms))
 
     # ---- e2e: HOST records in through the C ABI, counts back, wall clock -----------------------------
@@ -404,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--spinup", type=float, default=0.5, help="seconds of untimed stepping before the timed region")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--_cpu_worker", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-ents", type=int, default=0, help=argparse.SUPPRESS)

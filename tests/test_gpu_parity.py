@@ -59,9 +59,9 @@ def test_md2_batch_many_models(gpu_ctx, oracle):
 def test_md2_mixed_sizes_and_pair_order(gpu_ctx, oracle):
     """Different V/T in one launch, pairs given in light-major (the renderer's) order, entities
     with zero lights, and one light shared by many entities."""
-    shapes = [(8, 5), (16, 17), (24, 13), (64, 33), (3, 2)]
+    shapes = [(8, 5), (16, 17), (24, 13), (62, 34), (3, 2)]
     models = [Md2Model(oracle, s, r, frames=6, seed=10 + i) for i, (s, r) in enumerate(shapes)]
-    assert models[3].T == 4096 and models[4].T == 6            # MAX_TRIANGLES and a tiny double tetra-ish
+    assert models[3].V == 2048 and models[3].T == 4092 and models[4].T == 6    # MAX_VERTS; a double tetrahedron
     mids = [m.upload(gpu_ctx) for m in models]
     n = 20
     we, wl, _, _ = world_scene(n, 3, 6, n_models=len(models), seed=4242)
