@@ -88,6 +88,9 @@ struct bq2_ctx {
     DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
     DevBuf<uint32_t> facing_bits, indices, index_count;
     bq2_launch launch{};
+    /* entity-slot records are grouped by kernel: [0, n_warp) -> warp kernel, [n_warp, n_ent_slots) -> team kernel */
+    struct KLaunch { int n = 0, max_V = 0, max_T = 0, any_md2 = 0; } k_warp, k_team;
+    std::vector<int32_t> slot_record;                             /* entity slot -> record position */
     int max_V = 0, max_T = 0, any_md2 = 0;
     int32_t n_ent_slots = 0, n_pair_slots = 0, n_ents = 0, n_pairs = 0;
     uint64_t total_verts = 0;
@@ -141,6 +144,26 @@ void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t 
             dst[(size_t)(3 + k) * Tp + t] = (int16_t)(nb ? nb[3 * t + k] : -1);
         }
     for (int t = T; t < Tp; t++) for (int k = 0; k < 3; k++) dst[(size_t)(3 + k) * Tp + t] = -1;
+}
+
+/* the frame's kernels: warp-per-pair over the small-mesh records, CTA-per-pair over the rest */
+bq2_status launch_kernels(bq2_ctx *ctx)
+{
+    bq2_launch L = ctx->launch;
+    if (ctx->k_warp.n) {
+        L.n_ent_slots = ctx->k_warp.n;
+        CK((cudaError_t)bq2_launch_frame_warp(&L, ctx->k_warp.max_V, ctx->k_warp.max_T, ctx->k_warp.any_md2, ctx->stream),
+           "launch(bq2_frame_warp_kernel)");
+        ctx->launches++;
+    }
+    if (ctx->k_team.n) {
+        L.ents = ctx->launch.ents + ctx->k_warp.n;
+        L.n_ent_slots = ctx->k_team.n;
+        CK((cudaError_t)bq2_launch_frame(&L, ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2, ctx->stream),
+           "launch(bq2_frame_kernel)");
+        ctx->launches++;
+    }
+    return BQ2_OK;
 }
 
 } // namespace
@@ -230,7 +253,7 @@ bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, con
 
     const bool smooth = model_flags & BQ2_MODEL_SMOOTHVECS;
     const bool has_tb = tangents && binormals && (smooth || normals);
-    const int Tp = (T + 7) & ~7;
+    const int Tp = (T + 31) & ~31;
     const uint32_t vstride = up16(4u * (uint32_t)V);
     const uint32_t rows = smooth ? (uint32_t)V : (uint32_t)T, tbstride = up16(rows);
     const size_t off_tri = (size_t)F * vstride;
@@ -294,7 +317,7 @@ bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate,
     mo.hdr.assign(frame_translate, frame_translate + 3 * (size_t)F);   /* host-only: folded into bq2_entity.move */
     for (int mi = 0; mi < num_meshes; mi++) {
         const bq2_md3_mesh &me = meshes[mi];
-        const int V = me.num_verts, T = me.num_tris, Tp = (T + 7) & ~7;
+        const int V = me.num_verts, T = me.num_tris, Tp = (T + 31) & ~31;
         const uint32_t vstride = 16u * (uint32_t)V;
         const size_t off_tri = (size_t)F * vstride, total = off_tri + up16(12u * (uint32_t)Tp);
         std::vector<int32_t> idx(3 * (size_t)T);
@@ -415,6 +438,25 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     bq2_dev_ent  *he = (bq2_dev_ent *)ctx->h_records.p;
     bq2_dev_pair *hp = (bq2_dev_pair *)(ctx->h_records.p + (size_t)nES * sizeof(bq2_dev_ent));
 
+    /* which kernel takes each entity slot: small meshes -> one warp per pair; large meshes and the
+       tangent-space outputs -> the whole CTA per pair */
+    const bool team_only = (want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT)) != 0;
+    ctx->slot_record.resize((size_t)nES);
+    ctx->k_warp = bq2_ctx::KLaunch(); ctx->k_team = bq2_ctx::KLaunch();
+    for (int e = 0; e < nE; e++) {
+        const Model &mo = ctx->models[fd->ents[e].model];
+        for (int m = 0; m < mo.n_mesh; m++) {
+            const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
+            bool small = !team_only && me.V <= BQ2_WARP_MAX_V && me.T <= BQ2_WARP_MAX_T;
+            bq2_ctx::KLaunch &k = small ? ctx->k_warp : ctx->k_team;
+            ctx->slot_record[(size_t)ctx->ent_slot_first[e] + m] = small ? k.n : -1 - k.n;
+            k.n++; k.max_V = std::max(k.max_V, me.V); k.max_T = std::max(k.max_T, me.T);
+            if (!(me.flags & BQ2_MESH_MD3)) k.any_md2 = 1;
+        }
+    }
+    for (int s = 0; s < nES; s++)
+        if (ctx->slot_record[s] < 0) ctx->slot_record[s] = ctx->k_warp.n + (-1 - ctx->slot_record[s]);
+
     uint32_t voff = 0, tboff = 0;
     uint64_t total_verts = 0;
     for (int e = 0; e < nE; e++) {
@@ -425,7 +467,9 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
             if ((want & BQ2_WANT_NTB) && !(me.flags & BQ2_MESH_HAS_TB))
                 return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_NTB but the model was uploaded without tangent/binormal bytes");
-            bq2_dev_ent &d = he[s];
+            bq2_dev_ent &d = he[ctx->slot_record[s]];
+            d.cur = me.verts + (size_t)E.frame * me.vstride; d.old = me.verts + (size_t)E.oldframe * me.vstride;
+            d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.pad = 0;
             d.mesh = mo.first_mesh + m; d.frame = E.frame; d.oldframe = E.oldframe; d.flags = E.flags;
             d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
             for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
@@ -460,7 +504,11 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff;
     {
         uint32_t run = 0;
-        for (int s = 0; s < nES; s++) { uint32_t c = ctx->cursor[s]; he[s].pair_begin = run; he[s].pair_count = c; ctx->cursor[s] = run; run += c; }
+        for (int s = 0; s < nES; s++) {
+            uint32_t c = ctx->cursor[s];
+            bq2_dev_ent &d = he[ctx->slot_record[s]];
+            d.pair_begin = run; d.pair_count = c; ctx->cursor[s] = run; run += c;
+        }
     }
     for (int p = 0; p < nP; p++) {
         const bq2_pair &P = fd->pairs[p];
@@ -504,7 +552,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         CK(cudaStreamSynchronize(ctx->stream), "sync(mesh table)");   /* source is pageable */
         ctx->meshes_dirty = false;
     }
-    if (bq2_kernel_smem_bytes(maxV, maxT, anyMd2) > 227u * 1024u)
+    if (ctx->k_team.n && bq2_kernel_smem_bytes(ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2) > 227u * 1024u)
         return fail(ctx, BQ2_E_LIMIT, "bq2_frame: mesh too large for one CTA's shared memory");
 
     /* ---- go -------------------------------------------------------------------------------------- */
@@ -524,10 +572,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     ctx->max_V = maxV; ctx->max_T = maxT; ctx->any_md2 = anyMd2;
     ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
     ctx->total_verts = total_verts;
-    if (nES) {
-        CK((cudaError_t)bq2_launch_frame(&L, maxV, maxT, anyMd2, ctx->stream), "launch(bq2_frame_kernel)");
-        ctx->launches++;
-    }
+    { bq2_status ls = launch_kernels(ctx); if (ls != BQ2_OK) return ls; }
     if (nPS) CK(cudaMemcpyAsync(ctx->h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nPS,
                                 cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
     ctx->submitted = true;
@@ -573,9 +618,7 @@ bq2_status bq2_frame_replay(bq2_ctx *ctx)
 {
     if (!ctx) return BQ2_E_INVALID;
     if (!ctx->submitted || !ctx->n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
-    CK((cudaError_t)bq2_launch_frame(&ctx->launch, ctx->max_V, ctx->max_T, ctx->any_md2, ctx->stream), "launch(bq2_frame_kernel)");
-    ctx->launches++;
-    return BQ2_OK;
+    return launch_kernels(ctx);
 }
 
 const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->h_counts.p : nullptr; }

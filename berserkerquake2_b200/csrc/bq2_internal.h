@@ -8,7 +8,7 @@
  *                (dtrivertx_t, defs.h:3714-3718) padded to 16 B.  The 40-byte frame header
  *                (scale/translate/name) is NOT resident: the host folds it into move/frontv/backv.
  *           MD3: frames x V x 16 B maliasvertex_t rows (defs.h:4401-4407), already 16-byte records.
- *   tri     six s16 arrays of Tp = round_up(T, 8) entries each, back to back:
+ *   tri     six s16 arrays of Tp = round_up(T, 32) entries each, back to back:
  *                i0[Tp] i1[Tp] i2[Tp]   index_xyz[0..2]   (dtriangle_t / WORD indexes)
  *                n0[Tp] n1[Tp] n2[Tp]   neighbours[0..2]  (neighbours_t, -1 = open; T <= 8192 fits)
  *           12 bytes per triangle instead of the reference's 12 + 12, one 16-byte-aligned block so a
@@ -37,19 +37,26 @@ typedef struct bq2_dev_mesh {
     uint32_t pad;
 } bq2_dev_mesh;             /* 72 bytes */
 
-/* one entity slot = (entity, mesh) */
+/* one entity slot = (entity, mesh).  Self-contained: the two key-frame rows and the triangle table are
+ * addressed directly, so a CTA needs ONE record load before it can start its TMA copies. */
 typedef struct bq2_dev_ent {
-    int32_t  mesh;          /* index into the device mesh table */
+    const uint8_t *cur, *old;   /* vertex rows of frame / oldframe                    */
+    const int16_t *tri;         /* index + neighbour table                            */
+    int32_t  V, T, Tp;
+    uint32_t mflags;            /* BQ2_MESH_*                                         */
+    int32_t  mesh;              /* index into the device mesh table (N/T/B byte rows) */
     int32_t  frame, oldframe;
-    uint32_t flags;         /* BQ2_ENT_* */
+    uint32_t flags;             /* BQ2_ENT_* */
     float    backlerp, frontlerp;
     float    move[3], frontv[3], backv[3];
     float    shell_scale;
-    uint32_t vert_off;      /* first vertex row of this slot in lerped[]            */
-    uint32_t pair_begin;    /* first entry of this slot in the sorted pair-slot list */
+    uint32_t vert_off;          /* first vertex row of this slot in lerped[]            */
+    uint32_t pair_begin;        /* first entry of this slot in the sorted pair-slot list */
     uint32_t pair_count;
-    uint32_t tb_off;        /* first row in normals/tangents/binormals              */
-} bq2_dev_ent;              /* 80 bytes */
+    uint32_t tb_off;            /* first row in normals/tangents/binormals              */
+    uint32_t vstride;           /* bytes per frame row                                  */
+    uint32_t pad;
+} bq2_dev_ent;                  /* 128 bytes */
 
 typedef struct bq2_dev_pair {
     float    light[3];
@@ -76,10 +83,18 @@ typedef struct bq2_launch {
 #ifdef __cplusplus
 extern "C" {
 #endif
-/* returns cudaError_t as int; smem_bytes = dynamic shared memory for the largest mesh in the batch */
-int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);
+/* Two kernels share the records.  "warp" kernel: one warp per (entity, light) pair, one CTA per entity,
+ * for meshes with V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T (an MD2 player model is ~500 triangles).
+ * "team" kernel: the whole CTA works on one pair at a time; any mesh size, and the N/T/B + tangent-space
+ * light outputs.  Both return cudaError_t as int; max_V / max_T size the dynamic shared memory. */
+#define BQ2_WARP_MAX_V   1024
+#define BQ2_WARP_MAX_T   1024
+#define BQ2_WARP_WARPS   4
+int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);       /* team */
+int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);  /* warp */
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
+size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);
 #ifdef __cplusplus
 }
 #endif
