@@ -253,16 +253,11 @@ def run_gpu(args):
     clock_info = clocks.stop() if clocks else None
 
     # ---- reduce: max time over ranks; NCCL all_gather of the per-shard counters (the only collective) --
-    counters = torch.tensor([n_pairs, n_ents * V, total_indices // 3, total_indices, e2e_indices // 3],
-                            dtype=torch.int64, device=f"cuda:{local}")
-    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        gathered = [torch.zeros_like(counters) for _ in range(world)]
-        dist.all_gather(gathered, counters)
-        counters = torch.stack(gathered).sum(0)
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    g_pairs, g_verts, g_tris, g_indices, g_e2e_tris = [int(x) for x in counters.tolist()]
-    ms_total_max, e2e_ms_max = times.tolist()
+    from berserkerquake2_b200 import shard
+    dev = f"cuda:{local}"
+    per_rank = shard.gather_counters([n_pairs, n_ents * V, total_indices // 3, total_indices, e2e_indices // 3], dev, dist)
+    g_pairs, g_verts, g_tris, g_indices, g_e2e_tris = [int(x) for x in per_rank.sum(0)]
+    ms_total_max, e2e_ms_max = shard.max_over_ranks([ms_total, e2e_s * 1e3], dev, dist)
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps

@@ -10,8 +10,8 @@ buffers through ctypes.  There is no CPU fallback: without the built library imp
 from ._capi import (Bq2Error, ENTITY_DTYPE, PAIR_DTYPE, WORLD_ENTITY_DTYPE, WORLD_LIGHT_DTYPE,  # noqa: F401
                     WANT_SHADOW, WANT_NTB, WANT_TSLIGHT, WANT_NOLERPOUT, MODEL_SMOOTHVECS, lib, lib_path)
 from .context import Context, FrameResult  # noqa: F401
-from . import synth, host  # noqa: F401
+from . import synth, host, shard  # noqa: F401
 
-__all__ = ["Context", "FrameResult", "Bq2Error", "synth", "host", "ENTITY_DTYPE", "PAIR_DTYPE",
+__all__ = ["Context", "FrameResult", "Bq2Error", "synth", "host", "shard", "ENTITY_DTYPE", "PAIR_DTYPE",
            "WORLD_ENTITY_DTYPE", "WORLD_LIGHT_DTYPE", "WANT_SHADOW", "WANT_NTB", "WANT_TSLIGHT",
            "WANT_NOLERPOUT", "MODEL_SMOOTHVECS", "lib", "lib_path"]

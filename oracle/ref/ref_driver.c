@@ -75,7 +75,7 @@ void glVertexPointer(GLint size, GLenum type, GLsizei stride, const GLvoid *p)
 /* MD3 per-mesh results (the reference overwrites its globals for every mesh, M:63919) */
 typedef struct {
     float *lerped, *extruded, *tris_verts; uint8_t *viss; int *tris_counter;
-    const int *vert_off, *tri_off, *tv_off; int n; int drawn;
+    const int *vert_off, *tri_off, *tv_off; int n; int drawn; int draws;
 } md3_sink_t;
 static md3_sink_t md3_sink;
 static int md3_mesh_nverts[MD3_MAX_MESHES], md3_mesh_ntris[MD3_MAX_MESHES], md3_mesh_order[MD3_MAX_MESHES], md3_nmesh_cast;
@@ -87,7 +87,9 @@ void glDrawArrays(GLenum mode, GLint first, GLsizei count)
     for (int t = 0; t < CAP_TMUS; t++)
         if (cap_out[t] && cap_ptr[t]) memcpy(cap_out[t], cap_ptr[t], sizeof(float) * cap_size[t] * count);
     if (cap_vertex_out && cap_vertex_ptr) memcpy(cap_vertex_out, cap_vertex_ptr, sizeof(float) * 3 * count);
-    if (cap_mesh_hook && md3_sink.drawn < md3_nmesh_cast) {
+    /* with r_faststencil 0 every casting mesh is drawn twice (incr pass, decr pass; M:64016-64029):
+       capture on the second draw of each mesh */
+    if (cap_mesh_hook && (++md3_sink.draws & 1) == 0 && md3_sink.drawn < md3_nmesh_cast) {
         int m = md3_mesh_order[md3_sink.drawn++];
         int V = md3_mesh_nverts[m], T = md3_mesh_ntris[m];
         memcpy(md3_sink.lerped + 3 * md3_sink.vert_off[m], tempVertexArray, sizeof(float) * 3 * V);
@@ -336,7 +338,7 @@ int bq2ref_md3_shadow(int num_frames, const float *frame_translate, int num_mesh
     set_light(light_world, radius);
     md3_sink.lerped = lerped; md3_sink.extruded = extruded; md3_sink.viss = viss_out;
     md3_sink.tris_verts = tris_verts; md3_sink.tris_counter = tris_counter;
-    md3_sink.vert_off = vert_off; md3_sink.tri_off = tri_off; md3_sink.tv_off = tv_off; md3_sink.drawn = 0;
+    md3_sink.vert_off = vert_off; md3_sink.tri_off = tri_off; md3_sink.tv_off = tv_off; md3_sink.drawn = 0; md3_sink.draws = 0;
     cap_mesh_hook = 1;
     R_DrawMD3AliasShadowVolume();
     cap_mesh_hook = 0;
