@@ -134,16 +134,18 @@ struct md2_header {
 
 inline uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
 
-/* index + neighbour table -> six s16 arrays of Tp entries */
+/* index + neighbour table -> Tp records {a, b, c, n0+1} (8 B) followed by Tp records {n1+1, n2+1} (4 B);
+   neighbour + 1 so that 0 means "open edge" and no sign extension is needed on the device */
 void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t *nb /*[T][3] or null*/, int16_t *dst)
 {
+    uint16_t *t4 = (uint16_t *)dst, *n2 = t4 + 4 * (size_t)Tp;
     memset(dst, 0, sizeof(int16_t) * 6 * (size_t)Tp);
-    for (int t = 0; t < T; t++)
-        for (int k = 0; k < 3; k++) {
-            dst[(size_t)k * Tp + t] = (int16_t)idx[3 * t + k];
-            dst[(size_t)(3 + k) * Tp + t] = (int16_t)(nb ? nb[3 * t + k] : -1);
-        }
-    for (int t = T; t < Tp; t++) for (int k = 0; k < 3; k++) dst[(size_t)(3 + k) * Tp + t] = -1;
+    for (int t = 0; t < T; t++) {
+        t4[4 * t + 0] = (uint16_t)idx[3 * t]; t4[4 * t + 1] = (uint16_t)idx[3 * t + 1]; t4[4 * t + 2] = (uint16_t)idx[3 * t + 2];
+        t4[4 * t + 3] = (uint16_t)(nb ? nb[3 * t] + 1 : 0);
+        n2[2 * t + 0] = (uint16_t)(nb ? nb[3 * t + 1] + 1 : 0);
+        n2[2 * t + 1] = (uint16_t)(nb ? nb[3 * t + 2] + 1 : 0);
+    }
 }
 
 /* the frame's kernels: warp-per-pair over the small-mesh records, CTA-per-pair over the rest */

@@ -8,11 +8,11 @@
  *                (dtrivertx_t, defs.h:3714-3718) padded to 16 B.  The 40-byte frame header
  *                (scale/translate/name) is NOT resident: the host folds it into move/frontv/backv.
  *           MD3: frames x V x 16 B maliasvertex_t rows (defs.h:4401-4407), already 16-byte records.
- *   tri     six s16 arrays of Tp = round_up(T, 32) entries each, back to back:
- *                i0[Tp] i1[Tp] i2[Tp]   index_xyz[0..2]   (dtriangle_t / WORD indexes)
- *                n0[Tp] n1[Tp] n2[Tp]   neighbours[0..2]  (neighbours_t, -1 = open; T <= 8192 fits)
- *           12 bytes per triangle instead of the reference's 12 + 12, one 16-byte-aligned block so a
- *           single TMA bulk copy stages it.
+ *   tri     Tp = round_up(T, 32) records {u16 a, b, c, n0+1} (index_xyz[0..2] of dtriangle_t / WORD
+ *           indexes, first neighbour) followed by Tp records {u16 n1+1, n2+1}: neighbours_t with 0 = open
+ *           edge.  12 bytes per triangle instead of the reference's 12 + 12, one 16-byte-aligned block so
+ *           a single TMA bulk copy stages it; a triangle's corners are one LDS.64, its other two
+ *           neighbours one LDS.32.  T <= 8192 and V <= 4096 fit in 16 bits.
  *   tb/bn/nm  tangent / binormal (/ flat normal) anorm-index bytes, frames x tbstride (MD2 only;
  *           MD3 carries them inside the vertex rows).
  */
