@@ -345,6 +345,58 @@ int bq2ref_md3_shadow(int num_frames, const float *frame_translate, int num_mesh
     return md3_sink.drawn;
 }
 
+#ifdef BQ2_WITH_DROPIN
+/* The drop-in shim's MD3 per-mesh body (integration/bq2_dropin.c) under the same globals the reference's
+ * monolithic R_DrawMD3AliasShadowVolume sets up: light moved to model space by the reference's own lines
+ * (M:63806-63820 are the same statements as M:63733-63745, exercised here through R_DrawAliasShadowVolume's
+ * twin below), then one call per casting mesh. */
+int  bq2_dropin_md3_mesh(maliasmodel_t *mm, int nmesh);
+int bq2ref_dropin_md3(int num_frames, const float *frame_translate, int num_meshes,
+                      const int *num_verts, const int *num_tris, void *const *mesh_verts,
+                      void *const *mesh_indexes, void *const *mesh_neighbours, const int *casts,
+                      int frame, int oldframe, float backlerp,
+                      const float *origin, const float *oldorigin, const float *angles,
+                      const float *light_world, float radius,
+                      const int *vert_off, const int *tri_off, const int *tv_off,
+                      float *lerped, float *extruded, uint8_t *viss_out, float *tris_verts, int *tris_counter)
+{
+    static maliasmodel_t mm; static maliasmesh_t meshes[MD3_MAX_MESHES]; static maliasframe_t frames[MD3_MAX_FRAMES];
+    bq2ref_init();
+    memset(&mm, 0, sizeof mm); memset(meshes, 0, sizeof meshes);
+    for (int f = 0; f < num_frames; f++) for (int k = 0; k < 3; k++) frames[f].translate[k] = frame_translate[3*f+k];
+    mm.num_frames = num_frames; mm.frames = frames; mm.num_meshes = num_meshes; mm.meshes = meshes;
+    for (int m = 0; m < num_meshes; m++) {
+        meshes[m].num_verts = num_verts[m]; meshes[m].num_tris = num_tris[m];
+        meshes[m].vertexes = (maliasvertex_t *)mesh_verts[m]; meshes[m].indexes = (WORD *)mesh_indexes[m];
+        meshes[m].triangles = (neighbours_t *)mesh_neighbours[m];
+    }
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias_md3; mdl.extradata = &mm; currentmodel = &mdl;
+    set_entity(frame, oldframe, backlerp, origin, oldorigin, angles, 0);
+    set_light(light_world, radius);
+    {   /* light -> model space with the reference's AngleVectors */
+        vec3_t t, f, r, u;
+        VectorSubtract(light.origin, ent.origin, light.origin);
+        if (ent.angles[0] || ent.angles[1] || ent.angles[2]) {
+            AngleVectors(ent.angles, f, r, u);
+            VectorCopy(light.origin, t);
+            light.origin[0] = DotProduct(t, f); light.origin[1] = -DotProduct(t, r); light.origin[2] = DotProduct(t, u);
+        }
+    }
+    int done = 0;
+    for (int m = 0; m < num_meshes; m++) {
+        tris_counter[m] = -1;
+        if (!casts[m]) continue;                       /* the skin filter M:63862-63880 stays with the caller */
+        if (bq2_dropin_md3_mesh(&mm, m) != 0) return -1;
+        memcpy(lerped + 3 * vert_off[m], tempVertexArray, sizeof(float) * 3 * num_verts[m]);
+        memcpy(extruded + 3 * vert_off[m], extrudedVerts, sizeof(float) * 3 * num_verts[m]);
+        memcpy(viss_out + tri_off[m], viss, num_tris[m]);
+        memcpy(tris_verts + 3 * tv_off[m], TrisVerts, sizeof(float) * 3 * TrisCounter);
+        tris_counter[m] = TrisCounter; done++;
+    }
+    return done;
+}
+#endif
+
 /* MD3 light family, one mesh.  The reference lerps the mesh's verts in R_DrawMD3AliasObjectLight
  * (M:66892-66896) before calling these; callers pass the lerped verts they want used.
  * vp=0: TMU1 = LightP, TMU3 = tsH (M:65839).  vp=1: TMU1 = binormal, TMU2 = normal, TMU3 = tangent

@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libbq2ref.so")
+REF_DROPIN_SO = os.path.join(ROOT, "oracle", "_ref", "libbq2ref_dropin.so")
 
 vp, i32, f32 = C.c_void_p, C.c_int, C.c_float
 
@@ -214,13 +215,13 @@ class Reference:
     """The reference's own object code.  See oracle/ref/ref_driver.c for each entry point."""
 
     @staticmethod
-    def load():
-        if not os.path.exists(REF_SO):
+    def load(path=REF_SO):
+        if not os.path.exists(path):
             return None
-        return Reference()
+        return Reference(path)
 
-    def __init__(self):
-        L = self.lib = C.CDLL(REF_SO)
+    def __init__(self, path=REF_SO):
+        L = self.lib = C.CDLL(path)
         L.bq2ref_init()
         L.bq2ref_smooth_cosine.restype = f32
         L.bq2ref_anorms.restype = C.POINTER(C.c_float)
@@ -368,6 +369,41 @@ class Reference:
                             viss=viss[toff[m]:toff[m + 1]].copy(),
                             tris_verts=tv[tvoff[m]:tvoff[m] + cnt[m]].copy()))
         return drawn, out
+
+    def dropin_md3(self, frame_translate, meshes, frame, oldframe, backlerp, origin, oldorigin, angles,
+                   light_world, radius):
+        """integration/bq2_dropin.c: bq2_dropin_md3_mesh per casting mesh (libbq2ref_dropin.so only)."""
+        fn = self.lib.bq2ref_dropin_md3
+        fn.argtypes = [i32, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, f32, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp]
+        ft = np.ascontiguousarray(frame_translate, np.float32)
+        nm = len(meshes)
+        nv = np.array([m["verts"].shape[1] for m in meshes], np.int32)
+        nt = np.array([np.asarray(m["indexes"]).size // 3 for m in meshes], np.int32)
+        casts = np.array([1 if m.get("casts_shadow", True) else 0 for m in meshes], np.int32)
+        keep = []
+        def arr_of_ptrs(arrs):
+            a = (vp * nm)()
+            for i, x in enumerate(arrs):
+                keep.append(x); a[i] = x.ctypes.data
+            return a
+        pv = arr_of_ptrs([np.ascontiguousarray(m["verts"]) for m in meshes])
+        pi = arr_of_ptrs([np.ascontiguousarray(m["indexes"], np.uint16) for m in meshes])
+        pn = arr_of_ptrs([np.ascontiguousarray(m["neighbours"], np.int32) for m in meshes])
+        voff = np.concatenate([[0], np.cumsum(nv)]).astype(np.int32)
+        toff = np.concatenate([[0], np.cumsum(nt)]).astype(np.int32)
+        tvoff = np.concatenate([[0], np.cumsum(24 * nt)]).astype(np.int32)
+        lerped = np.zeros((voff[-1], 3), np.float32); ext = np.zeros((voff[-1], 3), np.float32)
+        viss = np.zeros(toff[-1], np.uint8); tv = np.zeros((tvoff[-1], 3), np.float32)
+        cnt = np.zeros(nm, np.int32)
+        done = fn(ft.shape[0], P(ft), nm, P(nv), P(nt), pv, pi, pn, P(casts), frame, oldframe, backlerp,
+                  P(f3(origin)), P(f3(oldorigin)), P(f3(angles)), P(f3(light_world)), radius,
+                  P(voff), P(toff), P(tvoff), P(lerped), P(ext), P(viss), P(tv), P(cnt))
+        out = []
+        for m in range(nm):
+            out.append(None if cnt[m] < 0 else dict(
+                lerped=lerped[voff[m]:voff[m + 1]].copy(), extruded=ext[voff[m]:voff[m + 1]].copy(),
+                viss=viss[toff[m]:toff[m + 1]].copy(), tris_verts=tv[tvoff[m]:tvoff[m] + cnt[m]].copy()))
+        return done, out
 
     def md3_light(self, mesh_verts, frame, oldframe, backlerp, lerped, light_model, view_model, vp_variant):
         F, V = mesh_verts.shape
