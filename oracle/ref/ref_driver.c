@@ -375,11 +375,13 @@ int bq2ref_dropin_md3(int num_frames, const float *frame_translate, int num_mesh
     set_light(light_world, radius);
     {   /* light -> model space with the reference's AngleVectors */
         vec3_t t, f, r, u;
-        VectorSubtract(light.origin, ent.origin, light.origin);
+        for (int k = 0; k < 3; k++) light.origin[k] = light.origin[k] - ent.origin[k];
         if (ent.angles[0] || ent.angles[1] || ent.angles[2]) {
             AngleVectors(ent.angles, f, r, u);
-            VectorCopy(light.origin, t);
-            light.origin[0] = DotProduct(t, f); light.origin[1] = -DotProduct(t, r); light.origin[2] = DotProduct(t, u);
+            for (int k = 0; k < 3; k++) t[k] = light.origin[k];
+            light.origin[0] = t[0]*f[0] + t[1]*f[1] + t[2]*f[2];
+            light.origin[1] = -(t[0]*r[0] + t[1]*r[1] + t[2]*r[2]);
+            light.origin[2] = t[0]*u[0] + t[1]*u[1] + t[2]*u[2];
         }
     }
     int done = 0;
