@@ -18,7 +18,7 @@
  * API: the renderer's per-light / per-entity loops (R_DrawEntsShadowVolumes M:64041-64133) collect
  * (entity, light) pairs, the trigonometry stays on the host in C (bq2_host_* below restate the
  * reference's own host lines so libm's sincosf is the same code on both sides), and one CUDA
- * launch does every pair.  berserkerquake2_b200/csrc/bq2_dropin.c shows the five reference
+ * launch does every pair.  integration/bq2_dropin.c shows the reference
  * signatures re-implemented on top of this header (batch of one).
  *
  * Plain C, plain pointers and sizes; no torch / C++ types.  All functions return BQ2_OK (0) or a
