@@ -95,6 +95,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_host_entity_md2_hdr", None, vp, vp, i32, i32, f32, vp, vp, vp, u32, vp),
     _sig("bq2_host_entity_md3", None, vp, vp, i32, i32, f32, vp, vp, vp, vp),
     _sig("bq2_host_point_to_model", None, vp, vp, vp, vp),
+    _sig("bq2_host_entity_basis", C.c_int, vp, vp),
+    _sig("bq2_host_point_to_model_basis", None, vp, vp, vp, vp),
     _sig("bq2_host_casts_shadow", C.c_int, u32, C.c_int, f32, f32),
     _sig("bq2_build_records", C.c_int, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, C.POINTER(i32)),
     _sig("bq2_host_md2_neighbours", C.c_int, vp, i32, vp),

@@ -20,7 +20,17 @@
 #include "bq2_gpu.h"
 #include "bq2_internal.h"
 
+#include <time.h>
 namespace {
+
+/* BQ2_TRACE=1: host time per phase of bq2_frame_submit, printed by bq2_destroy (diagnostics only) */
+struct Trace {
+    bool on = getenv("BQ2_TRACE") != nullptr;
+    double acc[8] = {0}; long n = 0; double t0 = 0;
+    static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
+    void start() { if (on) t0 = now(); }
+    void lap(int i) { if (on) { double t = now(); acc[i] += t - t0; t0 = t; } }
+};
 
 std::string g_create_error;
 
@@ -70,6 +80,7 @@ struct bq2_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     uint64_t launches = 0;
+    Trace trace;
 
     std::vector<Slab> slabs;
     std::vector<Model> models;
@@ -83,6 +94,7 @@ struct bq2_ctx {
     std::vector<uint32_t> pair_slot_ent, cursor;                 /* scratch for the counting sort */
     std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
     std::vector<int32_t>  pair_slot_entslot;
+    std::vector<float>    ent_basis;                             /* build_records scratch: f, r, u, state */
     PinBuf h_records, h_counts;
     DevBuf<unsigned char> d_records;
     DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
@@ -206,6 +218,11 @@ void bq2_destroy(bq2_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->trace.on && ctx->trace.n) {
+        static const char *nm[8] = {"validate+slots", "class split", "entity records", "pair offsets", "pair records",
+                                    "buffers", "h2d+launch+d2h calls", ""};
+        for (int i = 0; i < 7; i++) fprintf(stderr, "bq2 trace: %-22s %8.2f us/frame\n", nm[i], ctx->trace.acc[i] / ctx->trace.n);
+    }
     for (Slab &s : ctx->slabs) cudaFree(s.base);
     ctx->d_meshes.release(); ctx->d_records.release();
     ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
@@ -365,6 +382,8 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
         (n_pairs && (!lights || !pair_ent || !pair_light || !out_pairs)) || !n_pairs_out)
         return fail(ctx, BQ2_E_INVALID, "bq2_build_records: bad arguments");
     const int nModels = (int)ctx->models.size();
+    /* per entity: lerp constants, the rotation basis (AngleVectors once, not once per light) and the flag filter */
+    ctx->ent_basis.resize(10 * (size_t)n_ents);
     for (int e = 0; e < n_ents; e++) {
         const bq2_world_entity &W = ents[e];
         if (W.model < 0 || W.model >= nModels) return fail(ctx, BQ2_E_INVALID, "bq2_build_records: unknown model");
@@ -378,20 +397,26 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
             bq2_host_entity_md2_hdr(&mo.hdr[6 * (size_t)W.frame], &mo.hdr[6 * (size_t)W.oldframe], W.frame, W.oldframe,
                                     W.backlerp, W.origin, W.oldorigin, W.angles, W.rf_flags, &out_ents[e]);
         out_ents[e].model = W.model;
+        float *b = &ctx->ent_basis[10 * (size_t)e];
+        const bool casts = bq2_host_casts_shadow(W.rf_flags, 0, 0.0f, 2.0f) &&
+                           !(W.rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));             /* M:64089 */
+        b[9] = !casts ? -1.0f : (float)bq2_host_entity_basis(W.angles, b);
     }
     int kept = 0;
+    float view_local[3] = {0.0f, 0.0f, 0.0f};
     for (int k = 0; k < n_pairs; k++) {
-        int e = pair_ent[k], l = pair_light[k];
-        if (e < 0 || e >= n_ents || l < 0 || l >= n_lights) return fail(ctx, BQ2_E_INVALID, "bq2_build_records: pair out of range");
+        const int e = pair_ent[k], l = pair_light[k];
+        if ((unsigned)e >= (unsigned)n_ents || (unsigned)l >= (unsigned)n_lights)
+            return fail(ctx, BQ2_E_INVALID, "bq2_build_records: pair out of range");
+        const float *b = &ctx->ent_basis[10 * (size_t)e];
+        if (b[9] < 0.0f) continue;                                                  /* M:63722-63727 */
         const bq2_world_entity &W = ents[e];
-        if (!bq2_host_casts_shadow(W.rf_flags, 0, 0.0f, 2.0f)) continue;
-        if (W.rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT)) continue;          /* M:64089 */
         bq2_pair &P = out_pairs[kept++];
         P.entity = e;
-        bq2_host_point_to_model(lights[l].origin, W.origin, W.angles, P.light);
+        bq2_host_point_to_model_basis(lights[l].origin, W.origin, b[9] > 0.0f ? b : nullptr, P.light);
         P.scale = 32 * lights[l].radius;                                            /* M:63597 */
-        if (view_world) bq2_host_point_to_model(view_world, W.origin, W.angles, P.view);
-        else P.view[0] = P.view[1] = P.view[2] = 0.0f;
+        if (view_world) bq2_host_point_to_model_basis(view_world, W.origin, b[9] > 0.0f ? b : nullptr, P.view);
+        else { P.view[0] = view_local[0]; P.view[1] = view_local[1]; P.view[2] = view_local[2]; }
     }
     *n_pairs_out = kept;
     return BQ2_OK;
@@ -406,6 +431,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     const int nE = fd->n_ents, nP = fd->n_pairs;
     const int nModels = (int)ctx->models.size();
     const uint32_t want = fd->want;
+    Trace &tr = ctx->trace; tr.start(); tr.n++;
 
     /* ---- entity slots ------------------------------------------------------------------------- */
     ctx->ent_slot_first.resize((size_t)nE + 1);
@@ -440,6 +466,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     bq2_dev_ent  *he = (bq2_dev_ent *)ctx->h_records.p;
     bq2_dev_pair *hp = (bq2_dev_pair *)(ctx->h_records.p + (size_t)nES * sizeof(bq2_dev_ent));
 
+    tr.lap(0);
     /* which kernel takes each entity slot: small meshes -> one warp per pair; large meshes and the
        tangent-space outputs -> the whole CTA per pair */
     const bool team_only = (want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT)) != 0;
@@ -459,6 +486,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     for (int s = 0; s < nES; s++)
         if (ctx->slot_record[s] < 0) ctx->slot_record[s] = ctx->k_warp.n + (-1 - ctx->slot_record[s]);
 
+    tr.lap(1);
     uint32_t voff = 0, tboff = 0;
     uint64_t total_verts = 0;
     for (int e = 0; e < nE; e++) {
@@ -488,6 +516,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     ctx->ent_vert_off[nES] = voff; ctx->ent_tb_off[nES] = tboff;
     const uint32_t ent_verts = voff, tb_rows = tboff;
 
+    tr.lap(2);
     /* pair slots: offsets in caller order, then a counting sort by entity slot for the kernel */
     uint32_t pvoff = 0, pboff = 0;
     for (int p = 0; p < nP; p++) {
@@ -504,6 +533,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         }
     }
     ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff;
+    uint32_t n_dev_pairs = 0;
     {
         uint32_t run = 0;
         for (int s = 0; s < nES; s++) {
@@ -511,7 +541,9 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             bq2_dev_ent &d = he[ctx->slot_record[s]];
             d.pair_begin = run; d.pair_count = c; ctx->cursor[s] = run; run += c;
         }
+        n_dev_pairs = run;
     }
+    tr.lap(3);
     for (int p = 0; p < nP; p++) {
         const bq2_pair &P = fd->pairs[p];
         const Model &mo = ctx->models[fd->ents[P.entity].model];
@@ -525,6 +557,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         }
     }
 
+    tr.lap(4);
     uint32_t stride = fd->index_stride ? fd->index_stride : 12u * (uint32_t)maxT;
     stride = (stride + 3u) & ~3u;
 
@@ -558,9 +591,12 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         return fail(ctx, BQ2_E_LIMIT, "bq2_frame: mesh too large for one CTA's shared memory");
 
     /* ---- go -------------------------------------------------------------------------------------- */
+    tr.lap(5);
     if (rec_bytes)
         CK(cudaMemcpyAsync(ctx->d_records.p, ctx->h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(records)");
-    if (nPS) CK(cudaMemsetAsync(ctx->index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, ctx->stream), "cudaMemset(index_count)");
+    /* slots of non-casting MD3 meshes are never written by a kernel: only then is the clear needed */
+    if (nPS && n_dev_pairs != (uint32_t)nPS)
+        CK(cudaMemsetAsync(ctx->index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, ctx->stream), "cudaMemset(index_count)");
 
     bq2_launch &L = ctx->launch;
     L.meshes = ctx->d_meshes.p;
@@ -578,6 +614,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     if (nPS) CK(cudaMemcpyAsync(ctx->h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nPS,
                                 cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
     ctx->submitted = true;
+    tr.lap(6);
     return BQ2_OK;
 }
 

@@ -140,6 +140,28 @@ void bq2_host_point_to_model(const float world[3], const float origin[3], const 
     }
 }
 
+/* The same transform with the entity's AngleVectors evaluated once and reused for every light that hits the
+ * entity (the reference re-evaluates them per light; same inputs, same libm, same results).
+ * basis = forward[3], right[3], up[3]; returns 0 when all three angles are zero (identity, M:63737). */
+int bq2_host_entity_basis(const float angles[3], float basis[9])
+{
+    if (!(angles[0] || angles[1] || angles[2])) return 0;
+    bq2_host_angle_vectors(angles, basis, basis + 3, basis + 6);
+    return 1;
+}
+void bq2_host_point_to_model_basis(const float world[3], const float origin[3], const float *basis, float out[3])
+{
+    float t[3];
+    t[0] = world[0] - origin[0]; t[1] = world[1] - origin[1]; t[2] = world[2] - origin[2];
+    if (basis) {
+        out[0] = DOT(t, basis);
+        out[1] = -DOT(t, basis + 3);
+        out[2] = DOT(t, basis + 6);
+    } else {
+        out[0] = t[0]; out[1] = t[1]; out[2] = t[2];
+    }
+}
+
 /* M:63722-63727 */
 int bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow, float r_shadows)
 {

@@ -233,6 +233,11 @@ void bq2_host_entity_md3(const float frame_translate[3], const float oldframe_tr
 /* M:63733-63745: world-space point (light origin, or r_origin per M:66689-66715) -> model space. */
 void bq2_host_point_to_model(const float world[3], const float origin[3], const float angles[3],
                              float out[3]);
+/* The same with the entity's AngleVectors evaluated once (basis = forward, right, up; returns 0 for the
+ * identity) and reused for every light of that entity. */
+int  bq2_host_entity_basis(const float angles[3], float basis[9]);
+void bq2_host_point_to_model_basis(const float world[3], const float origin[3], const float *basis /* or NULL */,
+                                   float out[3]);
 /* Flag filter of R_DrawAliasShadowVolume M:63722-63727 (+ M:64089): 1 = entity casts a volume. */
 int  bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow, float r_shadows);
 
