@@ -231,46 +231,36 @@ def run_gpu(args):
     kept = C.c_int32(0)
     fd = c.FrameDesc(); fo = c.FrameOut()
 
-    def e2e_build():
-        st = c.lib.bq2_build_records(ctx._h, c.ptr(we_c), n_ents, c.ptr(wl_c), len(wl_c), c.ptr(pe), c.ptr(pl), n_pairs,
-                                     None, c.ptr(ents_h), c.ptr(pairs_h), C.byref(kept))
-        if st != 0:
-            raise RuntimeError(c.lib.bq2_last_error(ctx._h))
+    wd = ctx.world_desc(we_c, wl_c, pe, pl, None, bq2.WANT_SHADOW, 0)      # host arrays, as the engine holds them
 
-    def e2e_submit():
-        fd.ents = ents_h.ctypes.data; fd.n_ents = n_ents; fd.pairs = pairs_h.ctypes.data; fd.n_pairs = kept.value
-        fd.want = bq2.WANT_SHADOW; fd.index_stride = 0
-        if c.lib.bq2_frame_submit(ctx._h, C.byref(fd)) != 0:
-            raise RuntimeError(c.lib.bq2_last_error(ctx._h))
-
-    def e2e_wait():
-        if c.lib.bq2_frame_wait(ctx._h, C.byref(fo)) != 0:
+    def step_e2e():
+        """One frame through the public C ABI from HOST data: bq2_world_submit (per-entity host trig + record
+        packing -> pinned -> H2D -> 3 record-building kernels + the fused kernel -> D2H of per-pair counts and
+        totals) then bq2_frame_wait."""
+        if c.lib.bq2_world_submit(ctx._h, C.byref(wd)) != 0 or c.lib.bq2_frame_wait(ctx._h, C.byref(fo)) != 0:
             raise RuntimeError(c.lib.bq2_last_error(ctx._h))
         return fo.total_indices
 
-    def e2e_run(k):
-        """k frames, software-pipelined with the library's own async pair (bq2_frame_submit / bq2_frame_wait):
-        the host builds the records of frame i+1 while frame i is on the GPU.  Every frame does the full
-        host trig, packing, H2D, kernel and D2H of its per-pair counts."""
-        tot = 0
-        e2e_build(); e2e_submit()
-        for _ in range(k - 1):
-            e2e_build()                # bq2_frame_submit copied the previous records into its pinned buffer
-            tot += e2e_wait()
-            e2e_submit()
-        return tot + e2e_wait()
-
-    e2e_run(max(args.warmup, 3))
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
     barrier()
+    launches_e2e0 = ctx.kernel_launches
     t0 = time.perf_counter()
-    e2e_indices = e2e_run(args.steps)
+    e2e_indices = 0
+    for _ in range(args.steps):
+        e2e_indices += step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
-    # the same, strictly serial (build -> submit -> wait per frame), for the latency of one frame
+    launches_e2e = ctx.kernel_launches - launches_e2e0
+    # the older route for comparison: records built on the host (bq2_build_records + bq2_frame)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_build(); e2e_submit(); e2e_wait()
-    e2e_serial_s = time.perf_counter() - t0
+        c.lib.bq2_build_records(ctx._h, c.ptr(we_c), n_ents, c.ptr(wl_c), len(wl_c), c.ptr(pe), c.ptr(pl), n_pairs,
+                                None, c.ptr(ents_h), c.ptr(pairs_h), C.byref(kept))
+        fd.ents = ents_h.ctypes.data; fd.n_ents = n_ents; fd.pairs = pairs_h.ctypes.data; fd.n_pairs = kept.value
+        fd.want = bq2.WANT_SHADOW; fd.index_stride = 0
+        c.lib.bq2_frame(ctx._h, C.byref(fd), C.byref(fo))
+    e2e_host_s = time.perf_counter() - t0
     clock_info = clocks.stop() if clocks else None
 
     # ---- reduce: max time over ranks; NCCL all_gather of the per-shard counters (the only collective) --
@@ -302,12 +292,12 @@ def run_gpu(args):
                        "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset on the same stream, untimed)",
                        "timing": "CUDA events around each launch on the ctx stream, summed over K steps, max over ranks"},
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
-                    "ms_per_step": e2e_ms_max / args.steps, "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
-                    "h2d_bytes_per_step": n_ents * 128 + n_pairs * 48, "d2h_bytes_per_step": 4 * n_pairs,
-                    "what": "per frame: bq2_build_records (host C trig) + bq2_frame_submit (pack -> pinned -> H2D -> kernel "
-                            "-> D2H of per-pair index counts) + bq2_frame_wait, wall clock; frames software-pipelined "
-                            "(records of frame i+1 built while frame i is on the GPU); ms_per_step_serial = no overlap; "
-                            "vertex/index buffers stay in HBM for the draw"},
+                    "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
+                    "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
+                    "h2d_bytes_per_step": n_ents * (128 + 64) + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
+                    "what": "per frame, serial: bq2_world_submit (host: per-entity trig + record packing; pinned -> H2D; "
+                            "3 record-building kernels + the fused kernel; D2H of per-pair index counts + totals) + "
+                            "bq2_frame_wait, wall clock; vertex/index buffers stay in HBM for the draw"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None,

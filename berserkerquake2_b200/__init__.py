@@ -8,10 +8,10 @@ buffers through ctypes.  There is no CPU fallback: without the built library imp
 :mod:`berserkerquake2_b200._capi` raises, and without a B200 ``Context()`` raises ``Bq2Error``.
 """
 from ._capi import (Bq2Error, ENTITY_DTYPE, PAIR_DTYPE, WORLD_ENTITY_DTYPE, WORLD_LIGHT_DTYPE,  # noqa: F401
-                    WANT_SHADOW, WANT_NTB, WANT_TSLIGHT, WANT_NOLERPOUT, MODEL_SMOOTHVECS, lib, lib_path)
+                    WANT_SHADOW, WANT_NTB, WANT_TSLIGHT, WANT_NOLERPOUT, WANT_TABLES, MODEL_SMOOTHVECS, lib, lib_path)
 from .context import Context, FrameResult  # noqa: F401
 from . import synth, host, shard  # noqa: F401
 
 __all__ = ["Context", "FrameResult", "Bq2Error", "synth", "host", "shard", "ENTITY_DTYPE", "PAIR_DTYPE",
            "WORLD_ENTITY_DTYPE", "WORLD_LIGHT_DTYPE", "WANT_SHADOW", "WANT_NTB", "WANT_TSLIGHT",
-           "WANT_NOLERPOUT", "MODEL_SMOOTHVECS", "lib", "lib_path"]
+           "WANT_NOLERPOUT", "WANT_TABLES", "MODEL_SMOOTHVECS", "lib", "lib_path"]

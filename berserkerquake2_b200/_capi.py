@@ -20,7 +20,7 @@ class Bq2Error(RuntimeError):
 
 
 OK, E_INVALID, E_CUDA, E_NOMEM, E_LIMIT, E_OVERFLOW, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
-WANT_SHADOW, WANT_NTB, WANT_TSLIGHT, WANT_NOLERPOUT = 1, 2, 4, 8
+WANT_SHADOW, WANT_NTB, WANT_TSLIGHT, WANT_NOLERPOUT, WANT_TABLES = 1, 2, 4, 8, 16
 MODEL_SMOOTHVECS = 1
 ENT_SHELL = 1
 (A_LERPED, A_EXTRUDED, A_FACING_BITS, A_INDICES, A_INDEX_COUNT, A_NORMALS, A_TANGENTS, A_BINORMALS,
@@ -56,6 +56,12 @@ class FrameOut(C.Structure):
                 ("index_stride", C.c_uint32),
                 ("total_lerped_verts", C.c_uint64), ("total_indices", C.c_uint64), ("total_pairs", C.c_uint64),
                 ("overflow_pairs", C.c_int32)]
+
+
+class WorldDesc(C.Structure):
+    _fields_ = [("ents", C.c_void_p), ("n_ents", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
+                ("pair_ent", C.c_void_p), ("pair_light", C.c_void_p), ("n_pairs", C.c_int32),
+                ("view_world", C.c_void_p), ("want", C.c_uint32), ("index_stride", C.c_uint32)]
 
 
 class Md3Mesh(C.Structure):
@@ -101,6 +107,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_build_records", C.c_int, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, C.POINTER(i32)),
     _sig("bq2_host_md2_neighbours", C.c_int, vp, i32, vp),
     _sig("bq2_host_md3_neighbours", C.c_int, vp, i32, vp),
+    _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
+    _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),
 ]
 EXPORTS_SYNTH_H = [

@@ -119,6 +119,30 @@ class Context:
         st = self._check(c.lib.bq2_frame_wait(self._h, C.byref(out)), allow=(c.E_OVERFLOW,) if allow_overflow else ())
         return FrameResult(self, out, st)
 
+    def world_desc(self, world_ents, world_lights, pair_ent, pair_light, view_world=None, want=c.WANT_SHADOW,
+                   index_stride=0):
+        we = np.ascontiguousarray(world_ents, c.WORLD_ENTITY_DTYPE)
+        wl = np.ascontiguousarray(world_lights, c.WORLD_LIGHT_DTYPE)
+        pe = np.ascontiguousarray(pair_ent, np.int32); pl = np.ascontiguousarray(pair_light, np.int32)
+        vw = None if view_world is None else np.ascontiguousarray(view_world, np.float32)
+        self._keep = [we, wl, pe, pl, vw]
+        d = c.WorldDesc()
+        d.ents = we.ctypes.data if len(we) else None; d.n_ents = len(we)
+        d.lights = wl.ctypes.data if len(wl) else None; d.n_lights = len(wl)
+        d.pair_ent = pe.ctypes.data if len(pe) else None; d.pair_light = pl.ctypes.data if len(pl) else None
+        d.n_pairs = len(pe); d.view_world = None if vw is None else vw.ctypes.data
+        d.want = int(want); d.index_stride = int(index_stride)
+        return d
+
+    def world_frame(self, world_ents, world_lights, pair_ent, pair_light, view_world=None,
+                    want=c.WANT_SHADOW | c.WANT_TABLES, index_stride=0, allow_overflow=False):
+        """bq2_world_frame: records built on the device; pair slot p is caller pair p."""
+        d = self.world_desc(world_ents, world_lights, pair_ent, pair_light, view_world, want, index_stride)
+        out = c.FrameOut()
+        st = self._check(c.lib.bq2_world_frame(self._h, C.byref(d), C.byref(out)),
+                         allow=(c.E_OVERFLOW,) if allow_overflow else ())
+        return FrameResult(self, out, st)
+
     def replay(self):
         """Re-launch the last frame's kernel on the records already in HBM (no copies, no sync)."""
         self._check(c.lib.bq2_frame_replay(self._h))
@@ -140,8 +164,12 @@ class FrameResult:
         self.n_ent_slots, self.n_pair_slots = nes, nps
         self.ent_vert_offset = np.ctypeslib.as_array(out.ent_vert_offset, (nes + 1,)).copy()
         self.ent_tb_offset = np.ctypeslib.as_array(out.ent_tb_offset, (nes + 1,)).copy()
-        self.pair_vert_offset = np.ctypeslib.as_array(out.pair_vert_offset, (nps + 1,)).copy()
-        self.pair_bits_offset = np.ctypeslib.as_array(out.pair_bits_offset, (nps + 1,)).copy()
+        if out.pair_vert_offset and nps:      # absent for device-built frames submitted without WANT_TABLES
+            n_tab = nps + 1 if out.pair_slot_first else nps
+            self.pair_vert_offset = np.ctypeslib.as_array(out.pair_vert_offset, (n_tab,)).copy()
+            self.pair_bits_offset = np.ctypeslib.as_array(out.pair_bits_offset, (n_tab,)).copy()
+        else:
+            self.pair_vert_offset = self.pair_bits_offset = None
         self.index_stride = out.index_stride
         self.total_lerped_verts = out.total_lerped_verts
         self.total_indices = out.total_indices

@@ -99,6 +99,13 @@ struct bq2_ctx {
     DevBuf<unsigned char> d_records;
     DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
     DevBuf<uint32_t> facing_bits, indices, index_count;
+    /* world path (device-built pair records) */
+    DevBuf<unsigned char> d_world;                               /* dpairs | cnt | cursor | blk | tables | totals */
+    PinBuf h_totals;
+    bq2_world_launch wlaunch{};
+    bool world_mode = false, world_tables = false;
+    std::vector<bq2_entity> tmp_ents; std::vector<bq2_pair> tmp_pairs;     /* host-built fallback */
+    std::vector<uint32_t> world_pvoff, world_pboff;
     bq2_launch launch{};
     /* entity-slot records are grouped by kernel: [0, n_warp) -> warp kernel, [n_warp, n_ent_slots) -> team kernel */
     struct KLaunch { int n = 0, max_V = 0, max_T = 0, any_md2 = 0; } k_warp, k_team;
@@ -228,7 +235,7 @@ void bq2_destroy(bq2_ctx *ctx)
     ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
     ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release();
     ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
-    ctx->h_records.release(); ctx->h_counts.release();
+    ctx->h_records.release(); ctx->h_counts.release(); ctx->d_world.release(); ctx->h_totals.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -371,11 +378,27 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t id, int32_t *is_md3, int32
     return BQ2_OK;
 }
 
+static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
+                             const bq2_world_light *lights, int32_t n_lights,
+                             const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
+                             const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
+                             int32_t *n_pairs_out, bool keep_dead);
+
 bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
                              const bq2_world_light *lights, int32_t n_lights,
                              const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
                              const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
                              int32_t *n_pairs_out)
+{
+    return build_records_impl(ctx, ents, n_ents, lights, n_lights, pair_ent, pair_light, n_pairs, view_world,
+                              out_ents, out_pairs, n_pairs_out, false);
+}
+
+static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
+                             const bq2_world_light *lights, int32_t n_lights,
+                             const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
+                             const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
+                             int32_t *n_pairs_out, bool keep_dead)
 {
     if (!ctx) return BQ2_E_INVALID;
     if (n_ents < 0 || n_pairs < 0 || (n_ents && (!ents || !out_ents)) ||
@@ -409,7 +432,10 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
         if ((unsigned)e >= (unsigned)n_ents || (unsigned)l >= (unsigned)n_lights)
             return fail(ctx, BQ2_E_INVALID, "bq2_build_records: pair out of range");
         const float *b = &ctx->ent_basis[10 * (size_t)e];
-        if (b[9] < 0.0f) continue;                                                  /* M:63722-63727 */
+        if (b[9] < 0.0f) {                                                          /* M:63722-63727 */
+            if (keep_dead) { bq2_pair &D = out_pairs[kept++]; memset(&D, 0, sizeof D); D.entity = ~e; }
+            continue;
+        }
         const bq2_world_entity &W = ents[e];
         bq2_pair &P = out_pairs[kept++];
         P.entity = e;
@@ -453,6 +479,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     int nPS = 0;
     for (int p = 0; p < nP; p++) {
         int e = fd->pairs[p].entity;
+        if (e < 0) e = ~e;                                       /* a pair that keeps its slot but casts nothing */
         if (e < 0 || e >= nE) return fail(ctx, BQ2_E_INVALID, "bq2_frame: pair refers to an unknown entity");
         ctx->pair_slot_first[p] = nPS; nPS += ctx->models[fd->ents[e].model].n_mesh;
     }
@@ -521,6 +548,8 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     uint32_t pvoff = 0, pboff = 0;
     for (int p = 0; p < nP; p++) {
         int e = fd->pairs[p].entity;
+        const bool dead = e < 0;
+        if (dead) e = ~e;
         const Model &mo = ctx->models[fd->ents[e].model];
         for (int m = 0; m < mo.n_mesh; m++) {
             int ps = ctx->pair_slot_first[p] + m, es = ctx->ent_slot_first[e] + m;
@@ -529,7 +558,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             ctx->slot_mesh_V[ps] = me.V; ctx->slot_mesh_T[ps] = me.T; ctx->pair_slot_entslot[ps] = es;
             pvoff += (uint32_t)(me.V + 3) & ~3u;
             pboff += (uint32_t)(me.T + 31) >> 5;
-            if (mo.casts[m]) ctx->cursor[es]++;
+            if (mo.casts[m] && !dead) ctx->cursor[es]++;
         }
     }
     ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff;
@@ -546,6 +575,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     tr.lap(3);
     for (int p = 0; p < nP; p++) {
         const bq2_pair &P = fd->pairs[p];
+        if (P.entity < 0) continue;
         const Model &mo = ctx->models[fd->ents[P.entity].model];
         for (int m = 0; m < mo.n_mesh; m++) {
             if (!mo.casts[m]) continue;
@@ -606,7 +636,8 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
     L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
     L.normals = ctx->normals.p; L.tangents = ctx->tangents.p; L.binormals = ctx->binormals.p;
-    L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p;
+    L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p; L.totals = nullptr;
+    ctx->world_mode = false;
     ctx->max_V = maxV; ctx->max_T = maxT; ctx->any_md2 = anyMd2;
     ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
     ctx->total_verts = total_verts;
@@ -635,10 +666,19 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
     o.index_stride = ctx->launch.index_stride;
     o.total_lerped_verts = ctx->total_verts;
     o.total_pairs = 0; o.total_indices = 0; o.overflow_pairs = 0;
-    const uint32_t *cnt = (const uint32_t *)ctx->h_counts.p;
-    for (int i = 0; i < ctx->n_pair_slots; i++) {
-        o.total_indices += cnt[i];
-        if (cnt[i] > o.index_stride) o.overflow_pairs++;
+    if (ctx->world_mode) {                                       /* totals were accumulated by the kernels */
+        const unsigned long long *t = (const unsigned long long *)ctx->h_totals.p;
+        o.total_indices = t[0]; o.overflow_pairs = (int32_t)t[1];
+        o.pair_slot_first = nullptr;                             /* slot p is caller pair p */
+        o.pair_vert_offset = ctx->world_tables ? ctx->world_pvoff.data() : nullptr;
+        o.pair_bits_offset = ctx->world_tables ? ctx->world_pboff.data() : nullptr;
+        if (t[2]) { if (out) *out = o; return fail(ctx, BQ2_E_INVALID, "bq2_world: a pair refers to an entity or light out of range (it was skipped)"); }
+    } else {
+        const uint32_t *cnt = (const uint32_t *)ctx->h_counts.p;
+        for (int i = 0; i < ctx->n_pair_slots; i++) {
+            o.total_indices += cnt[i];
+            if (cnt[i] > o.index_stride) o.overflow_pairs++;
+        }
     }
     o.total_pairs = (uint64_t)ctx->n_pair_slots;
     if (out) *out = o;
@@ -653,10 +693,196 @@ bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
     return bq2_frame_wait(ctx, out);
 }
 
+bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!wd || wd->n_ents < 0 || wd->n_pairs < 0 || wd->n_lights < 0 || (wd->n_ents > 0 && !wd->ents) ||
+        (wd->n_pairs > 0 && (!wd->pair_ent || !wd->pair_light || !wd->lights)))
+        return fail(ctx, BQ2_E_INVALID, "bq2_world: bad descriptor");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const int nE = wd->n_ents, nP = wd->n_pairs, nL = wd->n_lights;
+    const int nModels = (int)ctx->models.size();
+    const uint32_t want = wd->want;
+
+    bool device_route = !(want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT));
+    for (int e = 0; e < nE && device_route; e++) {
+        int mid = wd->ents[e].model;
+        if (mid < 0 || mid >= nModels) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
+        if (ctx->models[mid].n_mesh != 1 || !ctx->models[mid].casts[0]) device_route = false;
+    }
+    if (!device_route) {
+        /* host-built records, same slot numbering (filtered pairs keep their slot) */
+        ctx->tmp_ents.resize((size_t)nE + 1); ctx->tmp_pairs.resize((size_t)nP + 1);
+        int32_t kept = 0;
+        bq2_status s = build_records_impl(ctx, wd->ents, nE, wd->lights, nL, wd->pair_ent, wd->pair_light, nP, wd->view_world,
+                                          ctx->tmp_ents.data(), ctx->tmp_pairs.data(), &kept, true);
+        if (s != BQ2_OK) return s;
+        bq2_frame_desc fd{};
+        fd.ents = ctx->tmp_ents.data(); fd.n_ents = nE; fd.pairs = ctx->tmp_pairs.data(); fd.n_pairs = kept;
+        fd.want = want & ~BQ2_WANT_TABLES; fd.index_stride = wd->index_stride;
+        return bq2_frame_submit(ctx, &fd);
+    }
+
+    /* ---- per entity (host): record, transform, class ------------------------------------------------ */
+    const int nblk = (nP + BQ2_WORLD_THREADS - 1) / BQ2_WORLD_THREADS;
+    const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_lights = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
+                 off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
+                 rec_bytes = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15);
+    CK(ctx->h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
+    CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
+    bq2_dev_ent   *he = (bq2_dev_ent *)ctx->h_records.p;
+    bq2_dev_xform *hx = (bq2_dev_xform *)(ctx->h_records.p + off_xf);
+
+    ctx->ent_slot_first.resize((size_t)nE + 1); ctx->ent_vert_off.resize((size_t)nE + 1); ctx->ent_tb_off.resize((size_t)nE + 1);
+    ctx->slot_record.resize((size_t)nE);
+    ctx->k_warp = bq2_ctx::KLaunch(); ctx->k_team = bq2_ctx::KLaunch();
+    for (int e = 0; e < nE; e++) {
+        const Model &mo = ctx->models[wd->ents[e].model];
+        const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
+        const bool small = me.V <= BQ2_WARP_MAX_V && me.T <= BQ2_WARP_MAX_T;
+        bq2_ctx::KLaunch &k = small ? ctx->k_warp : ctx->k_team;
+        ctx->slot_record[e] = small ? k.n : -1 - k.n;
+        k.n++; k.max_V = std::max(k.max_V, me.V); k.max_T = std::max(k.max_T, me.T);
+        if (!(me.flags & BQ2_MESH_MD3)) k.any_md2 = 1;
+    }
+    uint32_t voff = 0, maxVpad = 0, maxBitw = 0; int maxT = 0;
+    uint64_t total_verts = 0;
+    for (int e = 0; e < nE; e++) {
+        const bq2_world_entity &W = wd->ents[e];
+        const Model &mo = ctx->models[W.model];
+        if (W.frame < 0 || W.frame >= mo.F || W.oldframe < 0 || W.oldframe >= mo.F)
+            return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
+        const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
+        const int rec = ctx->slot_record[e] < 0 ? ctx->k_warp.n + (-1 - ctx->slot_record[e]) : ctx->slot_record[e];
+        ctx->slot_record[e] = rec;
+        bq2_entity E;
+        if (mo.md3)
+            bq2_host_entity_md3(&mo.hdr[3 * (size_t)W.frame], &mo.hdr[3 * (size_t)W.oldframe], W.frame, W.oldframe,
+                                W.backlerp, W.origin, W.oldorigin, W.angles, &E);
+        else
+            bq2_host_entity_md2_hdr(&mo.hdr[6 * (size_t)W.frame], &mo.hdr[6 * (size_t)W.oldframe], W.frame, W.oldframe,
+                                    W.backlerp, W.origin, W.oldorigin, W.angles, W.rf_flags, &E);
+        bq2_dev_ent &d = he[rec];
+        d.cur = me.verts + (size_t)W.frame * me.vstride; d.old = me.verts + (size_t)W.oldframe * me.vstride;
+        d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.pad = 0;
+        d.mesh = mo.first_mesh; d.frame = W.frame; d.oldframe = W.oldframe; d.flags = E.flags;
+        d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
+        for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
+        d.shell_scale = E.shell_scale;
+        d.vert_off = voff; d.tb_off = 0; d.pair_begin = 0; d.pair_count = 0;
+        ctx->ent_slot_first[e] = e; ctx->ent_vert_off[e] = voff; ctx->ent_tb_off[e] = 0;
+        const uint32_t vpad = (uint32_t)(me.V + 3) & ~3u, bitw = (uint32_t)(me.T + 31) >> 5;
+        voff += vpad; total_verts += (uint64_t)me.V;
+        maxVpad = std::max(maxVpad, vpad); maxBitw = std::max(maxBitw, bitw); maxT = std::max(maxT, me.T);
+        bq2_dev_xform &x = hx[e];
+        const bool casts = bq2_host_casts_shadow(W.rf_flags, 0, 0.0f, 2.0f) &&
+                           !(W.rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));             /* M:63722-63727, 64089 */
+        x.origin[0] = W.origin[0]; x.origin[1] = W.origin[1]; x.origin[2] = W.origin[2];
+        x.rec = casts ? rec : -1;
+        x.rotated = (uint32_t)bq2_host_entity_basis(W.angles, x.basis);
+        x.vpad = vpad; x.bitw = bitw;
+    }
+    ctx->ent_slot_first[nE] = nE; ctx->ent_vert_off[nE] = voff; ctx->ent_tb_off[nE] = 0;
+    if (nL) memcpy(ctx->h_records.p + off_lights, wd->lights, (size_t)nL * 16);
+    if (nP) { memcpy(ctx->h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(ctx->h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
+
+    uint32_t stride = wd->index_stride ? wd->index_stride : 12u * (uint32_t)maxT;
+    stride = (stride + 3u) & ~3u;
+    const bool tables = (want & BQ2_WANT_TABLES) != 0;
+
+    /* ---- capacity: per-pair rows are bounded by the largest mesh of the frame ------------------------ */
+    CK(ctx->lerped.ensure(3 * (size_t)voff + 4), "cudaMalloc(lerped)");
+    if (want & BQ2_WANT_SHADOW) {
+        CK(ctx->extruded.ensure(3 * (size_t)nP * maxVpad + 4), "cudaMalloc(extruded)");
+        CK(ctx->facing_bits.ensure((size_t)nP * maxBitw + 1), "cudaMalloc(facing_bits)");
+        CK(ctx->indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
+    }
+    CK(ctx->index_count.ensure((size_t)nP + 1), "cudaMalloc(index_count)");
+    CK(ctx->h_counts.ensure(sizeof(uint32_t) * ((size_t)nP + 1)), "cudaMallocHost(counts)");
+    CK(ctx->h_totals.ensure(64), "cudaMallocHost(totals)");
+    const size_t w_pairs = (size_t)nP * sizeof(bq2_dev_pair), w_cnt = (((size_t)nE * 8 + 15) & ~(size_t)15),
+                 w_blk = (((size_t)nblk * 8 + 15) & ~(size_t)15), w_tab = tables ? (((size_t)nP * 8 + 15) & ~(size_t)15) : 0;
+    CK(ctx->d_world.ensure(w_pairs + w_cnt + w_blk + w_tab + 64), "cudaMalloc(world scratch)");
+    if (ctx->meshes_dirty) {
+        CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
+        CK(cudaMemcpyAsync(ctx->d_meshes.p, ctx->meshes.data(), ctx->meshes.size() * sizeof(bq2_dev_mesh),
+                           cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(mesh table)");
+        CK(cudaStreamSynchronize(ctx->stream), "sync(mesh table)");
+        ctx->meshes_dirty = false;
+    }
+    if (ctx->k_team.n && bq2_kernel_smem_bytes(ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2) > 227u * 1024u)
+        return fail(ctx, BQ2_E_LIMIT, "bq2_world: mesh too large for one CTA's shared memory");
+
+    /* ---- go ----------------------------------------------------------------------------------------- */
+    unsigned char *dw = ctx->d_world.p;
+    bq2_world_launch &Wl = ctx->wlaunch;
+    Wl.xf = (const bq2_dev_xform *)(ctx->d_records.p + off_xf);
+    Wl.lights = (const float *)(ctx->d_records.p + off_lights);
+    Wl.pair_ent = (const int32_t *)(ctx->d_records.p + off_pe); Wl.pair_light = (const int32_t *)(ctx->d_records.p + off_pl);
+    Wl.n_pairs = nP; Wl.n_ents = nE; Wl.n_lights = nL; Wl.n_recs = nE; Wl.n_blocks = nblk;
+    Wl.ents = (bq2_dev_ent *)ctx->d_records.p;
+    Wl.dpairs = (bq2_dev_pair *)dw;
+    Wl.cnt = (uint32_t *)(dw + w_pairs); Wl.cursor = Wl.cnt + nE;
+    Wl.blk = (uint32_t *)(dw + w_pairs + w_cnt);
+    Wl.pvoff = tables ? (uint32_t *)(dw + w_pairs + w_cnt + w_blk) : nullptr; Wl.pboff = tables ? Wl.pvoff + nP : nullptr;
+    Wl.totals = (unsigned long long *)(dw + w_pairs + w_cnt + w_blk + w_tab);
+    Wl.index_count = ctx->index_count.p;
+    Wl.has_view = wd->view_world ? 1 : 0;
+    for (int k = 0; k < 3; k++) Wl.view[k] = wd->view_world ? wd->view_world[k] : 0.0f;
+
+    if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, ctx->h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
+    /* cnt | cursor | blk | tables | totals are one contiguous range after dpairs */
+    CK(cudaMemsetAsync(dw + w_pairs, 0, w_cnt + w_blk + w_tab + 64, ctx->stream), "cudaMemset(world scratch)");
+    if (nP && (want & BQ2_WANT_SHADOW)) {
+        CK((cudaError_t)bq2_launch_world_setup(&Wl, ctx->stream), "launch(bq2_world_* kernels)");
+        ctx->launches += 3;
+    }
+
+    bq2_launch &L = ctx->launch;
+    L.meshes = ctx->d_meshes.p;
+    L.ents = (const bq2_dev_ent *)ctx->d_records.p;
+    L.pairs = Wl.dpairs;
+    L.n_ent_slots = nE; L.want = want & ~BQ2_WANT_TABLES; L.index_stride = stride;
+    L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
+    L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
+    L.normals = nullptr; L.tangents = nullptr; L.binormals = nullptr; L.lightp = nullptr; L.tsh = nullptr;
+    L.totals = Wl.totals;
+    ctx->n_ent_slots = nE; ctx->n_pair_slots = nP; ctx->n_ents = nE; ctx->n_pairs = nP;
+    ctx->total_verts = total_verts;
+    ctx->world_mode = true; ctx->world_tables = tables;
+    /* per-slot host tables used by bq2_expand_trisverts */
+    ctx->slot_mesh_V.resize((size_t)nP); ctx->slot_mesh_T.resize((size_t)nP); ctx->pair_slot_entslot.resize((size_t)nP);
+    { bq2_status ls = launch_kernels(ctx); if (ls != BQ2_OK) return ls; }
+    if (nP) CK(cudaMemcpyAsync(ctx->h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
+    CK(cudaMemcpyAsync(ctx->h_totals.p, Wl.totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(totals)");
+    if (tables && nP) {
+        ctx->world_pvoff.resize((size_t)nP + 1); ctx->world_pboff.resize((size_t)nP + 1);
+        CK(cudaMemcpyAsync(ctx->world_pvoff.data(), Wl.pvoff, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(tables)");
+        CK(cudaMemcpyAsync(ctx->world_pboff.data(), Wl.pboff, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(tables)");
+        for (int p = 0; p < nP; p++) {                 /* test / shim convenience, not on the fast path */
+            int e = wd->pair_ent[p];
+            if (e < 0 || e >= nE) { ctx->slot_mesh_V[p] = 0; ctx->slot_mesh_T[p] = 0; ctx->pair_slot_entslot[p] = 0; continue; }
+            const bq2_dev_mesh &me = ctx->meshes[ctx->models[wd->ents[e].model].first_mesh];
+            ctx->slot_mesh_V[p] = me.V; ctx->slot_mesh_T[p] = me.T; ctx->pair_slot_entslot[p] = e;
+        }
+    } else if (tables) { ctx->world_pvoff.assign(1, 0u); ctx->world_pboff.assign(1, 0u); }
+    ctx->submitted = true;
+    return BQ2_OK;
+}
+
+bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *wd, bq2_frame_out *out)
+{
+    bq2_status s = bq2_world_submit(ctx, wd);
+    if (s != BQ2_OK) return s;
+    return bq2_frame_wait(ctx, out);
+}
+
 bq2_status bq2_frame_replay(bq2_ctx *ctx)
 {
     if (!ctx) return BQ2_E_INVALID;
     if (!ctx->submitted || !ctx->n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
+    if (ctx->world_mode)                                         /* the kernels add to the totals: start from zero */
+        CK(cudaMemsetAsync(ctx->wlaunch.totals, 0, 2 * sizeof(unsigned long long), ctx->stream), "cudaMemset(totals)");
     return launch_kernels(ctx);
 }
 
@@ -690,7 +916,10 @@ bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t ps, float *tris_verts, int
 {
     if (!ctx || !tris_verts || !tris_counter) return BQ2_E_INVALID;
     if (!ctx->submitted || ps < 0 || ps >= ctx->n_pair_slots) return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: bad pair slot");
+    if (ctx->world_mode && !ctx->world_tables)
+        return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: the frame was submitted without BQ2_WANT_TABLES");
     const int V = ctx->slot_mesh_V[ps];
+    const uint32_t pvoff = ctx->world_mode ? ctx->world_pvoff[ps] : ctx->pair_vert_off[ps];
     const uint32_t stride = ctx->launch.index_stride;
     uint32_t cnt = 0;
     bq2_status s = bq2_download(ctx, BQ2_A_INDEX_COUNT, (uint64_t)ps, 1, &cnt);
@@ -700,7 +929,7 @@ bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t ps, float *tris_verts, int
     std::vector<uint32_t> idx(cnt);
     s = bq2_download(ctx, BQ2_A_LERPED, 3ull * ctx->ent_vert_off[ctx->pair_slot_entslot[ps]], 3ull * V, pool.data());
     if (s != BQ2_OK) return s;
-    s = bq2_download(ctx, BQ2_A_EXTRUDED, 3ull * ctx->pair_vert_off[ps], 3ull * V, pool.data() + 3 * (size_t)V);
+    s = bq2_download(ctx, BQ2_A_EXTRUDED, 3ull * pvoff, 3ull * V, pool.data() + 3 * (size_t)V);
     if (s != BQ2_OK) return s;
     if (cnt) { s = bq2_download(ctx, BQ2_A_INDICES, (uint64_t)ps * stride, cnt, idx.data()); if (s != BQ2_OK) return s; }
     for (uint32_t k = 0; k < cnt; k++) memcpy(tris_verts + 3 * (size_t)k, &pool[3 * (size_t)idx[k]], 12);

@@ -68,6 +68,37 @@ typedef struct bq2_dev_pair {
     uint32_t pad[2];
 } bq2_dev_pair;             /* 48 bytes */
 
+/* ---- device-side record building ("world" path) ------------------------------------------------
+ * The host ships what it alone can compute (per ENTITY: lerp constants and, for rotated entities, the
+ * AngleVectors basis -- libm trig) plus the raw light and pair lists; three small kernels turn that into the
+ * per-pair records above: count pairs per entity, scan, then scatter each pair next to its entity with its
+ * light moved to model space (M:63733-63745; plain mul/add, bit-exact on the device). */
+typedef struct bq2_dev_xform {      /* one per world entity */
+    float    origin[3];
+    int32_t  rec;                   /* index of the entity's record, -1 = entity casts no volume          */
+    float    basis[9];              /* forward, right, up (AngleVectors M:37566) when rotated             */
+    uint32_t rotated;
+    uint32_t vpad;                  /* extruded row length of a pair of this entity (verts, multiple of 4) */
+    uint32_t bitw;                  /* facing words of a pair of this entity                               */
+} bq2_dev_xform;                    /* 64 bytes */
+
+typedef struct bq2_world_launch {
+    const bq2_dev_xform *xf;
+    const float    *lights;         /* [n_lights][4]: origin, radius (bq2_world_light)                     */
+    const int32_t  *pair_ent, *pair_light;
+    int32_t  n_pairs, n_ents, n_lights, n_recs, n_blocks;
+    bq2_dev_ent  *ents;             /* pair_begin / pair_count are filled here                             */
+    bq2_dev_pair *dpairs;
+    uint32_t *cnt, *cursor;         /* [n_recs] each, zeroed before the first kernel                       */
+    uint32_t *blk;                  /* [2][n_blocks] block sums -> block offsets                            */
+    uint32_t *pvoff, *pboff;        /* [n_pairs] offset tables for the caller, or NULL                      */
+    uint32_t *index_count;
+    unsigned long long *totals;     /* [0] sum of index counts, [1] overflowing pairs, [2] bad pairs        */
+    float    view[3];
+    int32_t  has_view;
+} bq2_world_launch;
+#define BQ2_WORLD_THREADS 1024
+
 typedef struct bq2_launch {
     const bq2_dev_mesh *meshes;
     const bq2_dev_ent  *ents;
@@ -78,6 +109,7 @@ typedef struct bq2_launch {
     float    *lerped, *extruded;
     uint32_t *facing_bits, *indices, *index_count;
     float    *normals, *tangents, *binormals, *lightp, *tsh;
+    unsigned long long *totals;     /* world path: [0] += index count, [1] += overflowing pair; or NULL     */
 } bq2_launch;
 
 #ifdef __cplusplus
@@ -92,6 +124,7 @@ extern "C" {
 #define BQ2_WARP_WARPS   4
 int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);       /* team */
 int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);  /* warp */
+int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);                                 /* 3 kernels */
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
 size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);

@@ -98,7 +98,8 @@ typedef struct bq2_entity {
  * (M:63733-63745; bq2_host_light_to_model), scale = 32 * light radius (M:63597), view[] is
  * r_origin in model space (M:66689-66715), only read when BQ2_WANT_TSLIGHT.  32 bytes. */
 typedef struct bq2_pair {
-    int32_t entity;        /* index into the frame's entity array */
+    int32_t entity;        /* index into the frame's entity array; ~index (negative) = the pair keeps its
+                              slot(s) but casts nothing (index_count 0)                                   */
     float   light[3];
     float   scale;
     float   view[3];
@@ -266,6 +267,27 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
                              const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
                              const float *view_world /* [3] or NULL */,
                              bq2_entity *out_ents, bq2_pair *out_pairs, int32_t *n_pairs_out);
+
+/* ---- the same, fused, with the per-pair records built ON THE DEVICE ----------------------------------- */
+/* bq2_build_records + bq2_frame in one call.  The host does only what needs libm or the model table (per
+ * ENTITY: lerp constants, AngleVectors for rotated entities, the flag filter); the light and pair lists are
+ * copied to HBM as they are and three small kernels build the per-pair records there (light -> model space
+ * is plain float arithmetic, bit-identical to the host's).  Differences from bq2_build_records + bq2_frame:
+ *   - pair slot p IS caller pair p (a pair whose entity casts no volume keeps its slot, index_count 0);
+ *   - the pair offset tables of bq2_frame_out are produced only with BQ2_WANT_TABLES (tests, the shim);
+ *   - an out-of-range pair_ent / pair_light is reported by bq2_frame_wait (BQ2_E_INVALID), not up front.
+ * Frames that use a multi-mesh MD3 model or ask for BQ2_WANT_NTB / BQ2_WANT_TSLIGHT take the host-built
+ * route internally, with the same slot numbering. */
+#define BQ2_WANT_TABLES  0x10u
+typedef struct bq2_world_desc {
+    const bq2_world_entity *ents;    int32_t n_ents;
+    const bq2_world_light  *lights;  int32_t n_lights;
+    const int32_t *pair_ent, *pair_light;  int32_t n_pairs;
+    const float   *view_world;       /* [3] or NULL */
+    uint32_t want, index_stride;
+} bq2_world_desc;
+bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *desc);     /* async; pair with bq2_frame_wait */
+bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *desc, bq2_frame_out *out);
 
 /* ---- multi-GPU plan (entity-major sharding) ---------------------------------------- */
 /* Rank r of n owns entities [first, first+count).  Pairs follow their entity. */

@@ -284,3 +284,113 @@ def test_c2_full_size_properties(gpu_ctx, oracle):
     from berserkerquake2_b200 import _capi
     cnt2 = gpu_ctx.download(_capi.A_INDEX_COUNT, 0, len(cnt), np.uint32)
     assert np.array_equal(cnt2, cnt) and np.array_equal(res.indices(sample[3]), before)
+
+
+# ------------------------------------------------------------------------------------------------------
+# bq2_world_frame: per-pair records built on the device
+def check_world(ctx, o, models, mids, we, wl, pe, pl, view=None):
+    res = ctx.world_frame(we, wl, pe, pl, view_world=view)
+    assert res.n_pair_slots == len(pe) and res.overflow_pairs == 0
+    total = 0
+    for p in range(len(pe)):
+        e = int(pe[p]); W = we[e]; m = models[mids.index(int(W["model"]))]
+        import berserkerquake2_b200.host as host
+        if not host.casts_shadow(int(W["rf_flags"])) or int(W["rf_flags"]) & (0x80000 | 0x10000000):
+            assert int(res.index_counts[p]) == 0, p
+            continue
+        w = o.md2_pair(m.blob, m.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                       W["oldorigin"], W["angles"], wl["origin"][pl[p]], float(wl["radius"][pl[p]]), idx=m.idx)
+        used = np.unique(m.idx)
+        assert np.array_equal(bits(res.lerped(e, m.V)), bits(w["lerped"])), p
+        assert np.array_equal(bits(res.extruded(p, m.V))[used], bits(w["extruded"])[used]), p
+        assert np.array_equal(res.facing(p, m.T), w["viss"]), p
+        assert np.array_equal(res.indices(p), w["indices"]), p
+        total += len(w["indices"])
+    assert int(res.total_indices) == total
+    return res
+
+
+def test_world_frame_matches_oracle(gpu_ctx, oracle):
+    """Mixed mesh sizes (both kernels), rotated entities, light-major pair order, a shared light, filtered
+    entities (shell / translucent / nocastshadow) that keep their slot with count 0."""
+    shapes = [(8, 5), (16, 17), (24, 13), (62, 34), (3, 2)]
+    models = [Md2Model(oracle, s, r, frames=6, seed=40 + i) for i, (s, r) in enumerate(shapes)]
+    mids = [m.upload(gpu_ctx) for m in models]
+    n = 24
+    we, wl, _, _ = world_scene(n, 3, 6, n_models=len(models), seed=999)
+    we["model"] = np.array(mids)[we["model"]]
+    we["angles"][5] = (10, 20, 30); we["angles"][6] = (0, 0, 90)
+    we["rf_flags"][2] = 0x400; we["rf_flags"][9] = 0x20; we["rf_flags"][11] = 0x80000
+    pe, pl = [], []
+    for l in range(3):
+        for e in range(n):
+            if e in (7, 13):
+                continue
+            pe.append(e); pl.append(0 if l == 0 else e * 3 + l)
+    pe, pl = np.array(pe, np.int32), np.array(pl, np.int32)
+    res = check_world(gpu_ctx, oracle, models, mids, we, wl, pe, pl)
+    for e in (2, 7, 13):                                     # shell entity / unlit entities are still lerped
+        m = models[mids.index(int(we["model"][e]))]
+        shell = bool(we["rf_flags"][e] & 0x1c00)
+        w = oracle.md2_lerp(m.blob, int(we["frame"][e]), int(we["oldframe"][e]), float(we["backlerp"][e]),
+                            we["origin"][e], we["oldorigin"][e], we["angles"][e], shell=shell, shell_scale=1.0 if shell else 0.0)
+        assert np.array_equal(bits(res.lerped(e, m.V)), bits(w)), e
+
+
+def test_world_frame_equals_host_built_frame_at_c2_size(gpu_ctx, oracle):
+    """Full C2 size: device-built records give exactly the arrays of bq2_build_records + bq2_frame."""
+    n_models = 32
+    models = [Md2Model(oracle, frames=8, seed=300 + s) for s in range(n_models)]
+    mids = [m.upload(gpu_ctx) for m in models]
+    we, wl, pe, pl = world_scene(1024, 4, 8, n_models=n_models, seed=2468)
+    we["model"] = np.array(mids)[we["model"]]
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    a = gpu_ctx.frame(ents, pairs)
+    V, T = models[0].V, models[0].T
+    sample = list(range(0, 4096, 211))
+    keep = [(a.extruded(p, V).copy(), a.facing(p, T).copy(), a.indices(p).copy()) for p in sample]
+    cnt_a, tot_a = a.index_counts.copy(), int(a.total_indices)
+    b = gpu_ctx.world_frame(we, wl, pe, pl)
+    assert np.array_equal(b.index_counts, cnt_a) and int(b.total_indices) == tot_a
+    assert np.array_equal(b.pair_vert_offset[:4096], a.pair_vert_offset[:4096])
+    for p, (ext, f, ind) in zip(sample, keep):
+        assert np.array_equal(bits(b.extruded(p, V)), bits(ext)) and np.array_equal(b.facing(p, T), f)
+        assert np.array_equal(b.indices(p), ind)
+    # replay keeps the totals exact (they are accumulated by the kernels)
+    gpu_ctx.replay(); r = gpu_ctx.wait()
+    assert int(r.total_indices) == tot_a
+
+
+def test_world_frame_bad_pair_is_reported(gpu_ctx, oracle):
+    m = Md2Model(oracle, 8, 5, frames=2, seed=1)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(2, 1, 2, seed=1)
+    we["model"] = mid
+    pe = np.array([0, 5, 1], np.int32); pl = np.array([0, 0, 9], np.int32)      # entity 5 and light 9 do not exist
+    with pytest.raises(bq2.Bq2Error) as e:
+        gpu_ctx.world_frame(we, wl, pe, pl)
+    assert e.value.status == -1
+    ok = gpu_ctx.world_frame(we, wl, pe[:1], pl[:1])
+    assert int(ok.index_counts[0]) > 0
+
+
+def test_world_frame_md3_and_tangent_space_take_the_host_route(gpu_ctx, oracle):
+    md3 = Md3Model(oracle, 12, 9, frames=4, num_meshes=2, seed=6)
+    mid = md3.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(3, 2, 4, seed=17)
+    we["model"] = mid
+    we["rf_flags"][1] = 0x20                                  # translucent: its two pairs keep their slots, count 0
+    res = gpu_ctx.world_frame(we, wl, pe, pl, want=bq2.WANT_SHADOW | bq2.WANT_TABLES)
+    assert res.n_pair_slots == 12
+    for p in range(6):
+        e = int(pe[p]); W = we[e]
+        for k, mesh in enumerate(md3.meshes):
+            ps = 2 * p + k
+            if e == 1:
+                assert int(res.index_counts[ps]) == 0
+                continue
+            w = oracle.md3_mesh_pair(mesh["verts"], mesh["indexes"], mesh["neighbours"], md3.frame_translate,
+                                     int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                                     W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0)
+            assert np.array_equal(res.indices(ps), w["indices"]), (p, k)
+            assert np.array_equal(bits(res.extruded(ps, mesh["verts"].shape[1])), bits(w["extruded"]))

@@ -66,27 +66,17 @@ def main():
                 flush.zero_(); e0.record(stream); ctx.replay(); e1.record(stream)
         torch.cuda.synchronize()
         k_ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
-        # end to end, pipelined like bench.py
-        eh = np.zeros(n_ents, c.ENTITY_DTYPE); ph = np.zeros(len(pe), c.PAIR_DTYPE); kept = C.c_int32(0)
-        fd = c.FrameDesc(); fo = c.FrameOut()
-
-        def build():
-            c.lib.bq2_build_records(ctx._h, c.ptr(we), n_ents, c.ptr(wl), len(wl), c.ptr(pe), c.ptr(pl), len(pe), None,
-                                    c.ptr(eh), c.ptr(ph), C.byref(kept))
-
-        def submit():
-            fd.ents = eh.ctypes.data; fd.n_ents = n_ents; fd.pairs = ph.ctypes.data; fd.n_pairs = kept.value
-            fd.want = bq2.WANT_SHADOW; fd.index_stride = 0
-            assert c.lib.bq2_frame_submit(ctx._h, C.byref(fd)) == 0
-
+        # end to end like bench.py: bq2_world_submit + bq2_frame_wait from host arrays
+        wd = ctx.world_desc(we, wl, pe, pl, None, bq2.WANT_SHADOW, 0)
+        fo = c.FrameOut()
         k = max(3, steps // 4)
-        build(); submit(); c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+        for _ in range(2):
+            assert c.lib.bq2_world_submit(ctx._h, C.byref(wd)) == 0 and c.lib.bq2_frame_wait(ctx._h, C.byref(fo)) == 0
         t0 = time.perf_counter()
-        build(); submit()
-        for _ in range(k - 1):
-            build(); c.lib.bq2_frame_wait(ctx._h, C.byref(fo)); submit()
-        c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+        for _ in range(k):
+            c.lib.bq2_world_submit(ctx._h, C.byref(wd)); c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
         e2e_ms = (time.perf_counter() - t0) * 1e3 / k
+        assert fo.total_indices == tot
         k_ms, e2e_ms = shard.max_over_ranks([k_ms, e2e_ms], f"cuda:{local}", dist)
         alg = bench.algorithmic_bytes(n_ents, len(pe), V, T, tot)
         mint = bench.min_traffic_bytes(n_ents, len(pe), V, T, tot)
