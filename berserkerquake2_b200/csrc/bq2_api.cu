@@ -95,13 +95,18 @@ struct bq2_ctx {
     std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
     std::vector<int32_t>  pair_slot_entslot;
     std::vector<float>    ent_basis;                             /* build_records scratch: f, r, u, state */
-    PinBuf h_records, h_counts;
+    /* host side of a frame is double-buffered so that frame i+1 can be packed and submitted while frame i is
+       still on the GPU (device arrays are reused: work on the stream is ordered) */
+    PinBuf hrec[2], hcnt[2], htot[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    struct Meta { bool world = false, tables = false; int32_t n_ent_slots = 0, n_pair_slots = 0; uint64_t total_verts = 0; uint32_t stride = 0; } meta[2];
+    uint64_t submit_seq = 0, wait_seq = 0;
+    int last_waited = 0;
     DevBuf<unsigned char> d_records;
     DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
     DevBuf<uint32_t> facing_bits, indices, index_count;
     /* world path (device-built pair records) */
     DevBuf<unsigned char> d_world;                               /* dpairs | cnt | cursor | blk | tables | totals */
-    PinBuf h_totals;
     bq2_world_launch wlaunch{};
     bool world_mode = false, world_tables = false;
     std::vector<bq2_entity> tmp_ents; std::vector<bq2_pair> tmp_pairs;     /* host-built fallback */
@@ -215,6 +220,8 @@ bq2_status bq2_create(int device, bq2_ctx **out)
         delete ctx; return BQ2_E_NODEVICE;
     }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaStreamCreate"); delete ctx; return BQ2_E_CUDA; }
+    for (int k = 0; k < 2; k++)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev[k], cudaEventDisableTiming)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaEventCreate"); cudaStreamDestroy(ctx->stream); delete ctx; return BQ2_E_CUDA; }
     if ((e = (cudaError_t)bq2_kernel_prepare()) != cudaSuccess) { fail_cuda(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)"); cudaStreamDestroy(ctx->stream); delete ctx; return BQ2_E_CUDA; }
     *out = ctx;
     return BQ2_OK;
@@ -226,7 +233,7 @@ void bq2_destroy(bq2_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->trace.on && ctx->trace.n) {
-        static const char *nm[8] = {"validate+slots", "class split", "entity records", "pair offsets", "pair records",
+        static const char *nm[8] = {"validate+slots/class", "class split", "entity records", "pair offsets/memcpy", "pair records",
                                     "buffers", "h2d+launch+d2h calls", ""};
         for (int i = 0; i < 7; i++) fprintf(stderr, "bq2 trace: %-22s %8.2f us/frame\n", nm[i], ctx->trace.acc[i] / ctx->trace.n);
     }
@@ -235,7 +242,8 @@ void bq2_destroy(bq2_ctx *ctx)
     ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
     ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release();
     ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
-    ctx->h_records.release(); ctx->h_counts.release(); ctx->d_world.release(); ctx->h_totals.release();
+    for (int k = 0; k < 2; k++) { ctx->hrec[k].release(); ctx->hcnt[k].release(); ctx->htot[k].release(); if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]); }
+    ctx->d_world.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -454,6 +462,9 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     if (!fd || fd->n_ents < 0 || fd->n_pairs < 0 || (fd->n_ents > 0 && !fd->ents) || (fd->n_pairs > 0 && !fd->pairs))
         return fail(ctx, BQ2_E_INVALID, "bq2_frame: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->submit_seq - ctx->wait_seq >= 2) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: two frames are already in flight, call bq2_frame_wait first");
+    const int slot_k = (int)(ctx->submit_seq & 1);
+    PinBuf &h_records = ctx->hrec[slot_k], &h_counts = ctx->hcnt[slot_k];
     const int nE = fd->n_ents, nP = fd->n_pairs;
     const int nModels = (int)ctx->models.size();
     const uint32_t want = fd->want;
@@ -488,10 +499,10 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     ctx->slot_mesh_V.resize((size_t)nPS); ctx->slot_mesh_T.resize((size_t)nPS); ctx->pair_slot_entslot.resize((size_t)nPS);
 
     size_t rec_bytes = (size_t)nES * sizeof(bq2_dev_ent) + (size_t)nPS * sizeof(bq2_dev_pair);
-    CK(ctx->h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
+    CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
     CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
-    bq2_dev_ent  *he = (bq2_dev_ent *)ctx->h_records.p;
-    bq2_dev_pair *hp = (bq2_dev_pair *)(ctx->h_records.p + (size_t)nES * sizeof(bq2_dev_ent));
+    bq2_dev_ent  *he = (bq2_dev_ent *)h_records.p;
+    bq2_dev_pair *hp = (bq2_dev_pair *)(h_records.p + (size_t)nES * sizeof(bq2_dev_ent));
 
     tr.lap(0);
     /* which kernel takes each entity slot: small meshes -> one warp per pair; large meshes and the
@@ -609,7 +620,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         CK(ctx->lightp.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(lightp)");
         CK(ctx->tsh.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(tsh)");
     }
-    CK(ctx->h_counts.ensure(sizeof(uint32_t) * ((size_t)nPS + 1)), "cudaMallocHost(counts)");
+    CK(h_counts.ensure(sizeof(uint32_t) * ((size_t)nPS + 1)), "cudaMallocHost(counts)");
     if (ctx->meshes_dirty) {
         CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
         CK(cudaMemcpyAsync(ctx->d_meshes.p, ctx->meshes.data(), ctx->meshes.size() * sizeof(bq2_dev_mesh),
@@ -623,7 +634,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     /* ---- go -------------------------------------------------------------------------------------- */
     tr.lap(5);
     if (rec_bytes)
-        CK(cudaMemcpyAsync(ctx->d_records.p, ctx->h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(records)");
+        CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(records)");
     /* slots of non-casting MD3 meshes are never written by a kernel: only then is the clear needed */
     if (nPS && n_dev_pairs != (uint32_t)nPS)
         CK(cudaMemsetAsync(ctx->index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, ctx->stream), "cudaMemset(index_count)");
@@ -642,9 +653,13 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
     ctx->total_verts = total_verts;
     { bq2_status ls = launch_kernels(ctx); if (ls != BQ2_OK) return ls; }
-    if (nPS) CK(cudaMemcpyAsync(ctx->h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nPS,
+    if (nPS) CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nPS,
                                 cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
     ctx->submitted = true;
+    { bq2_ctx::Meta &m = ctx->meta[slot_k]; m.world = false; m.tables = false; m.n_ent_slots = nES; m.n_pair_slots = nPS;
+      m.total_verts = total_verts; m.stride = stride; }
+    CK(cudaEventRecord(ctx->ev[slot_k], ctx->stream), "cudaEventRecord(frame)");
+    ctx->submit_seq++;
     tr.lap(6);
     return BQ2_OK;
 }
@@ -653,9 +668,18 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
 {
     if (!ctx) return BQ2_E_INVALID;
     if (!ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_frame_wait: nothing submitted");
-    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(frame)");
+    int k;
+    if (ctx->submit_seq == ctx->wait_seq) {                      /* nothing pending (e.g. after bq2_frame_replay) */
+        CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(frame)");
+        k = ctx->last_waited;
+    } else {                                                     /* the OLDEST frame in flight */
+        k = (int)(ctx->wait_seq & 1);
+        CK(cudaEventSynchronize(ctx->ev[k]), "cudaEventSynchronize(frame)");
+        ctx->wait_seq++; ctx->last_waited = k;
+    }
+    const bq2_ctx::Meta &m = ctx->meta[k];
     bq2_frame_out &o = ctx->out;
-    o.n_ent_slots = ctx->n_ent_slots; o.n_pair_slots = ctx->n_pair_slots;
+    o.n_ent_slots = m.n_ent_slots; o.n_pair_slots = m.n_pair_slots;
     o.ent_slot_first = ctx->ent_slot_first.data(); o.pair_slot_first = ctx->pair_slot_first.data();
     o.ent_vert_offset = ctx->ent_vert_off.data(); o.pair_vert_offset = ctx->pair_vert_off.data();
     o.pair_bits_offset = ctx->pair_bits_off.data(); o.ent_tb_offset = ctx->ent_tb_off.data();
@@ -663,24 +687,24 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
     o.indices = ctx->indices.p; o.index_count = ctx->index_count.p;
     o.normals = ctx->normals.p; o.tangents = ctx->tangents.p; o.binormals = ctx->binormals.p;
     o.lightp = ctx->lightp.p; o.tsh = ctx->tsh.p;
-    o.index_stride = ctx->launch.index_stride;
-    o.total_lerped_verts = ctx->total_verts;
+    o.index_stride = m.stride;
+    o.total_lerped_verts = m.total_verts;
     o.total_pairs = 0; o.total_indices = 0; o.overflow_pairs = 0;
-    if (ctx->world_mode) {                                       /* totals were accumulated by the kernels */
-        const unsigned long long *t = (const unsigned long long *)ctx->h_totals.p;
+    if (m.world) {                                               /* totals were accumulated by the kernels */
+        const unsigned long long *t = (const unsigned long long *)ctx->htot[k].p;
         o.total_indices = t[0]; o.overflow_pairs = (int32_t)t[1];
         o.pair_slot_first = nullptr;                             /* slot p is caller pair p */
-        o.pair_vert_offset = ctx->world_tables ? ctx->world_pvoff.data() : nullptr;
-        o.pair_bits_offset = ctx->world_tables ? ctx->world_pboff.data() : nullptr;
-        if (t[2]) { if (out) *out = o; return fail(ctx, BQ2_E_INVALID, "bq2_world: a pair refers to an entity or light out of range (it was skipped)"); }
+        o.pair_vert_offset = m.tables ? ctx->world_pvoff.data() : nullptr;
+        o.pair_bits_offset = m.tables ? ctx->world_pboff.data() : nullptr;
+        if (t[2]) { o.total_pairs = (uint64_t)m.n_pair_slots; if (out) *out = o; return fail(ctx, BQ2_E_INVALID, "bq2_world: a pair refers to an entity or light out of range (it was skipped)"); }
     } else {
-        const uint32_t *cnt = (const uint32_t *)ctx->h_counts.p;
-        for (int i = 0; i < ctx->n_pair_slots; i++) {
+        const uint32_t *cnt = (const uint32_t *)ctx->hcnt[k].p;
+        for (int i = 0; i < m.n_pair_slots; i++) {
             o.total_indices += cnt[i];
             if (cnt[i] > o.index_stride) o.overflow_pairs++;
         }
     }
-    o.total_pairs = (uint64_t)ctx->n_pair_slots;
+    o.total_pairs = (uint64_t)m.n_pair_slots;
     if (out) *out = o;
     if (o.overflow_pairs) return fail(ctx, BQ2_E_OVERFLOW, "bq2_frame: index_stride too small for at least one pair (counts are exact, indices truncated)");
     return BQ2_OK;
@@ -688,6 +712,7 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
 
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
 {
+    while (ctx && ctx->submit_seq != ctx->wait_seq) bq2_frame_wait(ctx, nullptr);     /* drain frames in flight */
     bq2_status s = bq2_frame_submit(ctx, fd);
     if (s != BQ2_OK) return s;
     return bq2_frame_wait(ctx, out);
@@ -700,6 +725,9 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         (wd->n_pairs > 0 && (!wd->pair_ent || !wd->pair_light || !wd->lights)))
         return fail(ctx, BQ2_E_INVALID, "bq2_world: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (ctx->submit_seq - ctx->wait_seq >= 2) return fail(ctx, BQ2_E_INVALID, "bq2_world_submit: two frames are already in flight, call bq2_frame_wait first");
+    const int slot_k = (int)(ctx->submit_seq & 1);
+    PinBuf &h_records = ctx->hrec[slot_k], &h_counts = ctx->hcnt[slot_k], &h_totals = ctx->htot[slot_k];
     const int nE = wd->n_ents, nP = wd->n_pairs, nL = wd->n_lights;
     const int nModels = (int)ctx->models.size();
     const uint32_t want = wd->want;
@@ -723,15 +751,16 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         return bq2_frame_submit(ctx, &fd);
     }
 
+    Trace &tr = ctx->trace; tr.start(); tr.n++;
     /* ---- per entity (host): record, transform, class ------------------------------------------------ */
     const int nblk = (nP + BQ2_WORLD_THREADS - 1) / BQ2_WORLD_THREADS;
     const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_lights = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
                  off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
                  rec_bytes = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15);
-    CK(ctx->h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
+    CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
     CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
-    bq2_dev_ent   *he = (bq2_dev_ent *)ctx->h_records.p;
-    bq2_dev_xform *hx = (bq2_dev_xform *)(ctx->h_records.p + off_xf);
+    bq2_dev_ent   *he = (bq2_dev_ent *)h_records.p;
+    bq2_dev_xform *hx = (bq2_dev_xform *)(h_records.p + off_xf);
 
     ctx->ent_slot_first.resize((size_t)nE + 1); ctx->ent_vert_off.resize((size_t)nE + 1); ctx->ent_tb_off.resize((size_t)nE + 1);
     ctx->slot_record.resize((size_t)nE);
@@ -745,6 +774,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         k.n++; k.max_V = std::max(k.max_V, me.V); k.max_T = std::max(k.max_T, me.T);
         if (!(me.flags & BQ2_MESH_MD3)) k.any_md2 = 1;
     }
+    tr.lap(0);
     uint32_t voff = 0, maxVpad = 0, maxBitw = 0; int maxT = 0;
     uint64_t total_verts = 0;
     for (int e = 0; e < nE; e++) {
@@ -783,9 +813,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         x.vpad = vpad; x.bitw = bitw;
     }
     ctx->ent_slot_first[nE] = nE; ctx->ent_vert_off[nE] = voff; ctx->ent_tb_off[nE] = 0;
-    if (nL) memcpy(ctx->h_records.p + off_lights, wd->lights, (size_t)nL * 16);
-    if (nP) { memcpy(ctx->h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(ctx->h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
+    tr.lap(2);
+    if (nL) memcpy(h_records.p + off_lights, wd->lights, (size_t)nL * 16);
+    if (nP) { memcpy(h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
 
+    tr.lap(3);
     uint32_t stride = wd->index_stride ? wd->index_stride : 12u * (uint32_t)maxT;
     stride = (stride + 3u) & ~3u;
     const bool tables = (want & BQ2_WANT_TABLES) != 0;
@@ -798,8 +830,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(ctx->indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
     CK(ctx->index_count.ensure((size_t)nP + 1), "cudaMalloc(index_count)");
-    CK(ctx->h_counts.ensure(sizeof(uint32_t) * ((size_t)nP + 1)), "cudaMallocHost(counts)");
-    CK(ctx->h_totals.ensure(64), "cudaMallocHost(totals)");
+    CK(h_counts.ensure(sizeof(uint32_t) * ((size_t)nP + 1)), "cudaMallocHost(counts)");
+    CK(h_totals.ensure(64), "cudaMallocHost(totals)");
     const size_t w_pairs = (size_t)nP * sizeof(bq2_dev_pair), w_cnt = (((size_t)nE * 8 + 15) & ~(size_t)15),
                  w_blk = (((size_t)nblk * 8 + 15) & ~(size_t)15), w_tab = tables ? (((size_t)nP * 8 + 15) & ~(size_t)15) : 0;
     CK(ctx->d_world.ensure(w_pairs + w_cnt + w_blk + w_tab + 64), "cudaMalloc(world scratch)");
@@ -814,6 +846,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         return fail(ctx, BQ2_E_LIMIT, "bq2_world: mesh too large for one CTA's shared memory");
 
     /* ---- go ----------------------------------------------------------------------------------------- */
+    tr.lap(5);
     unsigned char *dw = ctx->d_world.p;
     bq2_world_launch &Wl = ctx->wlaunch;
     Wl.xf = (const bq2_dev_xform *)(ctx->d_records.p + off_xf);
@@ -830,7 +863,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     Wl.has_view = wd->view_world ? 1 : 0;
     for (int k = 0; k < 3; k++) Wl.view[k] = wd->view_world ? wd->view_world[k] : 0.0f;
 
-    if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, ctx->h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
+    if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
     /* cnt | cursor | blk | tables | totals are one contiguous range after dpairs */
     CK(cudaMemsetAsync(dw + w_pairs, 0, w_cnt + w_blk + w_tab + 64, ctx->stream), "cudaMemset(world scratch)");
     if (nP && (want & BQ2_WANT_SHADOW)) {
@@ -853,8 +886,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     /* per-slot host tables used by bq2_expand_trisverts */
     ctx->slot_mesh_V.resize((size_t)nP); ctx->slot_mesh_T.resize((size_t)nP); ctx->pair_slot_entslot.resize((size_t)nP);
     { bq2_status ls = launch_kernels(ctx); if (ls != BQ2_OK) return ls; }
-    if (nP) CK(cudaMemcpyAsync(ctx->h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
-    CK(cudaMemcpyAsync(ctx->h_totals.p, Wl.totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(totals)");
+    if (nP) CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
+    CK(cudaMemcpyAsync(h_totals.p, Wl.totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(totals)");
     if (tables && nP) {
         ctx->world_pvoff.resize((size_t)nP + 1); ctx->world_pboff.resize((size_t)nP + 1);
         CK(cudaMemcpyAsync(ctx->world_pvoff.data(), Wl.pvoff, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(tables)");
@@ -867,11 +900,17 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         }
     } else if (tables) { ctx->world_pvoff.assign(1, 0u); ctx->world_pboff.assign(1, 0u); }
     ctx->submitted = true;
+    { bq2_ctx::Meta &m = ctx->meta[slot_k]; m.world = true; m.tables = tables; m.n_ent_slots = nE; m.n_pair_slots = nP;
+      m.total_verts = total_verts; m.stride = stride; }
+    CK(cudaEventRecord(ctx->ev[slot_k], ctx->stream), "cudaEventRecord(frame)");
+    ctx->submit_seq++;
+    tr.lap(6);
     return BQ2_OK;
 }
 
 bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *wd, bq2_frame_out *out)
 {
+    while (ctx && ctx->submit_seq != ctx->wait_seq) bq2_frame_wait(ctx, nullptr);     /* drain frames in flight */
     bq2_status s = bq2_world_submit(ctx, wd);
     if (s != BQ2_OK) return s;
     return bq2_frame_wait(ctx, out);
@@ -886,7 +925,7 @@ bq2_status bq2_frame_replay(bq2_ctx *ctx)
     return launch_kernels(ctx);
 }
 
-const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->h_counts.p : nullptr; }
+const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->hcnt[ctx->last_waited].p : nullptr; }
 
 bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host)
 {

@@ -194,6 +194,12 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
 /* Host records in, one fused launch per model family, per-slot counts back.  Equivalent to
  * bq2_frame_submit + bq2_frame_wait. */
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *desc, bq2_frame_out *out);
+/* Up to TWO frames may be in flight: bq2_frame_submit (or bq2_world_submit) for frame i+1 may be called
+ * before bq2_frame_wait for frame i, so the host packs the next frame while the GPU works; bq2_frame_wait
+ * always completes the OLDEST submitted frame.  The host-side buffers (pinned records, counts, totals) are
+ * double-buffered; the DEVICE result arrays are not -- they are those of the most recently submitted frame
+ * once its kernels run, so a caller that reads device results (or the host offset tables) of frame i must
+ * not submit frame i+1 before it is done with them.  bq2_frame / bq2_world_frame drain first. */
 bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *desc);   /* async on bq2_stream   */
 bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out);             /* sync + counts readback */
 /* Re-run the kernels of the last submitted frame on the records already resident in HBM

@@ -394,3 +394,34 @@ def test_world_frame_md3_and_tangent_space_take_the_host_route(gpu_ctx, oracle):
                                      W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0)
             assert np.array_equal(res.indices(ps), w["indices"]), (p, k)
             assert np.array_equal(bits(res.extruded(ps, mesh["verts"].shape[1])), bits(w["extruded"]))
+
+
+def test_two_frames_in_flight(gpu_ctx, oracle):
+    """bq2_world_submit for frame i+1 before bq2_frame_wait for frame i: waits complete the OLDEST frame and
+    every frame's counts/totals are its own; a third submit is refused."""
+    models = [Md2Model(oracle, frames=6, seed=70 + s) for s in range(4)]
+    mids = [m.upload(gpu_ctx) for m in models]
+    import ctypes as C
+    from berserkerquake2_b200 import _capi as c
+    scenes, serial = [], []
+    for i in range(5):
+        we, wl, pe, pl = world_scene(40 + 7 * i, 3, 6, n_models=4, seed=500 + i)
+        we["model"] = np.array(mids)[we["model"]]
+        r = gpu_ctx.world_frame(we, wl, pe, pl)
+        serial.append((int(r.total_indices), r.index_counts.copy()))
+        scenes.append(gpu_ctx.world_desc(we, wl, pe, pl, None, bq2.WANT_SHADOW, 0))
+        scenes[-1]._keep = gpu_ctx._keep
+    fo = c.FrameOut()
+    got = []
+    assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[0])) == 0
+    for i in range(1, 5):
+        assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
+        if i == 1:
+            assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[2])) == -1          # only two in flight
+        assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
+        cnt = np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()
+        got.append((int(fo.total_indices), cnt))
+    assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
+    got.append((int(fo.total_indices), np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()))
+    for (ta, ca), (tb, cb) in zip(serial, got):
+        assert ta == tb and np.array_equal(ca, cb)

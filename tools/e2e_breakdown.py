@@ -41,4 +41,15 @@ for it in range(N + 20):
     t3 = time.perf_counter()
     if it >= 20:
         t += (t1 - t0, t2 - t1, t3 - t2)
+wd = ctx.world_desc(we, wl, pe, pl, None, bq2.WANT_SHADOW, 0)
+tw = np.zeros(2)
+for it in range(N + 20):
+    t0 = time.perf_counter()
+    c.lib.bq2_world_submit(ctx._h, C.byref(wd))
+    t1 = time.perf_counter()
+    c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+    t2 = time.perf_counter()
+    if it >= 20:
+        tw += (t1 - t0, t2 - t1)
+print("world path us per step: submit %.1f  wait %.1f  total %.1f" % (*(tw / N * 1e6), tw.sum() / N * 1e6))
 print("us per step: build_records %.1f  frame_submit %.1f  frame_wait %.1f  total %.1f" % (*(t / N * 1e6), t.sum() / N * 1e6))
