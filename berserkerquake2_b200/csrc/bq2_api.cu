@@ -94,6 +94,7 @@ struct bq2_ctx {
     std::vector<uint32_t> pair_slot_ent, cursor;                 /* scratch for the counting sort */
     std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
     std::vector<int32_t>  pair_slot_entslot;
+    std::vector<bq2_model_row> model_rows;                       /* flat mirror of models for the C entity loop */
     std::vector<float>    ent_basis;                             /* build_records scratch: f, r, u, state */
     /* host side of a frame is double-buffered so that frame i+1 can be packed and submitted while frame i is
        still on the GPU (device arrays are reused: work on the stream is ordered) */
@@ -102,6 +103,11 @@ struct bq2_ctx {
     struct Meta { bool world = false, tables = false; int32_t n_ent_slots = 0, n_pair_slots = 0; uint64_t total_verts = 0; uint32_t stride = 0; } meta[2];
     uint64_t submit_seq = 0, wait_seq = 0;
     int last_waited = 0;
+    /* A frame is ~9 stream operations.  When two consecutive frames on the same host slot have the same shape
+       and buffers, the operations are captured once into a CUDA graph and replayed with one call. */
+    struct GraphKey { int32_t v[20]; const void *p[12]; };
+    struct GraphCache { GraphKey key{}; bool have_key = false; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; } gcache[2];
+    bool use_graphs = getenv("BQ2_NO_GRAPH") == nullptr;
     DevBuf<unsigned char> d_records;
     DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
     DevBuf<uint32_t> facing_bits, indices, index_count;
@@ -242,6 +248,7 @@ void bq2_destroy(bq2_ctx *ctx)
     ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
     ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release();
     ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
+    for (int k = 0; k < 2; k++) if (ctx->gcache[k].exec) cudaGraphExecDestroy(ctx->gcache[k].exec);
     for (int k = 0; k < 2; k++) { ctx->hrec[k].release(); ctx->hcnt[k].release(); ctx->htot[k].release(); if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]); }
     ctx->d_world.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -691,7 +698,7 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
     o.total_lerped_verts = m.total_verts;
     o.total_pairs = 0; o.total_indices = 0; o.overflow_pairs = 0;
     if (m.world) {                                               /* totals were accumulated by the kernels */
-        const unsigned long long *t = (const unsigned long long *)ctx->htot[k].p;
+        const unsigned long long *t = (const unsigned long long *)((const uint32_t *)ctx->hcnt[k].p + (((size_t)m.n_pair_slots + 1) & ~(size_t)1));
         o.total_indices = t[0]; o.overflow_pairs = (int32_t)t[1];
         o.pair_slot_first = nullptr;                             /* slot p is caller pair p */
         o.pair_vert_offset = m.tables ? ctx->world_pvoff.data() : nullptr;
@@ -732,14 +739,34 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     const int nModels = (int)ctx->models.size();
     const uint32_t want = wd->want;
 
-    bool device_route = !(want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT));
-    for (int e = 0; e < nE && device_route; e++) {
-        int mid = wd->ents[e].model;
-        if (mid < 0 || mid >= nModels) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
-        if (ctx->models[mid].n_mesh != 1 || !ctx->models[mid].casts[0]) device_route = false;
+    if (ctx->model_rows.size() != ctx->models.size()) {
+        ctx->model_rows.resize(ctx->models.size());
+        for (size_t i = 0; i < ctx->models.size(); i++) {
+            const Model &mo = ctx->models[i];
+            ctx->model_rows[i] = bq2_model_row{mo.hdr.data(), mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2};
+        }
     }
-    if (!device_route) {
-        /* host-built records, same slot numbering (filtered pairs keep their slot) */
+    const int nblk = (nP + BQ2_WORLD_THREADS - 1) / BQ2_WORLD_THREADS;
+    const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
+                 off_lights = off_view + 16,
+                 off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
+                 rec_bytes = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15);
+    Trace &tr = ctx->trace; tr.start(); tr.n++;
+    bq2_world_stats ws{};
+    int er = -3;
+    if (!(want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT))) {
+        CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
+        ctx->ent_slot_first.resize((size_t)nE + 1); ctx->ent_vert_off.resize((size_t)nE + 1); ctx->ent_tb_off.assign((size_t)nE + 1, 0u);
+        ctx->slot_record.resize((size_t)nE + 1);
+        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, ctx->meshes.data(),
+                                     (bq2_dev_ent *)h_records.p, (bq2_dev_xform *)(h_records.p + off_xf),
+                                     ctx->slot_record.data(), ctx->ent_vert_off.data(), &ws);
+        if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
+        if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
+    }
+    if (er != 0) {
+        /* multi-mesh models or tangent-space outputs: host-built records, same slot numbering (filtered pairs
+           keep their slot) */
         ctx->tmp_ents.resize((size_t)nE + 1); ctx->tmp_pairs.resize((size_t)nP + 1);
         int32_t kept = 0;
         bq2_status s = build_records_impl(ctx, wd->ents, nE, wd->lights, nL, wd->pair_ent, wd->pair_light, nP, wd->view_world,
@@ -750,70 +777,20 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         fd.want = want & ~BQ2_WANT_TABLES; fd.index_stride = wd->index_stride;
         return bq2_frame_submit(ctx, &fd);
     }
-
-    Trace &tr = ctx->trace; tr.start(); tr.n++;
-    /* ---- per entity (host): record, transform, class ------------------------------------------------ */
-    const int nblk = (nP + BQ2_WORLD_THREADS - 1) / BQ2_WORLD_THREADS;
-    const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_lights = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
-                 off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
-                 rec_bytes = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15);
-    CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
-    CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
-    bq2_dev_ent   *he = (bq2_dev_ent *)h_records.p;
-    bq2_dev_xform *hx = (bq2_dev_xform *)(h_records.p + off_xf);
-
-    ctx->ent_slot_first.resize((size_t)nE + 1); ctx->ent_vert_off.resize((size_t)nE + 1); ctx->ent_tb_off.resize((size_t)nE + 1);
-    ctx->slot_record.resize((size_t)nE);
-    ctx->k_warp = bq2_ctx::KLaunch(); ctx->k_team = bq2_ctx::KLaunch();
-    for (int e = 0; e < nE; e++) {
-        const Model &mo = ctx->models[wd->ents[e].model];
-        const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
-        const bool small = me.V <= BQ2_WARP_MAX_V && me.T <= BQ2_WARP_MAX_T;
-        bq2_ctx::KLaunch &k = small ? ctx->k_warp : ctx->k_team;
-        ctx->slot_record[e] = small ? k.n : -1 - k.n;
-        k.n++; k.max_V = std::max(k.max_V, me.V); k.max_T = std::max(k.max_T, me.T);
-        if (!(me.flags & BQ2_MESH_MD3)) k.any_md2 = 1;
-    }
-    tr.lap(0);
-    uint32_t voff = 0, maxVpad = 0, maxBitw = 0; int maxT = 0;
-    uint64_t total_verts = 0;
-    for (int e = 0; e < nE; e++) {
-        const bq2_world_entity &W = wd->ents[e];
-        const Model &mo = ctx->models[W.model];
-        if (W.frame < 0 || W.frame >= mo.F || W.oldframe < 0 || W.oldframe >= mo.F)
-            return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
-        const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
-        const int rec = ctx->slot_record[e] < 0 ? ctx->k_warp.n + (-1 - ctx->slot_record[e]) : ctx->slot_record[e];
-        ctx->slot_record[e] = rec;
-        bq2_entity E;
-        if (mo.md3)
-            bq2_host_entity_md3(&mo.hdr[3 * (size_t)W.frame], &mo.hdr[3 * (size_t)W.oldframe], W.frame, W.oldframe,
-                                W.backlerp, W.origin, W.oldorigin, W.angles, &E);
-        else
-            bq2_host_entity_md2_hdr(&mo.hdr[6 * (size_t)W.frame], &mo.hdr[6 * (size_t)W.oldframe], W.frame, W.oldframe,
-                                    W.backlerp, W.origin, W.oldorigin, W.angles, W.rf_flags, &E);
-        bq2_dev_ent &d = he[rec];
-        d.cur = me.verts + (size_t)W.frame * me.vstride; d.old = me.verts + (size_t)W.oldframe * me.vstride;
-        d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.pad = 0;
-        d.mesh = mo.first_mesh; d.frame = W.frame; d.oldframe = W.oldframe; d.flags = E.flags;
-        d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
-        for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
-        d.shell_scale = E.shell_scale;
-        d.vert_off = voff; d.tb_off = 0; d.pair_begin = 0; d.pair_count = 0;
-        ctx->ent_slot_first[e] = e; ctx->ent_vert_off[e] = voff; ctx->ent_tb_off[e] = 0;
-        const uint32_t vpad = (uint32_t)(me.V + 3) & ~3u, bitw = (uint32_t)(me.T + 31) >> 5;
-        voff += vpad; total_verts += (uint64_t)me.V;
-        maxVpad = std::max(maxVpad, vpad); maxBitw = std::max(maxBitw, bitw); maxT = std::max(maxT, me.T);
-        bq2_dev_xform &x = hx[e];
-        const bool casts = bq2_host_casts_shadow(W.rf_flags, 0, 0.0f, 2.0f) &&
-                           !(W.rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));             /* M:63722-63727, 64089 */
-        x.origin[0] = W.origin[0]; x.origin[1] = W.origin[1]; x.origin[2] = W.origin[2];
-        x.rec = casts ? rec : -1;
-        x.rotated = (uint32_t)bq2_host_entity_basis(W.angles, x.basis);
-        x.vpad = vpad; x.bitw = bitw;
-    }
-    ctx->ent_slot_first[nE] = nE; ctx->ent_vert_off[nE] = voff; ctx->ent_tb_off[nE] = 0;
     tr.lap(2);
+    CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
+    for (int e = 0; e <= nE; e++) ctx->ent_slot_first[e] = e;
+    ctx->k_warp = bq2_ctx::KLaunch(); ctx->k_team = bq2_ctx::KLaunch();
+    ctx->k_warp.n = ws.n_warp; ctx->k_warp.max_V = ws.warp_max_V; ctx->k_warp.max_T = ws.warp_max_T; ctx->k_warp.any_md2 = ws.warp_md2;
+    ctx->k_team.n = ws.n_team; ctx->k_team.max_V = ws.team_max_V; ctx->k_team.max_T = ws.team_max_T; ctx->k_team.any_md2 = ws.team_md2;
+    const uint32_t voff = ws.lerped_verts_padded, maxVpad = ws.max_vpad, maxBitw = ws.max_bitw;
+    const int maxT = ws.max_T;
+    const uint64_t total_verts = ws.total_verts;
+    {
+        float *hv = (float *)(h_records.p + off_view);
+        for (int k = 0; k < 3; k++) hv[k] = wd->view_world ? wd->view_world[k] : 0.0f;
+        hv[3] = wd->view_world ? 1.0f : 0.0f;
+    }
     if (nL) memcpy(h_records.p + off_lights, wd->lights, (size_t)nL * 16);
     if (nP) { memcpy(h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
 
@@ -829,9 +806,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(ctx->facing_bits.ensure((size_t)nP * maxBitw + 1), "cudaMalloc(facing_bits)");
         CK(ctx->indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
-    CK(ctx->index_count.ensure((size_t)nP + 1), "cudaMalloc(index_count)");
-    CK(h_counts.ensure(sizeof(uint32_t) * ((size_t)nP + 1)), "cudaMallocHost(counts)");
-    CK(h_totals.ensure(64), "cudaMallocHost(totals)");
+    /* index counts and, 8-byte aligned right behind them, the three 64-bit totals: one D2H copy brings both */
+    const size_t tot_word = ((size_t)nP + 1) & ~(size_t)1;
+    CK(ctx->index_count.ensure(tot_word + 8), "cudaMalloc(index_count)");
+    CK(h_counts.ensure(sizeof(uint32_t) * (tot_word + 8)), "cudaMallocHost(counts)");
+    (void)h_totals;
     const size_t w_pairs = (size_t)nP * sizeof(bq2_dev_pair), w_cnt = (((size_t)nE * 8 + 15) & ~(size_t)15),
                  w_blk = (((size_t)nblk * 8 + 15) & ~(size_t)15), w_tab = tables ? (((size_t)nP * 8 + 15) & ~(size_t)15) : 0;
     CK(ctx->d_world.ensure(w_pairs + w_cnt + w_blk + w_tab + 64), "cudaMalloc(world scratch)");
@@ -858,18 +837,9 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     Wl.cnt = (uint32_t *)(dw + w_pairs); Wl.cursor = Wl.cnt + nE;
     Wl.blk = (uint32_t *)(dw + w_pairs + w_cnt);
     Wl.pvoff = tables ? (uint32_t *)(dw + w_pairs + w_cnt + w_blk) : nullptr; Wl.pboff = tables ? Wl.pvoff + nP : nullptr;
-    Wl.totals = (unsigned long long *)(dw + w_pairs + w_cnt + w_blk + w_tab);
+    Wl.totals = (unsigned long long *)(ctx->index_count.p + tot_word);
     Wl.index_count = ctx->index_count.p;
-    Wl.has_view = wd->view_world ? 1 : 0;
-    for (int k = 0; k < 3; k++) Wl.view[k] = wd->view_world ? wd->view_world[k] : 0.0f;
-
-    if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
-    /* cnt | cursor | blk | tables | totals are one contiguous range after dpairs */
-    CK(cudaMemsetAsync(dw + w_pairs, 0, w_cnt + w_blk + w_tab + 64, ctx->stream), "cudaMemset(world scratch)");
-    if (nP && (want & BQ2_WANT_SHADOW)) {
-        CK((cudaError_t)bq2_launch_world_setup(&Wl, ctx->stream), "launch(bq2_world_* kernels)");
-        ctx->launches += 3;
-    }
+    Wl.view = (const float *)(ctx->d_records.p + off_view);
 
     bq2_launch &L = ctx->launch;
     L.meshes = ctx->d_meshes.p;
@@ -885,9 +855,61 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     ctx->world_mode = true; ctx->world_tables = tables;
     /* per-slot host tables used by bq2_expand_trisverts */
     ctx->slot_mesh_V.resize((size_t)nP); ctx->slot_mesh_T.resize((size_t)nP); ctx->pair_slot_entslot.resize((size_t)nP);
-    { bq2_status ls = launch_kernels(ctx); if (ls != BQ2_OK) return ls; }
-    if (nP) CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
-    CK(cudaMemcpyAsync(h_totals.p, Wl.totals, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(totals)");
+
+    /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals */
+    auto enqueue = [&]() -> bq2_status {
+        if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
+        if (nP && (want & BQ2_WANT_SHADOW)) {
+            CK((cudaError_t)bq2_launch_world_setup(&Wl, ctx->stream), "launch(bq2_world_* kernels)");
+            ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
+        } else
+            CK(cudaMemsetAsync(Wl.totals, 0, 3 * sizeof(unsigned long long), ctx->stream), "cudaMemset(totals)");
+        bq2_status ls = launch_kernels(ctx);
+        if (ls != BQ2_OK) return ls;
+        CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts + totals)");
+        return BQ2_OK;
+    };
+    bool enqueued = false;
+    if (ctx->use_graphs && !tables) {
+        bq2_ctx::GraphKey key{};
+        const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
+                                ws.team_max_V, ws.team_max_T, ws.team_md2, nblk, 0, 0, 0, 0, 0, 0};
+        memcpy(key.v, kv, sizeof kv);
+        const void *kp[12] = {ctx->d_records.p, ctx->d_world.p, h_records.p, h_counts.p, ctx->lerped.p, ctx->extruded.p, ctx->facing_bits.p,
+                              ctx->indices.p, ctx->index_count.p, ctx->d_meshes.p, nullptr, nullptr};
+        memcpy(key.p, kp, sizeof kp);
+        bq2_ctx::GraphCache &g = ctx->gcache[slot_k];
+        const bool same = g.have_key && memcmp(&g.key, &key, sizeof key) == 0;
+        if (same && g.exec) {
+            CK(cudaGraphLaunch(g.exec, ctx->stream), "cudaGraphLaunch(frame)");
+            ctx->launches += g.kernels;
+            enqueued = true;
+        } else if (same) {                               /* second frame of this shape: capture it */
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = ctx->launches;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                bq2_status es = enqueue();
+                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                if (es == BQ2_OK && ce == cudaSuccess && graph &&
+                    cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                    g.kernels = ctx->launches - l0;
+                    ctx->launches = l0;
+                    cudaGraphDestroy(graph);
+                    CK(cudaGraphLaunch(g.exec, ctx->stream), "cudaGraphLaunch(frame)");
+                    ctx->launches += g.kernels;
+                    enqueued = true;
+                } else {                                 /* capture is an optimisation only */
+                    if (graph) cudaGraphDestroy(graph);
+                    g.exec = nullptr; ctx->launches = l0; ctx->use_graphs = false;
+                    cudaGetLastError();
+                }
+            }
+        } else {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            g.key = key; g.have_key = true;
+        }
+    }
+    if (!enqueued) { bq2_status es = enqueue(); if (es != BQ2_OK) return es; }
     if (tables && nP) {
         ctx->world_pvoff.resize((size_t)nP + 1); ctx->world_pboff.resize((size_t)nP + 1);
         CK(cudaMemcpyAsync(ctx->world_pvoff.data(), Wl.pvoff, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(tables)");

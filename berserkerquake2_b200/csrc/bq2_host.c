@@ -186,6 +186,75 @@ void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *fi
     *count = base + (rank < rem ? 1 : 0);
 }
 
+/* ---- the per-entity half of the world path (bq2_world_submit), one pass, plain C ---------------------- */
+#include "bq2_internal.h"
+int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
+                            const bq2_dev_mesh *meshes, bq2_dev_ent *he, bq2_dev_xform *hx,
+                            int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
+{
+    uint32_t voff = 0;
+    int32_t e, k;
+    memset(st, 0, sizeof *st);
+    for (e = 0; e < n; e++) {
+        const bq2_world_entity *W = &ents[e];
+        const bq2_model_row *mo;
+        const bq2_dev_mesh *me;
+        bq2_entity E;
+        bq2_dev_ent *d;
+        bq2_dev_xform *x;
+        uint32_t vpad, bitw;
+        int32_t rec, small, casts;
+        if (W->model < 0 || W->model >= n_models) return -1;
+        mo = &models[W->model];
+        if (mo->n_mesh != 1) return -3;
+        if (W->frame < 0 || W->frame >= mo->F || W->oldframe < 0 || W->oldframe >= mo->F) return -2;
+        me = &meshes[mo->first_mesh];
+        small = me->V <= BQ2_WARP_MAX_V && me->T <= BQ2_WARP_MAX_T;
+        if (small) {                                    /* warp-kernel records grow up from 0 ... */
+            rec = st->n_warp++;
+            if (me->V > st->warp_max_V) st->warp_max_V = me->V;
+            if (me->T > st->warp_max_T) st->warp_max_T = me->T;
+            if (!(me->flags & BQ2_MESH_MD3)) st->warp_md2 = 1;
+        } else {                                        /* ... team-kernel records down from the end */
+            rec = n - 1 - st->n_team++;
+            if (me->V > st->team_max_V) st->team_max_V = me->V;
+            if (me->T > st->team_max_T) st->team_max_T = me->T;
+            if (!(me->flags & BQ2_MESH_MD3)) st->team_md2 = 1;
+        }
+        rec_of_ent[e] = rec;
+        if (mo->md3)
+            bq2_host_entity_md3(mo->hdr + 3 * (size_t)W->frame, mo->hdr + 3 * (size_t)W->oldframe, W->frame, W->oldframe,
+                                W->backlerp, W->origin, W->oldorigin, W->angles, &E);
+        else
+            bq2_host_entity_md2_hdr(mo->hdr + 6 * (size_t)W->frame, mo->hdr + 6 * (size_t)W->oldframe, W->frame, W->oldframe,
+                                    W->backlerp, W->origin, W->oldorigin, W->angles, W->rf_flags, &E);
+        d = &he[rec];
+        d->cur = me->verts + (size_t)W->frame * me->vstride; d->old = me->verts + (size_t)W->oldframe * me->vstride;
+        d->tri = me->tri; d->V = me->V; d->T = me->T; d->Tp = me->Tp; d->mflags = me->flags; d->vstride = me->vstride; d->pad = 0;
+        d->mesh = mo->first_mesh; d->frame = W->frame; d->oldframe = W->oldframe; d->flags = E.flags;
+        d->backlerp = E.backlerp; d->frontlerp = E.frontlerp;
+        for (k = 0; k < 3; k++) { d->move[k] = E.move[k]; d->frontv[k] = E.frontv[k]; d->backv[k] = E.backv[k]; }
+        d->shell_scale = E.shell_scale;
+        d->vert_off = voff; d->tb_off = 0; d->pair_begin = 0; d->pair_count = 0;
+        ent_vert_off[e] = voff;
+        vpad = (uint32_t)(me->V + 3) & ~3u; bitw = (uint32_t)(me->T + 31) >> 5;
+        voff += vpad; st->total_verts += (uint64_t)me->V;
+        if (vpad > st->max_vpad) st->max_vpad = vpad;
+        if (bitw > st->max_bitw) st->max_bitw = bitw;
+        if (me->T > st->max_T) st->max_T = me->T;
+        x = &hx[e];
+        casts = bq2_host_casts_shadow(W->rf_flags, 0, 0.0f, 2.0f) &&
+                !(W->rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));                 /* M:63722-63727, 64089 */
+        x->origin[0] = W->origin[0]; x->origin[1] = W->origin[1]; x->origin[2] = W->origin[2];
+        x->rec = casts ? rec : -1;
+        x->rotated = (uint32_t)bq2_host_entity_basis(W->angles, x->basis);
+        x->vpad = vpad; x->bitw = bitw;
+    }
+    ent_vert_off[n] = voff;
+    st->lerped_verts_padded = voff;
+    return 0;
+}
+
 /* ---- load-time neighbour tables, host C ------------------------------------- */
 /* Both reference builders scan every triangle for every edge (O(T^2): M:61782-61824, M:68646-68676).
  * These produce the same tables from one sorted edge list; every order-dependent rule of the reference

@@ -94,10 +94,10 @@ typedef struct bq2_world_launch {
     uint32_t *pvoff, *pboff;        /* [n_pairs] offset tables for the caller, or NULL                      */
     uint32_t *index_count;
     unsigned long long *totals;     /* [0] sum of index counts, [1] overflowing pairs, [2] bad pairs        */
-    float    view[3];
-    int32_t  has_view;
+    const float *view;              /* device [4]: r_origin in world space, [3] != 0 when present (M:66689)  */
 } bq2_world_launch;
 #define BQ2_WORLD_THREADS 1024
+#define BQ2_WORLD_SMALL_PAIRS 1024   /* at most this many pairs and records: one single-block kernel (one pass) */
 
 typedef struct bq2_launch {
     const bq2_dev_mesh *meshes;
@@ -112,9 +112,25 @@ typedef struct bq2_launch {
     unsigned long long *totals;     /* world path: [0] += index count, [1] += overflowing pair; or NULL     */
 } bq2_launch;
 
+/* host-side flat model table for the per-entity loop in C (bq2_host.c) */
+typedef struct bq2_model_row { const float *hdr; int32_t F, md3, first_mesh, n_mesh; } bq2_model_row;
+typedef struct bq2_world_stats {
+    int32_t n_warp, n_team;                 /* records [0, n_warp) -> warp kernel, [n - n_team, n) -> team kernel */
+    int32_t warp_max_V, warp_max_T, warp_md2, team_max_V, team_max_T, team_md2;
+    uint32_t lerped_verts_padded, max_vpad, max_bitw; int32_t max_T;
+    uint64_t total_verts;
+} bq2_world_stats;
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+struct bq2_world_entity;
+/* One pass over the world entities: record (lerp constants M:63526-63553 / 63825-63856, frame pointers,
+ * output offsets), transform (origin, AngleVectors basis, flag filter M:63722-63727) and kernel class.
+ * Returns 0, -1 unknown model, -2 frame out of range, -3 a model of the frame is not single-mesh. */
+int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
+                             const bq2_dev_mesh *meshes, bq2_dev_ent *he, bq2_dev_xform *hx,
+                             int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st);
 /* Two kernels share the records.  "warp" kernel: one warp per (entity, light) pair, one CTA per entity,
  * for meshes with V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T (an MD2 player model is ~500 triangles).
  * "team" kernel: the whole CTA works on one pair at a time; any mesh size, and the N/T/B + tangent-space
@@ -124,7 +140,8 @@ extern "C" {
 #define BQ2_WARP_WARPS   4
 int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);       /* team */
 int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);  /* warp */
-int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);                                 /* 3 kernels */
+int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* returns cudaError_t; 1 or 3 kernels */
+int  bq2_world_setup_launches(const bq2_world_launch *W);
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
 size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);
