@@ -22,6 +22,7 @@ class Bq2Error(RuntimeError):
 OK, E_INVALID, E_CUDA, E_NOMEM, E_LIMIT, E_OVERFLOW, E_NODEVICE = 0, -1, -2, -3, -4, -5, -6
 WANT_SHADOW, WANT_NTB, WANT_TSLIGHT, WANT_NOLERPOUT, WANT_TABLES = 1, 2, 4, 8, 16
 MODEL_SMOOTHVECS = 1
+MODEL_BUILD_NEIGHBOURS = 2
 ENT_SHELL = 1
 (A_LERPED, A_EXTRUDED, A_FACING_BITS, A_INDICES, A_INDEX_COUNT, A_NORMALS, A_TANGENTS, A_BINORMALS,
  A_LIGHTP, A_TSH) = range(10)
@@ -107,6 +108,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_build_records", C.c_int, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, C.POINTER(i32)),
     _sig("bq2_host_md2_neighbours", C.c_int, vp, i32, vp),
     _sig("bq2_host_md3_neighbours", C.c_int, vp, i32, vp),
+    _sig("bq2_gpu_md2_neighbours", C.c_int, vp, vp, i32, vp),
+    _sig("bq2_gpu_md3_neighbours", C.c_int, vp, vp, i32, vp),
     _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
     _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),

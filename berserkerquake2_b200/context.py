@@ -53,11 +53,12 @@ class Context:
         """blob: uint8 MD2 image as the reference holds it after Mod_LoadAliasModel (main.c:51216);
         neighbours: int32 [T][3] (model_t.triangles)."""
         blob = np.ascontiguousarray(blob, np.uint8)
-        nb = None if neighbours is None else np.ascontiguousarray(neighbours, np.int32)
+        nb = None if neighbours is None or isinstance(neighbours, str) else np.ascontiguousarray(neighbours, np.int32)
         tb = [None if a is None else np.ascontiguousarray(a, np.uint8) for a in (tangents, binormals, normals)]
         mid = C.c_int32(-1)
+        flags = (c.MODEL_SMOOTHVECS if smooth else 0) | (c.MODEL_BUILD_NEIGHBOURS if neighbours == "gpu" else 0)
         self._check(c.lib.bq2_upload_md2(self._h, c.ptr(blob), blob.nbytes, c.ptr(nb), c.ptr(tb[0]), c.ptr(tb[1]),
-                                         c.ptr(tb[2]), c.MODEL_SMOOTHVECS if smooth else 0, C.byref(mid)))
+                                         c.ptr(tb[2]), flags, C.byref(mid)))
         return mid.value
 
     def upload_md3(self, frame_translate, meshes):
@@ -68,16 +69,33 @@ class Context:
         keep = []
         for i, m in enumerate(meshes):
             v = np.ascontiguousarray(m["verts"]); ix = np.ascontiguousarray(m["indexes"], np.uint16)
-            nb = None if m.get("neighbours") is None else np.ascontiguousarray(m["neighbours"], np.int32)
+            gpu_nb = isinstance(m.get("neighbours"), str) and m["neighbours"] == "gpu"
+            nb = None if m.get("neighbours") is None or gpu_nb else np.ascontiguousarray(m["neighbours"], np.int32)
             keep += [v, ix, nb]
             assert v.shape[0] == ft.shape[0]
             arr[i].num_verts = v.shape[1]; arr[i].num_tris = ix.shape[0]
             arr[i].vertexes = v.ctypes.data; arr[i].indexes = ix.ctypes.data
             arr[i].neighbours = None if nb is None else nb.ctypes.data
-            arr[i].casts_shadow = 1 if m.get("casts_shadow", True) else 0
+            arr[i].casts_shadow = (1 if m.get("casts_shadow", True) else 0) | (2 if gpu_nb else 0)
         mid = C.c_int32(-1)
         self._check(c.lib.bq2_upload_md3(self._h, ft.shape[0], c.ptr(ft), arr, len(meshes), C.byref(mid)))
         return mid.value
+
+    def gpu_md2_neighbours(self, blob):
+        """model_t.triangles computed on the device (findneighbour rules, main.c:61782-61824)."""
+        h = np.ascontiguousarray(blob, np.uint8)[:68].view("<i4")
+        T, o = int(h[8]), int(h[13])
+        tris = np.ascontiguousarray(blob[o:o + 12 * T]).view(np.int16)
+        out = np.zeros((T, 3), np.int32)
+        self._check(c.lib.bq2_gpu_md2_neighbours(self._h, c.ptr(tris), T, c.ptr(out)))
+        return out
+
+    def gpu_md3_neighbours(self, indexes):
+        """maliasmesh_t.triangles computed on the device (R_BuildTriangleNeighbors, main.c:68646-68696)."""
+        ix = np.ascontiguousarray(indexes, np.uint16)
+        out = np.zeros((ix.size // 3, 3), np.int32)
+        self._check(c.lib.bq2_gpu_md3_neighbours(self._h, c.ptr(ix), ix.size // 3, c.ptr(out)))
+        return out
 
     # -- per frame -----------------------------------------------------------------------------------
     def build_records(self, world_ents, world_lights, pair_ent, pair_light, view_world=None):

@@ -136,6 +136,7 @@ bq2_status fail_cuda(bq2_ctx *c, cudaError_t e, const char *where)
 {
     std::string m = std::string(where) + ": " + cudaGetErrorString(e);
     if (c) c->err = m; else g_create_error = m;
+    cudaGetLastError();                      /* a launch error must not be reported again by the next call */
     return BQ2_E_CUDA;
 }
 #define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, where); } while (0)
@@ -260,6 +261,8 @@ void *bq2_stream(bq2_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 int bq2_device(const bq2_ctx *ctx) { return ctx ? ctx->device : -1; }
 uint64_t bq2_kernel_launches(const bq2_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
+static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, int32_t T, int md3, int32_t *out);
+
 bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, const int32_t *neighbours,
                           const uint8_t *tangents, const uint8_t *binormals, const uint8_t *normals,
                           uint32_t model_flags, int32_t *model_id)
@@ -288,6 +291,13 @@ bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, con
             if (v < 0 || v >= V) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: triangle index out of range");
             idx[3 * t + k] = v;
         }
+    std::vector<int32_t> built;
+    if (!neighbours && (model_flags & BQ2_MODEL_BUILD_NEIGHBOURS)) {         /* findneighbour rules, on the device */
+        built.resize(3 * (size_t)T);
+        bq2_status ns = gpu_neighbours(ctx, (const uint16_t *)tri, 6, T, 0, built.data());
+        if (ns != BQ2_OK) return ns;
+        neighbours = built.data();
+    }
     if (neighbours)
         for (size_t i = 0; i < 3 * (size_t)T; i++)
             if (neighbours[i] < -1 || neighbours[i] >= T) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: neighbour out of range");
@@ -364,7 +374,15 @@ bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate,
         std::vector<int32_t> idx(3 * (size_t)T);
         for (size_t i = 0; i < idx.size(); i++) idx[i] = me.indexes[i];
         std::vector<int16_t> tab(6 * (size_t)Tp);
-        pack_tri_table(T, Tp, idx.data(), me.neighbours, tab.data());
+        std::vector<int32_t> built;
+        const int32_t *nbp = me.neighbours;
+        if (!nbp && (me.casts_shadow & 2)) {                                 /* R_BuildTriangleNeighbors rules, on the device */
+            built.resize(3 * (size_t)T);
+            bq2_status ns = gpu_neighbours(ctx, me.indexes, 3, T, 1, built.data());
+            if (ns != BQ2_OK) return ns;
+            nbp = built.data();
+        }
+        pack_tri_table(T, Tp, idx.data(), nbp, tab.data());
         unsigned char *d = nullptr;
         bq2_status s = arena_alloc(ctx, total, &d);
         if (s != BQ2_OK) return s;
@@ -376,7 +394,7 @@ bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate,
         m.V = V; m.T = T; m.F = F; m.Tp = Tp; m.vstride = vstride; m.tbstride = 0;
         m.flags = BQ2_MESH_MD3 | BQ2_MESH_SMOOTH | BQ2_MESH_HAS_TB;
         ctx->meshes.push_back(m);
-        mo.V.push_back(V); mo.T.push_back(T); mo.casts.push_back(me.casts_shadow ? 1 : 0);
+        mo.V.push_back(V); mo.T.push_back(T); mo.casts.push_back((me.casts_shadow & 1) ? 1 : 0);
     }
     ctx->models.push_back(mo); ctx->meshes_dirty = true;
     *model_id = (int32_t)ctx->models.size() - 1;
@@ -724,6 +742,32 @@ bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
     if (s != BQ2_OK) return s;
     return bq2_frame_wait(ctx, out);
 }
+
+static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, int32_t T, int md3, int32_t *out)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!idx || !out || T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_neighbours: bad arguments");
+    if (T > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_neighbours: too many triangles");
+    int V = 0;
+    for (int t = 0; t < T; t++) for (int k = 0; k < 3; k++) V = std::max(V, (int)idx[(size_t)t * stride + k] + 1);
+    if (bq2_neighbours_smem_bytes(T, V) > 226u * 1024u) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_neighbours: mesh too large for one CTA");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t in_bytes = ((size_t)T * stride * 2 + 15) & ~(size_t)15, out_bytes = (size_t)T * 12;
+    DevBuf<unsigned char> buf;
+    CK(buf.ensure(in_bytes + out_bytes), "cudaMalloc(neighbours)");
+    cudaError_t e = cudaMemcpyAsync(buf.p, idx, (size_t)T * stride * 2, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = (cudaError_t)bq2_launch_neighbours((const uint16_t *)buf.p, stride, T, V, md3, (int32_t *)(buf.p + in_bytes), ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(out, buf.p + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    buf.release();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_neighbours");
+    return BQ2_OK;
+}
+
+bq2_status bq2_gpu_md2_neighbours(bq2_ctx *ctx, const int16_t *dtriangles, int32_t num_tris, int32_t *out)
+{ return gpu_neighbours(ctx, (const uint16_t *)dtriangles, 6, num_tris, 0, out); }
+bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t num_tris, int32_t *out)
+{ return gpu_neighbours(ctx, indexes, 3, num_tris, 1, out); }
 
 bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
 {

@@ -142,6 +142,10 @@ int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, vo
 int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);  /* warp */
 int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* returns cudaError_t; 1 or 3 kernels */
 int  bq2_world_setup_launches(const bq2_world_launch *W);
+/* neighbour tables of one mesh on the device: idx = u16 vertex indices, in_stride u16s per triangle (6 for
+   dtriangle_t, 3 for WORD indexes); out = int32[3*T] (device) */
+int  bq2_launch_neighbours(const uint16_t *idx, int in_stride, int T, int V, int md3, int32_t *out, void *stream);
+size_t bq2_neighbours_smem_bytes(int T, int V);
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
 size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);

@@ -73,6 +73,7 @@ typedef enum bq2_status {
 #define BQ2_ENT_SHELL        0x1u   /* add anorm[cur.lightnormalindex]*shell_scale  (M:63565-63572) */
 
 /* model flags */
+#define BQ2_MODEL_BUILD_NEIGHBOURS 0x2u /* neighbours == NULL: build the table on the device (bq2_gpu_md2_neighbours) */
 #define BQ2_MODEL_SMOOTHVECS 0x1u   /* RF_SMOOTHVECS: tangent/binormal bytes are per vertex (M:51661)
                                        otherwise per triangle, plus per-triangle normal bytes (M:51747) */
 
@@ -180,7 +181,8 @@ typedef struct bq2_md3_mesh {
                                    u8 normal, tangent, binormal, pad  (16 bytes, defs.h:4401-4407) */
     const uint16_t *indexes;    /* WORD[3*num_tris]                                                 */
     const int32_t  *neighbours; /* neighbours_t[num_tris]                                           */
-    int32_t casts_shadow;       /* 0 = the per-mesh skin filter M:63862-63880 rejects this mesh     */
+    int32_t casts_shadow;       /* bit 0: 0 = the per-mesh skin filter M:63862-63880 rejects this mesh;
+                                   bit 1: neighbours == NULL -> build them on the device               */
 } bq2_md3_mesh;
 
 bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t num_frames, const float *frame_translate /*[F][3]*/,
@@ -254,6 +256,11 @@ int  bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow
  * Return 0, or -1 when out of memory. */
 int  bq2_host_md2_neighbours(const int16_t *dtriangles, int32_t num_tris, int32_t *out);
 int  bq2_host_md3_neighbours(const uint16_t *indexes, int32_t num_tris, int32_t *out);
+
+/* The same tables computed ON THE DEVICE (one CTA per mesh, edges bucketed by vertex in shared memory) and
+ * returned to the host; bit-identical to the reference's builders.  num_verts = 1 + the largest index. */
+bq2_status bq2_gpu_md2_neighbours(bq2_ctx *ctx, const int16_t *dtriangles, int32_t num_tris, int32_t *out);
+bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t num_tris, int32_t *out);
 
 /* ---- the renderer's loop nest, flattened (host, C) -------------------------------------------- */
 /* The fields of entity_t (defs.h:573-618) and shadowlight_t (defs.h:3927-3973) this path reads. */
