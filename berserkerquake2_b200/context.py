@@ -56,7 +56,7 @@ class Context:
         nb = None if neighbours is None or isinstance(neighbours, str) else np.ascontiguousarray(neighbours, np.int32)
         tb = [None if a is None else np.ascontiguousarray(a, np.uint8) for a in (tangents, binormals, normals)]
         mid = C.c_int32(-1)
-        flags = (c.MODEL_SMOOTHVECS if smooth else 0) | (c.MODEL_BUILD_NEIGHBOURS if neighbours == "gpu" else 0)
+        flags = (c.MODEL_SMOOTHVECS if smooth else 0) | (c.MODEL_BUILD_NEIGHBOURS if isinstance(neighbours, str) and neighbours == "gpu" else 0)
         self._check(c.lib.bq2_upload_md2(self._h, c.ptr(blob), blob.nbytes, c.ptr(nb), c.ptr(tb[0]), c.ptr(tb[1]),
                                          c.ptr(tb[2]), flags, C.byref(mid)))
         return mid.value
