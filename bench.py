@@ -309,7 +309,7 @@ def run_gpu(args):
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
-                    "h2d_bytes_per_step": n_ents * (128 + 64) + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
+                    "h2d_bytes_per_step": n_ents * (128 + 64) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
                     "what": "per frame: bq2_world_submit (host: per-entity trig + record packing; pinned -> H2D; "
                             "3 record-building kernels + the fused kernel; D2H of per-pair index counts + totals) + "
                             "bq2_frame_wait, wall clock over K frames with two frames in flight (frame i+1 packed and "
@@ -319,7 +319,7 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "kernel": "bq2_frame_kernel", "kernel_ms": k_ms,
+                         "kernel": "bq2_frame_warp_kernel", "kernel_ms": k_ms,
                          "min_traffic_bytes_per_launch": mint,
                          "achieved_min_traffic": mint / (k_ms * 1e-3) / 1e9,
                          "frac_min_traffic": mint / (k_ms * 1e-3) / 1e9 / peak},
@@ -410,7 +410,7 @@ def cpu_arm(n_ents, lights, steps, warmup, budget_s=12.0, cores=None):
     times, tot = [], 0
     t_begin = time.perf_counter()
     k = 0
-    while (steps is not None and k < steps) or (steps is None and time.perf_counter() - t_begin < budget_s and k < 1000):
+    while (steps is not None and k < steps) or (steps is None and time.perf_counter() - t_begin < budget_s and k < 20000):
         dt, tot = one_step()
         times.append(dt); k += 1
     for p in procs:
