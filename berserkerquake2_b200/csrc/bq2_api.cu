@@ -109,7 +109,7 @@ struct bq2_ctx {
     struct GraphCache { GraphKey key{}; bool have_key = false; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; } gcache[2];
     bool use_graphs = getenv("BQ2_NO_GRAPH") == nullptr;
     DevBuf<unsigned char> d_records;
-    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
+    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh, tri_normals;
     DevBuf<uint32_t> facing_bits, indices, index_count;
     /* world path (device-built pair records) */
     DevBuf<unsigned char> d_world;                               /* dpairs | cnt | cursor | blk | tables | totals */
@@ -247,7 +247,7 @@ void bq2_destroy(bq2_ctx *ctx)
     for (Slab &s : ctx->slabs) cudaFree(s.base);
     ctx->d_meshes.release(); ctx->d_records.release();
     ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
-    ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release();
+    ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release(); ctx->tri_normals.release();
     ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
     for (int k = 0; k < 2; k++) if (ctx->gcache[k].exec) cudaGraphExecDestroy(ctx->gcache[k].exec);
     for (int k = 0; k < 2; k++) { ctx->hrec[k].release(); ctx->hcnt[k].release(); ctx->htot[k].release(); if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]); }
@@ -550,7 +550,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         if (ctx->slot_record[s] < 0) ctx->slot_record[s] = ctx->k_warp.n + (-1 - ctx->slot_record[s]);
 
     tr.lap(1);
-    uint32_t voff = 0, tboff = 0;
+    uint32_t voff = 0, tboff = 0, team_rows = 0;
     uint64_t total_verts = 0;
     for (int e = 0; e < nE; e++) {
         const bq2_entity &E = fd->ents[e];
@@ -562,7 +562,8 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
                 return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_NTB but the model was uploaded without tangent/binormal bytes");
             bq2_dev_ent &d = he[ctx->slot_record[s]];
             d.cur = me.verts + (size_t)E.frame * me.vstride; d.old = me.verts + (size_t)E.oldframe * me.vstride;
-            d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.pad = 0;
+            d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.nrm_off = 0;
+            if (ctx->slot_record[s] >= ctx->k_warp.n) { d.nrm_off = team_rows; team_rows += (uint32_t)me.Tp; }
             d.mesh = mo.first_mesh + m; d.frame = E.frame; d.oldframe = E.oldframe; d.flags = E.flags;
             d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
             for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
@@ -645,6 +646,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         CK(ctx->lightp.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(lightp)");
         CK(ctx->tsh.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(tsh)");
     }
+    if (team_rows) CK(ctx->tri_normals.ensure(4 * (size_t)team_rows + 4), "cudaMalloc(triangle normals)");
     CK(h_counts.ensure(sizeof(uint32_t) * ((size_t)nPS + 1)), "cudaMallocHost(counts)");
     if (ctx->meshes_dirty) {
         CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
@@ -672,7 +674,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
     L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
     L.normals = ctx->normals.p; L.tangents = ctx->tangents.p; L.binormals = ctx->binormals.p;
-    L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p; L.totals = nullptr;
+    L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p; L.totals = nullptr; L.tri_normals = ctx->tri_normals.p;
     ctx->world_mode = false;
     ctx->max_V = maxV; ctx->max_T = maxT; ctx->any_md2 = anyMd2;
     ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
@@ -850,6 +852,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(ctx->facing_bits.ensure((size_t)nP * maxBitw + 1), "cudaMalloc(facing_bits)");
         CK(ctx->indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
+    if (ws.team_normal_rows) CK(ctx->tri_normals.ensure(4 * (size_t)ws.team_normal_rows + 4), "cudaMalloc(triangle normals)");
     /* index counts and, 8-byte aligned right behind them, the three 64-bit totals: one D2H copy brings both */
     const size_t tot_word = ((size_t)nP + 1) & ~(size_t)1;
     CK(ctx->index_count.ensure(tot_word + 8), "cudaMalloc(index_count)");
@@ -893,7 +896,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
     L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
     L.normals = nullptr; L.tangents = nullptr; L.binormals = nullptr; L.lightp = nullptr; L.tsh = nullptr;
-    L.totals = Wl.totals;
+    L.totals = Wl.totals; L.tri_normals = ctx->tri_normals.p;
     ctx->n_ent_slots = nE; ctx->n_pair_slots = nP; ctx->n_ents = nE; ctx->n_pairs = nP;
     ctx->total_verts = total_verts;
     ctx->world_mode = true; ctx->world_tables = tables;
@@ -920,7 +923,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, nblk, 0, 0, 0, 0, 0, 0};
         memcpy(key.v, kv, sizeof kv);
         const void *kp[12] = {ctx->d_records.p, ctx->d_world.p, h_records.p, h_counts.p, ctx->lerped.p, ctx->extruded.p, ctx->facing_bits.p,
-                              ctx->indices.p, ctx->index_count.p, ctx->d_meshes.p, nullptr, nullptr};
+                              ctx->indices.p, ctx->index_count.p, ctx->d_meshes.p, ctx->tri_normals.p, nullptr};
         memcpy(key.p, kp, sizeof kp);
         bq2_ctx::GraphCache &g = ctx->gcache[slot_k];
         const bool same = g.have_key && memcmp(&g.key, &key, sizeof key) == 0;

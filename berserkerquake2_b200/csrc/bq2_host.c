@@ -230,7 +230,8 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
                                     W->backlerp, W->origin, W->oldorigin, W->angles, W->rf_flags, &E);
         d = &he[rec];
         d->cur = me->verts + (size_t)W->frame * me->vstride; d->old = me->verts + (size_t)W->oldframe * me->vstride;
-        d->tri = me->tri; d->V = me->V; d->T = me->T; d->Tp = me->Tp; d->mflags = me->flags; d->vstride = me->vstride; d->pad = 0;
+        d->tri = me->tri; d->V = me->V; d->T = me->T; d->Tp = me->Tp; d->mflags = me->flags; d->vstride = me->vstride; d->nrm_off = 0;
+        if (!small) { d->nrm_off = st->team_normal_rows; st->team_normal_rows += (uint32_t)me->Tp; }
         d->mesh = mo->first_mesh; d->frame = W->frame; d->oldframe = W->oldframe; d->flags = E.flags;
         d->backlerp = E.backlerp; d->frontlerp = E.frontlerp;
         for (k = 0; k < 3; k++) { d->move[k] = E.move[k]; d->frontv[k] = E.frontv[k]; d->backv[k] = E.backv[k]; }

@@ -55,7 +55,7 @@ typedef struct bq2_dev_ent {
     uint32_t pair_count;
     uint32_t tb_off;            /* first row in normals/tangents/binormals              */
     uint32_t vstride;           /* bytes per frame row                                  */
-    uint32_t pad;
+    uint32_t nrm_off;           /* team kernel: first float4 of this slot's triangle-normal scratch row */
 } bq2_dev_ent;                  /* 128 bytes */
 
 typedef struct bq2_dev_pair {
@@ -110,6 +110,7 @@ typedef struct bq2_launch {
     uint32_t *facing_bits, *indices, *index_count;
     float    *normals, *tangents, *binormals, *lightp, *tsh;
     unsigned long long *totals;     /* world path: [0] += index count, [1] += overflowing pair; or NULL     */
+    float    *tri_normals;          /* team kernel scratch: float4 {unit normal, P0.n} per triangle per slot  */
 } bq2_launch;
 
 /* host-side flat model table for the per-entity loop in C (bq2_host.c) */
@@ -118,6 +119,7 @@ typedef struct bq2_world_stats {
     int32_t n_warp, n_team;                 /* records [0, n_warp) -> warp kernel, [n - n_team, n) -> team kernel */
     int32_t warp_max_V, warp_max_T, warp_md2, team_max_V, team_max_T, team_md2;
     uint32_t lerped_verts_padded, max_vpad, max_bitw; int32_t max_T;
+    uint32_t team_normal_rows;              /* sum of Tp over team-kernel records */
     uint64_t total_verts;
 } bq2_world_stats;
 

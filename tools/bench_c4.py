@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""BASELINE config 4 as a measurement: high-poly multi-surface MD3 (4 surfaces x V=1026 / T=2048 = 8,192 tris)
+with the tangent-space basis (N/T/B rows, LightP / tsH) and the shadow volumes, E entities x L lights.
+
+  python tools/bench_c4.py [--entities 256] [--lights 4] [--steps 30] [--no-ntb]
+
+Reports kernel time (records resident, L2 flushed, CUDA events on the ctx stream) and the bytes the call has to
+move.  Tangent / binormal bytes are synthetic anorm indices (the kernel only decodes them); neighbours come from
+the product's own builder."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench                                            # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--entities", type=int, default=256)
+    ap.add_argument("--lights", type=int, default=4)
+    ap.add_argument("--models", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--no-ntb", action="store_true")
+    a = ap.parse_args()
+    import torch
+    import berserkerquake2_b200 as bq2
+    from berserkerquake2_b200 import synth, host
+    ctx = bq2.Context(0)
+    S, R, F, NM = 32, 33, 32, 4
+    V, T = synth.sphere_dims(S, R)
+    mids, nb = [], None
+    for m in range(a.models):
+        meshes = []
+        ft = np.zeros((F, 3), np.float32)
+        for k in range(NM):
+            verts, idx, st = synth.md3_mesh(S, R, F, m * NM + k, centre=(40.0 * k, 0.0, 0.0))
+            verts["tangent"] = (verts["normal"].astype(np.int32) + 17) % 162
+            verts["binormal"] = (verts["normal"].astype(np.int32) + 71) % 162
+            nb = host.md3_neighbours(idx) if nb is None else nb
+            meshes.append(dict(verts=verts, indexes=idx, neighbours=nb))
+        mids.append(ctx.upload_md3(ft, meshes))
+    we, wl, pe, pl = bench.make_scene(a.entities, a.lights)
+    we["model"] = np.array(mids, np.int32)[np.arange(a.entities) % len(mids)]
+    we["frame"] %= F; we["oldframe"] = (we["frame"] + F - 1) % F
+    view = np.array([100.0, -50.0, 80.0], np.float32)
+    want = bq2.WANT_SHADOW | (0 if a.no_ntb else bq2.WANT_NTB | bq2.WANT_TSLIGHT)
+    ents, pairs = ctx.build_records(we, wl, pe, pl, view_world=view)
+    res = ctx.frame(ents, pairs, want=want)
+    tot = int(res.total_indices)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    flush = torch.empty(bench.L2_FLUSH_BYTES, dtype=torch.uint8, device="cuda:0")
+    for _ in range(3):
+        with torch.cuda.stream(stream):
+            flush.zero_(); ctx.replay()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for e0, e1 in evs:
+        with torch.cuda.stream(stream):
+            flush.zero_(); e0.record(stream); ctx.replay(); e1.record(stream)
+    torch.cuda.synchronize()
+    ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
+    n_es, n_ps = a.entities * NM, a.entities * a.lights * NM
+    # bytes this layout must move: per entity slot two 16V-byte frame rows + 12T table + 128 B record in, 12V lerped
+    # (+36V N/T/B) out; per pair slot 48 B in, 12V extruded (+24V LightP/tsH) + facing words + count + indices out
+    ntb = 0 if a.no_ntb else 1
+    b = n_es * (2 * 16 * V + 12 * T + 128 + 12 * V + ntb * 36 * V) + n_ps * (48 + 12 * V + ntb * 24 * V + 4 * ((T + 31) // 32) + 4) + 4 * tot
+    peak, _ = bench.peaks()
+    print(json.dumps({"workload": f"C4: {a.entities} MD3 entities x {a.lights} lights, {NM} surfaces x (V={V}, T={T}), "
+                                  f"{'shadow only' if a.no_ntb else 'N/T/B + LightP/tsH + shadow volumes'}",
+                      "kernel_ms": ms, "pair_slots": n_ps, "tris_per_s": tot / 3 / (ms * 1e-3),
+                      "lerped_verts_per_s": n_es * V / (ms * 1e-3), "min_traffic_bytes": b,
+                      "GBps": b / (ms * 1e-3) / 1e9, "frac_of_measured_peak": b / (ms * 1e-3) / 1e9 / peak,
+                      "launches_per_step": 1}))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
