@@ -110,6 +110,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_host_md3_neighbours", C.c_int, vp, i32, vp),
     _sig("bq2_gpu_md2_neighbours", C.c_int, vp, vp, i32, vp),
     _sig("bq2_gpu_md3_neighbours", C.c_int, vp, vp, i32, vp),
+    _sig("bq2_gpu_md2_tangents", C.c_int, vp, vp, C.c_size_t, vp, f32, C.c_int, vp, vp, vp),
+    _sig("bq2_gpu_md3_tangents", C.c_int, vp, vp, i32, i32, vp, vp, i32),
     _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
     _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),

@@ -97,6 +97,27 @@ class Context:
         self._check(c.lib.bq2_gpu_md3_neighbours(self._h, c.ptr(ix), ix.size // 3, c.ptr(out)))
         return out
 
+    def gpu_md2_tangents(self, blob, st, smooth_cosine, smooth=True):
+        """model_t.tangents / binormals (/ normals when not smooth) computed on the device
+        (main.c:51661-51804).  Returns (normals or None, tangents, binormals), uint8 [frames][V or T]."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        h = blob[:68].view("<i4")
+        V, T, F = int(h[6]), int(h[8]), int(h[10])
+        rows = V if smooth else T
+        st = np.ascontiguousarray(st, np.float32)
+        n = None if smooth else np.zeros((F, rows), np.uint8)
+        t, b = np.zeros((F, rows), np.uint8), np.zeros((F, rows), np.uint8)
+        self._check(c.lib.bq2_gpu_md2_tangents(self._h, c.ptr(blob), blob.nbytes, c.ptr(st), float(smooth_cosine),
+                                               1 if smooth else 0, c.ptr(n), c.ptr(t), c.ptr(b)))
+        return n, t, b
+
+    def gpu_md3_tangents(self, verts, st, indexes):
+        """fills the tangent / binormal bytes of verts [F][V] (MD3 vertex dtype) in place (main.c:50993-51014)."""
+        assert verts.flags["C_CONTIGUOUS"]
+        F, V = verts.shape
+        st = np.ascontiguousarray(st, np.float32); ix = np.ascontiguousarray(indexes, np.uint16)
+        self._check(c.lib.bq2_gpu_md3_tangents(self._h, c.ptr(verts), F, V, c.ptr(st), c.ptr(ix), ix.size // 3))
+
     # -- per frame -----------------------------------------------------------------------------------
     def build_records(self, world_ents, world_lights, pair_ent, pair_light, view_world=None):
         """The renderer's (light x entity) loop nest flattened into bq2_entity / bq2_pair records, on the

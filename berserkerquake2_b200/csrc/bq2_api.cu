@@ -771,6 +771,77 @@ bq2_status bq2_gpu_md2_neighbours(bq2_ctx *ctx, const int16_t *dtriangles, int32
 bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t num_tris, int32_t *out)
 { return gpu_neighbours(ctx, indexes, 3, num_tris, 1, out); }
 
+bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *blob, size_t blob_bytes, const float *st, float smooth_cosine,
+                                int smooth, uint8_t *normals, uint8_t *tangents, uint8_t *binormals)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!blob || blob_bytes < sizeof(md2_header) || !st || !tangents || !binormals || (!smooth && !normals))
+        return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: bad arguments");
+    const md2_header *h = (const md2_header *)blob;
+    const int V = h->num_xyz, T = h->num_tris, F = h->num_frames, NS = h->num_st;
+    if (V <= 0 || T <= 0 || F <= 0 || NS <= 0 || V > BQ2_MD2_MAX_VERTS || T > BQ2_MD2_MAX_TRIANGLES)
+        return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md2_tangents: model outside the MD2 limits");
+    if (h->framesize < 40 + 4 * V || (size_t)h->ofs_tris + 12u * (size_t)T > blob_bytes ||
+        (size_t)h->ofs_frames + (size_t)F * (size_t)h->framesize > blob_bytes)
+        return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: offsets run past the blob");
+    const unsigned char *base = (const unsigned char *)blob;
+    const int16_t *tri = (const int16_t *)(base + h->ofs_tris);
+    for (int t = 0; t < T; t++) for (int k = 0; k < 3; k++)
+        if (tri[6 * t + k] < 0 || tri[6 * t + k] >= V || tri[6 * t + 3 + k] < 0 || tri[6 * t + 3 + k] >= NS)
+            return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: triangle index out of range");
+    const int mode = smooth ? 0 : 1;
+    if (bq2_tangents_smem_bytes(T, V, NS, mode) > 226u * 1024u) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md2_tangents: mesh too large for one CTA");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t rows = smooth ? (size_t)V : (size_t)T, vrow = (size_t)V * 4;
+    const size_t o_tri = 0, o_st = (12 * (size_t)T + 15) & ~(size_t)15, o_v = o_st + (((size_t)NS * 8 + 15) & ~(size_t)15),
+                 o_out = o_v + ((F * vrow + 15) & ~(size_t)15), total = o_out + 3 * F * rows;
+    std::vector<unsigned char> img(o_out, 0);
+    memcpy(&img[o_tri], tri, 12 * (size_t)T);
+    memcpy(&img[o_st], st, (size_t)NS * 8);
+    for (int f = 0; f < F; f++) memcpy(&img[o_v + f * vrow], base + h->ofs_frames + (size_t)f * h->framesize + 40, vrow);
+    DevBuf<unsigned char> buf;
+    CK(buf.ensure(total + 16), "cudaMalloc(tangents)");
+    cudaError_t e = cudaMemcpyAsync(buf.p, img.data(), o_out, cudaMemcpyHostToDevice, ctx->stream);
+    const uint16_t *dtri = (const uint16_t *)(buf.p + o_tri);
+    uint8_t *dout = buf.p + o_out;
+    if (e == cudaSuccess)
+        e = (cudaError_t)bq2_launch_tangents(dtri, 6, dtri + 3, 6, (const float *)(buf.p + o_st), NS, buf.p + o_v, vrow, F, T, V, mode,
+                                             smooth_cosine, dout, dout + F * rows, dout + 2 * F * rows, rows, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaStreamSynchronize(ctx->stream); }
+    if (e == cudaSuccess && !smooth) e = cudaMemcpy(normals, dout, F * rows, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(tangents, dout + F * rows, F * rows, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(binormals, dout + 2 * F * rows, F * rows, cudaMemcpyDeviceToHost);
+    buf.release();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_md2_tangents");
+    return BQ2_OK;
+}
+
+bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t F, int32_t V, const float *st,
+                                const uint16_t *indexes, int32_t T)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!vertexes || !st || !indexes || F <= 0 || V <= 0 || T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md3_tangents: bad arguments");
+    if (V > BQ2_MD3_MAX_VERTS || T > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md3_tangents: mesh outside the MD3 limits");
+    for (int i = 0; i < 3 * T; i++) if (indexes[i] >= V) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md3_tangents: index out of range");
+    if (bq2_tangents_smem_bytes(T, V, V, 2) > 226u * 1024u) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md3_tangents: mesh too large for one CTA");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t o_ix = 0, o_st = (6 * (size_t)T + 15) & ~(size_t)15, o_v = o_st + (((size_t)V * 8 + 15) & ~(size_t)15),
+                 vbytes = (size_t)F * V * 16, total = o_v + vbytes;
+    DevBuf<unsigned char> buf;
+    CK(buf.ensure(total + 16), "cudaMalloc(md3 tangents)");
+    cudaError_t e = cudaMemcpyAsync(buf.p + o_ix, indexes, 6 * (size_t)T, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(buf.p + o_st, st, (size_t)V * 8, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(buf.p + o_v, vertexes, vbytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+        e = (cudaError_t)bq2_launch_tangents((const uint16_t *)(buf.p + o_ix), 3, nullptr, 0, (const float *)(buf.p + o_st), V,
+                                             buf.p + o_v, (size_t)V * 16, F, T, V, 2, 0.0f, nullptr, nullptr, nullptr, 0, ctx->stream);
+    if (e == cudaSuccess) { ctx->launches++; e = cudaMemcpyAsync(vertexes, buf.p + o_v, vbytes, cudaMemcpyDeviceToHost, ctx->stream); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    buf.release();
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_md3_tangents");
+    return BQ2_OK;
+}
+
 bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
 {
     if (!ctx) return BQ2_E_INVALID;

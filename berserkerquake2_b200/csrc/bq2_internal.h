@@ -148,6 +148,12 @@ int  bq2_world_setup_launches(const bq2_world_launch *W);
    dtriangle_t, 3 for WORD indexes); out = int32[3*T] (device) */
 int  bq2_launch_neighbours(const uint16_t *idx, int in_stride, int T, int V, int md3, int32_t *out, void *stream);
 size_t bq2_neighbours_smem_bytes(int T, int V);
+/* tangent-space bytes of one mesh, one CTA per key-frame; device pointers; mode 0 MD2 smooth, 1 MD2 flat, 2 MD3 */
+int  bq2_launch_tangents(const uint16_t *idx_xyz, int xyz_stride, const uint16_t *idx_st, int st_stride,
+                         const float *st, int num_st, const uint8_t *verts, size_t frame_stride, int num_frames,
+                         int T, int V, int mode, float smooth_cosine,
+                         uint8_t *out_n, uint8_t *out_t, uint8_t *out_b, size_t out_stride, void *stream);
+size_t bq2_tangents_smem_bytes(int T, int V, int num_st, int mode);
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
 size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);

@@ -262,6 +262,18 @@ int  bq2_host_md3_neighbours(const uint16_t *indexes, int32_t num_tris, int32_t 
 bq2_status bq2_gpu_md2_neighbours(bq2_ctx *ctx, const int16_t *dtriangles, int32_t num_tris, int32_t *out);
 bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t num_tris, int32_t *out);
 
+/* Load-time tangent-space bytes on the device, bit-identical to the loader loops:
+ * MD2 (M:51661-51804): st = the loader's float st (fstvert_t, M:51322-51329), [num_st][2].  smooth != 0:
+ *   tangents / binormals = [num_frames][num_xyz] (RF_SMOOTHVECS, incl. the coincident-vertex merge with
+ *   smooth_cosine); smooth == 0: normals / tangents / binormals = [num_frames][num_tris].
+ * MD3 (M:50993-51014): fills the tangent / binormal bytes of vertexes (maliasvertex_t[num_frames][num_verts])
+ *   in place; st = [num_verts][2]. */
+bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *dmdl_blob, size_t blob_bytes, const float *st,
+                                float smooth_cosine, int smooth, uint8_t *normals, uint8_t *tangents,
+                                uint8_t *binormals);
+bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t num_frames, int32_t num_verts,
+                                const float *st, const uint16_t *indexes, int32_t num_tris);
+
 /* ---- the renderer's loop nest, flattened (host, C) -------------------------------------------- */
 /* The fields of entity_t (defs.h:573-618) and shadowlight_t (defs.h:3927-3973) this path reads. */
 typedef struct bq2_world_entity {
