@@ -56,7 +56,7 @@ class FrameOut(C.Structure):
                 ("lightp", C.c_void_p), ("tsh", C.c_void_p),
                 ("index_stride", C.c_uint32),
                 ("total_lerped_verts", C.c_uint64), ("total_indices", C.c_uint64), ("total_pairs", C.c_uint64),
-                ("overflow_pairs", C.c_int32)]
+                ("overflow_pairs", C.c_int32), ("pair_ts_offset", C.POINTER(C.c_uint32))]
 
 
 class WorldDesc(C.Structure):

@@ -209,6 +209,8 @@ class FrameResult:
             self.pair_bits_offset = np.ctypeslib.as_array(out.pair_bits_offset, (n_tab,)).copy()
         else:
             self.pair_vert_offset = self.pair_bits_offset = None
+        self.pair_ts_offset = (np.ctypeslib.as_array(out.pair_ts_offset, (nps + 1,)).copy()
+                               if out.pair_ts_offset and nps else None)
         self.index_stride = out.index_stride
         self.total_lerped_verts = out.total_lerped_verts
         self.total_indices = out.total_indices
@@ -236,9 +238,10 @@ class FrameResult:
         return tuple(self.ctx.download(w, o, 3 * rows, np.float32).reshape(rows, 3)
                      for w in (c.A_NORMALS, c.A_TANGENTS, c.A_BINORMALS))
 
-    def tslight(self, pair_slot, V):
-        o = 3 * int(self.pair_vert_offset[pair_slot])
-        return tuple(self.ctx.download(w, o, 3 * V, np.float32).reshape(V, 3) for w in (c.A_LIGHTP, c.A_TSH))
+    def tslight(self, pair_slot, rows):
+        """rows = V (per-vertex rows) or 3T (per-corner rows of a non-smooth MD2)"""
+        o = 3 * int(self.pair_ts_offset[pair_slot])
+        return tuple(self.ctx.download(w, o, 3 * rows, np.float32).reshape(rows, 3) for w in (c.A_LIGHTP, c.A_TSH))
 
     def trisverts(self, pair_slot, max_verts=36 * 8192 // 3):
         """The reference's expanded stream (TrisVerts, TrisCounter) for one pair slot."""

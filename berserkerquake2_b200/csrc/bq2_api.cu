@@ -90,7 +90,7 @@ struct bq2_ctx {
 
     /* frame state */
     std::vector<int32_t>  ent_slot_first, pair_slot_first;
-    std::vector<uint32_t> ent_vert_off, pair_vert_off, pair_bits_off, ent_tb_off;
+    std::vector<uint32_t> ent_vert_off, pair_vert_off, pair_bits_off, ent_tb_off, pair_ts_off;
     std::vector<uint32_t> pair_slot_ent, cursor;                 /* scratch for the counting sort */
     std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
     std::vector<int32_t>  pair_slot_entslot;
@@ -520,7 +520,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         ctx->pair_slot_first[p] = nPS; nPS += ctx->models[fd->ents[e].model].n_mesh;
     }
     ctx->pair_slot_first[nP] = nPS;
-    ctx->pair_vert_off.resize((size_t)nPS + 1); ctx->pair_bits_off.resize((size_t)nPS + 1);
+    ctx->pair_vert_off.resize((size_t)nPS + 1); ctx->pair_bits_off.resize((size_t)nPS + 1); ctx->pair_ts_off.resize((size_t)nPS + 1);
     ctx->slot_mesh_V.resize((size_t)nPS); ctx->slot_mesh_T.resize((size_t)nPS); ctx->pair_slot_entslot.resize((size_t)nPS);
 
     size_t rec_bytes = (size_t)nES * sizeof(bq2_dev_ent) + (size_t)nPS * sizeof(bq2_dev_pair);
@@ -582,7 +582,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
 
     tr.lap(2);
     /* pair slots: offsets in caller order, then a counting sort by entity slot for the kernel */
-    uint32_t pvoff = 0, pboff = 0;
+    uint32_t pvoff = 0, pboff = 0, ptsoff = 0;
     for (int p = 0; p < nP; p++) {
         int e = fd->pairs[p].entity;
         const bool dead = e < 0;
@@ -591,14 +591,16 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         for (int m = 0; m < mo.n_mesh; m++) {
             int ps = ctx->pair_slot_first[p] + m, es = ctx->ent_slot_first[e] + m;
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
-            ctx->pair_vert_off[ps] = pvoff; ctx->pair_bits_off[ps] = pboff;
+            ctx->pair_vert_off[ps] = pvoff; ctx->pair_bits_off[ps] = pboff; ctx->pair_ts_off[ps] = ptsoff;
+            /* LightP / tsH rows: per vertex, or per triangle corner for a non-smooth MD2 (M:64943-65017) */
+            ptsoff += (uint32_t)(((me.flags & BQ2_MESH_SMOOTH) ? me.V : 3 * me.T) + 3) & ~3u;
             ctx->slot_mesh_V[ps] = me.V; ctx->slot_mesh_T[ps] = me.T; ctx->pair_slot_entslot[ps] = es;
             pvoff += (uint32_t)(me.V + 3) & ~3u;
             pboff += (uint32_t)(me.T + 31) >> 5;
             if (mo.casts[m] && !dead) ctx->cursor[es]++;
         }
     }
-    ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff;
+    ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff; ctx->pair_ts_off[nPS] = ptsoff;
     uint32_t n_dev_pairs = 0;
     {
         uint32_t run = 0;
@@ -620,7 +622,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             bq2_dev_pair &d = hp[ctx->cursor[es]++];
             for (int k = 0; k < 3; k++) { d.light[k] = P.light[k]; d.view[k] = P.view[k]; }
             d.scale = P.scale; d.vert_off = ctx->pair_vert_off[ps]; d.bits_off = ctx->pair_bits_off[ps];
-            d.slot = (uint32_t)ps; d.pad[0] = d.pad[1] = 0;
+            d.slot = (uint32_t)ps; d.pad[0] = ctx->pair_ts_off[ps]; d.pad[1] = 0;
         }
     }
 
@@ -643,8 +645,8 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     }
     if (want & BQ2_WANT_TSLIGHT) {
         if (!(want & BQ2_WANT_NTB)) return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_TSLIGHT needs BQ2_WANT_NTB");
-        CK(ctx->lightp.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(lightp)");
-        CK(ctx->tsh.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(tsh)");
+        CK(ctx->lightp.ensure(3 * (size_t)ptsoff + 4), "cudaMalloc(lightp)");
+        CK(ctx->tsh.ensure(3 * (size_t)ptsoff + 4), "cudaMalloc(tsh)");
     }
     if (team_rows) CK(ctx->tri_normals.ensure(4 * (size_t)team_rows + 4), "cudaMalloc(triangle normals)");
     CK(h_counts.ensure(sizeof(uint32_t) * ((size_t)nPS + 1)), "cudaMallocHost(counts)");
@@ -710,6 +712,7 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
     o.ent_slot_first = ctx->ent_slot_first.data(); o.pair_slot_first = ctx->pair_slot_first.data();
     o.ent_vert_offset = ctx->ent_vert_off.data(); o.pair_vert_offset = ctx->pair_vert_off.data();
     o.pair_bits_offset = ctx->pair_bits_off.data(); o.ent_tb_offset = ctx->ent_tb_off.data();
+    o.pair_ts_offset = ctx->pair_ts_off.data();
     o.lerped = ctx->lerped.p; o.extruded = ctx->extruded.p; o.facing_bits = ctx->facing_bits.p;
     o.indices = ctx->indices.p; o.index_count = ctx->index_count.p;
     o.normals = ctx->normals.p; o.tangents = ctx->tangents.p; o.binormals = ctx->binormals.p;
@@ -721,6 +724,7 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
         const unsigned long long *t = (const unsigned long long *)((const uint32_t *)ctx->hcnt[k].p + (((size_t)m.n_pair_slots + 1) & ~(size_t)1));
         o.total_indices = t[0]; o.overflow_pairs = (int32_t)t[1];
         o.pair_slot_first = nullptr;                             /* slot p is caller pair p */
+        o.pair_ts_offset = nullptr;
         o.pair_vert_offset = m.tables ? ctx->world_pvoff.data() : nullptr;
         o.pair_bits_offset = m.tables ? ctx->world_pboff.data() : nullptr;
         if (t[2]) { o.total_pairs = (uint64_t)m.n_pair_slots; if (out) *out = o; return fail(ctx, BQ2_E_INVALID, "bq2_world: a pair refers to an entity or light out of range (it was skipped)"); }

@@ -62,10 +62,10 @@ typedef struct bq2_dev_pair {
     float    light[3];
     float    scale;
     float    view[3];
-    uint32_t vert_off;      /* first vertex row in extruded[] / lightp[] / tsh[] */
+    uint32_t vert_off;      /* first vertex row in extruded[]                     */
     uint32_t bits_off;      /* first u32 word in facing_bits[]                   */
     uint32_t slot;          /* pair slot in caller order: indices + slot*stride  */
-    uint32_t pad[2];
+    uint32_t pad[2];        /* [0] = first row in lightp[] / tsh[] (host-built records) */
 } bq2_dev_pair;             /* 48 bytes */
 
 /* ---- device-side record building ("world" path) ------------------------------------------------

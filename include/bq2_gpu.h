@@ -143,7 +143,7 @@ typedef struct bq2_frame_out {
     uint32_t *indices;         /* [n_pair_slots][index_stride] canonical index form, see DESIGN.md    */
     uint32_t *index_count;     /* [n_pair_slots]   == TrisCounter                                     */
     float    *normals, *tangents, *binormals;   /* [ent rows][3]  (BQ2_WANT_NTB)                      */
-    float    *lightp, *tsh;                     /* [pair verts][3] (BQ2_WANT_TSLIGHT, smooth models)  */
+    float    *lightp, *tsh;                     /* [pair ts rows][3] (BQ2_WANT_TSLIGHT), see pair_ts_offset */
     uint32_t index_stride;
     /* totals, valid after bq2_frame / bq2_frame_wait */
     uint64_t total_lerped_verts;   /* sum of V over entity slots                                      */
@@ -151,6 +151,9 @@ typedef struct bq2_frame_out {
     uint64_t total_pairs;          /* pair slots processed                                            */
     int32_t  overflow_pairs;       /* pair slots whose true count exceeded index_stride (count is the
                                       true count; only the first index_stride words were written)     */
+    const uint32_t *pair_ts_offset;     /* HOST, n_pair_slots+1 : first row of the slot in lightp / tsh.  Rows are
+                                           per vertex (MD3, MD2 with RF_SMOOTHVECS) or per triangle corner, 3T of
+                                           them in (triangle, corner) order, for a non-smooth MD2 (M:64943-65017) */
 } bq2_frame_out;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

@@ -203,7 +203,7 @@ def test_gpu_md2_light_family(gpu_ctx, kind):
         ents = np.array([host.entity_md2(blob, f, of, bl, z, z, z, model=mid)], bq2.ENTITY_DTYPE)
         pairs = np.zeros(1, bq2.PAIR_DTYPE)
         pairs["light"][0] = G["light/light"]; pairs["view"][0] = G["light/view"]; pairs["scale"][0] = 9600
-        want = bq2.WANT_SHADOW | bq2.WANT_NTB | (bq2.WANT_TSLIGHT if kind == "smooth" else 0)
+        want = bq2.WANT_SHADOW | bq2.WANT_NTB | bq2.WANT_TSLIGHT
         res = gpu_ctx.frame(ents, pairs, want=want)
         rows = V if kind == "smooth" else T
         row = idx.reshape(-1) if kind == "smooth" else np.repeat(np.arange(T), 3)
@@ -212,6 +212,9 @@ def test_gpu_md2_light_family(gpu_ctx, kind):
         if kind == "smooth":        # the reference expands per corner; per-vertex rows gathered by index are identical
             lp, ts = res.tslight(0, V)
             assert same(lp[row], G[f"{tag}/{i}/lightp"]) and same(ts[row], G[f"{tag}/{i}/tsh"])
+        else:                       # per-corner rows, exactly the reference's arrays
+            lp, ts = res.tslight(0, 3 * T)
+            assert same(lp, G[f"{tag}/{i}/lightp"]) and same(ts, G[f"{tag}/{i}/tsh"])
 
 
 @pytest.mark.gpu

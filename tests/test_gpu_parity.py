@@ -202,7 +202,7 @@ def test_md2_tangent_space_basis(gpu_ctx, oracle, smooth):
     we["model"] = mid
     view = np.array([100.0, -50.0, 80.0], np.float32)
     ents, pairs = gpu_ctx.build_records(we, wl, pe, pl, view_world=view)
-    want = bq2.WANT_SHADOW | bq2.WANT_NTB | (bq2.WANT_TSLIGHT if smooth else 0)
+    want = bq2.WANT_SHADOW | bq2.WANT_NTB | bq2.WANT_TSLIGHT
     res = gpu_ctx.frame(ents, pairs, want=want)
     from berserkerquake2_b200 import synth
     for e in range(5):
@@ -217,13 +217,18 @@ def test_md2_tangent_space_basis(gpu_ctx, oracle, smooth):
         N, T_, B = oracle.ntb_rows(nc, no, m.tangents[f], m.tangents[of], m.binormals[f], m.binormals[of], bl, fl)
         gN, gT, gB = res.ntb(e, rows)
         assert np.array_equal(bits(gN), bits(N)) and np.array_equal(bits(gT), bits(T_)) and np.array_equal(bits(gB), bits(B))
-        if smooth:
-            P = oracle.md2_lerp(m.blob, f, of, bl, we["origin"][e], we["oldorigin"][e], we["angles"][e])
-            for l in range(2):
-                p = 2 * e + l
+        P = oracle.md2_lerp(m.blob, f, of, bl, we["origin"][e], we["oldorigin"][e], we["angles"][e])
+        corner = m.idx.reshape(-1)
+        for l in range(2):
+            p = 2 * e + l
+            if smooth:
                 lp, ts = oracle.tslight(P, N, T_, B, pairs["light"][p], pairs["view"][p])
                 gl, gt = res.tslight(p, m.V)
-                assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
+            else:                           # per corner, the triangle's basis (M:64972-64986)
+                row = np.repeat(np.arange(m.T), 3)
+                lp, ts = oracle.tslight(P[corner], N[row], T_[row], B[row], pairs["light"][p], pairs["view"][p])
+                gl, gt = res.tslight(p, 3 * m.T)
+            assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
 
 
 def test_md3_tangent_space_basis(gpu_ctx, oracle):
