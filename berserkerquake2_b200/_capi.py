@@ -112,6 +112,14 @@ EXPORTS_GPU_H = [
     _sig("bq2_gpu_md3_neighbours", C.c_int, vp, vp, i32, vp),
     _sig("bq2_gpu_md2_tangents", C.c_int, vp, vp, C.c_size_t, vp, f32, C.c_int, vp, vp, vp),
     _sig("bq2_gpu_md3_tangents", C.c_int, vp, vp, i32, i32, vp, vp, i32),
+    _sig("bq2_block_checksum", C.c_uint32, vp, C.c_size_t),
+    _sig("bq2_host_md2_from_file", C.c_int, vp, C.c_size_t, f32, C.c_int, vp, C.c_size_t, vp),
+    _sig("bq2_md2_cache_bytes", C.c_size_t, C.c_int, i32, i32, i32),
+    _sig("bq2_md2_cache_write", C.c_int, vp, C.c_size_t, C.c_int, f32, vp, i32, i32, i32, vp, vp, vp),
+    _sig("bq2_md2_cache_read", C.c_int, vp, C.c_size_t, C.c_int, f32, i32, i32, i32, vp, vp, vp, vp, C.POINTER(i32)),
+    _sig("bq2_md3_cache_bytes", C.c_size_t, i32, i32),
+    _sig("bq2_md3_cache_write", C.c_int, vp, C.c_size_t, u32, vp, i32, i32),
+    _sig("bq2_md3_cache_read", C.c_int, vp, C.c_size_t, u32, vp, i32, i32),
     _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
     _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),

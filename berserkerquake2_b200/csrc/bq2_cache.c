@@ -1,0 +1,203 @@
+/*
+ * bq2_cache.c -- the data formats either side of the path, host C:
+ *   - an MD2 file image -> the in-memory image the engine (and bq2_upload_md2) works on
+ *     (Mod_LoadAliasModel M:51216-51345: sanity checks, load scale, optional winding inversion, float st);
+ *   - the engine's precompute cache files, so a model's neighbour table and tangent-space bytes can be
+ *     exchanged with an existing installation instead of being recomputed:
+ *       MD2  <gamedir>/cache/<model>        write M:51811-51838, read + validation M:51501-51606
+ *       MD3  <gamedir>/cache/<model>_<mesh> write M:51017-51034, read M:50919-50947
+ *   - Com_BlockChecksum (M:40589-40602): the four words of an MD4 digest (RFC 1320) XOR-ed together.
+ * Everything works on memory buffers; the caller does the file I/O.
+ */
+#include "bq2_gpu.h"
+#include <string.h>
+
+/* ---- MD4 (RFC 1320), folded to 32 bits as Com_BlockChecksum does --------------------------------------- */
+#define ROL(x, n) (((x) << (n)) | ((x) >> (32 - (n))))
+static void md4_block(uint32_t st[4], const uint8_t *p)
+{
+    uint32_t x[16], a = st[0], b = st[1], c = st[2], d = st[3];
+    static const int r1[4] = {3, 7, 11, 19}, r2[4] = {3, 5, 9, 13}, r3[4] = {3, 9, 11, 15};
+    static const int o2[16] = {0, 4, 8, 12, 1, 5, 9, 13, 2, 6, 10, 14, 3, 7, 11, 15};
+    static const int o3[16] = {0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15};
+    int i;
+    for (i = 0; i < 16; i++)
+        x[i] = (uint32_t)p[4*i] | (uint32_t)p[4*i+1] << 8 | (uint32_t)p[4*i+2] << 16 | (uint32_t)p[4*i+3] << 24;
+    for (i = 0; i < 16; i++) {          /* round 1: F(b,c,d) = (b & c) | (~b & d) */
+        uint32_t t = a + ((b & c) | (~b & d)) + x[i];
+        a = d; d = c; c = b; b = ROL(t, r1[i & 3]);
+    }
+    for (i = 0; i < 16; i++) {          /* round 2: G = majority, + 0x5A827999 */
+        uint32_t t = a + ((b & c) | (b & d) | (c & d)) + x[o2[i]] + 0x5A827999u;
+        a = d; d = c; c = b; b = ROL(t, r2[i & 3]);
+    }
+    for (i = 0; i < 16; i++) {          /* round 3: H = xor, + 0x6ED9EBA1 */
+        uint32_t t = a + (b ^ c ^ d) + x[o3[i]] + 0x6ED9EBA1u;
+        a = d; d = c; c = b; b = ROL(t, r3[i & 3]);
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d;
+}
+
+uint32_t bq2_block_checksum(const void *buffer, size_t length)
+{
+    uint32_t st[4] = {0x67452301u, 0xefcdab89u, 0x98badcfeu, 0x10325476u};
+    const uint8_t *p = (const uint8_t *)buffer;
+    uint8_t tail[128];
+    size_t n = length, rem, pad;
+    uint64_t bits = (uint64_t)length * 8;
+    int i;
+    while (n >= 64) { md4_block(st, p); p += 64; n -= 64; }
+    rem = n;
+    memset(tail, 0, sizeof tail);
+    if (rem) memcpy(tail, p, rem);
+    tail[rem] = 0x80;
+    pad = rem < 56 ? 64 : 128;
+    for (i = 0; i < 8; i++) tail[pad - 8 + i] = (uint8_t)(bits >> (8 * i));
+    md4_block(st, tail);
+    if (pad == 128) md4_block(st, tail + 64);
+    return st[0] ^ st[1] ^ st[2] ^ st[3];
+}
+
+/* ---- MD2 file -> in-memory image (M:51216-51345) ------------------------------------------------------- */
+typedef struct {
+    int32_t ident, version, skinwidth, skinheight, framesize;
+    int32_t num_skins, num_xyz, num_st, num_tris, num_glcmds, num_frames;
+    int32_t ofs_skins, ofs_st, ofs_tris, ofs_frames, ofs_glcmds, ofs_end;
+} md2_header;
+
+bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float scale, int invert,
+                                  void *blob_out, size_t blob_capacity, float *st_out)
+{
+    const md2_header *h = (const md2_header *)file;
+    const uint8_t *in = (const uint8_t *)file;
+    uint8_t *out = (uint8_t *)blob_out;
+    int i, j;
+    if (!file || !blob_out || file_bytes < sizeof *h) return BQ2_E_INVALID;
+    if (scale <= 0.001) return BQ2_E_INVALID;                                   /* "invalid scale" */
+    if (h->version != 8) return BQ2_E_INVALID;                                  /* ALIAS_VERSION */
+    if (h->num_xyz <= 0 || h->num_st <= 0 || h->num_tris <= 0 || h->num_frames <= 0) return BQ2_E_INVALID;
+    if (h->num_xyz > BQ2_MD2_MAX_VERTS || h->num_tris > BQ2_MD2_MAX_TRIANGLES) return BQ2_E_LIMIT;
+    if (h->ofs_end < (int32_t)sizeof *h || (size_t)h->ofs_end > file_bytes || (size_t)h->ofs_end > blob_capacity) return BQ2_E_INVALID;
+    if (h->framesize < 40 + 4 * h->num_xyz || h->ofs_tris < 0 || h->ofs_frames < 0 || h->ofs_st < 0 ||
+        (size_t)h->ofs_tris + 12u * (size_t)h->num_tris > (size_t)h->ofs_end ||
+        (size_t)h->ofs_st + 4u * (size_t)h->num_st > (size_t)h->ofs_end ||
+        (size_t)h->ofs_frames + (size_t)h->num_frames * (size_t)h->framesize > (size_t)h->ofs_end)
+        return BQ2_E_INVALID;
+    memcpy(out, in, (size_t)h->ofs_end);                    /* little-endian host: LittleLong/LittleShort are identities */
+    {
+        const int16_t *pin = (const int16_t *)(in + h->ofs_tris);
+        int16_t *pout = (int16_t *)(out + h->ofs_tris);
+        if (invert)                                         /* invert the index sequence, M:51274-51281 */
+            for (i = 0; i < h->num_tris; i++)
+                for (j = 0; j < 3; j++) { pout[6*i + j] = pin[6*i + 2 - j]; pout[6*i + 3 + j] = pin[6*i + 3 + 2 - j]; }
+    }
+    for (i = 0; i < h->num_frames; i++) {
+        const float *fi = (const float *)(in + h->ofs_frames + (size_t)i * h->framesize);
+        float *fo = (float *)(out + h->ofs_frames + (size_t)i * h->framesize);
+        for (j = 0; j < 3; j++) { fo[j] = fi[j] * scale; fo[3 + j] = fi[3 + j] * scale; }
+        if (invert) { fo[1] = -fo[1]; fo[4] = -fo[4]; }
+    }
+    if (st_out) {                                           /* fstvert_t, M:51322-51329 */
+        const int16_t *pst = (const int16_t *)(in + h->ofs_st);
+        float iw = 1.0 / h->skinwidth, ih = 1.0 / h->skinheight;
+        for (i = 0; i < h->num_st; i++) {
+            float s = pst[2*i], t = pst[2*i + 1];
+            st_out[2*i] = (s - 0.5) * iw;
+            st_out[2*i + 1] = (t - 0.5) * ih;
+        }
+    }
+    return BQ2_OK;
+}
+
+/* ---- MD2 cache file ------------------------------------------------------------------------------------ */
+/* layout (M:51811-51838): u8 smooth; u32 (unsigned)(smooth_cosine * 0x7fffffff); u32 crc; neighbours_t[T];
+ * u32 crc; binormals[rows*F]; u32 crc; tangents[rows*F]; and when !smooth: u32 crc; normals[rows*F] */
+size_t bq2_md2_cache_bytes(int smooth, int32_t num_tris, int32_t rows, int32_t num_frames)
+{
+    size_t cx = (size_t)rows * (size_t)num_frames;
+    return 1 + 4 + 4 + 12 * (size_t)num_tris + (smooth ? 2 : 3) * (4 + cx);
+}
+static uint32_t cache_angle(float smooth_cosine) { return (unsigned)(smooth_cosine * 0x7fffffff); }
+static uint8_t *put(uint8_t *p, const void *src, size_t n) { memcpy(p, src, n); return p + n; }
+
+bq2_status bq2_md2_cache_write(void *out, size_t capacity, int smooth, float smooth_cosine,
+                               const int32_t *neighbours, int32_t num_tris, int32_t rows, int32_t num_frames,
+                               const uint8_t *binormals, const uint8_t *tangents, const uint8_t *normals)
+{
+    uint8_t *p = (uint8_t *)out, sm = smooth ? 1 : 0;
+    size_t cx = (size_t)rows * (size_t)num_frames, ax = 12 * (size_t)num_tris;
+    uint32_t w;
+    if (!out || !neighbours || !binormals || !tangents || (!smooth && !normals) || num_tris <= 0 || rows <= 0 || num_frames <= 0)
+        return BQ2_E_INVALID;
+    if (capacity < bq2_md2_cache_bytes(smooth, num_tris, rows, num_frames)) return BQ2_E_LIMIT;
+    p = put(p, &sm, 1);
+    w = cache_angle(smooth_cosine); p = put(p, &w, 4);
+    w = bq2_block_checksum(neighbours, ax); p = put(p, &w, 4); p = put(p, neighbours, ax);
+    w = bq2_block_checksum(binormals, cx); p = put(p, &w, 4); p = put(p, binormals, cx);
+    w = bq2_block_checksum(tangents, cx); p = put(p, &w, 4); p = put(p, tangents, cx);
+    if (!smooth) { w = bq2_block_checksum(normals, cx); p = put(p, &w, 4); p = put(p, normals, cx); }
+    return BQ2_OK;
+}
+
+/* Returns BQ2_OK; BQ2_E_INVALID for "invalid cache" (smooth flag or angle differs, truncated, neighbour checksum);
+ * BQ2_E_OVERFLOW is never used here; a tangent-space checksum mismatch ("invalid checksum!") is BQ2_E_LIMIT + 0:
+ * reported as BQ2_E_INVALID too, with *why = 2 (1 = invalid cache). */
+bq2_status bq2_md2_cache_read(const void *in, size_t bytes, int smooth, float smooth_cosine,
+                              int32_t num_tris, int32_t rows, int32_t num_frames,
+                              int32_t *neighbours, uint8_t *binormals, uint8_t *tangents, uint8_t *normals, int32_t *why)
+{
+    const uint8_t *p = (const uint8_t *)in;
+    size_t cx = (size_t)rows * (size_t)num_frames, ax = 12 * (size_t)num_tris;
+    uint32_t ang, cs_tris, cs_b, cs_t, cs_n = 0;
+    if (why) *why = 1;
+    if (!in || !neighbours || !binormals || !tangents || (!smooth && !normals)) return BQ2_E_INVALID;
+    if (bytes < 1 || (p[0] != 0) != (smooth != 0)) return BQ2_E_INVALID;            /* M:51503 */
+    if (bytes < bq2_md2_cache_bytes(smooth, num_tris, rows, num_frames)) return BQ2_E_INVALID;
+    memcpy(&ang, p + 1, 4);
+    if (ang != cache_angle(smooth_cosine)) return BQ2_E_INVALID;                     /* M:51508 */
+    p += 5;
+    memcpy(&cs_tris, p, 4); p += 4; memcpy(neighbours, p, ax); p += ax;
+    memcpy(&cs_b, p, 4); p += 4; memcpy(binormals, p, cx); p += cx;
+    memcpy(&cs_t, p, 4); p += 4; memcpy(tangents, p, cx); p += cx;
+    if (!smooth) { memcpy(&cs_n, p, 4); p += 4; memcpy(normals, p, cx); p += cx; }
+    if (bq2_block_checksum(neighbours, ax) != cs_tris) return BQ2_E_INVALID;          /* M:51580-51586 */
+    if (why) *why = 2;
+    if (bq2_block_checksum(binormals, cx) != cs_b || bq2_block_checksum(tangents, cx) != cs_t ||
+        (!smooth && bq2_block_checksum(normals, cx) != cs_n)) return BQ2_E_INVALID;  /* M:51590-51604 */
+    if (why) *why = 0;
+    return BQ2_OK;
+}
+
+/* ---- MD3 per-mesh cache file (M:51017-51034 / M:50919-50947) ------------------------------------------- */
+/* u32 file checksum (Com_BlockChecksum of the .md3 file), then {normal, tangent, binormal} per vertex per frame.
+ * vertexes = maliasvertex_t[num_frames * num_verts] (16 bytes each, bytes 12..14). */
+size_t bq2_md3_cache_bytes(int32_t num_frames, int32_t num_verts) { return 4 + 3 * (size_t)num_frames * (size_t)num_verts; }
+
+bq2_status bq2_md3_cache_write(void *out, size_t capacity, uint32_t file_checksum, const void *vertexes,
+                               int32_t num_frames, int32_t num_verts)
+{
+    uint8_t *p = (uint8_t *)out;
+    const uint8_t *v = (const uint8_t *)vertexes;
+    size_t n = (size_t)num_frames * (size_t)num_verts, i;
+    if (!out || !vertexes || num_frames <= 0 || num_verts <= 0) return BQ2_E_INVALID;
+    if (capacity < bq2_md3_cache_bytes(num_frames, num_verts)) return BQ2_E_LIMIT;
+    memcpy(p, &file_checksum, 4); p += 4;
+    for (i = 0; i < n; i++) { p[0] = v[16*i + 12]; p[1] = v[16*i + 13]; p[2] = v[16*i + 14]; p += 3; }
+    return BQ2_OK;
+}
+
+bq2_status bq2_md3_cache_read(const void *in, size_t bytes, uint32_t file_checksum, void *vertexes,
+                              int32_t num_frames, int32_t num_verts)
+{
+    const uint8_t *p = (const uint8_t *)in;
+    uint8_t *v = (uint8_t *)vertexes;
+    size_t n = (size_t)num_frames * (size_t)num_verts, i;
+    uint32_t cs;
+    if (!in || !vertexes || bytes < 4) return BQ2_E_INVALID;
+    memcpy(&cs, p, 4);
+    if (cs != file_checksum) return BQ2_E_INVALID;                                    /* "invalid cache", M:50921-50923 */
+    if (bytes < bq2_md3_cache_bytes(num_frames, num_verts)) return BQ2_E_INVALID;     /* short read, M:50929-50937 */
+    p += 4;
+    for (i = 0; i < n; i++) { v[16*i + 12] = p[0]; v[16*i + 13] = p[1]; v[16*i + 14] = p[2]; p += 3; }
+    return BQ2_OK;
+}

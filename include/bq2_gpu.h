@@ -277,6 +277,33 @@ bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *dmdl_blob, size_t blob
 bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t num_frames, int32_t num_verts,
                                 const float *st, const uint16_t *indexes, int32_t num_tris);
 
+/* ---- the data formats either side of the path (host C, memory buffers) ------------------ */
+/* Com_BlockChecksum, M:40589-40602: the four words of an MD4 digest XOR-ed. */
+uint32_t   bq2_block_checksum(const void *buffer, size_t length);
+/* An MD2 FILE image -> the in-memory image the engine keeps (Mod_LoadAliasModel M:51216-51345: the load-time
+ * checks, frame scale/translate multiplied by `scale`, winding inverted when `invert`) and its float st
+ * (st_out = float[num_st][2], may be NULL).  blob_out needs header.ofs_end bytes. */
+bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float scale, int invert,
+                                  void *blob_out, size_t blob_capacity, float *st_out);
+/* The engine's MD2 precompute cache file <gamedir>/cache/<model> (write M:51811-51838, read M:51501-51606).
+ * rows = num_xyz when smooth (RF_SMOOTHVECS) else num_tris.  read: *why = 0 ok, 1 "invalid cache" (flag, angle,
+ * size or neighbour checksum), 2 "invalid checksum!" (a tangent-space array). */
+size_t     bq2_md2_cache_bytes(int smooth, int32_t num_tris, int32_t rows, int32_t num_frames);
+bq2_status bq2_md2_cache_write(void *out, size_t capacity, int smooth, float smooth_cosine,
+                               const int32_t *neighbours, int32_t num_tris, int32_t rows, int32_t num_frames,
+                               const uint8_t *binormals, const uint8_t *tangents, const uint8_t *normals);
+bq2_status bq2_md2_cache_read(const void *in, size_t bytes, int smooth, float smooth_cosine,
+                              int32_t num_tris, int32_t rows, int32_t num_frames,
+                              int32_t *neighbours, uint8_t *binormals, uint8_t *tangents, uint8_t *normals,
+                              int32_t *why);
+/* The per-mesh MD3 cache file <gamedir>/cache/<model>_<mesh> (M:51017-51034, 50919-50947): the .md3 file's
+ * checksum, then {normal, tangent, binormal} per vertex per frame, to / from maliasvertex_t rows. */
+size_t     bq2_md3_cache_bytes(int32_t num_frames, int32_t num_verts);
+bq2_status bq2_md3_cache_write(void *out, size_t capacity, uint32_t file_checksum, const void *vertexes,
+                               int32_t num_frames, int32_t num_verts);
+bq2_status bq2_md3_cache_read(const void *in, size_t bytes, uint32_t file_checksum, void *vertexes,
+                              int32_t num_frames, int32_t num_verts);
+
 /* ---- the renderer's loop nest, flattened (host, C) -------------------------------------------- */
 /* The fields of entity_t (defs.h:573-618) and shadowlight_t (defs.h:3927-3973) this path reads. */
 typedef struct bq2_world_entity {

@@ -449,5 +449,7 @@ void bq2ref_vecs_for_tris(float *v0, float *v1, float *v2, float *st0, float *st
 { VecsForTris(v0, v1, v2, st0, st1, st2, tan, bin); }
 void bq2ref_tangent_for_tri_md3(uint16_t *index, void *verts, float *st, float *tan, float *bin)
 { TangentForTrimd3((WORD *)index, (maliasvertex_t *)verts, (maliascoord_t *)st, tan, bin); }
+unsigned Com_BlockChecksum(void *buffer, int length);                 /* M:40589 */
+unsigned bq2ref_block_checksum(void *buffer, int length) { return Com_BlockChecksum(buffer, length); }
 void bq2ref_angle_vectors(float *angles, float *f, float *r, float *u) { AngleVectors(angles, f, r, u); }
 float bq2ref_vector_normalize(float *v) { return VectorNormalize(v); }

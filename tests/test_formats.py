@@ -1,0 +1,164 @@
+"""the data formats either side of the path -- MD2 file -> in-memory image, the engine's
+precompute cache files, Com_BlockChecksum.  CPU tests; the last one (gpu) runs a model from file bytes to shadow
+volumes with every load-time table computed on the device and exchanged through a cache file."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import berserkerquake2_b200 as bq2
+from berserkerquake2_b200 import _capi as c, synth, host
+from scenes import SMOOTH_COSINE, bits
+
+L = c.lib
+
+
+def checksum(buf):
+    a = np.ascontiguousarray(buf).view(np.uint8)
+    return int(L.bq2_block_checksum(c.ptr(a) if a.size else None, a.size))
+
+
+def test_md4_published_vectors():
+    """RFC 1320 appendix A.5 digests, folded the way Com_BlockChecksum (M:40589-40602) folds them."""
+    kat = {b"": "31d6cfe0d16ae931b73c59d7e0c089c0", b"a": "bde52cb31de33e46245e05fbdbd6fb24",
+           b"abc": "a448017aaf21d8525fc10ae87aa6729d", b"message digest": "d9130a8164549fe818874806e1c7014b",
+           b"abcdefghijklmnopqrstuvwxyz": "d79e1c308aa5bbcdeea8ed63df412da9",
+           b"ABCDEFGHIJKLMNOPQRSTUVWXYZabcdefghijklmnopqrstuvwxyz0123456789": "043f8582f241db351ce627e153e7f0e4",
+           b"1234567890" * 8: "e33b4ddc9c38f2199c3e7b164fcc0536"}
+    for msg, hexd in kat.items():
+        w = np.frombuffer(bytes.fromhex(hexd), "<u4")
+        assert checksum(np.frombuffer(msg, np.uint8)) == int(w[0] ^ w[1] ^ w[2] ^ w[3]), msg
+
+
+def test_checksum_matches_reference(ref):
+    ref.lib.bq2ref_block_checksum.restype = C.c_uint32
+    ref.lib.bq2ref_block_checksum.argtypes = [C.c_void_p, C.c_int]
+    rng = np.random.RandomState(0)
+    for n in list(range(0, 130)) + [255, 256, 1000, 6144, 12288, 51084]:
+        a = rng.randint(0, 256, n).astype(np.uint8)
+        want = ref.lib.bq2ref_block_checksum(a.ctypes.data_as(C.c_void_p) if n else None, n)
+        assert checksum(a) == want, n
+
+
+def md2_from_file(file, scale=1.0, invert=False):
+    h = synth.md2_header(file)
+    blob = np.zeros(int(h["ofs_end"]), np.uint8)
+    st = np.zeros((int(h["num_st"]), 2), np.float32)
+    rc = L.bq2_host_md2_from_file(c.ptr(file), file.nbytes, scale, int(invert), c.ptr(blob), blob.nbytes, c.ptr(st))
+    return rc, blob, st
+
+
+def test_md2_file_to_memory():
+    file = synth.md2(8, 5, 3, 4)                      # the generator emits the on-disk layout with scale 1
+    rc, blob, st = md2_from_file(file)
+    assert rc == 0 and np.array_equal(blob, file) and np.array_equal(st, synth.md2_st(file))
+    rc, blob, _ = md2_from_file(file, scale=2.5)
+    assert rc == 0
+    h = synth.md2_header(file)
+    for f in range(3):
+        o = int(h["ofs_frames"]) + f * int(h["framesize"])
+        assert np.array_equal(blob[o:o + 24].view("<f4"), file[o:o + 24].view("<f4") * np.float32(2.5))
+        assert np.array_equal(blob[o + 24:o + int(h["framesize"])], file[o + 24:o + int(h["framesize"])])
+    rc, inv, _ = md2_from_file(file, invert=True)      # winding reversed, y mirrored (M:51274-51281, 51303-51307)
+    assert rc == 0
+    assert np.array_equal(synth.md2_tris(inv)[:, :3], synth.md2_tris(file)[:, 2::-1])
+    assert np.array_equal(synth.md2_tris(inv)[:, 3:], synth.md2_tris(file)[:, :2:-1])
+    o = int(h["ofs_frames"])
+    a, b = inv[o:o + 24].view("<f4"), file[o:o + 24].view("<f4")
+    assert a[1] == -b[1] and a[4] == -b[4] and a[0] == b[0] and a[5] == b[5]
+    # the loader's checks (Com_Error in the reference, status codes here)
+    bad = file.copy(); bad[4:8].view("<i4")[0] = 7
+    assert md2_from_file(bad)[0] == -1                                   # wrong version number
+    bad = file.copy(); bad[24:28].view("<i4")[0] = 5000
+    assert md2_from_file(bad)[0] == -4                                   # too many vertices
+    bad = file.copy(); bad[32:36].view("<i4")[0] = 0
+    assert md2_from_file(bad)[0] == -1                                   # no triangles
+    assert md2_from_file(file, scale=0.0)[0] == -1                       # invalid scale
+    assert md2_from_file(file[:100])[0] == -1                            # truncated
+
+
+@pytest.mark.parametrize("smooth", [True, False])
+def test_md2_cache_roundtrip_and_validation(oracle, smooth):
+    blob = synth.md2(10, 7, 4, 6); st = synth.md2_st(blob)
+    h = synth.md2_header(blob); V, T, F = int(h["num_xyz"]), int(h["num_tris"]), int(h["num_frames"])
+    nb = host.md2_neighbours(blob)
+    if smooth:
+        nm = None; tn, bn = oracle.md2_tangents_smooth(blob, st, SMOOTH_COSINE); rows = V
+    else:
+        nm, tn, bn = oracle.md2_tangents_flat(blob, st); rows = T
+    n = L.bq2_md2_cache_bytes(int(smooth), T, rows, F)
+    assert n == 1 + 4 + 4 + 12 * T + (2 if smooth else 3) * (4 + rows * F)
+    buf = np.zeros(n, np.uint8)
+    assert L.bq2_md2_cache_write(c.ptr(buf), n, int(smooth), SMOOTH_COSINE, c.ptr(nb), T, rows, F, c.ptr(bn), c.ptr(tn), c.ptr(nm)) == 0
+    # layout, field by field (M:51811-51838)
+    assert buf[0] == int(smooth) and buf[1:5].view("<u4")[0] == int(np.float32(SMOOTH_COSINE) * np.float32(0x7fffffff))
+    assert buf[5:9].view("<u4")[0] == checksum(nb) and np.array_equal(buf[9:9 + 12 * T].view("<i4").reshape(T, 3), nb)
+    o = 9 + 12 * T
+    assert buf[o:o + 4].view("<u4")[0] == checksum(bn) and np.array_equal(buf[o + 4:o + 4 + rows * F], bn.reshape(-1))
+
+    def read(b, sm=smooth, cosine=SMOOTH_COSINE):
+        nb2 = np.zeros((T, 3), np.int32); o_ = [np.zeros((F, rows), np.uint8) for _ in range(3)]
+        why = C.c_int32(-1)
+        rc = L.bq2_md2_cache_read(c.ptr(b), b.nbytes, int(sm), cosine, T, rows, F, c.ptr(nb2), c.ptr(o_[0]), c.ptr(o_[1]), c.ptr(o_[2]), C.byref(why))
+        return rc, why.value, nb2, o_
+    rc, why, nb2, (b2, t2, n2) = read(buf)
+    assert rc == 0 and why == 0 and np.array_equal(nb2, nb) and np.array_equal(b2, bn) and np.array_equal(t2, tn)
+    if not smooth:
+        assert np.array_equal(n2, nm)
+    assert read(buf, sm=not smooth)[:2] == (-1, 1)                       # smooth flag differs -> invalid cache
+    assert read(buf, cosine=0.5)[:2] == (-1, 1)                          # r_smoothangle changed -> invalid cache
+    assert read(buf[:-1].copy())[:2] == (-1, 1)                          # truncated
+    bad = buf.copy(); bad[20] ^= 1
+    assert read(bad)[:2] == (-1, 1)                                      # neighbour table corrupted
+    bad = buf.copy(); bad[-1] ^= 1
+    assert read(bad)[:2] == (-1, 2)                                      # "invalid checksum!"
+
+
+def test_md3_cache_roundtrip(oracle):
+    verts, idx, st = synth.md3_mesh(8, 5, 3, 2)
+    oracle.md3_tangents(verts, st, idx)
+    F, V = verts.shape
+    n = L.bq2_md3_cache_bytes(F, V)
+    assert n == 4 + 3 * F * V
+    buf = np.zeros(n, np.uint8)
+    assert L.bq2_md3_cache_write(c.ptr(buf), n, 0xdeadbeef, c.ptr(verts), F, V) == 0
+    assert buf[:4].view("<u4")[0] == 0xdeadbeef
+    assert np.array_equal(buf[4:].reshape(F * V, 3), np.stack([verts["normal"], verts["tangent"], verts["binormal"]], -1).reshape(-1, 3))
+    back = verts.copy(); back["normal"] = 0; back["tangent"] = 0; back["binormal"] = 0
+    assert L.bq2_md3_cache_read(c.ptr(buf), n, 0xdeadbeef, c.ptr(back), F, V) == 0
+    assert np.array_equal(back, verts)
+    assert L.bq2_md3_cache_read(c.ptr(buf), n, 0x12345678, c.ptr(back), F, V) == -1      # another .md3 file
+    assert L.bq2_md3_cache_read(c.ptr(buf), n - 1, 0xdeadbeef, c.ptr(back), F, V) == -1  # truncated
+
+
+@pytest.mark.gpu
+def test_file_to_shadow_volume_with_device_precompute(gpu_ctx, oracle):
+    """file bytes -> bq2_host_md2_from_file -> neighbours + tangent bytes on the device -> cache file -> read back
+    -> upload -> frame: the same index buffers and N/T/B rows as the oracle on the oracle's own tables."""
+    from scenes import world_scene
+    import oracle_lib
+    file = synth.md2(12, 9, 5, 33)
+    rc, blob, st = md2_from_file(file, scale=1.5)
+    assert rc == 0
+    h = synth.md2_header(blob); V, T, F = int(h["num_xyz"]), int(h["num_tris"]), int(h["num_frames"])
+    nb = gpu_ctx.gpu_md2_neighbours(blob)
+    _, tn, bn = gpu_ctx.gpu_md2_tangents(blob, st, SMOOTH_COSINE, smooth=True)
+    n = L.bq2_md2_cache_bytes(1, T, V, F)
+    cache = np.zeros(n, np.uint8)
+    assert L.bq2_md2_cache_write(c.ptr(cache), n, 1, SMOOTH_COSINE, c.ptr(nb), T, V, F, c.ptr(bn), c.ptr(tn), None) == 0
+    nb2 = np.zeros((T, 3), np.int32); bn2 = np.zeros((F, V), np.uint8); tn2 = np.zeros((F, V), np.uint8); why = C.c_int32()
+    assert L.bq2_md2_cache_read(c.ptr(cache), n, 1, SMOOTH_COSINE, T, V, F, c.ptr(nb2), c.ptr(bn2), c.ptr(tn2), None, C.byref(why)) == 0
+    assert np.array_equal(nb2, oracle.md2_neighbours(blob))
+    ot, ob = oracle.md2_tangents_smooth(blob, st, SMOOTH_COSINE)
+    assert np.array_equal(tn2, ot) and np.array_equal(bn2, ob)
+    mid = gpu_ctx.upload_md2(blob, nb2, tn2, bn2, None, smooth=True)
+    we, wl, pe, pl = world_scene(3, 2, F, seed=44)
+    we["model"] = mid
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    res = gpu_ctx.frame(ents, pairs, want=bq2.WANT_SHADOW | bq2.WANT_NTB)
+    idx = oracle_lib.md2_idx(blob)
+    for p in range(len(pe)):
+        W = we[pe[p]]
+        w = oracle.md2_pair(blob, nb2, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"], W["oldorigin"],
+                            W["angles"], wl["origin"][pl[p]], 300.0, idx=idx)
+        assert np.array_equal(res.indices(p), w["indices"]) and np.array_equal(bits(res.lerped(int(pe[p]), V)), bits(w["lerped"]))
