@@ -120,6 +120,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_md3_cache_bytes", C.c_size_t, i32, i32),
     _sig("bq2_md3_cache_write", C.c_int, vp, C.c_size_t, u32, vp, i32, i32),
     _sig("bq2_md3_cache_read", C.c_int, vp, C.c_size_t, u32, vp, i32, i32),
+    _sig("bq2_md3_file_info", C.c_int, vp, C.c_size_t, C.POINTER(i32), C.POINTER(i32), vp, vp),
+    _sig("bq2_host_md3_mesh_from_file", C.c_int, vp, C.c_size_t, i32, f32, C.c_int, vp, vp, vp, vp),
     _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
     _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),

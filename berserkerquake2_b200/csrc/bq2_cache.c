@@ -201,3 +201,119 @@ bq2_status bq2_md3_cache_read(const void *in, size_t bytes, uint32_t file_checks
     for (i = 0; i < n; i++) { v[16*i + 12] = p[0]; v[16*i + 13] = p[1]; v[16*i + 14] = p[2]; p += 3; }
     return BQ2_OK;
 }
+
+/* ---- MD3 file -> the engine's in-memory meshes (Mod_LoadAliasMD3Model M:50584-51060) ---------------------- */
+/* on-disk structs, defs.h:4298-4391 (little-endian, packed naturally) */
+typedef struct { int32_t id, version; char filename[64]; int32_t flags, num_frames, num_tags, num_meshes, num_skins,
+                 ofs_frames, ofs_tags, ofs_meshes, ofs_end; } md3_file_header;                       /* dmd3_t */
+typedef struct { float mins[3], maxs[3], translate[3], radius; char creator[16]; } md3_file_frame;    /* dmd3frame_t */
+typedef struct { char id[4]; char name[64]; int32_t flags, num_frames, num_skins, num_verts, num_tris,
+                 ofs_tris, ofs_skins, ofs_tcs, ofs_verts, meshsize; } md3_file_mesh;                  /* dmd3mesh_t */
+typedef struct { int16_t point[3]; int16_t norm; } md3_file_vertex;                                   /* dmd3vertex_t */
+
+#define _GNU_SOURCE
+#include <math.h>
+extern void sincosf(float, float *, float *);
+extern uint8_t bq2_host_normal2index(const float v[3]);          /* bq2_synth.c: Normal2Index M:25206-25223 */
+
+static const md3_file_mesh *md3_mesh_at(const uint8_t *file, size_t bytes, const md3_file_header *h, int m, size_t *off_out)
+{
+    size_t off = (size_t)h->ofs_meshes;
+    int i;
+    for (i = 0;; i++) {
+        const md3_file_mesh *pm;
+        if (off + sizeof(md3_file_mesh) > bytes) return NULL;
+        pm = (const md3_file_mesh *)(file + off);
+        if (i == m) { if (off_out) *off_out = off; return pm; }
+        if (pm->meshsize <= 0) return NULL;
+        off += (size_t)pm->meshsize;
+    }
+}
+
+/* Header checks of the loader (M:50620-50660, 50722-50756) and the mesh dimensions.  num_verts / num_tris =
+ * int32[num_meshes] (may be NULL). */
+bq2_status bq2_md3_file_info(const void *file, size_t bytes, int32_t *num_frames, int32_t *num_meshes,
+                             int32_t *num_verts, int32_t *num_tris)
+{
+    const md3_file_header *h = (const md3_file_header *)file;
+    int m;
+    if (!file || bytes < sizeof *h) return BQ2_E_INVALID;
+    if (h->version != 15) return BQ2_E_INVALID;                                   /* MD3_ALIAS_VERSION */
+    if (h->num_frames <= 0 || h->num_meshes <= 0) return BQ2_E_INVALID;
+    if (h->num_frames > 1024 || h->num_meshes > BQ2_MD3_MAX_MESHES) return BQ2_E_LIMIT;
+    if (h->ofs_frames < 0 || (size_t)h->ofs_frames + (size_t)h->num_frames * sizeof(md3_file_frame) > bytes) return BQ2_E_INVALID;
+    for (m = 0; m < h->num_meshes; m++) {
+        size_t off;
+        const md3_file_mesh *pm = md3_mesh_at((const uint8_t *)file, bytes, h, m, &off);
+        if (!pm || memcmp(pm->id, "IDP3", 4)) return BQ2_E_INVALID;               /* "wrong id" */
+        if (pm->num_skins <= 0 || pm->num_tris <= 0 || pm->num_verts <= 0) return BQ2_E_INVALID;
+        if (pm->num_skins > 32 || pm->num_tris > BQ2_MD3_MAX_TRIANGLES || pm->num_verts > BQ2_MD3_MAX_VERTS) return BQ2_E_LIMIT;
+        if (pm->ofs_tris < 0 || pm->ofs_tcs < 0 || pm->ofs_verts < 0 ||
+            off + (size_t)pm->ofs_tris + 12u * (size_t)pm->num_tris > bytes ||
+            off + (size_t)pm->ofs_tcs + 8u * (size_t)pm->num_verts > bytes ||
+            off + (size_t)pm->ofs_verts + 8u * (size_t)pm->num_verts * (size_t)h->num_frames > bytes) return BQ2_E_INVALID;
+        if (num_verts) num_verts[m] = pm->num_verts;
+        if (num_tris) num_tris[m] = pm->num_tris;
+    }
+    if (num_frames) *num_frames = h->num_frames;
+    if (num_meshes) *num_meshes = h->num_meshes;
+    return BQ2_OK;
+}
+
+/* One mesh: vertexes = maliasvertex_t[num_frames * num_verts] with point de-quantised (short * (1/64 * scale),
+ * y mirrored when invert) and the normal byte from the lat/lng pair (M:50963-50989); tangent / binormal bytes are
+ * left 0 for bq2_gpu_md3_tangents or bq2_md3_cache_read.  indexes = u16[3 * num_tris] (winding reversed when
+ * invert), st = float[num_verts][2].  frame_translate = float[num_frames][3] (may be NULL; same for every mesh). */
+bq2_status bq2_host_md3_mesh_from_file(const void *file, size_t bytes, int32_t mesh, float scale, int invert,
+                                       float *frame_translate, void *vertexes, uint16_t *indexes, float *st)
+{
+    const md3_file_header *h = (const md3_file_header *)file;
+    const uint8_t *base = (const uint8_t *)file;
+    const md3_file_mesh *pm;
+    size_t off = 0;
+    float invscale[3];
+    int i, j, l, y;
+    bq2_status s = bq2_md3_file_info(file, bytes, NULL, NULL, NULL, NULL);
+    if (s != BQ2_OK) return s;
+    if (scale <= 0.001 || mesh < 0 || mesh >= h->num_meshes || !vertexes || !indexes) return BQ2_E_INVALID;
+    pm = md3_mesh_at(base, bytes, h, mesh, &off);
+    if (!pm) return BQ2_E_INVALID;
+    invscale[0] = (1.0 / 64) * scale; invscale[1] = invert ? -(1.0 / 64) * scale : (1.0 / 64) * scale; invscale[2] = (1.0 / 64) * scale;
+    if (frame_translate) {
+        const md3_file_frame *pf = (const md3_file_frame *)(base + h->ofs_frames);
+        for (i = 0; i < h->num_frames; i++) {
+            for (j = 0; j < 3; j++) frame_translate[3*i + j] = pf[i].translate[j] * scale;           /* M:50672 */
+            if (invert) frame_translate[3*i + 1] = -frame_translate[3*i + 1];
+        }
+    }
+    {
+        const uint32_t *pin = (const uint32_t *)(base + off + pm->ofs_tris);
+        for (j = 0; j < pm->num_tris; j++, pin += 3) {
+            if (pin[0] >= (uint32_t)pm->num_verts || pin[1] >= (uint32_t)pm->num_verts || pin[2] >= (uint32_t)pm->num_verts) return BQ2_E_INVALID;
+            indexes[3*j + 0] = (uint16_t)(invert ? pin[2] : pin[0]);
+            indexes[3*j + 1] = (uint16_t)pin[1];
+            indexes[3*j + 2] = (uint16_t)(invert ? pin[0] : pin[2]);
+        }
+    }
+    if (st) memcpy(st, base + off + pm->ofs_tcs, 8u * (size_t)pm->num_verts);
+    {
+        const md3_file_vertex *pv = (const md3_file_vertex *)(base + off + pm->ofs_verts);
+        uint8_t *out = (uint8_t *)vertexes;
+        for (l = 0; l < h->num_frames; l++)
+            for (j = 0; j < pm->num_verts; j++, pv++, out += 16) {
+                float *pt = (float *)out, lat, lng, norma[3], slat, clat, slng, clng;
+                for (y = 0; y < 3; y++) pt[y] = (float)pv->point[y] * invscale[y];
+                lat = (pv->norm >> 8) & 0xff;
+                lng = (pv->norm & 0xff);
+                lat *= M_PI / 128;
+                lng *= M_PI / 128;
+                sincosf(lat, &slat, &clat);
+                sincosf(lng, &slng, &clng);
+                norma[0] = clat * slng;
+                norma[1] = invert ? -slat * slng : slat * slng;
+                norma[2] = clng;
+                out[12] = bq2_host_normal2index(norma); out[13] = 0; out[14] = 0; out[15] = 0;
+            }
+    }
+    return BQ2_OK;
+}

@@ -304,6 +304,17 @@ bq2_status bq2_md3_cache_write(void *out, size_t capacity, uint32_t file_checksu
 bq2_status bq2_md3_cache_read(const void *in, size_t bytes, uint32_t file_checksum, void *vertexes,
                               int32_t num_frames, int32_t num_verts);
 
+/* An MD3 FILE image -> the engine's in-memory meshes (Mod_LoadAliasMD3Model M:50584-51060).  bq2_md3_file_info:
+ * the loader's header checks and the mesh dimensions (num_verts / num_tris = int32[num_meshes], may be NULL).
+ * bq2_host_md3_mesh_from_file, one mesh: vertexes = maliasvertex_t[num_frames * num_verts], points de-quantised
+ * (short * (1/64 * scale), y mirrored when invert), normal byte from the lat/lng pair (M:50963-50989), tangent /
+ * binormal bytes 0 (fill with bq2_gpu_md3_tangents or bq2_md3_cache_read); indexes = u16[3 * num_tris] (winding
+ * reversed when invert); st = float[num_verts][2]; frame_translate = float[num_frames][3] or NULL. */
+bq2_status bq2_md3_file_info(const void *file, size_t bytes, int32_t *num_frames, int32_t *num_meshes,
+                             int32_t *num_verts, int32_t *num_tris);
+bq2_status bq2_host_md3_mesh_from_file(const void *file, size_t bytes, int32_t mesh, float scale, int invert,
+                                       float *frame_translate, void *vertexes, uint16_t *indexes, float *st);
+
 /* ---- the renderer's loop nest, flattened (host, C) -------------------------------------------- */
 /* The fields of entity_t (defs.h:573-618) and shadowlight_t (defs.h:3927-3973) this path reads. */
 typedef struct bq2_world_entity {

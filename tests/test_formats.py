@@ -162,3 +162,113 @@ def test_file_to_shadow_volume_with_device_precompute(gpu_ctx, oracle):
         w = oracle.md2_pair(blob, nb2, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"], W["oldorigin"],
                             W["angles"], wl["origin"][pl[p]], 300.0, idx=idx)
         assert np.array_equal(res.indices(p), w["indices"]) and np.array_equal(bits(res.lerped(int(pe[p]), V)), bits(w["lerped"]))
+
+
+# ---------------------------------------------------------------------------------------------- MD3 files
+def build_md3_file(meshes, frame_translate, frame_extra=None):
+    """A Quake III .md3 image (defs.h:4298-4391): header, frames, then each mesh = header, skins, triangles,
+    texture coordinates, vertices (shorts + packed lat/lng normal)."""
+    import struct
+    F = len(frame_translate)
+    frames = b"".join(struct.pack("<10f16s", -1, -2, -3, 1, 2, 3, *map(float, t), 9.0, b"test") for t in frame_translate)
+    body = b""
+    for m in meshes:
+        V, T = m["points"].shape[1], len(m["tris"])
+        skins = struct.pack("<64si", b"models/x/skin.tga", 0)
+        tris = np.asarray(m["tris"], "<u4").tobytes()
+        tcs = np.asarray(m["st"], "<f4").tobytes()
+        verts = np.zeros((F, V, 4), "<i2"); verts[:, :, :3] = m["points"]; verts[:, :, 3] = m["norm"]
+        ofs_tris = 108 + len(skins); ofs_tcs = ofs_tris + len(tris); ofs_verts = ofs_tcs + len(tcs)
+        size = ofs_verts + verts.nbytes
+        body += struct.pack("<4s64s11i", b"IDP3", b"mesh", 0, F, 1, V, T, ofs_tris, 108, ofs_tcs, ofs_verts, size, 0)[:108]
+        body += skins + tris + tcs + verts.tobytes()
+    ofs_frames = 108
+    hdr = struct.pack("<ii64s9i", 0x33504449, 15, b"test.md3", 0, F, 0, len(meshes), 0, ofs_frames, ofs_frames + len(frames),
+                      ofs_frames + len(frames), ofs_frames + len(frames) + len(body))
+    assert len(hdr) == 108
+    return np.frombuffer(hdr + frames + body, np.uint8).copy()
+
+
+def test_md3_file_to_memory(oracle):
+    import ctypes.util
+    libm = C.CDLL(ctypes.util.find_library("m"))
+    libm.sincosf.argtypes = [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    rng = np.random.RandomState(8)
+    F = 3
+    meshes = []
+    for V, T in ((20, 30), (7, 5)):
+        meshes.append(dict(points=rng.randint(-3000, 3000, (F, V, 3)), norm=rng.randint(-32768, 32767, (F, V)),
+                           tris=rng.randint(0, V, (T, 3)), st=rng.rand(V, 2).astype(np.float32)))
+    ft = rng.randn(F, 3).astype(np.float32) * 10
+    file = build_md3_file(meshes, ft)
+    nf, nm = C.c_int32(), C.c_int32(); nv = np.zeros(32, np.int32); nt = np.zeros(32, np.int32)
+    assert L.bq2_md3_file_info(c.ptr(file), file.nbytes, C.byref(nf), C.byref(nm), c.ptr(nv), c.ptr(nt)) == 0
+    assert (nf.value, nm.value, list(nv[:2]), list(nt[:2])) == (3, 2, [20, 7], [30, 5])
+    for invert in (False, True):
+        for scale in (1.0, 0.75):
+            for k, m in enumerate(meshes):
+                V, T = nv[k], nt[k]
+                verts = np.zeros((F, V), synth.MD3_VERTEX); idx = np.zeros((T, 3), np.uint16); st = np.zeros((V, 2), np.float32)
+                tr = np.zeros((F, 3), np.float32)
+                assert L.bq2_host_md3_mesh_from_file(c.ptr(file), file.nbytes, k, scale, int(invert), c.ptr(tr), c.ptr(verts), c.ptr(idx), c.ptr(st)) == 0
+                inv = np.array([1.0 / 64 * np.float32(scale)] * 3).astype(np.float32)      # (1.0/64)*scale in double, stored as float
+                if invert:
+                    inv[1] = -inv[1]
+                assert np.array_equal(bits(verts["point"]), bits(m["points"].astype(np.float32) * inv[None, None, :]))   # M:50968
+                want_tr = ft * np.float32(scale)
+                if invert:
+                    want_tr[:, 1] = -want_tr[:, 1]
+                assert np.array_equal(bits(tr), bits(want_tr))
+                assert np.array_equal(idx, m["tris"][:, ::-1] if invert else m["tris"]) and np.array_equal(st, m["st"])
+                for f in range(F):                                  # lat/lng -> vector -> Normal2Index, M:50972-50989
+                    for v in range(V):
+                        n16 = int(m["norm"][f, v])
+                        lat = np.float32(np.float64(np.float32((n16 >> 8) & 0xff)) * (np.pi / 128))
+                        lng = np.float32(np.float64(np.float32(n16 & 0xff)) * (np.pi / 128))
+                        sl, cl, sg, cg = (C.c_float() for _ in range(4))
+                        libm.sincosf(lat, C.byref(sl), C.byref(cl)); libm.sincosf(lng, C.byref(sg), C.byref(cg))
+                        sl, cl, sg, cg = (np.float32(x.value) for x in (sl, cl, sg, cg))
+                        vec = np.array([cl * sg, (-sl * sg) if invert else sl * sg, cg], np.float32)
+                        assert verts["normal"][f, v] == oracle.normal2index(vec), (f, v)
+                assert not verts["tangent"].any() and not verts["binormal"].any()
+    bad = file.copy(); bad[4:8].view("<i4")[0] = 14
+    assert L.bq2_md3_file_info(c.ptr(bad), bad.nbytes, None, None, None, None) == -1            # wrong version number
+    bad = file.copy(); bad[108 + 3 * 56:108 + 3 * 56 + 4] = np.frombuffer(b"XXXX", np.uint8)
+    assert L.bq2_md3_file_info(c.ptr(bad), bad.nbytes, None, None, None, None) == -1            # mesh has wrong id
+    assert L.bq2_md3_file_info(c.ptr(file), 300, None, None, None, None) == -1                  # truncated
+
+
+@pytest.mark.gpu
+def test_md3_file_to_shadow_volume(gpu_ctx, oracle):
+    """.md3 bytes -> meshes -> neighbours + tangent bytes on the device -> upload -> frame, against the oracle."""
+    from scenes import world_scene
+    F = 4
+    meshes_in, raw = [], []
+    for k in range(2):
+        verts, idx, st = synth.md3_mesh(10, 7, F, 50 + k, centre=(30.0 * k, 0, 0))
+        pts = np.round(verts["point"] * 64).astype(np.int32)
+        meshes_in.append(dict(points=pts, norm=np.full(pts.shape[:2], 0x2040, np.int32), tris=idx.astype(np.int32), st=st))
+    ft = np.array([[0, 0, 0], [1, 0, 2], [2, 1, 0], [0, 3, 1]], np.float32)
+    file = build_md3_file(meshes_in, ft)
+    tr = np.zeros((F, 3), np.float32)
+    meshes = []
+    for k in range(2):
+        V, T = meshes_in[k]["points"].shape[1], len(meshes_in[k]["tris"])
+        verts = np.zeros((F, V), synth.MD3_VERTEX); idx = np.zeros((T, 3), np.uint16); st = np.zeros((V, 2), np.float32)
+        assert L.bq2_host_md3_mesh_from_file(c.ptr(file), file.nbytes, k, 1.0, 0, c.ptr(tr), c.ptr(verts), c.ptr(idx), c.ptr(st)) == 0
+        gpu_ctx.gpu_md3_tangents(verts, st, idx)
+        want = verts.copy(); oracle.md3_tangents(want, st, idx)
+        assert np.array_equal(verts, want)
+        meshes.append(dict(verts=verts, indexes=idx, neighbours="gpu"))
+    mid = gpu_ctx.upload_md3(tr, meshes)
+    we, wl, pe, pl = world_scene(2, 2, F, seed=21)
+    we["model"] = mid
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    res = gpu_ctx.frame(ents, pairs)
+    for p in range(len(pe)):
+        W = we[pe[p]]
+        for k in range(2):
+            nb = oracle.md3_neighbours(meshes[k]["indexes"])
+            w = oracle.md3_mesh_pair(meshes[k]["verts"], meshes[k]["indexes"], nb, tr, int(W["frame"]), int(W["oldframe"]),
+                                     float(W["backlerp"]), W["origin"], W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0)
+            assert np.array_equal(res.indices(2 * p + k), w["indices"]), (p, k)
