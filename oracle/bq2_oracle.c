@@ -295,6 +295,44 @@ long long bq2o_md2_world_bench(void *const *blobs, void *const *neighbours, int 
     return total;
 }
 
+/* R_DrawBrushModelVolumes M:63326-63499 on flat arrays: returns ib; *vb_out = vertex pairs.
+ * vcache = [2*vb][3]: vertex then its extrusion; icache = indices into it. */
+int bq2o_brush_volume(int n_polys, const int32_t *numverts, const float *verts, const int32_t *neighbours,
+                      const uint8_t *lit, const uint8_t *fence, const float light[3], float scale,
+                      float *vcache, uint32_t *icache, int *vb_out)
+{
+    int vb = 0, ib = 0, first = 0, surf_base = 0;
+    for (int p = 0; p < n_polys; first += numverts[p], p++) {          /* vertex buffer, M:63384-63403 */
+        if (!lit[p] || fence[p]) continue;
+        for (int j = 0; j < numverts[p]; j++) {
+            const float *v = verts + 3 * (first + j);
+            float *o = vcache + 6 * vb;
+            o[0] = v[0]; o[1] = v[1]; o[2] = v[2];
+            extrude_point(v, light, scale, o + 3);
+            vb++;
+        }
+    }
+    first = 0;
+    for (int p = 0; p < n_polys; first += numverts[p], p++) {          /* index buffer, M:63406-63460 */
+        int n = numverts[p];
+        if (!lit[p] || fence[p]) continue;
+        for (int j = 0; j < n; j++) {
+            int nb = neighbours[first + j];
+            int shadow = nb < 0 ? 1 : (lit[nb] != lit[p]);               /* neighbour stamped by another light pass */
+            if (shadow) {
+                int jj = (j + 1) % n;
+                icache[ib++] = j * 2 + 0 + surf_base;  icache[ib++] = j * 2 + 1 + surf_base;  icache[ib++] = jj * 2 + 1 + surf_base;
+                icache[ib++] = j * 2 + 0 + surf_base;  icache[ib++] = jj * 2 + 1 + surf_base; icache[ib++] = jj * 2 + 0 + surf_base;
+            }
+        }
+        for (int j = 0; j < n - 2; j++) { icache[ib++] = 0 + surf_base; icache[ib++] = (j + 1) * 2 + 0 + surf_base; icache[ib++] = (j + 2) * 2 + 0 + surf_base; }
+        for (int j = 0; j < n - 2; j++) { icache[ib++] = 1 + surf_base; icache[ib++] = (j + 2) * 2 + 1 + surf_base; icache[ib++] = (j + 1) * 2 + 1 + surf_base; }
+        surf_base += n * 2;
+    }
+    *vb_out = vb;
+    return ib;
+}
+
 /* a10.  MD2 writes old*backlerp + cur*frontlerp (M:65220), MD3 cur*frontlerp + old*backlerp
  * (M:65714); IEEE addition commutes, the two are bit-identical. */
 void bq2o_ntb(const uint8_t *n_cur, const uint8_t *n_old, int n_stride,

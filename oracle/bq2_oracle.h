@@ -79,6 +79,11 @@ long long bq2o_md2_world_bench(void *const *blobs, void *const *neighbours, int 
                                const float *origins, const float *oldorigins, const float *angles,
                                const float *lights_world, const float *radii);
 
+/* M:63326-63499 (brush-model volumes); light in model space, scale = 32 * radius */
+int bq2o_brush_volume(int n_polys, const int32_t *numverts, const float *verts, const int32_t *neighbours,
+                      const uint8_t *lit, const uint8_t *fence, const float light[3], float scale,
+                      float *vcache, uint32_t *icache, int *vb_out);
+
 /* precompute (SURVEY 8f "next" rows 1-2) */
 uint8_t bq2o_normal2index(const float v[3]);                                  /* M:25206-25223 */
 void bq2o_md2_neighbours(const int16_t *tris /*dtriangle_t[T]*/, int num_tris, int32_t *out); /* M:51643-51653 + 61782-61824 */

@@ -100,10 +100,12 @@ void glDrawArrays(GLenum mode, GLint first, GLsizei count)
     }
 }
 
+static int cap_elems_count = -1;
 static int cap_elems_nverts;                    /* MD3 light family draws indexed: copy this many rows */
 void glDrawElements(GLenum mode, GLsizei count, GLenum type, const GLvoid *indices)
 {
-    (void)mode; (void)count; (void)type; (void)indices;
+    (void)mode; (void)type; (void)indices;
+    cap_elems_count = count;
     for (int t = 0; t < CAP_TMUS; t++)
         if (cap_out[t] && cap_ptr[t]) memcpy(cap_out[t], cap_ptr[t], sizeof(float) * cap_size[t] * cap_elems_nverts);
 }
@@ -427,6 +429,63 @@ int bq2ref_md3_light(void *mesh_verts, int num_verts, int frame, int oldframe, f
     else    GL_DrawMD3AliasFrameLerpLightARB(&mesh, SHADER_ARB6_VALUE, 0);
     for (int t = 0; t < CAP_TMUS; t++) { cap_out[t] = 0; if (sizes) sizes[t] = cap_ptr[t] ? cap_size[t] : 0; }
     return num_verts;
+}
+
+/* ---- brush-model dynamic volumes ------------------------------------------------ */
+extern int       r_lightTimestamp;                               /* data.h:2716 */
+extern vec3_t    vcache[];                                       /* data.h:2787 */
+extern unsigned  icache[];                                       /* data.h:2788 */
+void R_DrawBrushModelVolumes(void);                              /* M:63326 */
+
+/* R_DrawBrushModelVolumes whole on a brush model described by flat arrays: polygon p has numverts[p] vertices at
+ * verts[first[p]..], neighbours[first[p] + j] = polygon across edge j or -1, lit[p] = the light's marking pass
+ * stamped it (lightTimestamp == r_lightTimestamp, done elsewhere in the engine), fence[p] = its texture is a
+ * non-casting SURF_FENCE one (M:63387-63389).  Returns ib (the index count handed to glDrawElements, 0 when
+ * nothing is drawn); *vb_out = vertex pairs written to vcache. */
+int bq2ref_brush_volume(int n_polys, const int *numverts, const float *verts, const int *neighbours,
+                        const uint8_t *lit, const uint8_t *fence,
+                        const float *origin, const float *angles, const float *light_world, float radius,
+                        float *vcache_out, unsigned *icache_out, int *vb_out)
+{
+    static image_t img_cast, img_fence; static mtexinfo_t ti_cast, ti_fence;
+    bq2ref_init();
+    glpoly_t **polys = (glpoly_t **)calloc((size_t)n_polys, sizeof *polys);
+    msurface_t *surfs = (msurface_t *)calloc((size_t)n_polys, sizeof *surfs);
+    memset(&img_cast, 0, sizeof img_cast); img_cast.CastShadow = true;
+    memset(&img_fence, 0, sizeof img_fence); img_fence.CastShadow = false;
+    memset(&ti_cast, 0, sizeof ti_cast); ti_cast.image = &img_cast;
+    memset(&ti_fence, 0, sizeof ti_fence); ti_fence.image = &img_fence; ti_fence.flags = SURF_FENCE;
+    r_lightTimestamp = 7;
+    int first = 0, vb = 0;
+    for (int p = 0; p < n_polys; p++) {
+        int n = numverts[p];
+        glpoly_t *g = (glpoly_t *)calloc(1, sizeof(glpoly_t) + sizeof(float) * VERTEXSIZE * (size_t)(n > 4 ? n - 4 : 0));
+        g->numverts = n; g->lightTimestamp = lit[p] ? r_lightTimestamp : 3;
+        g->neighbours = (glpoly_t **)calloc((size_t)n, sizeof(glpoly_t *));
+        for (int j = 0; j < n; j++) for (int k = 0; k < 3; k++) g->verts[j][k] = verts[3 * (first + j) + k];
+        polys[p] = g;
+        surfs[p].polys = g; surfs[p].numedges = n; surfs[p].texinfo = fence[p] ? &ti_fence : &ti_cast;
+        if (lit[p] && !fence[p]) vb += n;
+        first += n;
+    }
+    first = 0;
+    for (int p = 0; p < n_polys; p++) {
+        for (int j = 0; j < numverts[p]; j++) { int nb = neighbours[first + j]; polys[p]->neighbours[j] = nb < 0 ? NULL : polys[nb]; }
+        first += numverts[p];
+    }
+    memset(&mdl, 0, sizeof mdl); mdl.type = mod_brush; mdl.surfaces = surfs; mdl.firstmodelsurface = 0; mdl.nummodelsurfaces = n_polys;
+    static const float zero[3] = {0, 0, 0};
+    set_entity(0, 0, 0.0f, origin, zero, angles, 0);
+    set_light(light_world, radius);
+    cap_elems_count = 0;
+    R_DrawBrushModelVolumes();
+    int ib = cap_elems_count;
+    memcpy(vcache_out, vcache, sizeof(float) * 3 * 2 * (size_t)vb);
+    memcpy(icache_out, icache, sizeof(unsigned) * (size_t)ib);
+    *vb_out = vb;
+    for (int p = 0; p < n_polys; p++) { free(polys[p]->neighbours); free(polys[p]); }
+    free(polys); free(surfs);
+    return ib;
 }
 
 /* ---- precompute ------------------------------------------------------------------------------ */

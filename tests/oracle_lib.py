@@ -153,6 +153,17 @@ class Oracle:
                               P(lp), P(ts))
         return lp, ts
 
+    def brush_volume(self, bm, lit, light_model, radius):
+        """R_DrawBrushModelVolumes M:63326-63499; light already in model space"""
+        self.lib.bq2o_brush_volume.argtypes = [i32, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp]
+        self.lib.bq2o_brush_volume.restype = i32
+        nv = int(bm.first[-1])
+        vc = np.zeros((2 * nv, 3), np.float32); ic = np.zeros(12 * nv, np.uint32); vb = C.c_int(0)
+        lit = np.ascontiguousarray(lit, np.uint8)
+        ib = self.lib.bq2o_brush_volume(bm.n_polys, P(bm.numverts), P(bm.verts), P(bm.neighbours), P(lit), P(bm.fence),
+                                        P(f3(light_model)), float(np.float32(32) * np.float32(radius)), P(vc), P(ic), C.byref(vb))
+        return vc[:2 * vb.value].copy(), ic[:ib].copy()
+
     def normal2index(self, v):
         return int(self.lib.bq2o_normal2index(P(f3(v))))
 
@@ -404,6 +415,17 @@ class Reference:
                 lerped=lerped[voff[m]:voff[m + 1]].copy(), extruded=ext[voff[m]:voff[m + 1]].copy(),
                 viss=viss[toff[m]:toff[m + 1]].copy(), tris_verts=tv[tvoff[m]:tvoff[m] + cnt[m]].copy()))
         return done, out
+
+    def brush_volume(self, bm, lit, origin, angles, light_world, radius):
+        """the reference's R_DrawBrushModelVolumes whole (world-space light in)"""
+        fn = self.lib.bq2ref_brush_volume
+        fn.argtypes = [i32, vp, vp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp]; fn.restype = i32
+        nv = int(bm.first[-1])
+        vc = np.zeros((2 * nv, 3), np.float32); ic = np.zeros(12 * nv, np.uint32); vb = C.c_int(0)
+        lit = np.ascontiguousarray(lit, np.uint8)
+        ib = fn(bm.n_polys, P(bm.numverts), P(bm.verts), P(bm.neighbours), P(lit), P(bm.fence), P(f3(origin)), P(f3(angles)),
+                P(f3(light_world)), radius, P(vc), P(ic), C.byref(vb))
+        return vc[:2 * vb.value].copy(), ic[:ib].copy()
 
     def md3_light(self, mesh_verts, frame, oldframe, backlerp, lerped, light_model, view_model, vp_variant):
         F, V = mesh_verts.shape

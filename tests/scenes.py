@@ -66,3 +66,55 @@ def near_zero_facing(o_pair, idx, eps=1e-4):
     dl = (tn * L[None, :]).sum(1)
     dp = (P[idx[:, 0]] * tn).sum(1)
     return np.abs(dl - dp) <= eps * np.maximum(1.0, np.abs(dp))
+
+
+class BrushModel:
+    """A closed convex-ish brush made of polygons with 3..S vertices (a lat-long drum: S-gon caps, quad bands,
+    a few quads split into triangles), each polygon with its own vertex copies and per-edge neighbour polygon,
+    as glpoly_t holds them (defs.h:3329-3338).  Vertex coordinates are quantised to 1/8 like BSP geometry."""
+
+    def __init__(self, slices=8, bands=3, seed=0, open_edges=0):
+        rng = np.random.RandomState(seed)
+        S = slices
+        ring = []
+        for r in range(bands + 1):
+            z = 40.0 * (r / bands) - 20.0
+            rad = 30.0 + 6.0 * np.sin(1.3 * r + seed)
+            ring.append([(rad * np.cos(2 * np.pi * s / S), rad * np.sin(2 * np.pi * s / S), z) for s in range(S)])
+        polys = [list(reversed(ring[0])), list(ring[bands])]                  # bottom and top caps (outward winding)
+        for r in range(bands):
+            for s in range(S):
+                a, b = ring[r][s], ring[r][(s + 1) % S]
+                c_, d = ring[r + 1][(s + 1) % S], ring[r + 1][s]
+                if rng.rand() < 0.25:
+                    polys += [[a, b, c_], [a, c_, d]]
+                else:
+                    polys.append([a, b, c_, d])
+        self.numverts = np.array([len(p) for p in polys], np.int32)
+        self.first = np.concatenate([[0], np.cumsum(self.numverts)]).astype(np.int32)
+        self.verts = (np.round(np.array([v for p in polys for v in p], np.float64) * 8) / 8).astype(np.float32)
+        key = lambda v: tuple(np.round(np.asarray(v) * 8).astype(np.int64))
+        edges = {}
+        for p, poly in enumerate(polys):
+            for j in range(len(poly)):
+                k = tuple(sorted((key(poly[j]), key(poly[(j + 1) % len(poly)]))))
+                edges.setdefault(k, []).append((p, j))
+        self.neighbours = np.full(int(self.first[-1]), -1, np.int32)
+        for lst in edges.values():
+            if len(lst) == 2:
+                (p0, j0), (p1, j1) = lst
+                self.neighbours[self.first[p0] + j0] = p1
+                self.neighbours[self.first[p1] + j1] = p0
+        for _ in range(open_edges):
+            self.neighbours[rng.randint(len(self.neighbours))] = -1
+        self.n_polys = len(polys)
+        self.fence = (rng.rand(self.n_polys) < 0.1).astype(np.uint8)
+        self.normals = np.zeros((self.n_polys, 3)); self.centroids = np.zeros((self.n_polys, 3))
+        for p in range(self.n_polys):
+            v = self.verts[self.first[p]:self.first[p + 1]].astype(np.float64)
+            self.normals[p] = np.cross(v[1] - v[0], v[2] - v[0]); self.centroids[p] = v.mean(0)
+
+    def lit(self, light_model):
+        """what the engine's light-marking pass stamps: polygons facing the light"""
+        d = ((np.asarray(light_model, np.float64)[None, :] - self.centroids) * self.normals).sum(1)
+        return (d > 0).astype(np.uint8)

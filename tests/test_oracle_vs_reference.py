@@ -217,3 +217,27 @@ def test_md3_tangent_precompute(oracle, ref):
         tn = tan_r.copy(); bn = bin_r.copy()
         for k in idx[t]:
             assert one[0]["tangent"][k] == ref.normal2index(tn) and one[0]["binormal"][k] == ref.normal2index(bn)
+
+
+def test_brush_model_volumes(oracle, ref):
+    """R_DrawBrushModelVolumes M:63326-63499 whole: vcache + icache, rotated entities,
+    fence surfaces, open edges, everything lit / nothing lit."""
+    from scenes import BrushModel
+    rng = np.random.RandomState(12)
+    n = 0
+    for seed, (S, B, oe) in enumerate([(8, 3, 0), (5, 2, 3), (12, 4, 0), (3, 1, 1)]):
+        bm = BrushModel(S, B, seed, oe)
+        for trial in range(6):
+            origin = rng.randn(3) * 50
+            angles = np.zeros(3) if trial % 2 == 0 else rng.uniform(-180, 180, 3)
+            light_world = origin + rng.randn(3) * 120
+            lm = oracle.point_to_model(light_world, origin, angles)
+            lit = bm.lit(lm)
+            if trial == 4: lit[:] = 1
+            if trial == 5: lit[:] = 0
+            vr, ir = ref.brush_volume(bm, lit, origin, angles, light_world, 300.0)
+            vo, io = oracle.brush_volume(bm, lit, lm, 300.0)
+            assert np.array_equal(bits(vo), bits(vr)) and np.array_equal(io, ir), (seed, trial)
+            assert (len(io) > 0) == bool((lit & (1 - bm.fence)).any())
+            n += len(io)
+    assert n > 1000
