@@ -65,6 +65,14 @@ class WorldDesc(C.Structure):
                 ("view_world", C.c_void_p), ("want", C.c_uint32), ("index_stride", C.c_uint32)]
 
 
+class BrushOut(C.Structure):
+    _fields_ = [("vcache", C.c_void_p), ("icache", C.c_void_p), ("counts", C.POINTER(C.c_uint32)),
+                ("vert_stride", C.c_uint32), ("index_stride", C.c_uint32)]
+
+
+BRUSH_PAIR_DTYPE = np.dtype([("brush", "<i4"), ("light", "<f4", 3), ("scale", "<f4")])
+
+
 class Md3Mesh(C.Structure):
     _fields_ = [("num_verts", C.c_int32), ("num_tris", C.c_int32), ("vertexes", C.c_void_p),
                 ("indexes", C.c_void_p), ("neighbours", C.c_void_p), ("casts_shadow", C.c_int32)]
@@ -122,6 +130,9 @@ EXPORTS_GPU_H = [
     _sig("bq2_md3_cache_read", C.c_int, vp, C.c_size_t, u32, vp, i32, i32),
     _sig("bq2_md3_file_info", C.c_int, vp, C.c_size_t, C.POINTER(i32), C.POINTER(i32), vp, vp),
     _sig("bq2_host_md3_mesh_from_file", C.c_int, vp, C.c_size_t, i32, f32, C.c_int, vp, vp, vp, vp),
+    _sig("bq2_upload_brush", C.c_int, vp, i32, vp, vp, vp, vp, C.POINTER(i32)),
+    _sig("bq2_brush_volumes", C.c_int, vp, vp, i32, vp, C.POINTER(BrushOut)),
+    _sig("bq2_brush_download", C.c_int, vp, i32, vp, vp),
     _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
     _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),

@@ -118,6 +118,29 @@ class Context:
         st = np.ascontiguousarray(st, np.float32); ix = np.ascontiguousarray(indexes, np.uint16)
         self._check(c.lib.bq2_gpu_md3_tangents(self._h, c.ptr(verts), F, V, c.ptr(st), c.ptr(ix), ix.size // 3))
 
+    # -- brush-model volumes (main.c:63326-63499) -------------------------------------------------------
+    def upload_brush(self, numverts, verts, neighbours, fence=None):
+        nv = np.ascontiguousarray(numverts, np.int32); v = np.ascontiguousarray(verts, np.float32)
+        nb = np.ascontiguousarray(neighbours, np.int32)
+        fe = None if fence is None else np.ascontiguousarray(fence, np.uint8)
+        bid = C.c_int32(-1)
+        self._check(c.lib.bq2_upload_brush(self._h, len(nv), c.ptr(nv), c.ptr(v), c.ptr(nb), c.ptr(fe), C.byref(bid)))
+        return bid.value
+
+    def brush_volumes(self, pairs, lit):
+        """pairs: BRUSH_PAIR_DTYPE array (light in model space); lit: uint8, the pairs' polygon flags concatenated.
+        Returns a list of (vcache [vb*2][3], icache [ib]) per pair."""
+        pr = np.ascontiguousarray(pairs, c.BRUSH_PAIR_DTYPE); li = np.ascontiguousarray(lit, np.uint8)
+        out = c.BrushOut()
+        self._check(c.lib.bq2_brush_volumes(self._h, c.ptr(pr), len(pr), c.ptr(li), C.byref(out)))
+        res = []
+        for k in range(len(pr)):
+            vb, ib = int(out.counts[2 * k]), int(out.counts[2 * k + 1])
+            vc = np.zeros((2 * vb, 3), np.float32); ic = np.zeros(ib, np.uint32)
+            self._check(c.lib.bq2_brush_download(self._h, k, c.ptr(vc), c.ptr(ic)))
+            res.append((vc, ic))
+        return res
+
     # -- per frame -----------------------------------------------------------------------------------
     def build_records(self, world_ents, world_lights, pair_ent, pair_light, view_world=None):
         """The renderer's (light x entity) loop nest flattened into bq2_entity / bq2_pair records, on the

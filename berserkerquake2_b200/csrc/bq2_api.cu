@@ -117,6 +117,11 @@ struct bq2_ctx {
     bool world_mode = false, world_tables = false;
     std::vector<bq2_entity> tmp_ents; std::vector<bq2_pair> tmp_pairs;     /* host-built fallback */
     std::vector<uint32_t> world_pvoff, world_pboff;
+    /* brush models (8f.4) */
+    struct Brush { int n_polys = 0, n_slots = 0, worst_indices = 0; };
+    std::vector<Brush> brushes; std::vector<bq2_brush_dev_h> brush_dev; DevBuf<bq2_brush_dev_h> d_brushes;
+    DevBuf<unsigned char> d_brush_in; DevBuf<float> brush_vcache; DevBuf<uint32_t> brush_icache, brush_counts;
+    std::vector<uint32_t> h_brush_counts; uint32_t brush_vstride = 0, brush_istride = 0; int brush_pairs = 0;
     bq2_launch launch{};
     /* entity-slot records are grouped by kernel: [0, n_warp) -> warp kernel, [n_warp, n_ent_slots) -> team kernel */
     struct KLaunch { int n = 0, max_V = 0, max_T = 0, any_md2 = 0; } k_warp, k_team;
@@ -251,7 +256,8 @@ void bq2_destroy(bq2_ctx *ctx)
     ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
     for (int k = 0; k < 2; k++) if (ctx->gcache[k].exec) cudaGraphExecDestroy(ctx->gcache[k].exec);
     for (int k = 0; k < 2; k++) { ctx->hrec[k].release(); ctx->hcnt[k].release(); ctx->htot[k].release(); if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]); }
-    ctx->d_world.release();
+    ctx->d_world.release(); ctx->d_brushes.release(); ctx->d_brush_in.release(); ctx->brush_vcache.release();
+    ctx->brush_icache.release(); ctx->brush_counts.release();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -843,6 +849,96 @@ bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t F, int32_t
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     buf.release();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_md3_tangents");
+    return BQ2_OK;
+}
+
+bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numverts, const float *verts,
+                            const int32_t *neighbours, const uint8_t *fence, int32_t *brush_id)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (n_polys <= 0 || !numverts || !verts || !neighbours || !brush_id) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: bad arguments");
+    if (n_polys > BQ2_BRUSH_MAX_POLYS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_brush: too many polygons");
+    std::vector<uint32_t> first((size_t)n_polys + 1);
+    uint32_t ns = 0; int worst = 0;
+    for (int p = 0; p < n_polys; p++) {
+        if (numverts[p] < 3) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: polygon with fewer than 3 vertices");
+        first[p] = ns; ns += (uint32_t)numverts[p]; worst += 6 * numverts[p] + 6 * (numverts[p] - 2);
+    }
+    first[n_polys] = ns;
+    std::vector<uint32_t> slot_poly(ns);
+    for (int p = 0; p < n_polys; p++) for (uint32_t k = first[p]; k < first[p + 1]; k++) slot_poly[k] = (uint32_t)p;
+    for (uint32_t k = 0; k < ns; k++) if (neighbours[k] < -1 || neighbours[k] >= n_polys) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: neighbour out of range");
+    const size_t o_first = 0, o_nbr = 4 * ((size_t)n_polys + 1), o_sp = o_nbr + 4 * (size_t)ns, o_v = o_sp + 4 * (size_t)ns,
+                 o_f = o_v + 12 * (size_t)ns, total = o_f + (size_t)n_polys;
+    std::vector<unsigned char> img(total, 0);
+    memcpy(&img[o_first], first.data(), 4 * ((size_t)n_polys + 1));
+    memcpy(&img[o_nbr], neighbours, 4 * (size_t)ns);
+    memcpy(&img[o_sp], slot_poly.data(), 4 * (size_t)ns);
+    memcpy(&img[o_v], verts, 12 * (size_t)ns);
+    if (fence) memcpy(&img[o_f], fence, (size_t)n_polys);
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    unsigned char *d = nullptr;
+    bq2_status st = arena_alloc(ctx, total, &d);
+    if (st != BQ2_OK) return st;
+    CK(cudaMemcpyAsync(d, img.data(), total, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(brush)");
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(brush)");
+    bq2_brush_dev_h bd{};
+    bd.first = (const uint32_t *)(d + o_first); bd.nbr = (const int32_t *)(d + o_nbr); bd.slot_poly = (const uint32_t *)(d + o_sp);
+    bd.verts = (const float *)(d + o_v); bd.fence = d + o_f; bd.n_polys = n_polys; bd.n_slots = (int32_t)ns;
+    ctx->brush_dev.push_back(bd);
+    bq2_ctx::Brush b; b.n_polys = n_polys; b.n_slots = (int)ns; b.worst_indices = worst;
+    ctx->brushes.push_back(b);
+    CK(ctx->d_brushes.ensure(ctx->brush_dev.size()), "cudaMalloc(brush table)");
+    CK(cudaMemcpy(ctx->d_brushes.p, ctx->brush_dev.data(), ctx->brush_dev.size() * sizeof(bq2_brush_dev_h), cudaMemcpyHostToDevice), "cudaMemcpy(brush table)");
+    *brush_id = (int32_t)ctx->brushes.size() - 1;
+    return BQ2_OK;
+}
+
+bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t n_pairs, const uint8_t *lit, bq2_brush_out *out)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (n_pairs < 0 || (n_pairs && (!pairs || !lit)) || !out) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: bad arguments");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    std::vector<bq2_brush_pair_dev_h> hp((size_t)n_pairs + 1);
+    uint32_t lit_bytes = 0, vstride = 4, istride = 4; int max_polys = 1;
+    for (int k = 0; k < n_pairs; k++) {
+        if (pairs[k].brush < 0 || pairs[k].brush >= (int32_t)ctx->brushes.size()) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: unknown brush");
+        const bq2_ctx::Brush &b = ctx->brushes[pairs[k].brush];
+        hp[k].brush = pairs[k].brush; hp[k].scale = pairs[k].scale; hp[k].lit_off = lit_bytes;
+        for (int c = 0; c < 3; c++) hp[k].light[c] = pairs[k].light[c];
+        lit_bytes += (uint32_t)b.n_polys;
+        vstride = std::max(vstride, (uint32_t)b.n_slots); istride = std::max(istride, (uint32_t)b.worst_indices);
+        max_polys = std::max(max_polys, b.n_polys);
+    }
+    const size_t o_lit = (((size_t)n_pairs * sizeof(bq2_brush_pair_dev_h)) + 15) & ~(size_t)15;
+    CK(ctx->d_brush_in.ensure(o_lit + lit_bytes + 16), "cudaMalloc(brush pairs)");
+    CK(ctx->brush_vcache.ensure(6 * (size_t)n_pairs * vstride + 4), "cudaMalloc(brush vcache)");
+    CK(ctx->brush_icache.ensure((size_t)n_pairs * istride + 4), "cudaMalloc(brush icache)");
+    CK(ctx->brush_counts.ensure(2 * (size_t)n_pairs + 2), "cudaMalloc(brush counts)");
+    ctx->h_brush_counts.assign(2 * (size_t)n_pairs + 2, 0u);
+    if (n_pairs) {
+        CK(cudaMemcpyAsync(ctx->d_brush_in.p, hp.data(), (size_t)n_pairs * sizeof(bq2_brush_pair_dev_h), cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(brush pairs)");
+        CK(cudaMemcpyAsync(ctx->d_brush_in.p + o_lit, lit, lit_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(lit)");
+        CK((cudaError_t)bq2_launch_brush(ctx->d_brushes.p, ctx->d_brush_in.p, ctx->d_brush_in.p + o_lit, ctx->brush_vcache.p, ctx->brush_icache.p,
+                                         ctx->brush_counts.p, vstride, istride, n_pairs, max_polys, ctx->stream), "launch(bq2_brush_kernel)");
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->h_brush_counts.data(), ctx->brush_counts.p, 8 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(brush counts)");
+    }
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(brush)");
+    ctx->brush_vstride = vstride; ctx->brush_istride = istride; ctx->brush_pairs = n_pairs;
+    out->vcache = ctx->brush_vcache.p; out->icache = ctx->brush_icache.p; out->counts = ctx->h_brush_counts.data();
+    out->vert_stride = vstride; out->index_stride = istride;
+    return BQ2_OK;
+}
+
+bq2_status bq2_brush_download(bq2_ctx *ctx, int32_t pair, float *vcache, uint32_t *icache)
+{
+    if (!ctx || !vcache || !icache) return BQ2_E_INVALID;
+    if (pair < 0 || pair >= ctx->brush_pairs) return fail(ctx, BQ2_E_INVALID, "bq2_brush_download: bad pair");
+    const uint32_t vb = ctx->h_brush_counts[2 * (size_t)pair], ib = ctx->h_brush_counts[2 * (size_t)pair + 1];
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (vb) CK(cudaMemcpy(vcache, ctx->brush_vcache.p + 6 * (size_t)pair * ctx->brush_vstride, 24 * (size_t)vb, cudaMemcpyDeviceToHost), "cudaMemcpy(vcache)");
+    if (ib) CK(cudaMemcpy(icache, ctx->brush_icache.p + (size_t)pair * ctx->brush_istride, 4 * (size_t)ib, cudaMemcpyDeviceToHost), "cudaMemcpy(icache)");
     return BQ2_OK;
 }
 

@@ -277,6 +277,27 @@ bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *dmdl_blob, size_t blob
 bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t num_frames, int32_t num_verts,
                                 const float *st, const uint16_t *indexes, int32_t num_tris);
 
+/* ---- brush-model dynamic volumes: R_DrawBrushModelVolumes M:63326-63499 ---------------- */
+/* A brush model as the renderer holds it for this function: polygon p has numverts[p] vertices (glpoly_t.verts,
+ * x/y/z only) stored consecutively in verts, neighbours[slot] = polygon across edge j or -1 (glpoly_t.neighbours),
+ * fence[p] != 0 = non-casting SURF_FENCE texture (M:63387-63389; NULL = none).  At most 5,120 polygons. */
+bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numverts, const float *verts,
+                            const int32_t *neighbours, const uint8_t *fence, int32_t *brush_id);
+/* One (brush entity, light): light already in the entity's model space (bq2_host_point_to_model, the same lines
+ * M:63341-63356), scale = 32 * radius (M:63361). */
+typedef struct bq2_brush_pair { int32_t brush; float light[3]; float scale; } bq2_brush_pair;
+typedef struct bq2_brush_out {
+    float    *vcache;           /* DEVICE [n_pairs][vert_stride] x {vertex, extruded vertex} x 3 floats          */
+    uint32_t *icache;           /* DEVICE [n_pairs][index_stride] indices into the pair's vcache rows             */
+    const uint32_t *counts;     /* HOST   [n_pairs][2]: vertex pairs written (vb), indices (ib)                  */
+    uint32_t vert_stride, index_stride;
+} bq2_brush_out;
+/* lit = for pair k the n_polys bytes of its brush, concatenated in pair order: polygon stamped by the light's
+ * marking pass (lightTimestamp == r_lightTimestamp, M:63384).  Synchronous. */
+bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t n_pairs, const uint8_t *lit,
+                             bq2_brush_out *out);
+bq2_status bq2_brush_download(bq2_ctx *ctx, int32_t pair, float *vcache /*[vb][2][3]*/, uint32_t *icache /*[ib]*/);
+
 /* ---- the data formats either side of the path (host C, memory buffers) ------------------ */
 /* Com_BlockChecksum, M:40589-40602: the four words of an MD4 digest XOR-ed. */
 uint32_t   bq2_block_checksum(const void *buffer, size_t length);
