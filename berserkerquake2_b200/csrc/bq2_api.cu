@@ -1046,22 +1046,25 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     tr.lap(5);
     unsigned char *dw = ctx->d_world.p;
     bq2_world_launch &Wl = ctx->wlaunch;
-    Wl.xf = (const bq2_dev_xform *)(ctx->d_records.p + off_xf);
-    Wl.lights = (const float *)(ctx->d_records.p + off_lights);
-    Wl.pair_ent = (const int32_t *)(ctx->d_records.p + off_pe); Wl.pair_light = (const int32_t *)(ctx->d_records.p + off_pl);
+    /* (reading the pinned host records directly from the kernels instead of copying them was measured: the copy
+       stage disappears but the record-building kernels and the frame kernel get 13 + 6 us slower at C2) */
+    unsigned char *rb = ctx->d_records.p;
+    Wl.xf = (const bq2_dev_xform *)(rb + off_xf);
+    Wl.lights = (const float *)(rb + off_lights);
+    Wl.pair_ent = (const int32_t *)(rb + off_pe); Wl.pair_light = (const int32_t *)(rb + off_pl);
     Wl.n_pairs = nP; Wl.n_ents = nE; Wl.n_lights = nL; Wl.n_recs = nE; Wl.n_blocks = nblk;
-    Wl.ents = (bq2_dev_ent *)ctx->d_records.p;
+    Wl.ents = (bq2_dev_ent *)rb;
     Wl.dpairs = (bq2_dev_pair *)dw;
     Wl.cnt = (uint32_t *)(dw + w_pairs); Wl.cursor = Wl.cnt + nE;
     Wl.blk = (uint32_t *)(dw + w_pairs + w_cnt);
     Wl.pvoff = tables ? (uint32_t *)(dw + w_pairs + w_cnt + w_blk) : nullptr; Wl.pboff = tables ? Wl.pvoff + nP : nullptr;
     Wl.totals = (unsigned long long *)(ctx->index_count.p + tot_word);
     Wl.index_count = ctx->index_count.p;
-    Wl.view = (const float *)(ctx->d_records.p + off_view);
+    Wl.view = (const float *)(rb + off_view);
 
     bq2_launch &L = ctx->launch;
     L.meshes = ctx->d_meshes.p;
-    L.ents = (const bq2_dev_ent *)ctx->d_records.p;
+    L.ents = (const bq2_dev_ent *)rb;
     L.pairs = Wl.dpairs;
     L.n_ent_slots = nE; L.want = want & ~BQ2_WANT_TABLES; L.index_stride = stride;
     L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
@@ -1088,7 +1091,27 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         return BQ2_OK;
     };
     bool enqueued = false;
-    if (ctx->use_graphs && !tables) {
+    if (tr.on) {                                        /* BQ2_TRACE: GPU time of each stage of the frame, direct launches */
+        static cudaEvent_t ev[5]; static bool init = false; static double acc[4] = {0, 0, 0, 0}; static long nfr = 0;
+        if (!init) { for (auto &e : ev) cudaEventCreate(&e); init = true; }
+        cudaEventRecord(ev[0], ctx->stream);
+        if (rec_bytes) cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream);
+        cudaEventRecord(ev[1], ctx->stream);
+        if (nP && (want & BQ2_WANT_SHADOW)) { bq2_launch_world_setup(&Wl, ctx->stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
+        else cudaMemsetAsync(Wl.totals, 0, 24, ctx->stream);
+        cudaEventRecord(ev[2], ctx->stream);
+        launch_kernels(ctx);
+        cudaEventRecord(ev[3], ctx->stream);
+        cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(ev[4], ctx->stream);
+        cudaEventSynchronize(ev[4]);
+        for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms * 1e3; }
+        if (++nfr % 100 == 0)
+            fprintf(stderr, "bq2 trace (GPU, us/frame): H2D %.1f  record-building kernels %.1f  frame kernel(s) %.1f  D2H %.1f\n",
+                    acc[0] / nfr, acc[1] / nfr, acc[2] / nfr, acc[3] / nfr);
+        enqueued = true;
+    }
+    if (!enqueued && ctx->use_graphs && !tables) {
         bq2_ctx::GraphKey key{};
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, nblk, 0, 0, 0, 0, 0, 0};
