@@ -244,7 +244,7 @@ def run_gpu(args):
 
     def e2e_run(k):
         """k frames through the public C ABI from HOST data.  Each frame: bq2_world_submit (host: per-entity trig +
-        record packing -> pinned -> H2D; 3 record-building kernels + the fused kernel; D2H of the per-pair index
+        record packing -> pinned -> H2D; the record-building kernel + the fused kernel; D2H of the per-pair index
         counts and totals) and bq2_frame_wait.  Two frames in flight (the library's documented mode): frame i+1
         is packed and submitted while frame i is on the GPU."""
         tot = 0
@@ -311,7 +311,7 @@ def run_gpu(args):
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
                     "h2d_bytes_per_step": n_ents * (128 + 64) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
                     "what": "per frame: bq2_world_submit (host: per-entity trig + record packing; pinned -> H2D; "
-                            "3 record-building kernels + the fused kernel; D2H of per-pair index counts + totals) + "
+                            "the record-building kernel + the fused kernel; D2H of per-pair index counts + totals) + "
                             "bq2_frame_wait, wall clock over K frames with two frames in flight (frame i+1 packed and "
                             "submitted while frame i is on the GPU); ms_per_step_serial = one at a time; "
                             "vertex/index buffers stay in HBM for the draw"},

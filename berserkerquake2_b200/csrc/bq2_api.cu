@@ -196,6 +196,7 @@ bq2_status launch_kernels(bq2_ctx *ctx)
     }
     if (ctx->k_team.n) {
         L.ents = ctx->launch.ents + ctx->k_warp.n;
+        L.rec_base = (uint32_t)ctx->k_warp.n;
         L.n_ent_slots = ctx->k_team.n;
         CK((cudaError_t)bq2_launch_frame(&L, ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2, ctx->stream),
            "launch(bq2_frame_kernel)");
@@ -683,6 +684,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
     L.normals = ctx->normals.p; L.tangents = ctx->tangents.p; L.binormals = ctx->binormals.p;
     L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p; L.totals = nullptr; L.tri_normals = ctx->tri_normals.p;
+    L.bucket_cnt = nullptr; L.bucket = nullptr; L.ohead = nullptr; L.onext = nullptr; L.rec_base = 0;
     ctx->world_mode = false;
     ctx->max_V = maxV; ctx->max_T = maxT; ctx->any_md2 = anyMd2;
     ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
@@ -963,7 +965,6 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
             ctx->model_rows[i] = bq2_model_row{mo.hdr.data(), mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2};
         }
     }
-    const int nblk = (nP + BQ2_WORLD_THREADS - 1) / BQ2_WORLD_THREADS;
     const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
                  off_lights = off_view + 16,
                  off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
@@ -1024,14 +1025,16 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(ctx->indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
     if (ws.team_normal_rows) CK(ctx->tri_normals.ensure(4 * (size_t)ws.team_normal_rows + 4), "cudaMalloc(triangle normals)");
-    /* index counts and, 8-byte aligned right behind them, the three 64-bit totals: one D2H copy brings both */
-    const size_t tot_word = ((size_t)nP + 1) & ~(size_t)1;
-    CK(ctx->index_count.ensure(tot_word + 8), "cudaMalloc(index_count)");
+    /* one buffer: index counts | 8-byte aligned, three 64-bit totals (one D2H copy brings both) | pairs per record |
+       overflow-chain heads.  One memset clears totals .. heads (heads to 0: a chain is only walked for as many nodes
+       as were pushed). */
+    const size_t tot_word = ((size_t)nP + 1) & ~(size_t)1, cnt_word = tot_word + 8;
+    CK(ctx->index_count.ensure(cnt_word + 2 * (size_t)nE + 8), "cudaMalloc(index_count)");
     CK(h_counts.ensure(sizeof(uint32_t) * (tot_word + 8)), "cudaMallocHost(counts)");
     (void)h_totals;
-    const size_t w_pairs = (size_t)nP * sizeof(bq2_dev_pair), w_cnt = (((size_t)nE * 8 + 15) & ~(size_t)15),
-                 w_blk = (((size_t)nblk * 8 + 15) & ~(size_t)15), w_tab = tables ? (((size_t)nP * 8 + 15) & ~(size_t)15) : 0;
-    CK(ctx->d_world.ensure(w_pairs + w_cnt + w_blk + w_tab + 64), "cudaMalloc(world scratch)");
+    const size_t w_pairs = ((size_t)nP * sizeof(bq2_dev_pair) + 15) & ~(size_t)15, w_bucket = (size_t)nE * BQ2_BUCKET * 4,
+                 w_next = (size_t)nP * 4;
+    CK(ctx->d_world.ensure(w_pairs + w_bucket + w_next + 64), "cudaMalloc(world scratch)");
     if (ctx->meshes_dirty) {
         CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
         CK(cudaMemcpyAsync(ctx->d_meshes.p, ctx->meshes.data(), ctx->meshes.size() * sizeof(bq2_dev_mesh),
@@ -1052,13 +1055,12 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     Wl.xf = (const bq2_dev_xform *)(rb + off_xf);
     Wl.lights = (const float *)(rb + off_lights);
     Wl.pair_ent = (const int32_t *)(rb + off_pe); Wl.pair_light = (const int32_t *)(rb + off_pl);
-    Wl.n_pairs = nP; Wl.n_ents = nE; Wl.n_lights = nL; Wl.n_recs = nE; Wl.n_blocks = nblk;
-    Wl.ents = (bq2_dev_ent *)rb;
+    Wl.n_pairs = nP; Wl.n_ents = nE; Wl.n_lights = nL; Wl.n_recs = nE;
     Wl.dpairs = (bq2_dev_pair *)dw;
-    Wl.cnt = (uint32_t *)(dw + w_pairs); Wl.cursor = Wl.cnt + nE;
-    Wl.blk = (uint32_t *)(dw + w_pairs + w_cnt);
-    Wl.pvoff = tables ? (uint32_t *)(dw + w_pairs + w_cnt + w_blk) : nullptr; Wl.pboff = tables ? Wl.pvoff + nP : nullptr;
+    Wl.bucket = (uint32_t *)(dw + w_pairs); Wl.onext = (uint32_t *)(dw + w_pairs + w_bucket);
     Wl.totals = (unsigned long long *)(ctx->index_count.p + tot_word);
+    Wl.bucket_cnt = ctx->index_count.p + cnt_word; Wl.ohead = Wl.bucket_cnt + nE;
+    Wl.vert_stride = maxVpad; Wl.bits_stride = maxBitw;
     Wl.index_count = ctx->index_count.p;
     Wl.view = (const float *)(rb + off_view);
 
@@ -1071,6 +1073,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
     L.normals = nullptr; L.tangents = nullptr; L.binormals = nullptr; L.lightp = nullptr; L.tsh = nullptr;
     L.totals = Wl.totals; L.tri_normals = ctx->tri_normals.p;
+    L.bucket_cnt = Wl.bucket_cnt; L.bucket = Wl.bucket; L.ohead = Wl.ohead; L.onext = Wl.onext; L.rec_base = 0;
     ctx->n_ent_slots = nE; ctx->n_pair_slots = nP; ctx->n_ents = nE; ctx->n_pairs = nP;
     ctx->total_verts = total_verts;
     ctx->world_mode = true; ctx->world_tables = tables;
@@ -1080,11 +1083,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals */
     auto enqueue = [&]() -> bq2_status {
         if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
+        CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), ctx->stream), "cudaMemset(totals, pair lists)");
         if (nP && (want & BQ2_WANT_SHADOW)) {
-            CK((cudaError_t)bq2_launch_world_setup(&Wl, ctx->stream), "launch(bq2_world_* kernels)");
+            CK((cudaError_t)bq2_launch_world_setup(&Wl, ctx->stream), "launch(bq2_world_link_kernel)");
             ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
-        } else
-            CK(cudaMemsetAsync(Wl.totals, 0, 3 * sizeof(unsigned long long), ctx->stream), "cudaMemset(totals)");
+        }
         bq2_status ls = launch_kernels(ctx);
         if (ls != BQ2_OK) return ls;
         CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts + totals)");
@@ -1097,8 +1100,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         cudaEventRecord(ev[0], ctx->stream);
         if (rec_bytes) cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream);
         cudaEventRecord(ev[1], ctx->stream);
+        cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), ctx->stream);
         if (nP && (want & BQ2_WANT_SHADOW)) { bq2_launch_world_setup(&Wl, ctx->stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
-        else cudaMemsetAsync(Wl.totals, 0, 24, ctx->stream);
         cudaEventRecord(ev[2], ctx->stream);
         launch_kernels(ctx);
         cudaEventRecord(ev[3], ctx->stream);
@@ -1114,7 +1117,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     if (!enqueued && ctx->use_graphs && !tables) {
         bq2_ctx::GraphKey key{};
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
-                                ws.team_max_V, ws.team_max_T, ws.team_md2, nblk, 0, 0, 0, 0, 0, 0};
+                                ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, 0, 0, 0, 0, 0};
         memcpy(key.v, kv, sizeof kv);
         const void *kp[12] = {ctx->d_records.p, ctx->d_world.p, h_records.p, h_counts.p, ctx->lerped.p, ctx->extruded.p, ctx->facing_bits.p,
                               ctx->indices.p, ctx->index_count.p, ctx->d_meshes.p, ctx->tri_normals.p, nullptr};
@@ -1153,8 +1156,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     if (!enqueued) { bq2_status es = enqueue(); if (es != BQ2_OK) return es; }
     if (tables && nP) {
         ctx->world_pvoff.resize((size_t)nP + 1); ctx->world_pboff.resize((size_t)nP + 1);
-        CK(cudaMemcpyAsync(ctx->world_pvoff.data(), Wl.pvoff, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(tables)");
-        CK(cudaMemcpyAsync(ctx->world_pboff.data(), Wl.pboff, sizeof(uint32_t) * (size_t)nP, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(tables)");
+        for (int p = 0; p <= nP; p++) { ctx->world_pvoff[p] = (uint32_t)p * maxVpad; ctx->world_pboff[p] = (uint32_t)p * maxBitw; }
         for (int p = 0; p < nP; p++) {                 /* test / shim convenience, not on the fast path */
             int e = wd->pair_ent[p];
             if (e < 0 || e >= nE) { ctx->slot_mesh_V[p] = 0; ctx->slot_mesh_T[p] = 0; ctx->pair_slot_entslot[p] = 0; continue; }

@@ -71,8 +71,8 @@ typedef struct bq2_dev_pair {
 /* ---- device-side record building ("world" path) ------------------------------------------------
  * The host ships what it alone can compute (per ENTITY: lerp constants and, for rotated entities, the
  * AngleVectors basis -- libm trig) plus the raw light and pair lists; three small kernels turn that into the
- * per-pair records above: count pairs per entity, scan, then scatter each pair next to its entity with its
- * light moved to model space (M:63733-63745; plain mul/add, bit-exact on the device). */
+ * per-pair records above: one kernel writes every pair's record (light moved to model space, M:63733-63745;
+ * plain mul/add, bit-exact on the device) and files the pair under its entity (bucket + overflow chain). */
 typedef struct bq2_dev_xform {      /* one per world entity */
     float    origin[3];
     int32_t  rec;                   /* index of the entity's record, -1 = entity casts no volume          */
@@ -86,18 +86,17 @@ typedef struct bq2_world_launch {
     const bq2_dev_xform *xf;
     const float    *lights;         /* [n_lights][4]: origin, radius (bq2_world_light)                     */
     const int32_t  *pair_ent, *pair_light;
-    int32_t  n_pairs, n_ents, n_lights, n_recs, n_blocks;
-    bq2_dev_ent  *ents;             /* pair_begin / pair_count are filled here                             */
-    bq2_dev_pair *dpairs;
-    uint32_t *cnt, *cursor;         /* [n_recs] each, zeroed before the first kernel                       */
-    uint32_t *blk;                  /* [2][n_blocks] block sums -> block offsets                            */
-    uint32_t *pvoff, *pboff;        /* [n_pairs] offset tables for the caller, or NULL                      */
+    int32_t  n_pairs, n_ents, n_lights, n_recs;
+    bq2_dev_pair *dpairs;           /* [n_pairs], caller order                                              */
+    uint32_t *bucket_cnt;           /* [n_recs] pairs of each entity record, zeroed before the kernel       */
+    uint32_t *bucket;               /* [n_recs][BQ2_BUCKET] pair indices                                    */
+    uint32_t *ohead, *onext;        /* overflow chains: [n_recs] heads, [n_pairs] links                     */
+    uint32_t vert_stride, bits_stride;   /* output rows of pair p start at p * stride                       */
     uint32_t *index_count;
     unsigned long long *totals;     /* [0] sum of index counts, [1] overflowing pairs, [2] bad pairs        */
     const float *view;              /* device [4]: r_origin in world space, [3] != 0 when present (M:66689)  */
 } bq2_world_launch;
-#define BQ2_WORLD_THREADS 1024
-#define BQ2_WORLD_SMALL_PAIRS 1024   /* at most this many pairs and records: one single-block kernel (one pass) */
+#define BQ2_BUCKET 8                /* pairs per entity held in its bucket; further ones chain              */
 
 typedef struct bq2_launch {
     const bq2_dev_mesh *meshes;
@@ -111,6 +110,9 @@ typedef struct bq2_launch {
     float    *normals, *tangents, *binormals, *lightp, *tsh;
     unsigned long long *totals;     /* world path: [0] += index count, [1] += overflowing pair; or NULL     */
     float    *tri_normals;          /* team kernel scratch: float4 {unit normal, P0.n} per triangle per slot  */
+    /* device-built pair lists (world path), NULL for host-built records */
+    const uint32_t *bucket_cnt, *bucket, *ohead, *onext;
+    uint32_t rec_base;              /* record index of this launch's first CTA                                */
 } bq2_launch;
 
 /* host-side flat model table for the per-entity loop in C (bq2_host.c) */
@@ -142,7 +144,7 @@ int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, con
 #define BQ2_WARP_WARPS   4
 int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);       /* team */
 int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);  /* warp */
-int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* returns cudaError_t; 1 or 3 kernels */
+int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* returns cudaError_t; one kernel */
 int  bq2_world_setup_launches(const bq2_world_launch *W);
 /* neighbour tables of one mesh on the device: idx = u16 vertex indices, in_stride u16s per triangle (6 for
    dtriangle_t, 3 for WORD indexes); out = int32[3*T] (device) */

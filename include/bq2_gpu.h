@@ -358,7 +358,7 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
 /* ---- the same, fused, with the per-pair records built ON THE DEVICE ----------------------------------- */
 /* bq2_build_records + bq2_frame in one call.  The host does only what needs libm or the model table (per
  * ENTITY: lerp constants, AngleVectors for rotated entities, the flag filter); the light and pair lists are
- * copied to HBM as they are and three small kernels build the per-pair records there (light -> model space
+ * copied to HBM as they are and one small kernel builds the per-pair records there (light -> model space
  * is plain float arithmetic, bit-identical to the host's).  Differences from bq2_build_records + bq2_frame:
  *   - pair slot p IS caller pair p (a pair whose entity casts no volume keeps its slot, index_count 0);
  *   - the pair offset tables of bq2_frame_out are produced only with BQ2_WANT_TABLES (tests, the shim);

@@ -430,3 +430,36 @@ def test_two_frames_in_flight(gpu_ctx, oracle):
     got.append((int(fo.total_indices), np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()))
     for (ta, ca), (tb, cb) in zip(serial, got):
         assert ta == tb and np.array_equal(ca, cb)
+
+
+def test_world_frame_single_mesh_md3_and_many_lights(gpu_ctx, oracle):
+    """Device-built records with a one-surface MD3 (float vertices in the warp kernel) next to MD2s, and an entity lit
+    by more lights than the per-entity bucket of the fast record-building path holds (the library must fall back)."""
+    md3 = Md3Model(oracle, 12, 9, frames=4, num_meshes=1, seed=12)
+    m2 = Md2Model(oracle, 10, 7, frames=4, seed=12)
+    id3, id2 = md3.upload(gpu_ctx), m2.upload(gpu_ctx)
+    we, wl, _, _ = world_scene(6, 24, 4, seed=61)
+    we["model"] = [id3, id2, id3, id2, id2, id3]
+    pe, pl = [], []
+    for l in range(24):                       # entity 1 and 2 get all 24 lights, the others 3
+        for e in range(6):
+            if e in (1, 2) or l < 3:
+                pe.append(e); pl.append(e * 24 + l)
+    pe, pl = np.array(pe, np.int32), np.array(pl, np.int32)
+    res = gpu_ctx.world_frame(we, wl, pe, pl)
+    assert res.n_pair_slots == len(pe)
+    mesh = md3.meshes[0]
+    for p in range(len(pe)):
+        e = int(pe[p]); W = we[e]
+        if int(W["model"]) == id3:
+            w = oracle.md3_mesh_pair(mesh["verts"], mesh["indexes"], mesh["neighbours"], md3.frame_translate, int(W["frame"]),
+                                     int(W["oldframe"]), float(W["backlerp"]), W["origin"], W["oldorigin"], W["angles"],
+                                     wl["origin"][pl[p]], 300.0)
+            V, T = mesh["verts"].shape[1], len(mesh["indexes"])
+        else:
+            w = oracle.md2_pair(m2.blob, m2.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                                W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0, idx=m2.idx)
+            V, T = m2.V, m2.T
+        assert np.array_equal(bits(res.lerped(e, V)), bits(w["lerped"])), p
+        assert np.array_equal(bits(res.extruded(p, V)), bits(w["extruded"])), p
+        assert np.array_equal(res.facing(p, T), w["viss"]) and np.array_equal(res.indices(p), w["indices"]), p
