@@ -463,3 +463,29 @@ def test_world_frame_single_mesh_md3_and_many_lights(gpu_ctx, oracle):
         assert np.array_equal(bits(res.lerped(e, V)), bits(w["lerped"])), p
         assert np.array_equal(bits(res.extruded(p, V)), bits(w["extruded"])), p
         assert np.array_equal(res.facing(p, T), w["viss"]) and np.array_equal(res.indices(p), w["indices"]), p
+
+
+def test_world_frame_graph_replay_sees_new_data(gpu_ctx, oracle):
+    """Same-shape frames replay a captured CUDA graph from the third frame on: the graph must pick up each
+    frame's NEW records (different frames, lights, view) from the pinned buffers it was captured with."""
+    m = Md2Model(oracle, 10, 7, frames=6, seed=77)
+    mid = m.upload(gpu_ctx)
+    for it in range(7):
+        we, wl, pe, pl = world_scene(12, 3, 6, seed=900 + it)        # same shape, different content
+        we["model"] = mid
+        res = gpu_ctx.world_frame(we, wl, pe, pl, want=bq2.WANT_SHADOW)      # no tables: the graph-eligible route
+        tot = 0
+        for p in range(len(pe)):
+            W = we[pe[p]]
+            w = oracle.md2_pair(m.blob, m.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                                W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0, idx=m.idx)
+            assert int(res.index_counts[p]) == len(w["indices"]), (it, p)
+            got = gpu_ctx.download(_capi_module().A_INDICES, p * int(res.index_stride), len(w["indices"]), np.uint32)
+            assert np.array_equal(got, w["indices"]), (it, p)
+            tot += len(w["indices"])
+        assert int(res.total_indices) == tot, it
+
+
+def _capi_module():
+    from berserkerquake2_b200 import _capi
+    return _capi
