@@ -489,3 +489,25 @@ def test_world_frame_graph_replay_sees_new_data(gpu_ctx, oracle):
 def _capi_module():
     from berserkerquake2_b200 import _capi
     return _capi
+
+
+def test_world_frame_degenerate_shapes(gpu_ctx, oracle):
+    """no pairs, no entities, an entity nobody lights, one pair."""
+    m = Md2Model(oracle, 8, 5, frames=3, seed=2)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(3, 1, 3, seed=5)
+    we["model"] = mid
+    r = gpu_ctx.world_frame(we, wl, pe[:0], pl[:0])                       # lerp only
+    assert r.n_pair_slots == 0 and int(r.total_indices) == 0 and int(r.total_lerped_verts) == 3 * m.V
+    for e in range(3):
+        w = oracle.md2_lerp(m.blob, int(we["frame"][e]), int(we["oldframe"][e]), float(we["backlerp"][e]),
+                            we["origin"][e], we["oldorigin"][e], we["angles"][e])
+        assert np.array_equal(bits(r.lerped(e, m.V)), bits(w))
+    r = gpu_ctx.world_frame(we[:0], wl, pe[:0], pl[:0])                   # nothing at all
+    assert r.n_ent_slots == 0 and r.n_pair_slots == 0
+    r = gpu_ctx.world_frame(we, wl, pe[1:2], pl[1:2])                     # one pair; entities 0 and 2 unlit
+    w = oracle.md2_pair(m.blob, m.nb, int(we["frame"][1]), int(we["oldframe"][1]), float(we["backlerp"][1]),
+                        we["origin"][1], we["oldorigin"][1], we["angles"][1], wl["origin"][1], 300.0, idx=m.idx)
+    assert np.array_equal(r.indices(0), w["indices"])
+    from berserkerquake2_b200 import _capi as c
+    assert gpu_ctx.brush_volumes(np.zeros(0, c.BRUSH_PAIR_DTYPE), np.zeros(0, np.uint8)) == []
