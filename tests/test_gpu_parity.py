@@ -511,3 +511,53 @@ def test_world_frame_degenerate_shapes(gpu_ctx, oracle):
     assert np.array_equal(r.indices(0), w["indices"])
     from berserkerquake2_b200 import _capi as c
     assert gpu_ctx.brush_volumes(np.zeros(0, c.BRUSH_PAIR_DTYPE), np.zeros(0, np.uint8)) == []
+
+
+def test_kernel_class_boundary(gpu_ctx, oracle):
+    """T = 1,024 is the last mesh the warp kernel takes (32 ballot words per warp), T = 1,088 the first for the team
+    kernel; V = 1,022 / 1,026 straddle the vertex limit."""
+    shapes = [(16, 33), (17, 33), (30, 35), (32, 33)]
+    models = [Md2Model(oracle, s, r, frames=3, seed=20 + i) for i, (s, r) in enumerate(shapes)]
+    assert [m.T for m in models] == [1024, 1088, 2040, 2048] and [m.V for m in models] == [514, 546, 1022, 1026]
+    mids = [m.upload(gpu_ctx) for m in models]
+    we, wl, pe, pl = world_scene(8, 3, 3, n_models=4, seed=31)
+    we["model"] = np.array(mids)[we["model"]]
+    check_md2_pairs(gpu_ctx, oracle, models, mids, we, wl, pe, pl)
+    check_world(gpu_ctx, oracle, models, mids, we, wl, pe, pl)
+
+
+def test_every_edge_a_silhouette(gpu_ctx, oracle):
+    """Neighbour tables with no neighbours at all (r_simple-style / fully open meshes): every edge of every facing
+    triangle is a silhouette edge, S = 3F -- far more than either kernel stages in shared memory, so the
+    write-through paths carry the frame.  Both kernel classes, host-built and device-built records, and a
+    truncating index_stride on the team kernel."""
+    shapes = [(16, 17), (16, 33), (32, 33), (62, 34)]
+    models = [Md2Model(oracle, s, r, frames=3, seed=50 + i) for i, (s, r) in enumerate(shapes)]
+    for m in models:
+        m.nb = np.full_like(m.nb, -1)
+    mids = [m.upload(gpu_ctx) for m in models]
+    we, wl, pe, pl = world_scene(8, 2, 3, n_models=4, seed=77)
+    we["model"] = np.array(mids)[we["model"]]
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    stride = 24 * 4092
+    res = gpu_ctx.frame(ents, pairs, index_stride=stride)
+    res_w = gpu_ctx.world_frame(we, wl, pe, pl, index_stride=stride)
+    want = []
+    for p in range(len(pe)):
+        W = we[pe[p]]; m = models[mids.index(int(W["model"]))]
+        w = oracle.md2_pair(m.blob, m.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                            W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0, idx=m.idx)
+        assert len(w["indices"]) == 24 * int(w["viss"].sum())
+        want.append(w["indices"])
+    # FrameResult objects share the device arrays: compare the later frame (world) first, then redo the host-built one
+    for p in range(len(pe)):
+        assert np.array_equal(res_w.indices(p), want[p]), ("world", p)
+    res = gpu_ctx.frame(ents, pairs, index_stride=stride)
+    for p in range(len(pe)):
+        assert np.array_equal(res.indices(p), want[p]), ("host-built", p)
+    small = gpu_ctx.frame(ents, pairs, index_stride=6000, allow_overflow=True)       # truncation: prefix only, exact counts
+    assert small.status == -5
+    for p in range(len(pe)):
+        assert int(small.index_counts[p]) == len(want[p])
+        n = min(len(want[p]), 6000)
+        assert np.array_equal(small.indices(p), want[p][:n]), ("truncated", p)
