@@ -561,3 +561,43 @@ def test_every_edge_a_silhouette(gpu_ctx, oracle):
         assert int(small.index_counts[p]) == len(want[p])
         n = min(len(want[p]), 6000)
         assert np.array_equal(small.indices(p), want[p][:n]), ("truncated", p)
+
+
+def test_want_flag_combinations_and_many_lights(gpu_ctx, oracle):
+    """9 lights on one entity through host-built records (each warp takes several), BQ2_WANT_NOLERPOUT, and
+    tangent space without shadow volumes."""
+    m = Md2Model(oracle, 10, 7, frames=4, seed=5, tangent_space=True, smooth=True)
+    mid = m.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(2, 9, 4, seed=9)
+    we["model"] = mid
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl, view_world=np.array([1, 2, 3], np.float32))
+    res = gpu_ctx.frame(ents, pairs)
+    want = []
+    for p in range(18):
+        W = we[pe[p]]
+        want.append(oracle.md2_pair(m.blob, m.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                                    W["oldorigin"], W["angles"], wl["origin"][pl[p]], 300.0, idx=m.idx))
+        assert np.array_equal(res.indices(p), want[p]["indices"]), p
+    # shadow-only caller: lerped[] is not written (poison it first through a frame with other content)
+    gpu_ctx.frame(ents[::-1].copy(), None)
+    before = res.lerped(0, m.V).copy()
+    res2 = gpu_ctx.frame(ents, pairs, want=bq2.WANT_SHADOW | bq2.WANT_NOLERPOUT)
+    assert np.array_equal(bits(res2.lerped(0, m.V)), bits(before))                 # untouched
+    assert not np.array_equal(bits(before), bits(want[0]["lerped"]))
+    for p in range(18):
+        assert np.array_equal(res2.indices(p), want[p]["indices"]) and np.array_equal(bits(res2.extruded(p, m.V)), bits(want[p]["extruded"]))
+    # tangent space only
+    res3 = gpu_ctx.frame(ents, pairs, want=bq2.WANT_NTB | bq2.WANT_TSLIGHT)
+    from berserkerquake2_b200 import synth
+    for e in range(2):
+        f, of = int(we["frame"][e]), int(we["oldframe"][e]); bl = float(we["backlerp"][e]); fl = float(ents["frontlerp"][e])
+        N, T_, B = oracle.ntb_rows(synth.md2_frame_verts(m.blob, f)[:, 3], synth.md2_frame_verts(m.blob, of)[:, 3],
+                                   m.tangents[f], m.tangents[of], m.binormals[f], m.binormals[of], bl, fl)
+        gN, gT, gB = res3.ntb(e, m.V)
+        assert np.array_equal(bits(gN), bits(N)) and np.array_equal(bits(gT), bits(T_)) and np.array_equal(bits(gB), bits(B))
+        P = want[9 * e]["lerped"]
+        for l in range(9):
+            p = 9 * e + l
+            lp, ts = oracle.tslight(P, N, T_, B, pairs["light"][p], pairs["view"][p])
+            gl, gt = res3.tslight(p, m.V)
+            assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
