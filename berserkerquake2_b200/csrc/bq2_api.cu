@@ -864,9 +864,11 @@ bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numver
     uint32_t ns = 0; int worst = 0;
     for (int p = 0; p < n_polys; p++) {
         if (numverts[p] < 3) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: polygon with fewer than 3 vertices");
+        if (numverts[p] > 255) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_brush: polygon with more than 255 vertices");
         first[p] = ns; ns += (uint32_t)numverts[p]; worst += 6 * numverts[p] + 6 * (numverts[p] - 2);
     }
     first[n_polys] = ns;
+    if (ns > BQ2_BRUSH_MAX_SLOTS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_brush: too many polygon vertices");
     std::vector<uint32_t> slot_poly(ns);
     for (int p = 0; p < n_polys; p++) for (uint32_t k = first[p]; k < first[p + 1]; k++) slot_poly[k] = (uint32_t)p;
     for (uint32_t k = 0; k < ns; k++) if (neighbours[k] < -1 || neighbours[k] >= n_polys) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: neighbour out of range");
@@ -902,7 +904,7 @@ bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t 
     if (n_pairs < 0 || (n_pairs && (!pairs || !lit)) || !out) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     std::vector<bq2_brush_pair_dev_h> hp((size_t)n_pairs + 1);
-    uint32_t lit_bytes = 0, vstride = 4, istride = 4; int max_polys = 1;
+    uint32_t lit_bytes = 0, vstride = 4, istride = 4; int max_polys = 1, max_slots = 1;
     for (int k = 0; k < n_pairs; k++) {
         if (pairs[k].brush < 0 || pairs[k].brush >= (int32_t)ctx->brushes.size()) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: unknown brush");
         const bq2_ctx::Brush &b = ctx->brushes[pairs[k].brush];
@@ -910,7 +912,7 @@ bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t 
         for (int c = 0; c < 3; c++) hp[k].light[c] = pairs[k].light[c];
         lit_bytes += (uint32_t)b.n_polys;
         vstride = std::max(vstride, (uint32_t)b.n_slots); istride = std::max(istride, (uint32_t)b.worst_indices);
-        max_polys = std::max(max_polys, b.n_polys);
+        max_polys = std::max(max_polys, b.n_polys); max_slots = std::max(max_slots, b.n_slots);
     }
     const size_t o_lit = (((size_t)n_pairs * sizeof(bq2_brush_pair_dev_h)) + 15) & ~(size_t)15;
     CK(ctx->d_brush_in.ensure(o_lit + lit_bytes + 16), "cudaMalloc(brush pairs)");
@@ -922,7 +924,7 @@ bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t 
         CK(cudaMemcpyAsync(ctx->d_brush_in.p, hp.data(), (size_t)n_pairs * sizeof(bq2_brush_pair_dev_h), cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(brush pairs)");
         CK(cudaMemcpyAsync(ctx->d_brush_in.p + o_lit, lit, lit_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(lit)");
         CK((cudaError_t)bq2_launch_brush(ctx->d_brushes.p, ctx->d_brush_in.p, ctx->d_brush_in.p + o_lit, ctx->brush_vcache.p, ctx->brush_icache.p,
-                                         ctx->brush_counts.p, vstride, istride, n_pairs, max_polys, ctx->stream), "launch(bq2_brush_kernel)");
+                                         ctx->brush_counts.p, vstride, istride, n_pairs, max_polys, max_slots, ctx->stream), "launch(bq2_brush_kernel)");
         ctx->launches++;
         CK(cudaMemcpyAsync(ctx->h_brush_counts.data(), ctx->brush_counts.p, 8 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(brush counts)");
     }

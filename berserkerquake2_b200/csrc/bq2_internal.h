@@ -160,9 +160,11 @@ size_t bq2_tangents_smem_bytes(int T, int V, int num_st, int mode);
 typedef struct bq2_brush_dev_h { const uint32_t *first; const int32_t *nbr; const uint32_t *slot_poly; const float *verts;
                                  const uint8_t *fence; int32_t n_polys, n_slots; } bq2_brush_dev_h;
 typedef struct bq2_brush_pair_dev_h { int32_t brush; float light[3]; float scale; uint32_t lit_off; } bq2_brush_pair_dev_h;
-#define BQ2_BRUSH_MAX_POLYS 5120        /* two u32 per polygon in 48 KB of shared memory (default limit) */
+#define BQ2_BRUSH_MAX_POLYS 4096        /* 10 bytes per polygon + 3 per polygon vertex of shared memory          */
+#define BQ2_BRUSH_MAX_SLOTS 24576       /* a polygon has at most 255 shadow edges in front of an edge (u8 rank)  */
 int  bq2_launch_brush(const void *brushes, const void *pairs, const uint8_t *lit, float *vcache, uint32_t *icache,
-                      uint32_t *counts, uint32_t vert_stride, uint32_t index_stride, int n_pairs, int max_polys, void *stream);
+                      uint32_t *counts, uint32_t vert_stride, uint32_t index_stride, int n_pairs, int max_polys, int max_slots,
+                      void *stream);
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
 size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);

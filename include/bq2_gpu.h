@@ -280,7 +280,7 @@ bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t num_frames
 /* ---- brush-model dynamic volumes: R_DrawBrushModelVolumes M:63326-63499 ---------------- */
 /* A brush model as the renderer holds it for this function: polygon p has numverts[p] vertices (glpoly_t.verts,
  * x/y/z only) stored consecutively in verts, neighbours[slot] = polygon across edge j or -1 (glpoly_t.neighbours),
- * fence[p] != 0 = non-casting SURF_FENCE texture (M:63387-63389; NULL = none).  At most 5,120 polygons. */
+ * fence[p] != 0 = non-casting SURF_FENCE texture (M:63387-63389; NULL = none).  At most 4,096 polygons, 24,576 polygon vertices in all and 255 per polygon. */
 bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numverts, const float *verts,
                             const int32_t *neighbours, const uint8_t *fence, int32_t *brush_id);
 /* One (brush entity, light): light already in the entity's model space (bq2_host_point_to_model, the same lines
