@@ -38,6 +38,7 @@ WORKLOADS = {
 SLICES, RINGS, FRAMES = 16, 17, 198
 RADIUS = 300.0
 L2_FLUSH_BYTES = 256 << 20
+E2E_IN_FLIGHT = 3          # frames the e2e leg keeps in flight (the library allows three; results of each stay separate)
 
 
 def peaks():
@@ -224,6 +225,22 @@ def run_gpu(args):
             torch.cuda.synchronize()
         clocks.freeze()
     ms_total = float(sum(kernel_ms))
+    # informational: the same step when L2 holds none of its data but no foreign DIRTY lines either (the memset is
+    # followed by a read of a second buffer, so the step's stores evict clean lines, as in back-to-back frames)
+    flush2 = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
+    evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            for _ in range(min(args.steps, 50))]
+    for a, b in evs2:
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            flush2.sum()
+            a.record(stream)
+            ctx.replay()
+            b.record(stream)
+    torch.cuda.synchronize()
+    kernel_ms_clean = float(np.mean([a.elapsed_time(b) for a, b in evs2]))
+    launches_extra = len(evs2)
+    del flush2
 
     # ---- e2e: HOST records in through the C ABI, counts back, wall clock -----------------------------
     we_c = np.ascontiguousarray(we); wl_c = np.ascontiguousarray(wl)
@@ -245,16 +262,21 @@ def run_gpu(args):
     def e2e_run(k):
         """k frames through the public C ABI from HOST data.  Each frame: bq2_world_submit (host: per-entity trig +
         record packing -> pinned -> H2D; the record-building kernel + the fused kernel; D2H of the per-pair index
-        counts and totals) and bq2_frame_wait.  Two frames in flight (the library's documented mode): frame i+1
-        is packed and submitted while frame i is on the GPU."""
+        counts and totals) and bq2_frame_wait.  E2E_IN_FLIGHT frames in flight (the library's documented mode: each
+        frame has its own records, result arrays and stream, so frames i+1, i+2 are packed, copied and computed
+        while frame i is on the GPU and every frame's results stay valid for the consumer)."""
         tot = 0
-        e2e_submit()
-        for _ in range(k - 1):
+        depth = min(E2E_IN_FLIGHT, k)
+        for _ in range(depth - 1):
+            e2e_submit()
+        for _ in range(k - (depth - 1)):
             e2e_submit()
             tot += e2e_wait()
-        return tot + e2e_wait()
+        for _ in range(depth - 1):
+            tot += e2e_wait()
+        return tot
 
-    e2e_run(max(args.warmup, 6))       # both host slots have captured their graph before the timed frames
+    e2e_run(max(args.warmup, 12))      # every frame state of the ring has captured its graph before the timed frames
     barrier()
     launches_e2e0 = ctx.kernel_launches
     t0 = time.perf_counter()
@@ -312,8 +334,9 @@ def run_gpu(args):
                     "h2d_bytes_per_step": n_ents * (128 + 64) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
                     "what": "per frame: bq2_world_submit (host: per-entity trig + record packing; pinned -> H2D; "
                             "the record-building kernel + the fused kernel; D2H of per-pair index counts + totals) + "
-                            "bq2_frame_wait, wall clock over K frames with two frames in flight (frame i+1 packed and "
-                            "submitted while frame i is on the GPU); ms_per_step_serial = one at a time; "
+                            "bq2_frame_wait, wall clock over K frames with %d frames in flight (each has its own records, "
+                            "result arrays and stream); ms_per_step_serial = one at a time; " % E2E_IN_FLIGHT +
+                            
                             "vertex/index buffers stay in HBM for the draw"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
@@ -321,6 +344,7 @@ def run_gpu(args):
                          "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel": "bq2_frame_warp_kernel", "kernel_ms": k_ms,
+                         "kernel_ms_l2_clean_lines": kernel_ms_clean,
                          "min_traffic_bytes_per_launch": mint,
                          "achieved_min_traffic": mint / (k_ms * 1e-3) / 1e9,
                          "frac_min_traffic": mint / (k_ms * 1e-3) / 1e9 / peak},

@@ -41,7 +41,7 @@ class Context:
 
     @property
     def stream(self):
-        """cudaStream_t (int) all work of this context is launched on."""
+        """cudaStream_t (int) of the most recently submitted frame (fixed unless frames are overlapped)."""
         return c.lib.bq2_stream(self._h) or 0
 
     @property
@@ -204,6 +204,10 @@ class Context:
         st = self._check(c.lib.bq2_world_frame(self._h, C.byref(d), C.byref(out)),
                          allow=(c.E_OVERFLOW,) if allow_overflow else ())
         return FrameResult(self, out, st)
+
+    def world_submit(self, desc):
+        """bq2_world_submit of a descriptor made by world_desc (keep it alive); pair with wait()."""
+        self._check(c.lib.bq2_world_submit(self._h, C.byref(desc)))
 
     def replay(self):
         """Re-launch the last frame's kernel on the records already in HBM (no copies, no sync)."""

@@ -26,6 +26,7 @@ namespace {
 /* BQ2_TRACE=1: host time per phase of bq2_frame_submit, printed by bq2_destroy (diagnostics only) */
 struct Trace {
     bool on = getenv("BQ2_TRACE") != nullptr;
+    bool gpu = on && strcmp(getenv("BQ2_TRACE"), "host") != 0;   /* BQ2_TRACE=host: host laps only, frames stay pipelined */
     double acc[8] = {0}; long n = 0; double t0 = 0;
     static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
     void start() { if (on) t0 = now(); }
@@ -73,11 +74,55 @@ struct PinBuf {
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
+/* everything that belongs to ONE frame */
+#define BQ2_FRAME_STATES   4
+#define BQ2_MAX_IN_FLIGHT  3
+struct FrameState {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev = nullptr;
+    std::vector<int32_t>  ent_slot_first, pair_slot_first;
+    std::vector<uint32_t> ent_vert_off, pair_vert_off, pair_bits_off, ent_tb_off, pair_ts_off;
+    std::vector<uint32_t> cursor;                                /* scratch for the counting sort */
+    std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
+    std::vector<int32_t>  pair_slot_entslot;
+    std::vector<int32_t>  slot_record;                           /* entity slot -> record position */
+    std::vector<uint32_t> world_pvoff, world_pboff;
+    PinBuf hrec, hcnt;
+    struct Meta { bool world = false, tables = false; int32_t n_ent_slots = 0, n_pair_slots = 0; uint64_t total_verts = 0; uint32_t stride = 0; } meta;
+    /* A frame is ~6 stream operations.  When two consecutive frames on the same state have the same shape
+       and buffers, the operations are captured once into a CUDA graph and replayed with one call. */
+    struct GraphKey { int32_t v[20]; const void *p[12]; };
+    struct GraphCache { GraphKey key{}; bool have_key = false; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; } gcache;
+    DevBuf<unsigned char> d_records;
+    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh, tri_normals;
+    DevBuf<uint32_t> facing_bits, indices, index_count;
+    DevBuf<unsigned char> d_world;                               /* world path: dpairs | buckets | overflow chain */
+    bq2_world_launch wlaunch{};
+    bool world_mode = false, world_tables = false;
+    bq2_launch launch{};
+    /* entity-slot records are grouped by kernel: [0, n_warp) -> warp kernel, [n_warp, n_ent_slots) -> team kernel */
+    struct KLaunch { int n = 0, max_V = 0, max_T = 0, any_md2 = 0; } k_warp, k_team;
+    int max_V = 0, max_T = 0, any_md2 = 0;
+    int32_t n_ent_slots = 0, n_pair_slots = 0, n_ents = 0, n_pairs = 0;
+    uint64_t total_verts = 0;
+    bq2_frame_out out{};
+    void release() {
+        if (gcache.exec) cudaGraphExecDestroy(gcache.exec);
+        gcache.exec = nullptr;
+        d_records.release(); lerped.release(); extruded.release(); normals.release(); tangents.release(); binormals.release();
+        lightp.release(); tsh.release(); tri_normals.release(); facing_bits.release(); indices.release(); index_count.release();
+        d_world.release(); hrec.release(); hcnt.release();
+        if (ev) cudaEventDestroy(ev);
+        if (stream) cudaStreamDestroy(stream);
+        ev = nullptr; stream = nullptr;
+    }
+};
+
 } // namespace
 
 struct bq2_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;                               /* = fs[0].stream: uploads, load-time kernels, brush pairs */
     std::string err;
     uint64_t launches = 0;
     Trace trace;
@@ -88,49 +133,24 @@ struct bq2_ctx {
     DevBuf<bq2_dev_mesh> d_meshes;
     bool meshes_dirty = false;
 
-    /* frame state */
-    std::vector<int32_t>  ent_slot_first, pair_slot_first;
-    std::vector<uint32_t> ent_vert_off, pair_vert_off, pair_bits_off, ent_tb_off, pair_ts_off;
-    std::vector<uint32_t> pair_slot_ent, cursor;                 /* scratch for the counting sort */
-    std::vector<int32_t>  slot_mesh_V, slot_mesh_T;              /* per pair slot, for expand    */
-    std::vector<int32_t>  pair_slot_entslot;
     std::vector<bq2_model_row> model_rows;                       /* flat mirror of models for the C entity loop */
     std::vector<float>    ent_basis;                             /* build_records scratch: f, r, u, state */
-    /* host side of a frame is double-buffered so that frame i+1 can be packed and submitted while frame i is
-       still on the GPU (device arrays are reused: work on the stream is ordered) */
-    PinBuf hrec[2], hcnt[2], htot[2];
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    struct Meta { bool world = false, tables = false; int32_t n_ent_slots = 0, n_pair_slots = 0; uint64_t total_verts = 0; uint32_t stride = 0; } meta[2];
+    std::vector<bq2_entity> tmp_ents; std::vector<bq2_pair> tmp_pairs;     /* host-built fallback of the world path */
+    /* Complete frame states (host tables, pinned buffers, device records AND device result arrays, stream, event,
+       graph) used as a ring: frames i+1, i+2 are packed, copied and computed while frame i is still on the GPU or
+       being consumed.  A submit takes the next state of the ring when a frame is in flight, the same one otherwise;
+       with at most BQ2_MAX_IN_FLIGHT in flight the state bq2_frame_wait returned last is never the one taken next. */
+    FrameState fs[BQ2_FRAME_STATES];
+    int cur = 0;                                                 /* state of the most recently submitted frame */
     uint64_t submit_seq = 0, wait_seq = 0;
     int last_waited = 0;
-    /* A frame is ~9 stream operations.  When two consecutive frames on the same host slot have the same shape
-       and buffers, the operations are captured once into a CUDA graph and replayed with one call. */
-    struct GraphKey { int32_t v[20]; const void *p[12]; };
-    struct GraphCache { GraphKey key{}; bool have_key = false; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; } gcache[2];
     bool use_graphs = getenv("BQ2_NO_GRAPH") == nullptr;
-    DevBuf<unsigned char> d_records;
-    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh, tri_normals;
-    DevBuf<uint32_t> facing_bits, indices, index_count;
-    /* world path (device-built pair records) */
-    DevBuf<unsigned char> d_world;                               /* dpairs | cnt | cursor | blk | tables | totals */
-    bq2_world_launch wlaunch{};
-    bool world_mode = false, world_tables = false;
-    std::vector<bq2_entity> tmp_ents; std::vector<bq2_pair> tmp_pairs;     /* host-built fallback */
-    std::vector<uint32_t> world_pvoff, world_pboff;
+    bool submitted = false;
     /* brush models (8f.4) */
     struct Brush { int n_polys = 0, n_slots = 0, worst_indices = 0; };
     std::vector<Brush> brushes; std::vector<bq2_brush_dev_h> brush_dev; DevBuf<bq2_brush_dev_h> d_brushes;
     DevBuf<unsigned char> d_brush_in; DevBuf<float> brush_vcache; DevBuf<uint32_t> brush_icache, brush_counts;
     std::vector<uint32_t> h_brush_counts; uint32_t brush_vstride = 0, brush_istride = 0; int brush_pairs = 0;
-    bq2_launch launch{};
-    /* entity-slot records are grouped by kernel: [0, n_warp) -> warp kernel, [n_warp, n_ent_slots) -> team kernel */
-    struct KLaunch { int n = 0, max_V = 0, max_T = 0, any_md2 = 0; } k_warp, k_team;
-    std::vector<int32_t> slot_record;                             /* entity slot -> record position */
-    int max_V = 0, max_T = 0, any_md2 = 0;
-    int32_t n_ent_slots = 0, n_pair_slots = 0, n_ents = 0, n_pairs = 0;
-    uint64_t total_verts = 0;
-    bool submitted = false;
-    bq2_frame_out out{};
 };
 
 namespace {
@@ -185,20 +205,20 @@ void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t 
 }
 
 /* the frame's kernels: warp-per-pair over the small-mesh records, CTA-per-pair over the rest */
-bq2_status launch_kernels(bq2_ctx *ctx)
+bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F)
 {
-    bq2_launch L = ctx->launch;
-    if (ctx->k_warp.n) {
-        L.n_ent_slots = ctx->k_warp.n;
-        CK((cudaError_t)bq2_launch_frame_warp(&L, ctx->k_warp.max_V, ctx->k_warp.max_T, ctx->k_warp.any_md2, ctx->stream),
+    bq2_launch L = F.launch;
+    if (F.k_warp.n) {
+        L.n_ent_slots = F.k_warp.n;
+        CK((cudaError_t)bq2_launch_frame_warp(&L, F.k_warp.max_V, F.k_warp.max_T, F.k_warp.any_md2, F.stream),
            "launch(bq2_frame_warp_kernel)");
         ctx->launches++;
     }
-    if (ctx->k_team.n) {
-        L.ents = ctx->launch.ents + ctx->k_warp.n;
-        L.rec_base = (uint32_t)ctx->k_warp.n;
-        L.n_ent_slots = ctx->k_team.n;
-        CK((cudaError_t)bq2_launch_frame(&L, ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2, ctx->stream),
+    if (F.k_team.n) {
+        L.ents = F.launch.ents + F.k_warp.n;
+        L.rec_base = (uint32_t)F.k_warp.n;
+        L.n_ent_slots = F.k_team.n;
+        CK((cudaError_t)bq2_launch_frame(&L, F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2, F.stream),
            "launch(bq2_frame_kernel)");
         ctx->launches++;
     }
@@ -232,10 +252,20 @@ bq2_status bq2_create(int device, bq2_ctx **out)
         g_create_error = "bq2_create: kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
         delete ctx; return BQ2_E_NODEVICE;
     }
-    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaStreamCreate"); delete ctx; return BQ2_E_CUDA; }
-    for (int k = 0; k < 2; k++)
-        if ((e = cudaEventCreateWithFlags(&ctx->ev[k], cudaEventDisableTiming)) != cudaSuccess) { fail_cuda(nullptr, e, "cudaEventCreate"); cudaStreamDestroy(ctx->stream); delete ctx; return BQ2_E_CUDA; }
-    if ((e = (cudaError_t)bq2_kernel_prepare()) != cudaSuccess) { fail_cuda(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)"); cudaStreamDestroy(ctx->stream); delete ctx; return BQ2_E_CUDA; }
+    for (int k = 0; k < BQ2_FRAME_STATES; k++) {
+        if ((e = cudaStreamCreateWithFlags(&ctx->fs[k].stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&ctx->fs[k].ev, cudaEventDisableTiming)) != cudaSuccess) {
+            fail_cuda(nullptr, e, "cudaStreamCreate / cudaEventCreate");
+            for (FrameState &f : ctx->fs) f.release();
+            delete ctx; return BQ2_E_CUDA;
+        }
+    }
+    ctx->stream = ctx->fs[0].stream;
+    if ((e = (cudaError_t)bq2_kernel_prepare()) != cudaSuccess) {
+        fail_cuda(nullptr, e, "cudaFuncSetAttribute(max dynamic smem)");
+        for (FrameState &f : ctx->fs) f.release();
+            delete ctx; return BQ2_E_CUDA;
+    }
     *out = ctx;
     return BQ2_OK;
 }
@@ -244,27 +274,22 @@ void bq2_destroy(bq2_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (FrameState &f : ctx->fs) if (f.stream) cudaStreamSynchronize(f.stream);
     if (ctx->trace.on && ctx->trace.n) {
         static const char *nm[8] = {"validate+slots/class", "class split", "entity records", "pair offsets/memcpy", "pair records",
                                     "buffers", "h2d+launch+d2h calls", ""};
         for (int i = 0; i < 7; i++) fprintf(stderr, "bq2 trace: %-22s %8.2f us/frame\n", nm[i], ctx->trace.acc[i] / ctx->trace.n);
     }
     for (Slab &s : ctx->slabs) cudaFree(s.base);
-    ctx->d_meshes.release(); ctx->d_records.release();
-    ctx->lerped.release(); ctx->extruded.release(); ctx->normals.release(); ctx->tangents.release();
-    ctx->binormals.release(); ctx->lightp.release(); ctx->tsh.release(); ctx->tri_normals.release();
-    ctx->facing_bits.release(); ctx->indices.release(); ctx->index_count.release();
-    for (int k = 0; k < 2; k++) if (ctx->gcache[k].exec) cudaGraphExecDestroy(ctx->gcache[k].exec);
-    for (int k = 0; k < 2; k++) { ctx->hrec[k].release(); ctx->hcnt[k].release(); ctx->htot[k].release(); if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]); }
-    ctx->d_world.release(); ctx->d_brushes.release(); ctx->d_brush_in.release(); ctx->brush_vcache.release();
+    ctx->d_meshes.release();
+    ctx->d_brushes.release(); ctx->d_brush_in.release(); ctx->brush_vcache.release();
     ctx->brush_icache.release(); ctx->brush_counts.release();
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    for (FrameState &f : ctx->fs) f.release();                   /* streams and events included */
     delete ctx;
 }
 
 const char *bq2_last_error(const bq2_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
-void *bq2_stream(bq2_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+void *bq2_stream(bq2_ctx *ctx) { return ctx ? (void *)ctx->fs[ctx->cur].stream : nullptr; }   /* of the last submitted frame */
 int bq2_device(const bq2_ctx *ctx) { return ctx ? ctx->device : -1; }
 uint64_t bq2_kernel_launches(const bq2_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
@@ -494,16 +519,17 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     if (!fd || fd->n_ents < 0 || fd->n_pairs < 0 || (fd->n_ents > 0 && !fd->ents) || (fd->n_pairs > 0 && !fd->pairs))
         return fail(ctx, BQ2_E_INVALID, "bq2_frame: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    if (ctx->submit_seq - ctx->wait_seq >= 2) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: two frames are already in flight, call bq2_frame_wait first");
-    const int slot_k = (int)(ctx->submit_seq & 1);
-    PinBuf &h_records = ctx->hrec[slot_k], &h_counts = ctx->hcnt[slot_k];
+    if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: three frames are already in flight, call bq2_frame_wait first");
+    const int slot_k = (ctx->submit_seq != ctx->wait_seq) ? (ctx->cur + 1) % BQ2_FRAME_STATES : ctx->cur;   /* ring */
+    FrameState &F = ctx->fs[slot_k];
+    PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
     const int nE = fd->n_ents, nP = fd->n_pairs;
     const int nModels = (int)ctx->models.size();
     const uint32_t want = fd->want;
     Trace &tr = ctx->trace; tr.start(); tr.n++;
 
     /* ---- entity slots ------------------------------------------------------------------------- */
-    ctx->ent_slot_first.resize((size_t)nE + 1);
+    F.ent_slot_first.resize((size_t)nE + 1);
     int nES = 0, maxV = 0, maxT = 0, anyMd2 = 0;
     for (int e = 0; e < nE; e++) {
         int mid = fd->ents[e].model;
@@ -511,28 +537,28 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         const Model &mo = ctx->models[mid];
         if (fd->ents[e].frame < 0 || fd->ents[e].frame >= mo.F || fd->ents[e].oldframe < 0 || fd->ents[e].oldframe >= mo.F)
             return fail(ctx, BQ2_E_INVALID, "bq2_frame: frame out of range");
-        ctx->ent_slot_first[e] = nES; nES += mo.n_mesh;
+        F.ent_slot_first[e] = nES; nES += mo.n_mesh;
     }
-    ctx->ent_slot_first[nE] = nES;
-    ctx->ent_vert_off.resize((size_t)nES + 1); ctx->ent_tb_off.resize((size_t)nES + 1);
-    ctx->cursor.assign((size_t)nES + 1, 0u);                    /* pair-slot count per entity slot */
+    F.ent_slot_first[nE] = nES;
+    F.ent_vert_off.resize((size_t)nES + 1); F.ent_tb_off.resize((size_t)nES + 1);
+    F.cursor.assign((size_t)nES + 1, 0u);                    /* pair-slot count per entity slot */
 
     /* ---- pair slots ---------------------------------------------------------------------------- */
-    ctx->pair_slot_first.resize((size_t)nP + 1);
+    F.pair_slot_first.resize((size_t)nP + 1);
     int nPS = 0;
     for (int p = 0; p < nP; p++) {
         int e = fd->pairs[p].entity;
         if (e < 0) e = ~e;                                       /* a pair that keeps its slot but casts nothing */
         if (e < 0 || e >= nE) return fail(ctx, BQ2_E_INVALID, "bq2_frame: pair refers to an unknown entity");
-        ctx->pair_slot_first[p] = nPS; nPS += ctx->models[fd->ents[e].model].n_mesh;
+        F.pair_slot_first[p] = nPS; nPS += ctx->models[fd->ents[e].model].n_mesh;
     }
-    ctx->pair_slot_first[nP] = nPS;
-    ctx->pair_vert_off.resize((size_t)nPS + 1); ctx->pair_bits_off.resize((size_t)nPS + 1); ctx->pair_ts_off.resize((size_t)nPS + 1);
-    ctx->slot_mesh_V.resize((size_t)nPS); ctx->slot_mesh_T.resize((size_t)nPS); ctx->pair_slot_entslot.resize((size_t)nPS);
+    F.pair_slot_first[nP] = nPS;
+    F.pair_vert_off.resize((size_t)nPS + 1); F.pair_bits_off.resize((size_t)nPS + 1); F.pair_ts_off.resize((size_t)nPS + 1);
+    F.slot_mesh_V.resize((size_t)nPS); F.slot_mesh_T.resize((size_t)nPS); F.pair_slot_entslot.resize((size_t)nPS);
 
     size_t rec_bytes = (size_t)nES * sizeof(bq2_dev_ent) + (size_t)nPS * sizeof(bq2_dev_pair);
     CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
-    CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
+    CK(F.d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
     bq2_dev_ent  *he = (bq2_dev_ent *)h_records.p;
     bq2_dev_pair *hp = (bq2_dev_pair *)(h_records.p + (size_t)nES * sizeof(bq2_dev_ent));
 
@@ -540,21 +566,21 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     /* which kernel takes each entity slot: small meshes -> one warp per pair; large meshes and the
        tangent-space outputs -> the whole CTA per pair */
     const bool team_only = (want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT)) != 0;
-    ctx->slot_record.resize((size_t)nES);
-    ctx->k_warp = bq2_ctx::KLaunch(); ctx->k_team = bq2_ctx::KLaunch();
+    F.slot_record.resize((size_t)nES);
+    F.k_warp = FrameState::KLaunch(); F.k_team = FrameState::KLaunch();
     for (int e = 0; e < nE; e++) {
         const Model &mo = ctx->models[fd->ents[e].model];
         for (int m = 0; m < mo.n_mesh; m++) {
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
             bool small = !team_only && me.V <= BQ2_WARP_MAX_V && me.T <= BQ2_WARP_MAX_T;
-            bq2_ctx::KLaunch &k = small ? ctx->k_warp : ctx->k_team;
-            ctx->slot_record[(size_t)ctx->ent_slot_first[e] + m] = small ? k.n : -1 - k.n;
+            FrameState::KLaunch &k = small ? F.k_warp : F.k_team;
+            F.slot_record[(size_t)F.ent_slot_first[e] + m] = small ? k.n : -1 - k.n;
             k.n++; k.max_V = std::max(k.max_V, me.V); k.max_T = std::max(k.max_T, me.T);
             if (!(me.flags & BQ2_MESH_MD3)) k.any_md2 = 1;
         }
     }
     for (int s = 0; s < nES; s++)
-        if (ctx->slot_record[s] < 0) ctx->slot_record[s] = ctx->k_warp.n + (-1 - ctx->slot_record[s]);
+        if (F.slot_record[s] < 0) F.slot_record[s] = F.k_warp.n + (-1 - F.slot_record[s]);
 
     tr.lap(1);
     uint32_t voff = 0, tboff = 0, team_rows = 0;
@@ -563,20 +589,20 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         const bq2_entity &E = fd->ents[e];
         const Model &mo = ctx->models[E.model];
         for (int m = 0; m < mo.n_mesh; m++) {
-            int s = ctx->ent_slot_first[e] + m;
+            int s = F.ent_slot_first[e] + m;
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
             if ((want & BQ2_WANT_NTB) && !(me.flags & BQ2_MESH_HAS_TB))
                 return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_NTB but the model was uploaded without tangent/binormal bytes");
-            bq2_dev_ent &d = he[ctx->slot_record[s]];
+            bq2_dev_ent &d = he[F.slot_record[s]];
             d.cur = me.verts + (size_t)E.frame * me.vstride; d.old = me.verts + (size_t)E.oldframe * me.vstride;
             d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.nrm_off = 0;
-            if (ctx->slot_record[s] >= ctx->k_warp.n) { d.nrm_off = team_rows; team_rows += (uint32_t)me.Tp; }
+            if (F.slot_record[s] >= F.k_warp.n) { d.nrm_off = team_rows; team_rows += (uint32_t)me.Tp; }
             d.mesh = mo.first_mesh + m; d.frame = E.frame; d.oldframe = E.oldframe; d.flags = E.flags;
             d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
             for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
             d.shell_scale = E.shell_scale;
             d.vert_off = voff; d.tb_off = tboff; d.pair_begin = 0; d.pair_count = 0;
-            ctx->ent_vert_off[s] = voff; ctx->ent_tb_off[s] = tboff;
+            F.ent_vert_off[s] = voff; F.ent_tb_off[s] = tboff;
             voff += (uint32_t)(me.V + 3) & ~3u;
             tboff += (uint32_t)(((me.flags & BQ2_MESH_SMOOTH) ? me.V : me.T) + 3) & ~3u;
             total_verts += (uint64_t)me.V;
@@ -584,7 +610,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             if (!(me.flags & BQ2_MESH_MD3)) anyMd2 = 1;
         }
     }
-    ctx->ent_vert_off[nES] = voff; ctx->ent_tb_off[nES] = tboff;
+    F.ent_vert_off[nES] = voff; F.ent_tb_off[nES] = tboff;
     const uint32_t ent_verts = voff, tb_rows = tboff;
 
     tr.lap(2);
@@ -596,25 +622,25 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         if (dead) e = ~e;
         const Model &mo = ctx->models[fd->ents[e].model];
         for (int m = 0; m < mo.n_mesh; m++) {
-            int ps = ctx->pair_slot_first[p] + m, es = ctx->ent_slot_first[e] + m;
+            int ps = F.pair_slot_first[p] + m, es = F.ent_slot_first[e] + m;
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
-            ctx->pair_vert_off[ps] = pvoff; ctx->pair_bits_off[ps] = pboff; ctx->pair_ts_off[ps] = ptsoff;
+            F.pair_vert_off[ps] = pvoff; F.pair_bits_off[ps] = pboff; F.pair_ts_off[ps] = ptsoff;
             /* LightP / tsH rows: per vertex, or per triangle corner for a non-smooth MD2 (M:64943-65017) */
             ptsoff += (uint32_t)(((me.flags & BQ2_MESH_SMOOTH) ? me.V : 3 * me.T) + 3) & ~3u;
-            ctx->slot_mesh_V[ps] = me.V; ctx->slot_mesh_T[ps] = me.T; ctx->pair_slot_entslot[ps] = es;
+            F.slot_mesh_V[ps] = me.V; F.slot_mesh_T[ps] = me.T; F.pair_slot_entslot[ps] = es;
             pvoff += (uint32_t)(me.V + 3) & ~3u;
             pboff += (uint32_t)(me.T + 31) >> 5;
-            if (mo.casts[m] && !dead) ctx->cursor[es]++;
+            if (mo.casts[m] && !dead) F.cursor[es]++;
         }
     }
-    ctx->pair_vert_off[nPS] = pvoff; ctx->pair_bits_off[nPS] = pboff; ctx->pair_ts_off[nPS] = ptsoff;
+    F.pair_vert_off[nPS] = pvoff; F.pair_bits_off[nPS] = pboff; F.pair_ts_off[nPS] = ptsoff;
     uint32_t n_dev_pairs = 0;
     {
         uint32_t run = 0;
         for (int s = 0; s < nES; s++) {
-            uint32_t c = ctx->cursor[s];
-            bq2_dev_ent &d = he[ctx->slot_record[s]];
-            d.pair_begin = run; d.pair_count = c; ctx->cursor[s] = run; run += c;
+            uint32_t c = F.cursor[s];
+            bq2_dev_ent &d = he[F.slot_record[s]];
+            d.pair_begin = run; d.pair_count = c; F.cursor[s] = run; run += c;
         }
         n_dev_pairs = run;
     }
@@ -625,11 +651,11 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         const Model &mo = ctx->models[fd->ents[P.entity].model];
         for (int m = 0; m < mo.n_mesh; m++) {
             if (!mo.casts[m]) continue;
-            int ps = ctx->pair_slot_first[p] + m, es = ctx->ent_slot_first[P.entity] + m;
-            bq2_dev_pair &d = hp[ctx->cursor[es]++];
+            int ps = F.pair_slot_first[p] + m, es = F.ent_slot_first[P.entity] + m;
+            bq2_dev_pair &d = hp[F.cursor[es]++];
             for (int k = 0; k < 3; k++) { d.light[k] = P.light[k]; d.view[k] = P.view[k]; }
-            d.scale = P.scale; d.vert_off = ctx->pair_vert_off[ps]; d.bits_off = ctx->pair_bits_off[ps];
-            d.slot = (uint32_t)ps; d.pad[0] = ctx->pair_ts_off[ps]; d.pad[1] = 0;
+            d.scale = P.scale; d.vert_off = F.pair_vert_off[ps]; d.bits_off = F.pair_bits_off[ps];
+            d.slot = (uint32_t)ps; d.pad[0] = F.pair_ts_off[ps]; d.pad[1] = 0;
         }
     }
 
@@ -638,65 +664,65 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     stride = (stride + 3u) & ~3u;
 
     /* ---- output capacity ------------------------------------------------------------------------ */
-    CK(ctx->lerped.ensure(3 * (size_t)ent_verts + 4), "cudaMalloc(lerped)");
+    CK(F.lerped.ensure(3 * (size_t)ent_verts + 4), "cudaMalloc(lerped)");
     if (want & BQ2_WANT_SHADOW) {
-        CK(ctx->extruded.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(extruded)");
-        CK(ctx->facing_bits.ensure((size_t)pboff + 1), "cudaMalloc(facing_bits)");
-        CK(ctx->indices.ensure((size_t)nPS * stride + 4), "cudaMalloc(indices)");
+        CK(F.extruded.ensure(3 * (size_t)pvoff + 4), "cudaMalloc(extruded)");
+        CK(F.facing_bits.ensure((size_t)pboff + 1), "cudaMalloc(facing_bits)");
+        CK(F.indices.ensure((size_t)nPS * stride + 4), "cudaMalloc(indices)");
     }
-    CK(ctx->index_count.ensure((size_t)nPS + 1), "cudaMalloc(index_count)");
+    CK(F.index_count.ensure((size_t)nPS + 1), "cudaMalloc(index_count)");
     if (want & BQ2_WANT_NTB) {
-        CK(ctx->normals.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(normals)");
-        CK(ctx->tangents.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(tangents)");
-        CK(ctx->binormals.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(binormals)");
+        CK(F.normals.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(normals)");
+        CK(F.tangents.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(tangents)");
+        CK(F.binormals.ensure(3 * (size_t)tb_rows + 4), "cudaMalloc(binormals)");
     }
     if (want & BQ2_WANT_TSLIGHT) {
         if (!(want & BQ2_WANT_NTB)) return fail(ctx, BQ2_E_INVALID, "bq2_frame: BQ2_WANT_TSLIGHT needs BQ2_WANT_NTB");
-        CK(ctx->lightp.ensure(3 * (size_t)ptsoff + 4), "cudaMalloc(lightp)");
-        CK(ctx->tsh.ensure(3 * (size_t)ptsoff + 4), "cudaMalloc(tsh)");
+        CK(F.lightp.ensure(3 * (size_t)ptsoff + 4), "cudaMalloc(lightp)");
+        CK(F.tsh.ensure(3 * (size_t)ptsoff + 4), "cudaMalloc(tsh)");
     }
-    if (team_rows) CK(ctx->tri_normals.ensure(4 * (size_t)team_rows + 4), "cudaMalloc(triangle normals)");
+    if (team_rows) CK(F.tri_normals.ensure(4 * (size_t)team_rows + 4), "cudaMalloc(triangle normals)");
     CK(h_counts.ensure(sizeof(uint32_t) * ((size_t)nPS + 1)), "cudaMallocHost(counts)");
     if (ctx->meshes_dirty) {
         CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
         CK(cudaMemcpyAsync(ctx->d_meshes.p, ctx->meshes.data(), ctx->meshes.size() * sizeof(bq2_dev_mesh),
-                           cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(mesh table)");
-        CK(cudaStreamSynchronize(ctx->stream), "sync(mesh table)");   /* source is pageable */
+                           cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(mesh table)");
+        CK(cudaStreamSynchronize(F.stream), "sync(mesh table)");   /* source is pageable */
         ctx->meshes_dirty = false;
     }
-    if (ctx->k_team.n && bq2_kernel_smem_bytes(ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2) > 227u * 1024u)
+    if (F.k_team.n && bq2_kernel_smem_bytes(F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2) > 227u * 1024u)
         return fail(ctx, BQ2_E_LIMIT, "bq2_frame: mesh too large for one CTA's shared memory");
 
     /* ---- go -------------------------------------------------------------------------------------- */
     tr.lap(5);
     if (rec_bytes)
-        CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(records)");
+        CK(cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(records)");
     /* slots of non-casting MD3 meshes are never written by a kernel: only then is the clear needed */
     if (nPS && n_dev_pairs != (uint32_t)nPS)
-        CK(cudaMemsetAsync(ctx->index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, ctx->stream), "cudaMemset(index_count)");
+        CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, F.stream), "cudaMemset(index_count)");
 
-    bq2_launch &L = ctx->launch;
+    bq2_launch &L = F.launch;
     L.meshes = ctx->d_meshes.p;
-    L.ents = (const bq2_dev_ent *)ctx->d_records.p;
-    L.pairs = (const bq2_dev_pair *)(ctx->d_records.p + (size_t)nES * sizeof(bq2_dev_ent));
+    L.ents = (const bq2_dev_ent *)F.d_records.p;
+    L.pairs = (const bq2_dev_pair *)(F.d_records.p + (size_t)nES * sizeof(bq2_dev_ent));
     L.n_ent_slots = nES; L.want = want; L.index_stride = stride;
-    L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
-    L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
-    L.normals = ctx->normals.p; L.tangents = ctx->tangents.p; L.binormals = ctx->binormals.p;
-    L.lightp = ctx->lightp.p; L.tsh = ctx->tsh.p; L.totals = nullptr; L.tri_normals = ctx->tri_normals.p;
+    L.lerped = F.lerped.p; L.extruded = F.extruded.p; L.facing_bits = F.facing_bits.p;
+    L.indices = F.indices.p; L.index_count = F.index_count.p;
+    L.normals = F.normals.p; L.tangents = F.tangents.p; L.binormals = F.binormals.p;
+    L.lightp = F.lightp.p; L.tsh = F.tsh.p; L.totals = nullptr; L.tri_normals = F.tri_normals.p;
     L.bucket_cnt = nullptr; L.bucket = nullptr; L.ohead = nullptr; L.onext = nullptr; L.rec_base = 0;
-    ctx->world_mode = false;
-    ctx->max_V = maxV; ctx->max_T = maxT; ctx->any_md2 = anyMd2;
-    ctx->n_ent_slots = nES; ctx->n_pair_slots = nPS; ctx->n_ents = nE; ctx->n_pairs = nP;
-    ctx->total_verts = total_verts;
-    { bq2_status ls = launch_kernels(ctx); if (ls != BQ2_OK) return ls; }
-    if (nPS) CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (size_t)nPS,
-                                cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts)");
+    F.world_mode = false;
+    F.max_V = maxV; F.max_T = maxT; F.any_md2 = anyMd2;
+    F.n_ent_slots = nES; F.n_pair_slots = nPS; F.n_ents = nE; F.n_pairs = nP;
+    F.total_verts = total_verts;
+    { bq2_status ls = launch_kernels(ctx, F); if (ls != BQ2_OK) return ls; }
+    if (nPS) CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (size_t)nPS,
+                                cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts)");
     ctx->submitted = true;
-    { bq2_ctx::Meta &m = ctx->meta[slot_k]; m.world = false; m.tables = false; m.n_ent_slots = nES; m.n_pair_slots = nPS;
+    { FrameState::Meta &m = F.meta; m.world = false; m.tables = false; m.n_ent_slots = nES; m.n_pair_slots = nPS;
       m.total_verts = total_verts; m.stride = stride; }
-    CK(cudaEventRecord(ctx->ev[slot_k], ctx->stream), "cudaEventRecord(frame)");
-    ctx->submit_seq++;
+    CK(cudaEventRecord(F.ev, F.stream), "cudaEventRecord(frame)");
+    ctx->submit_seq++; ctx->cur = slot_k;
     tr.lap(6);
     return BQ2_OK;
 }
@@ -707,37 +733,38 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
     if (!ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_frame_wait: nothing submitted");
     int k;
     if (ctx->submit_seq == ctx->wait_seq) {                      /* nothing pending (e.g. after bq2_frame_replay) */
-        CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(frame)");
+        CK(cudaStreamSynchronize(ctx->fs[ctx->cur].stream), "cudaStreamSynchronize(frame)");
         k = ctx->last_waited;
     } else {                                                     /* the OLDEST frame in flight */
-        k = (int)(ctx->wait_seq & 1);
-        CK(cudaEventSynchronize(ctx->ev[k]), "cudaEventSynchronize(frame)");
+        k = (ctx->cur + BQ2_FRAME_STATES - (int)(ctx->submit_seq - ctx->wait_seq - 1)) % BQ2_FRAME_STATES;
+        CK(cudaEventSynchronize(ctx->fs[k].ev), "cudaEventSynchronize(frame)");
         ctx->wait_seq++; ctx->last_waited = k;
     }
-    const bq2_ctx::Meta &m = ctx->meta[k];
-    bq2_frame_out &o = ctx->out;
+    FrameState &F = ctx->fs[k];
+    const FrameState::Meta &m = F.meta;
+    bq2_frame_out &o = F.out;
     o.n_ent_slots = m.n_ent_slots; o.n_pair_slots = m.n_pair_slots;
-    o.ent_slot_first = ctx->ent_slot_first.data(); o.pair_slot_first = ctx->pair_slot_first.data();
-    o.ent_vert_offset = ctx->ent_vert_off.data(); o.pair_vert_offset = ctx->pair_vert_off.data();
-    o.pair_bits_offset = ctx->pair_bits_off.data(); o.ent_tb_offset = ctx->ent_tb_off.data();
-    o.pair_ts_offset = ctx->pair_ts_off.data();
-    o.lerped = ctx->lerped.p; o.extruded = ctx->extruded.p; o.facing_bits = ctx->facing_bits.p;
-    o.indices = ctx->indices.p; o.index_count = ctx->index_count.p;
-    o.normals = ctx->normals.p; o.tangents = ctx->tangents.p; o.binormals = ctx->binormals.p;
-    o.lightp = ctx->lightp.p; o.tsh = ctx->tsh.p;
+    o.ent_slot_first = F.ent_slot_first.data(); o.pair_slot_first = F.pair_slot_first.data();
+    o.ent_vert_offset = F.ent_vert_off.data(); o.pair_vert_offset = F.pair_vert_off.data();
+    o.pair_bits_offset = F.pair_bits_off.data(); o.ent_tb_offset = F.ent_tb_off.data();
+    o.pair_ts_offset = F.pair_ts_off.data();
+    o.lerped = F.lerped.p; o.extruded = F.extruded.p; o.facing_bits = F.facing_bits.p;
+    o.indices = F.indices.p; o.index_count = F.index_count.p;
+    o.normals = F.normals.p; o.tangents = F.tangents.p; o.binormals = F.binormals.p;
+    o.lightp = F.lightp.p; o.tsh = F.tsh.p;
     o.index_stride = m.stride;
     o.total_lerped_verts = m.total_verts;
     o.total_pairs = 0; o.total_indices = 0; o.overflow_pairs = 0;
     if (m.world) {                                               /* totals were accumulated by the kernels */
-        const unsigned long long *t = (const unsigned long long *)((const uint32_t *)ctx->hcnt[k].p + (((size_t)m.n_pair_slots + 1) & ~(size_t)1));
+        const unsigned long long *t = (const unsigned long long *)((const uint32_t *)F.hcnt.p + (((size_t)m.n_pair_slots + 1) & ~(size_t)1));
         o.total_indices = t[0]; o.overflow_pairs = (int32_t)t[1];
         o.pair_slot_first = nullptr;                             /* slot p is caller pair p */
         o.pair_ts_offset = nullptr;
-        o.pair_vert_offset = m.tables ? ctx->world_pvoff.data() : nullptr;
-        o.pair_bits_offset = m.tables ? ctx->world_pboff.data() : nullptr;
+        o.pair_vert_offset = m.tables ? F.world_pvoff.data() : nullptr;
+        o.pair_bits_offset = m.tables ? F.world_pboff.data() : nullptr;
         if (t[2]) { o.total_pairs = (uint64_t)m.n_pair_slots; if (out) *out = o; return fail(ctx, BQ2_E_INVALID, "bq2_world: a pair refers to an entity or light out of range (it was skipped)"); }
     } else {
-        const uint32_t *cnt = (const uint32_t *)ctx->hcnt[k].p;
+        const uint32_t *cnt = (const uint32_t *)F.hcnt.p;
         for (int i = 0; i < m.n_pair_slots; i++) {
             o.total_indices += cnt[i];
             if (cnt[i] > o.index_stride) o.overflow_pairs++;
@@ -953,9 +980,10 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         (wd->n_pairs > 0 && (!wd->pair_ent || !wd->pair_light || !wd->lights)))
         return fail(ctx, BQ2_E_INVALID, "bq2_world: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    if (ctx->submit_seq - ctx->wait_seq >= 2) return fail(ctx, BQ2_E_INVALID, "bq2_world_submit: two frames are already in flight, call bq2_frame_wait first");
-    const int slot_k = (int)(ctx->submit_seq & 1);
-    PinBuf &h_records = ctx->hrec[slot_k], &h_counts = ctx->hcnt[slot_k], &h_totals = ctx->htot[slot_k];
+    if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_world_submit: three frames are already in flight, call bq2_frame_wait first");
+    const int slot_k = (ctx->submit_seq != ctx->wait_seq) ? (ctx->cur + 1) % BQ2_FRAME_STATES : ctx->cur;   /* ring */
+    FrameState &F = ctx->fs[slot_k];
+    PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
     const int nE = wd->n_ents, nP = wd->n_pairs, nL = wd->n_lights;
     const int nModels = (int)ctx->models.size();
     const uint32_t want = wd->want;
@@ -976,11 +1004,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     int er = -3;
     if (!(want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT))) {
         CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
-        ctx->ent_slot_first.resize((size_t)nE + 1); ctx->ent_vert_off.resize((size_t)nE + 1); ctx->ent_tb_off.assign((size_t)nE + 1, 0u);
-        ctx->slot_record.resize((size_t)nE + 1);
+        F.ent_slot_first.resize((size_t)nE + 1); F.ent_vert_off.resize((size_t)nE + 1); F.ent_tb_off.assign((size_t)nE + 1, 0u);
+        F.slot_record.resize((size_t)nE + 1);
         er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, ctx->meshes.data(),
                                      (bq2_dev_ent *)h_records.p, (bq2_dev_xform *)(h_records.p + off_xf),
-                                     ctx->slot_record.data(), ctx->ent_vert_off.data(), &ws);
+                                     F.slot_record.data(), F.ent_vert_off.data(), &ws);
         if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
         if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
     }
@@ -998,11 +1026,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         return bq2_frame_submit(ctx, &fd);
     }
     tr.lap(2);
-    CK(ctx->d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
-    for (int e = 0; e <= nE; e++) ctx->ent_slot_first[e] = e;
-    ctx->k_warp = bq2_ctx::KLaunch(); ctx->k_team = bq2_ctx::KLaunch();
-    ctx->k_warp.n = ws.n_warp; ctx->k_warp.max_V = ws.warp_max_V; ctx->k_warp.max_T = ws.warp_max_T; ctx->k_warp.any_md2 = ws.warp_md2;
-    ctx->k_team.n = ws.n_team; ctx->k_team.max_V = ws.team_max_V; ctx->k_team.max_T = ws.team_max_T; ctx->k_team.any_md2 = ws.team_md2;
+    CK(F.d_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMalloc(records)");
+    for (int e = 0; e <= nE; e++) F.ent_slot_first[e] = e;
+    F.k_warp = FrameState::KLaunch(); F.k_team = FrameState::KLaunch();
+    F.k_warp.n = ws.n_warp; F.k_warp.max_V = ws.warp_max_V; F.k_warp.max_T = ws.warp_max_T; F.k_warp.any_md2 = ws.warp_md2;
+    F.k_team.n = ws.n_team; F.k_team.max_V = ws.team_max_V; F.k_team.max_T = ws.team_max_T; F.k_team.any_md2 = ws.team_md2;
     const uint32_t voff = ws.lerped_verts_padded, maxVpad = ws.max_vpad, maxBitw = ws.max_bitw;
     const int maxT = ws.max_T;
     const uint64_t total_verts = ws.total_verts;
@@ -1020,95 +1048,94 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     const bool tables = (want & BQ2_WANT_TABLES) != 0;
 
     /* ---- capacity: per-pair rows are bounded by the largest mesh of the frame ------------------------ */
-    CK(ctx->lerped.ensure(3 * (size_t)voff + 4), "cudaMalloc(lerped)");
+    CK(F.lerped.ensure(3 * (size_t)voff + 4), "cudaMalloc(lerped)");
     if (want & BQ2_WANT_SHADOW) {
-        CK(ctx->extruded.ensure(3 * (size_t)nP * maxVpad + 4), "cudaMalloc(extruded)");
-        CK(ctx->facing_bits.ensure((size_t)nP * maxBitw + 1), "cudaMalloc(facing_bits)");
-        CK(ctx->indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
+        CK(F.extruded.ensure(3 * (size_t)nP * maxVpad + 4), "cudaMalloc(extruded)");
+        CK(F.facing_bits.ensure((size_t)nP * maxBitw + 1), "cudaMalloc(facing_bits)");
+        CK(F.indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
-    if (ws.team_normal_rows) CK(ctx->tri_normals.ensure(4 * (size_t)ws.team_normal_rows + 4), "cudaMalloc(triangle normals)");
+    if (ws.team_normal_rows) CK(F.tri_normals.ensure(4 * (size_t)ws.team_normal_rows + 4), "cudaMalloc(triangle normals)");
     /* one buffer: index counts | 8-byte aligned, three 64-bit totals (one D2H copy brings both) | pairs per record |
        overflow-chain heads.  One memset clears totals .. heads (heads to 0: a chain is only walked for as many nodes
        as were pushed). */
     const size_t tot_word = ((size_t)nP + 1) & ~(size_t)1, cnt_word = tot_word + 8;
-    CK(ctx->index_count.ensure(cnt_word + 2 * (size_t)nE + 8), "cudaMalloc(index_count)");
+    CK(F.index_count.ensure(cnt_word + 2 * (size_t)nE + 8), "cudaMalloc(index_count)");
     CK(h_counts.ensure(sizeof(uint32_t) * (tot_word + 8)), "cudaMallocHost(counts)");
-    (void)h_totals;
     const size_t w_pairs = ((size_t)nP * sizeof(bq2_dev_pair) + 15) & ~(size_t)15, w_bucket = (size_t)nE * BQ2_BUCKET * 4,
                  w_next = (size_t)nP * 4;
-    CK(ctx->d_world.ensure(w_pairs + w_bucket + w_next + 64), "cudaMalloc(world scratch)");
+    CK(F.d_world.ensure(w_pairs + w_bucket + w_next + 64), "cudaMalloc(world scratch)");
     if (ctx->meshes_dirty) {
         CK(ctx->d_meshes.ensure(ctx->meshes.size()), "cudaMalloc(mesh table)");
         CK(cudaMemcpyAsync(ctx->d_meshes.p, ctx->meshes.data(), ctx->meshes.size() * sizeof(bq2_dev_mesh),
-                           cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(mesh table)");
-        CK(cudaStreamSynchronize(ctx->stream), "sync(mesh table)");
+                           cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(mesh table)");
+        CK(cudaStreamSynchronize(F.stream), "sync(mesh table)");
         ctx->meshes_dirty = false;
     }
-    if (ctx->k_team.n && bq2_kernel_smem_bytes(ctx->k_team.max_V, ctx->k_team.max_T, ctx->k_team.any_md2) > 227u * 1024u)
+    if (F.k_team.n && bq2_kernel_smem_bytes(F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2) > 227u * 1024u)
         return fail(ctx, BQ2_E_LIMIT, "bq2_world: mesh too large for one CTA's shared memory");
 
     /* ---- go ----------------------------------------------------------------------------------------- */
     tr.lap(5);
-    unsigned char *dw = ctx->d_world.p;
-    bq2_world_launch &Wl = ctx->wlaunch;
+    unsigned char *dw = F.d_world.p;
+    bq2_world_launch &Wl = F.wlaunch;
     /* (reading the pinned host records directly from the kernels instead of copying them was measured: the copy
        stage disappears but the record-building kernels and the frame kernel get 13 + 6 us slower at C2) */
-    unsigned char *rb = ctx->d_records.p;
+    unsigned char *rb = F.d_records.p;
     Wl.xf = (const bq2_dev_xform *)(rb + off_xf);
     Wl.lights = (const float *)(rb + off_lights);
     Wl.pair_ent = (const int32_t *)(rb + off_pe); Wl.pair_light = (const int32_t *)(rb + off_pl);
     Wl.n_pairs = nP; Wl.n_ents = nE; Wl.n_lights = nL; Wl.n_recs = nE;
     Wl.dpairs = (bq2_dev_pair *)dw;
     Wl.bucket = (uint32_t *)(dw + w_pairs); Wl.onext = (uint32_t *)(dw + w_pairs + w_bucket);
-    Wl.totals = (unsigned long long *)(ctx->index_count.p + tot_word);
-    Wl.bucket_cnt = ctx->index_count.p + cnt_word; Wl.ohead = Wl.bucket_cnt + nE;
+    Wl.totals = (unsigned long long *)(F.index_count.p + tot_word);
+    Wl.bucket_cnt = F.index_count.p + cnt_word; Wl.ohead = Wl.bucket_cnt + nE;
     Wl.vert_stride = maxVpad; Wl.bits_stride = maxBitw;
-    Wl.index_count = ctx->index_count.p;
+    Wl.index_count = F.index_count.p;
     Wl.view = (const float *)(rb + off_view);
 
-    bq2_launch &L = ctx->launch;
+    bq2_launch &L = F.launch;
     L.meshes = ctx->d_meshes.p;
     L.ents = (const bq2_dev_ent *)rb;
     L.pairs = Wl.dpairs;
     L.n_ent_slots = nE; L.want = want & ~BQ2_WANT_TABLES; L.index_stride = stride;
-    L.lerped = ctx->lerped.p; L.extruded = ctx->extruded.p; L.facing_bits = ctx->facing_bits.p;
-    L.indices = ctx->indices.p; L.index_count = ctx->index_count.p;
+    L.lerped = F.lerped.p; L.extruded = F.extruded.p; L.facing_bits = F.facing_bits.p;
+    L.indices = F.indices.p; L.index_count = F.index_count.p;
     L.normals = nullptr; L.tangents = nullptr; L.binormals = nullptr; L.lightp = nullptr; L.tsh = nullptr;
-    L.totals = Wl.totals; L.tri_normals = ctx->tri_normals.p;
+    L.totals = Wl.totals; L.tri_normals = F.tri_normals.p;
     L.bucket_cnt = Wl.bucket_cnt; L.bucket = Wl.bucket; L.ohead = Wl.ohead; L.onext = Wl.onext; L.rec_base = 0;
-    ctx->n_ent_slots = nE; ctx->n_pair_slots = nP; ctx->n_ents = nE; ctx->n_pairs = nP;
-    ctx->total_verts = total_verts;
-    ctx->world_mode = true; ctx->world_tables = tables;
+    F.n_ent_slots = nE; F.n_pair_slots = nP; F.n_ents = nE; F.n_pairs = nP;
+    F.total_verts = total_verts;
+    F.world_mode = true; F.world_tables = tables;
     /* per-slot host tables used by bq2_expand_trisverts */
-    ctx->slot_mesh_V.resize((size_t)nP); ctx->slot_mesh_T.resize((size_t)nP); ctx->pair_slot_entslot.resize((size_t)nP);
+    F.slot_mesh_V.resize((size_t)nP); F.slot_mesh_T.resize((size_t)nP); F.pair_slot_entslot.resize((size_t)nP);
 
     /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals */
     auto enqueue = [&]() -> bq2_status {
-        if (rec_bytes) CK(cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(world records)");
-        CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), ctx->stream), "cudaMemset(totals, pair lists)");
+        if (rec_bytes) CK(cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
+        CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
         if (nP && (want & BQ2_WANT_SHADOW)) {
-            CK((cudaError_t)bq2_launch_world_setup(&Wl, ctx->stream), "launch(bq2_world_link_kernel)");
+            CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
             ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
         }
-        bq2_status ls = launch_kernels(ctx);
+        bq2_status ls = launch_kernels(ctx, F);
         if (ls != BQ2_OK) return ls;
-        CK(cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(counts + totals)");
+        CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts + totals)");
         return BQ2_OK;
     };
     bool enqueued = false;
-    if (tr.on) {                                        /* BQ2_TRACE: GPU time of each stage of the frame, direct launches */
+    if (tr.gpu) {                                       /* BQ2_TRACE: GPU time of each stage of the frame, direct launches */
         static cudaEvent_t ev[5]; static bool init = false; static double acc[4] = {0, 0, 0, 0}; static long nfr = 0;
         if (!init) { for (auto &e : ev) cudaEventCreate(&e); init = true; }
-        cudaEventRecord(ev[0], ctx->stream);
-        if (rec_bytes) cudaMemcpyAsync(ctx->d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, ctx->stream);
-        cudaEventRecord(ev[1], ctx->stream);
-        cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), ctx->stream);
-        if (nP && (want & BQ2_WANT_SHADOW)) { bq2_launch_world_setup(&Wl, ctx->stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
-        cudaEventRecord(ev[2], ctx->stream);
-        launch_kernels(ctx);
-        cudaEventRecord(ev[3], ctx->stream);
-        cudaMemcpyAsync(h_counts.p, ctx->index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaEventRecord(ev[4], ctx->stream);
+        cudaEventRecord(ev[0], F.stream);
+        if (rec_bytes) cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream);
+        cudaEventRecord(ev[1], F.stream);
+        cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream);
+        if (nP && (want & BQ2_WANT_SHADOW)) { bq2_launch_world_setup(&Wl, F.stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
+        cudaEventRecord(ev[2], F.stream);
+        launch_kernels(ctx, F);
+        cudaEventRecord(ev[3], F.stream);
+        cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, F.stream);
+        cudaEventRecord(ev[4], F.stream);
         cudaEventSynchronize(ev[4]);
         for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms * 1e3; }
         if (++nfr % 100 == 0)
@@ -1117,31 +1144,31 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         enqueued = true;
     }
     if (!enqueued && ctx->use_graphs && !tables) {
-        bq2_ctx::GraphKey key{};
+        FrameState::GraphKey key{};
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, 0, 0, 0, 0, 0};
         memcpy(key.v, kv, sizeof kv);
-        const void *kp[12] = {ctx->d_records.p, ctx->d_world.p, h_records.p, h_counts.p, ctx->lerped.p, ctx->extruded.p, ctx->facing_bits.p,
-                              ctx->indices.p, ctx->index_count.p, ctx->d_meshes.p, ctx->tri_normals.p, nullptr};
+        const void *kp[12] = {F.d_records.p, F.d_world.p, h_records.p, h_counts.p, F.lerped.p, F.extruded.p, F.facing_bits.p,
+                              F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, nullptr};
         memcpy(key.p, kp, sizeof kp);
-        bq2_ctx::GraphCache &g = ctx->gcache[slot_k];
+        FrameState::GraphCache &g = F.gcache;
         const bool same = g.have_key && memcmp(&g.key, &key, sizeof key) == 0;
         if (same && g.exec) {
-            CK(cudaGraphLaunch(g.exec, ctx->stream), "cudaGraphLaunch(frame)");
+            CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
             ctx->launches += g.kernels;
             enqueued = true;
         } else if (same) {                               /* second frame of this shape: capture it */
             cudaGraph_t graph = nullptr;
             const uint64_t l0 = ctx->launches;
-            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            if (cudaStreamBeginCapture(F.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
                 bq2_status es = enqueue();
-                cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+                cudaError_t ce = cudaStreamEndCapture(F.stream, &graph);
                 if (es == BQ2_OK && ce == cudaSuccess && graph &&
                     cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
                     g.kernels = ctx->launches - l0;
                     ctx->launches = l0;
                     cudaGraphDestroy(graph);
-                    CK(cudaGraphLaunch(g.exec, ctx->stream), "cudaGraphLaunch(frame)");
+                    CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
                     ctx->launches += g.kernels;
                     enqueued = true;
                 } else {                                 /* capture is an optimisation only */
@@ -1157,20 +1184,20 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     }
     if (!enqueued) { bq2_status es = enqueue(); if (es != BQ2_OK) return es; }
     if (tables && nP) {
-        ctx->world_pvoff.resize((size_t)nP + 1); ctx->world_pboff.resize((size_t)nP + 1);
-        for (int p = 0; p <= nP; p++) { ctx->world_pvoff[p] = (uint32_t)p * maxVpad; ctx->world_pboff[p] = (uint32_t)p * maxBitw; }
+        F.world_pvoff.resize((size_t)nP + 1); F.world_pboff.resize((size_t)nP + 1);
+        for (int p = 0; p <= nP; p++) { F.world_pvoff[p] = (uint32_t)p * maxVpad; F.world_pboff[p] = (uint32_t)p * maxBitw; }
         for (int p = 0; p < nP; p++) {                 /* test / shim convenience, not on the fast path */
             int e = wd->pair_ent[p];
-            if (e < 0 || e >= nE) { ctx->slot_mesh_V[p] = 0; ctx->slot_mesh_T[p] = 0; ctx->pair_slot_entslot[p] = 0; continue; }
+            if (e < 0 || e >= nE) { F.slot_mesh_V[p] = 0; F.slot_mesh_T[p] = 0; F.pair_slot_entslot[p] = 0; continue; }
             const bq2_dev_mesh &me = ctx->meshes[ctx->models[wd->ents[e].model].first_mesh];
-            ctx->slot_mesh_V[p] = me.V; ctx->slot_mesh_T[p] = me.T; ctx->pair_slot_entslot[p] = e;
+            F.slot_mesh_V[p] = me.V; F.slot_mesh_T[p] = me.T; F.pair_slot_entslot[p] = e;
         }
-    } else if (tables) { ctx->world_pvoff.assign(1, 0u); ctx->world_pboff.assign(1, 0u); }
+    } else if (tables) { F.world_pvoff.assign(1, 0u); F.world_pboff.assign(1, 0u); }
     ctx->submitted = true;
-    { bq2_ctx::Meta &m = ctx->meta[slot_k]; m.world = true; m.tables = tables; m.n_ent_slots = nE; m.n_pair_slots = nP;
+    { FrameState::Meta &m = F.meta; m.world = true; m.tables = tables; m.n_ent_slots = nE; m.n_pair_slots = nP;
       m.total_verts = total_verts; m.stride = stride; }
-    CK(cudaEventRecord(ctx->ev[slot_k], ctx->stream), "cudaEventRecord(frame)");
-    ctx->submit_seq++;
+    CK(cudaEventRecord(F.ev, F.stream), "cudaEventRecord(frame)");
+    ctx->submit_seq++; ctx->cur = slot_k;
     tr.lap(6);
     return BQ2_OK;
 }
@@ -1186,54 +1213,57 @@ bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *wd, bq2_frame_out
 bq2_status bq2_frame_replay(bq2_ctx *ctx)
 {
     if (!ctx) return BQ2_E_INVALID;
-    if (!ctx->submitted || !ctx->n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
-    if (ctx->world_mode)                                         /* the kernels add to the totals: start from zero */
-        CK(cudaMemsetAsync(ctx->wlaunch.totals, 0, 2 * sizeof(unsigned long long), ctx->stream), "cudaMemset(totals)");
-    return launch_kernels(ctx);
+    FrameState &F = ctx->fs[ctx->cur];
+    if (!ctx->submitted || !F.n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
+    if (F.world_mode)                                            /* the kernels add to the totals: start from zero */
+        CK(cudaMemsetAsync(F.wlaunch.totals, 0, 2 * sizeof(unsigned long long), F.stream), "cudaMemset(totals)");
+    return launch_kernels(ctx, F);
 }
 
-const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->hcnt[ctx->last_waited].p : nullptr; }
+const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->fs[ctx->last_waited].hcnt.p : nullptr; }
 
 bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host)
 {
     if (!ctx || !host) return BQ2_E_INVALID;
+    FrameState &F = ctx->fs[ctx->last_waited];                   /* the frame bq2_frame_wait returned last */
     const void *src = nullptr; size_t cap = 0;
     switch (which) {
-    case BQ2_A_LERPED:      src = ctx->lerped.p;      cap = ctx->lerped.cap; break;
-    case BQ2_A_EXTRUDED:    src = ctx->extruded.p;    cap = ctx->extruded.cap; break;
-    case BQ2_A_FACING_BITS: src = ctx->facing_bits.p; cap = ctx->facing_bits.cap; break;
-    case BQ2_A_INDICES:     src = ctx->indices.p;     cap = ctx->indices.cap; break;
-    case BQ2_A_INDEX_COUNT: src = ctx->index_count.p; cap = ctx->index_count.cap; break;
-    case BQ2_A_NORMALS:     src = ctx->normals.p;     cap = ctx->normals.cap; break;
-    case BQ2_A_TANGENTS:    src = ctx->tangents.p;    cap = ctx->tangents.cap; break;
-    case BQ2_A_BINORMALS:   src = ctx->binormals.p;   cap = ctx->binormals.cap; break;
-    case BQ2_A_LIGHTP:      src = ctx->lightp.p;      cap = ctx->lightp.cap; break;
-    case BQ2_A_TSH:         src = ctx->tsh.p;         cap = ctx->tsh.cap; break;
+    case BQ2_A_LERPED:      src = F.lerped.p;      cap = F.lerped.cap; break;
+    case BQ2_A_EXTRUDED:    src = F.extruded.p;    cap = F.extruded.cap; break;
+    case BQ2_A_FACING_BITS: src = F.facing_bits.p; cap = F.facing_bits.cap; break;
+    case BQ2_A_INDICES:     src = F.indices.p;     cap = F.indices.cap; break;
+    case BQ2_A_INDEX_COUNT: src = F.index_count.p; cap = F.index_count.cap; break;
+    case BQ2_A_NORMALS:     src = F.normals.p;     cap = F.normals.cap; break;
+    case BQ2_A_TANGENTS:    src = F.tangents.p;    cap = F.tangents.cap; break;
+    case BQ2_A_BINORMALS:   src = F.binormals.p;   cap = F.binormals.cap; break;
+    case BQ2_A_LIGHTP:      src = F.lightp.p;      cap = F.lightp.cap; break;
+    case BQ2_A_TSH:         src = F.tsh.p;         cap = F.tsh.cap; break;
     default: return fail(ctx, BQ2_E_INVALID, "bq2_download: unknown array");
     }
     if (!src || first + count > cap) return fail(ctx, BQ2_E_INVALID, "bq2_download: range outside the array");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    CK(cudaMemcpyAsync(host, (const uint32_t *)src + first, count * 4, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(download)");
-    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(download)");
+    CK(cudaMemcpyAsync(host, (const uint32_t *)src + first, count * 4, cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(download)");
+    CK(cudaStreamSynchronize(F.stream), "cudaStreamSynchronize(download)");
     return BQ2_OK;
 }
 
 bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t ps, float *tris_verts, int32_t max_verts, int32_t *tris_counter)
 {
     if (!ctx || !tris_verts || !tris_counter) return BQ2_E_INVALID;
-    if (!ctx->submitted || ps < 0 || ps >= ctx->n_pair_slots) return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: bad pair slot");
-    if (ctx->world_mode && !ctx->world_tables)
+    FrameState &F = ctx->fs[ctx->last_waited];
+    if (!ctx->submitted || ps < 0 || ps >= F.n_pair_slots) return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: bad pair slot");
+    if (F.world_mode && !F.world_tables)
         return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: the frame was submitted without BQ2_WANT_TABLES");
-    const int V = ctx->slot_mesh_V[ps];
-    const uint32_t pvoff = ctx->world_mode ? ctx->world_pvoff[ps] : ctx->pair_vert_off[ps];
-    const uint32_t stride = ctx->launch.index_stride;
+    const int V = F.slot_mesh_V[ps];
+    const uint32_t pvoff = F.world_mode ? F.world_pvoff[ps] : F.pair_vert_off[ps];
+    const uint32_t stride = F.launch.index_stride;
     uint32_t cnt = 0;
     bq2_status s = bq2_download(ctx, BQ2_A_INDEX_COUNT, (uint64_t)ps, 1, &cnt);
     if (s != BQ2_OK) return s;
     if (cnt > stride || (int32_t)cnt > max_verts) return fail(ctx, BQ2_E_OVERFLOW, "bq2_expand_trisverts: output too small");
     std::vector<float> pool(6 * (size_t)V);
     std::vector<uint32_t> idx(cnt);
-    s = bq2_download(ctx, BQ2_A_LERPED, 3ull * ctx->ent_vert_off[ctx->pair_slot_entslot[ps]], 3ull * V, pool.data());
+    s = bq2_download(ctx, BQ2_A_LERPED, 3ull * F.ent_vert_off[F.pair_slot_entslot[ps]], 3ull * V, pool.data());
     if (s != BQ2_OK) return s;
     s = bq2_download(ctx, BQ2_A_EXTRUDED, 3ull * pvoff, 3ull * V, pool.data() + 3 * (size_t)V);
     if (s != BQ2_OK) return s;

@@ -61,11 +61,31 @@ static void move_delta(const float origin[3], const float oldorigin[3], const fl
     }
 }
 
+/* the same with the entity's AngleVectors already evaluated (basis = forward, right, up; NULL = all angles zero) */
+static void move_delta_basis(const float origin[3], const float oldorigin[3], const float *basis, float move[3])
+{
+    move[0] = oldorigin[0] - origin[0];
+    move[1] = oldorigin[1] - origin[1];
+    move[2] = oldorigin[2] - origin[2];
+    if (basis) {
+        float temp[3];
+        temp[0] = move[0]; temp[1] = move[1]; temp[2] = move[2];
+        move[0] = DOT(temp, basis);
+        move[1] = -DOT(temp, basis + 3);
+        move[2] = DOT(temp, basis + 6);
+    }
+}
+
 typedef struct {
     int32_t ident, version, skinwidth, skinheight, framesize;
     int32_t num_skins, num_xyz, num_st, num_tris, num_glcmds, num_frames;
     int32_t ofs_skins, ofs_st, ofs_tris, ofs_frames, ofs_glcmds, ofs_end;
 } md2_header;    /* dmdl_t, defs.h:3682-3706 */
+
+static void entity_md2_finish(const float *fr, const float *ofr, int32_t frame, int32_t oldframe, float backlerp,
+                              float move[3], uint32_t rf_flags, bq2_entity *out);
+static void entity_md3_finish(const float frame_translate[3], const float oldframe_translate[3], int32_t frame,
+                              int32_t oldframe, float backlerp, float move[3], bq2_entity *out);
 
 static void shell_flags(uint32_t rf_flags, bq2_entity *out)
 {
@@ -92,10 +112,16 @@ void bq2_host_entity_md2_hdr(const float *fr, const float *ofr, int32_t frame, i
                              float backlerp, const float origin[3], const float oldorigin[3],
                              const float angles[3], uint32_t rf_flags, bq2_entity *out)
 {
-    float frontlerp = 1.0 - backlerp;                 /* M:63531: double subtract, float store */
     float move[3];
-    int i;
     move_delta(origin, oldorigin, angles, move);
+    entity_md2_finish(fr, ofr, frame, oldframe, backlerp, move, rf_flags, out);
+}
+
+static void entity_md2_finish(const float *fr, const float *ofr, int32_t frame, int32_t oldframe, float backlerp,
+                              float move[3], uint32_t rf_flags, bq2_entity *out)
+{
+    float frontlerp = 1.0 - backlerp;                 /* M:63531: double subtract, float store */
+    int i;
     for (i = 0; i < 3; i++) move[i] = move[i] + ofr[3 + i];                /* M:63546 */
     out->frame = frame; out->oldframe = oldframe; out->flags = 0; out->shell_scale = 0;
     out->backlerp = backlerp; out->frontlerp = frontlerp;
@@ -113,9 +139,16 @@ void bq2_host_entity_md3(const float frame_translate[3], const float oldframe_tr
                          const float origin[3], const float oldorigin[3], const float angles[3],
                          bq2_entity *out)
 {
-    float move[3], frontlerp;
-    int j;
+    float move[3];
     move_delta(origin, oldorigin, angles, move);
+    entity_md3_finish(frame_translate, oldframe_translate, frame, oldframe, backlerp, move, out);
+}
+
+static void entity_md3_finish(const float frame_translate[3], const float oldframe_translate[3], int32_t frame,
+                              int32_t oldframe, float backlerp, float move[3], bq2_entity *out)
+{
+    float frontlerp;
+    int j;
     frontlerp = 1.0 - backlerp;                                             /* M:63850 */
     for (j = 0; j < 3; j++) move[j] = move[j] + oldframe_translate[j];     /* M:63854 */
     for (j = 0; j < 3; j++) move[j] = backlerp * move[j] + frontlerp * frame_translate[j];
@@ -204,6 +237,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         bq2_dev_xform *x;
         uint32_t vpad, bitw;
         int32_t rec, small, casts;
+        float mv[3];
         if (W->model < 0 || W->model >= n_models) return -1;
         mo = &models[W->model];
         if (mo->n_mesh != 1) return -3;
@@ -222,12 +256,17 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
             if (!(me->flags & BQ2_MESH_MD3)) st->team_md2 = 1;
         }
         rec_of_ent[e] = rec;
+        /* AngleVectors once per entity: the reference evaluates them again for the move delta and for every light
+           (same inputs, same libm, same values) */
+        x = &hx[e];
+        x->rotated = (uint32_t)bq2_host_entity_basis(W->angles, x->basis);
+        move_delta_basis(W->origin, W->oldorigin, x->rotated ? x->basis : NULL, mv);
         if (mo->md3)
-            bq2_host_entity_md3(mo->hdr + 3 * (size_t)W->frame, mo->hdr + 3 * (size_t)W->oldframe, W->frame, W->oldframe,
-                                W->backlerp, W->origin, W->oldorigin, W->angles, &E);
+            entity_md3_finish(mo->hdr + 3 * (size_t)W->frame, mo->hdr + 3 * (size_t)W->oldframe, W->frame, W->oldframe,
+                              W->backlerp, mv, &E);
         else
-            bq2_host_entity_md2_hdr(mo->hdr + 6 * (size_t)W->frame, mo->hdr + 6 * (size_t)W->oldframe, W->frame, W->oldframe,
-                                    W->backlerp, W->origin, W->oldorigin, W->angles, W->rf_flags, &E);
+            entity_md2_finish(mo->hdr + 6 * (size_t)W->frame, mo->hdr + 6 * (size_t)W->oldframe, W->frame, W->oldframe,
+                              W->backlerp, mv, W->rf_flags, &E);
         d = &he[rec];
         d->cur = me->verts + (size_t)W->frame * me->vstride; d->old = me->verts + (size_t)W->oldframe * me->vstride;
         d->tri = me->tri; d->V = me->V; d->T = me->T; d->Tp = me->Tp; d->mflags = me->flags; d->vstride = me->vstride; d->nrm_off = 0;
@@ -243,12 +282,10 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         if (vpad > st->max_vpad) st->max_vpad = vpad;
         if (bitw > st->max_bitw) st->max_bitw = bitw;
         if (me->T > st->max_T) st->max_T = me->T;
-        x = &hx[e];
         casts = bq2_host_casts_shadow(W->rf_flags, 0, 0.0f, 2.0f) &&
                 !(W->rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));                 /* M:63722-63727, 64089 */
         x->origin[0] = W->origin[0]; x->origin[1] = W->origin[1]; x->origin[2] = W->origin[2];
         x->rec = casts ? rec : -1;
-        x->rotated = (uint32_t)bq2_host_entity_basis(W->angles, x->basis);
         x->vpad = vpad; x->bitw = bitw;
     }
     ent_vert_off[n] = voff;

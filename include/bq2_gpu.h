@@ -123,7 +123,7 @@ typedef struct bq2_frame_desc {
 } bq2_frame_desc;
 
 /* Where the results of the last frame live.  All pointers are DEVICE pointers owned by the ctx,
- * valid until the next bq2_frame*(ctx) or bq2_destroy.  "Slots": MD2 entities/pairs occupy one
+ * valid until the next bq2_frame*(ctx) (see "two frames in flight" below) or bq2_destroy.  "Slots": MD2 entities/pairs occupy one
  * slot; an MD3 entity/pair occupies one slot per mesh (the reference draws per mesh, M:63858).
  *   ent_slot_first[e]  .. +n meshes : slots of entity e        (n_ents + 1 entries, host array)
  *   pair_slot_first[p] .. +n meshes : slots of pair p          (n_pairs + 1 entries, host array)
@@ -161,7 +161,9 @@ int          bq2_abi_version(void);
 bq2_status   bq2_create(int device, bq2_ctx **out);
 void         bq2_destroy(bq2_ctx *ctx);
 const char  *bq2_last_error(const bq2_ctx *ctx);          /* ctx may be NULL: last create error   */
-void        *bq2_stream(bq2_ctx *ctx);                     /* cudaStream_t the ctx launches on     */
+void        *bq2_stream(bq2_ctx *ctx);                     /* cudaStream_t of the most recently submitted frame (each of
+                                                              the two frame states has its own; fixed for callers that
+                                                              never overlap frames) */
 int          bq2_device(const bq2_ctx *ctx);
 uint64_t     bq2_kernel_launches(const bq2_ctx *ctx);      /* kernels launched by this ctx so far  */
 
@@ -199,12 +201,15 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
 /* Host records in, one fused launch per model family, per-slot counts back.  Equivalent to
  * bq2_frame_submit + bq2_frame_wait. */
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *desc, bq2_frame_out *out);
-/* Up to TWO frames may be in flight: bq2_frame_submit (or bq2_world_submit) for frame i+1 may be called
- * before bq2_frame_wait for frame i, so the host packs the next frame while the GPU works; bq2_frame_wait
- * always completes the OLDEST submitted frame.  The host-side buffers (pinned records, counts, totals) are
- * double-buffered; the DEVICE result arrays are not -- they are those of the most recently submitted frame
- * once its kernels run, so a caller that reads device results (or the host offset tables) of frame i must
- * not submit frame i+1 before it is done with them.  bq2_frame / bq2_world_frame drain first. */
+/* Up to THREE frames may be in flight: bq2_frame_submit (or bq2_world_submit) for frames i+1 and i+2 may be
+ * called before bq2_frame_wait for frame i, so the host packs the next frames while the GPU works; bq2_frame_wait
+ * always completes the OLDEST submitted frame.  The ctx holds a ring of four complete frame states -- pinned host
+ * buffers, device records, device RESULT arrays, host offset tables, stream, CUDA graph -- and a submit takes the
+ * next one when a frame is in flight: the copies and kernels of consecutive frames overlap on the GPU, and what
+ * bq2_frame_wait returned for frame i (device pointers, offset tables, bq2_download / bq2_expand_trisverts) stays
+ * valid while the next frames are computed -- until the first submit after the NEXT bq2_frame_wait.  A caller that
+ * never overlaps (bq2_frame / bq2_world_frame, or submit then wait) uses one state only: its results are valid
+ * until the next submit, and no further set of arrays is allocated. */
 bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *desc);   /* async on bq2_stream   */
 bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out);             /* sync + counts readback */
 /* Re-run the kernels of the last submitted frame on the records already resident in HBM

@@ -403,7 +403,7 @@ def test_world_frame_md3_and_tangent_space_take_the_host_route(gpu_ctx, oracle):
 
 def test_two_frames_in_flight(gpu_ctx, oracle):
     """bq2_world_submit for frame i+1 before bq2_frame_wait for frame i: waits complete the OLDEST frame and
-    every frame's counts/totals are its own; a third submit is refused."""
+    every frame's counts/totals are its own; a fourth submit is refused."""
     models = [Md2Model(oracle, frames=6, seed=70 + s) for s in range(4)]
     mids = [m.upload(gpu_ctx) for m in models]
     import ctypes as C
@@ -419,17 +419,61 @@ def test_two_frames_in_flight(gpu_ctx, oracle):
     fo = c.FrameOut()
     got = []
     assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[0])) == 0
-    for i in range(1, 5):
+    assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[1])) == 0
+    for i in range(2, 5):
         assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
-        if i == 1:
-            assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[2])) == -1          # only two in flight
+        if i == 2:
+            assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[3])) == -1          # only three in flight
         assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
         cnt = np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()
         got.append((int(fo.total_indices), cnt))
-    assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
-    got.append((int(fo.total_indices), np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()))
+    for _ in range(2):
+        assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
+        got.append((int(fo.total_indices), np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()))
     for (ta, ca), (tb, cb) in zip(serial, got):
         assert ta == tb and np.array_equal(ca, cb)
+
+
+def test_overlapped_frames_keep_their_own_device_results(gpu_ctx, oracle):
+    """Frame i+1 is submitted (and may run) before frame i is waited for: the vertex / facing / index arrays that
+    bq2_frame_wait returns for frame i are still frame i's (each of the two frame states owns its result arrays),
+    for alternating shapes, over several rounds (graph replays included)."""
+    models = [Md2Model(oracle, s, r, frames=6, seed=90 + i) for i, (s, r) in enumerate([(8, 5), (16, 17), (62, 34)])]
+    mids = [m.upload(gpu_ctx) for m in models]
+    want = bq2.WANT_SHADOW | bq2.WANT_TABLES
+    scenes = []
+    for i in range(2):
+        we, wl, pe, pl = world_scene(30 + 11 * i, 2 + i, 6, n_models=3, seed=800 + i)
+        we["model"] = np.array(mids)[we["model"]]
+        scenes.append((we, wl, pe, pl))
+
+    def snapshot(res, we, pe):
+        out = []
+        for p in range(len(pe)):
+            m = models[mids.index(int(we["model"][pe[p]]))]
+            out.append((bits(res.lerped(int(pe[p]), m.V)).copy(), bits(res.extruded(p, m.V)).copy(),
+                        res.facing(p, m.T).copy(), res.indices(p).copy()))
+        return out
+
+    serial = []
+    for we, wl, pe, pl in scenes:
+        res = check_world(gpu_ctx, oracle, models, mids, we, wl, pe, pl)          # oracle-checked, one at a time
+        serial.append(snapshot(res, we, pe))
+    descs = []
+    for we, wl, pe, pl in scenes:
+        d = gpu_ctx.world_desc(we, wl, pe, pl, None, want, 0); d._keep = gpu_ctx._keep
+        descs.append(d)
+    gpu_ctx.world_submit(descs[0]); gpu_ctx.world_submit(descs[1])
+    n_rounds = 11
+    for rnd in range(2, n_rounds + 2):
+        if rnd < n_rounds:
+            gpu_ctx.world_submit(descs[rnd & 1])                                 # frame rnd goes in (third in flight) ...
+        res = gpu_ctx.wait()                                                     # ... frame rnd-2 comes out
+        k = (rnd - 2) & 1
+        got = snapshot(res, scenes[k][0], scenes[k][2])
+        for p, (a, b) in enumerate(zip(serial[k], got)):
+            for x, y in zip(a, b):
+                assert np.array_equal(x, y), (rnd, p)
 
 
 def test_world_frame_single_mesh_md3_and_many_lights(gpu_ctx, oracle):

@@ -28,7 +28,7 @@ ents_h = np.zeros(n_ents, c.ENTITY_DTYPE); pairs_h = np.zeros(n_pairs, c.PAIR_DT
 kept = C.c_int32(0); fd = c.FrameDesc(); fo = c.FrameOut()
 t = np.zeros(3)
 N = 300
-for it in range(N + 20):
+for it in range(0 if os.environ.get('BQ2_WORLD_ONLY') else N + 20):
     t0 = time.perf_counter()
     c.lib.bq2_build_records(ctx._h, c.ptr(we), n_ents, c.ptr(wl), len(wl), c.ptr(pe), c.ptr(pl), n_pairs, None,
                             c.ptr(ents_h), c.ptr(pairs_h), C.byref(kept))
@@ -53,3 +53,20 @@ for it in range(N + 20):
         tw += (t1 - t0, t2 - t1)
 print("world path us per step: submit %.1f  wait %.1f  total %.1f" % (*(tw / N * 1e6), tw.sum() / N * 1e6))
 print("us per step: build_records %.1f  frame_submit %.1f  frame_wait %.1f  total %.1f" % (*(t / N * 1e6), t.sum() / N * 1e6))
+# pipelined, as bench.py's e2e leg runs it: three frames in flight (submit frame i+2, then wait for frame i)
+for depth in (2, 3):
+    tp = np.zeros(2)
+    for _ in range(depth - 1):
+        c.lib.bq2_world_submit(ctx._h, C.byref(wd))
+    for it in range(N + 20):
+        t0 = time.perf_counter()
+        c.lib.bq2_world_submit(ctx._h, C.byref(wd))
+        t1 = time.perf_counter()
+        c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+        t2 = time.perf_counter()
+        if it >= 20:
+            tp += (t1 - t0, t2 - t1)
+    for _ in range(depth - 1):
+        c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+    print("world path, %d frames in flight, us per frame: submit %.1f  wait %.1f  total %.1f"
+          % (depth, *(tp / N * 1e6), tp.sum() / N * 1e6))
