@@ -224,6 +224,7 @@ def run_gpu(args):
             step_resident()
             torch.cuda.synchronize()
         clocks.freeze()
+    clock_info = clocks.stop() if clocks else None     # (the sampler polls the driver: not during the wall-clock leg)
     ms_total = float(sum(kernel_ms))
     # informational: the same step when L2 holds none of its data but no foreign DIRTY lines either (the memset is
     # followed by a read of a second buffer, so the step's stores evict clean lines, as in back-to-back frames)
@@ -259,31 +260,32 @@ def run_gpu(args):
             raise RuntimeError(c.lib.bq2_last_error(ctx._h))
         return fo.total_indices
 
-    def e2e_run(k):
-        """k frames through the public C ABI from HOST data.  Each frame: bq2_world_submit (host: per-entity trig +
-        record packing -> pinned -> H2D; the record-building kernel + the fused kernel; D2H of the per-pair index
-        counts and totals) and bq2_frame_wait.  E2E_IN_FLIGHT frames in flight (the library's documented mode: each
-        frame has its own records, result arrays and stream, so frames i+1, i+2 are packed, copied and computed
-        while frame i is on the GPU and every frame's results stay valid for the consumer)."""
+    def e2e_run(k, timed=False):
+        """k frames through the public C ABI from HOST data.  Each frame: bq2_world_submit (host: per-entity
+        validation, numbering and AngleVectors -> pinned -> H2D; the record-building kernel + the fused kernel; D2H of
+        the per-pair index counts and totals) and bq2_frame_wait.  E2E_IN_FLIGHT frames in flight (the library's
+        documented mode: each frame has its own records, result arrays and stream, so frames i+1, i+2 are packed,
+        copied and computed while frame i is on the GPU and every frame's results stay valid for the consumer).
+        timed: the clock runs over k submit+wait iterations of the full pipeline (k frames in, k frames out)."""
         tot = 0
-        depth = min(E2E_IN_FLIGHT, k)
+        depth = E2E_IN_FLIGHT
         for _ in range(depth - 1):
             e2e_submit()
-        for _ in range(k - (depth - 1)):
+        t0 = time.perf_counter()
+        for _ in range(k):
             e2e_submit()
             tot += e2e_wait()
+        dt = time.perf_counter() - t0
         for _ in range(depth - 1):
-            tot += e2e_wait()
-        return tot
+            e2e_wait()
+        return (tot, dt) if timed else tot
 
     e2e_run(max(args.warmup, 12))      # every frame state of the ring has captured its graph before the timed frames
     barrier()
     launches_e2e0 = ctx.kernel_launches
-    t0 = time.perf_counter()
-    e2e_indices = e2e_run(args.steps)
+    e2e_indices, e2e_s = e2e_run(args.steps, timed=True)
+    launches_e2e = ctx.kernel_launches - launches_e2e0 - 2 * (E2E_IN_FLIGHT - 1)   # the frames that fill the pipeline
     barrier()
-    e2e_s = time.perf_counter() - t0
-    launches_e2e = ctx.kernel_launches - launches_e2e0
     t0 = time.perf_counter()                                      # one frame at a time (latency of a frame)
     for _ in range(args.steps):
         e2e_submit(); e2e_wait()
@@ -297,7 +299,6 @@ def run_gpu(args):
         fd.want = bq2.WANT_SHADOW; fd.index_stride = 0
         c.lib.bq2_frame(ctx._h, C.byref(fd), C.byref(fo))
     e2e_host_s = time.perf_counter() - t0
-    clock_info = clocks.stop() if clocks else None
 
     # ---- reduce: max time over ranks; NCCL all_gather of the per-shard counters (the only collective) --
     from berserkerquake2_b200 import shard
@@ -331,11 +332,13 @@ def run_gpu(args):
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
-                    "h2d_bytes_per_step": n_ents * (128 + 64) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
-                    "what": "per frame: bq2_world_submit (host: per-entity trig + record packing; pinned -> H2D; "
-                            "the record-building kernel + the fused kernel; D2H of per-pair index counts + totals) + "
+                    "h2d_bytes_per_step": n_ents * (64 + 56) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
+                    "what": "per frame: bq2_world_submit (host: per-entity validation, numbering and AngleVectors; "
+                            "pinned -> H2D of the caller's entities, lights, pairs; the record-building kernel + the "
+                            "fused kernel; D2H of per-pair index counts + totals) + "
                             "bq2_frame_wait, wall clock over K frames with %d frames in flight (each has its own records, "
-                            "result arrays and stream); ms_per_step_serial = one at a time; " % E2E_IN_FLIGHT +
+                            "result arrays and stream; the clock runs over K submit+wait iterations of the full pipeline, K "
+                            "frames in and K frames out); ms_per_step_serial = one at a time; " % E2E_IN_FLIGHT +
                             
                             "vertex/index buffers stay in HBM for the draw"},
             "gpu_launches": int(launches),

@@ -30,7 +30,7 @@ struct Trace {
     double acc[8] = {0}; long n = 0; double t0 = 0;
     static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; }
     void start() { if (on) t0 = now(); }
-    void lap(int i) { if (on) { double t = now(); acc[i] += t - t0; t0 = t; } }
+    void lap(int i) { if (on) { double t = now(); if (n > 64) acc[i] += t - t0; t0 = t; } }   /* first frames allocate */
 };
 
 std::string g_create_error;
@@ -45,6 +45,7 @@ struct Model {
     std::vector<int> V, T, casts;
     std::vector<float> hdr;      /* MD2: F x {scale[3], translate[3]} (daliasframe_t header);
                                     MD3: F x translate[3] (maliasframe_t.translate)            */
+    const float *d_hdr = nullptr;/* the same on the device (world path: lerp constants are computed there) */
 };
 
 template <typename T> struct DevBuf {
@@ -131,6 +132,8 @@ struct bq2_ctx {
     std::vector<Model> models;
     std::vector<bq2_dev_mesh> meshes;           /* host mirror of the device mesh table */
     DevBuf<bq2_dev_mesh> d_meshes;
+    std::vector<bq2_dev_model> dev_models;      /* host mirror of the device model table */
+    DevBuf<bq2_dev_model> d_models;
     bool meshes_dirty = false;
 
     std::vector<bq2_model_row> model_rows;                       /* flat mirror of models for the C entity loop */
@@ -179,6 +182,18 @@ bq2_status arena_alloc(bq2_ctx *ctx, size_t bytes, unsigned char **out)
     CK(cudaMalloc((void **)&s.base, s.size), "cudaMalloc(model slab)");
     ctx->slabs.push_back(s);
     *out = s.base;
+    return BQ2_OK;
+}
+
+/* frame headers of a model to the device */
+bq2_status upload_hdr(bq2_ctx *ctx, Model &mo)
+{
+    unsigned char *d = nullptr;
+    bq2_status s = arena_alloc(ctx, mo.hdr.size() * sizeof(float), &d);
+    if (s != BQ2_OK) return s;
+    CK(cudaMemcpyAsync(d, mo.hdr.data(), mo.hdr.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(frame headers)");
+    CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(frame headers)");
+    mo.d_hdr = (const float *)d;
     return BQ2_OK;
 }
 
@@ -275,13 +290,13 @@ void bq2_destroy(bq2_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (FrameState &f : ctx->fs) if (f.stream) cudaStreamSynchronize(f.stream);
-    if (ctx->trace.on && ctx->trace.n) {
+    if (ctx->trace.on && ctx->trace.n > 64) {
         static const char *nm[8] = {"validate+slots/class", "class split", "entity records", "pair offsets/memcpy", "pair records",
                                     "buffers", "h2d+launch+d2h calls", ""};
-        for (int i = 0; i < 7; i++) fprintf(stderr, "bq2 trace: %-22s %8.2f us/frame\n", nm[i], ctx->trace.acc[i] / ctx->trace.n);
+        for (int i = 0; i < 7; i++) fprintf(stderr, "bq2 trace: %-22s %8.2f us/frame\n", nm[i], ctx->trace.acc[i] / (ctx->trace.n - 64));
     }
     for (Slab &s : ctx->slabs) cudaFree(s.base);
-    ctx->d_meshes.release();
+    ctx->d_meshes.release(); ctx->d_models.release();
     ctx->d_brushes.release(); ctx->d_brush_in.release(); ctx->brush_vcache.release();
     ctx->brush_icache.release(); ctx->brush_counts.release();
     for (FrameState &f : ctx->fs) f.release();                   /* streams and events included */
@@ -371,6 +386,7 @@ bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, con
     mo.V.push_back(V); mo.T.push_back(T); mo.casts.push_back(1);
     mo.hdr.resize(6 * (size_t)F);
     for (int f = 0; f < F; f++) memcpy(&mo.hdr[6 * (size_t)f], base + h->ofs_frames + (size_t)f * h->framesize, 24);
+    if ((s = upload_hdr(ctx, mo)) != BQ2_OK) return s;
     ctx->meshes.push_back(m); ctx->models.push_back(mo); ctx->meshes_dirty = true;
     *model_id = (int32_t)ctx->models.size() - 1;
     return BQ2_OK;
@@ -428,6 +444,7 @@ bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate,
         ctx->meshes.push_back(m);
         mo.V.push_back(V); mo.T.push_back(T); mo.casts.push_back((me.casts_shadow & 1) ? 1 : 0);
     }
+    { bq2_status hs = upload_hdr(ctx, mo); if (hs != BQ2_OK) return hs; }
     ctx->models.push_back(mo); ctx->meshes_dirty = true;
     *model_id = (int32_t)ctx->models.size() - 1;
     return BQ2_OK;
@@ -992,13 +1009,17 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         ctx->model_rows.resize(ctx->models.size());
         for (size_t i = 0; i < ctx->models.size(); i++) {
             const Model &mo = ctx->models[i];
-            ctx->model_rows[i] = bq2_model_row{mo.hdr.data(), mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2};
+            const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
+            ctx->model_rows[i] = bq2_model_row{mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2,
+                                               me.V, me.T, me.Tp, me.flags};
         }
     }
     const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
                  off_lights = off_view + 16,
                  off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
-                 rec_bytes = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15);
+                 off_w = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15),
+                 rec_bytes = off_w + (((size_t)nE * sizeof(bq2_world_entity) + 15) & ~(size_t)15);
+    /* [0, off_xf) = the entity records: device only, written by the record-building kernel; the copy starts at off_xf */
     Trace &tr = ctx->trace; tr.start(); tr.n++;
     bq2_world_stats ws{};
     int er = -3;
@@ -1006,8 +1027,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
         F.ent_slot_first.resize((size_t)nE + 1); F.ent_vert_off.resize((size_t)nE + 1); F.ent_tb_off.assign((size_t)nE + 1, 0u);
         F.slot_record.resize((size_t)nE + 1);
-        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, ctx->meshes.data(),
-                                     (bq2_dev_ent *)h_records.p, (bq2_dev_xform *)(h_records.p + off_xf),
+        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, (bq2_dev_xform *)(h_records.p + off_xf),
                                      F.slot_record.data(), F.ent_vert_off.data(), &ws);
         if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
         if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
@@ -1041,6 +1061,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     }
     if (nL) memcpy(h_records.p + off_lights, wd->lights, (size_t)nL * 16);
     if (nP) { memcpy(h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
+    if (nE) memcpy(h_records.p + off_w, wd->ents, (size_t)nE * sizeof(bq2_world_entity));
 
     tr.lap(3);
     uint32_t stride = wd->index_stride ? wd->index_stride : 12u * (uint32_t)maxT;
@@ -1071,6 +1092,15 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(cudaStreamSynchronize(F.stream), "sync(mesh table)");
         ctx->meshes_dirty = false;
     }
+    if (ctx->dev_models.size() != ctx->models.size()) {          /* device model table: frame headers + first mesh */
+        ctx->dev_models.resize(ctx->models.size());
+        for (size_t i = 0; i < ctx->models.size(); i++)
+            ctx->dev_models[i] = bq2_dev_model{ctx->models[i].d_hdr, ctx->models[i].first_mesh, ctx->models[i].md3 ? 1 : 0};
+        CK(ctx->d_models.ensure(ctx->dev_models.size()), "cudaMalloc(model table)");
+        CK(cudaMemcpyAsync(ctx->d_models.p, ctx->dev_models.data(), ctx->dev_models.size() * sizeof(bq2_dev_model),
+                           cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(model table)");
+        CK(cudaStreamSynchronize(F.stream), "sync(model table)");
+    }
     if (F.k_team.n && bq2_kernel_smem_bytes(F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2) > 227u * 1024u)
         return fail(ctx, BQ2_E_LIMIT, "bq2_world: mesh too large for one CTA's shared memory");
 
@@ -1082,6 +1112,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
        stage disappears but the record-building kernels and the frame kernel get 13 + 6 us slower at C2) */
     unsigned char *rb = F.d_records.p;
     Wl.xf = (const bq2_dev_xform *)(rb + off_xf);
+    Wl.wents = (const bq2_world_entity *)(rb + off_w);
+    Wl.models = ctx->d_models.p; Wl.meshes = ctx->d_meshes.p; Wl.ents_out = (bq2_dev_ent *)rb;
     Wl.lights = (const float *)(rb + off_lights);
     Wl.pair_ent = (const int32_t *)(rb + off_pe); Wl.pair_light = (const int32_t *)(rb + off_pl);
     Wl.n_pairs = nP; Wl.n_ents = nE; Wl.n_lights = nL; Wl.n_recs = nE;
@@ -1111,9 +1143,10 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
 
     /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals */
     auto enqueue = [&]() -> bq2_status {
-        if (rec_bytes) CK(cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
+        if (rec_bytes > off_xf) CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, rec_bytes - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
         CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
-        if (nP && (want & BQ2_WANT_SHADOW)) {
+        Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;         /* the entity records are always built */
+        if (nP || nE) {
             CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
             ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
         }
@@ -1127,10 +1160,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         static cudaEvent_t ev[5]; static bool init = false; static double acc[4] = {0, 0, 0, 0}; static long nfr = 0;
         if (!init) { for (auto &e : ev) cudaEventCreate(&e); init = true; }
         cudaEventRecord(ev[0], F.stream);
-        if (rec_bytes) cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream);
+        if (rec_bytes > off_xf) cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, rec_bytes - off_xf, cudaMemcpyHostToDevice, F.stream);
         cudaEventRecord(ev[1], F.stream);
         cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream);
-        if (nP && (want & BQ2_WANT_SHADOW)) { bq2_launch_world_setup(&Wl, F.stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
+        Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;
+        if (nP || nE) { bq2_launch_world_setup(&Wl, F.stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
         cudaEventRecord(ev[2], F.stream);
         launch_kernels(ctx, F);
         cudaEventRecord(ev[3], F.stream);
@@ -1149,7 +1183,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, 0, 0, 0, 0, 0};
         memcpy(key.v, kv, sizeof kv);
         const void *kp[12] = {F.d_records.p, F.d_world.p, h_records.p, h_counts.p, F.lerped.p, F.extruded.p, F.facing_bits.p,
-                              F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, nullptr};
+                              F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, ctx->d_models.p};
         memcpy(key.p, kp, sizeof kp);
         FrameState::GraphCache &g = F.gcache;
         const bool same = g.have_key && memcmp(&g.key, &key, sizeof key) == 0;

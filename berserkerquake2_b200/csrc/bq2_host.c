@@ -14,19 +14,26 @@
 
 #define DOT(x, y) ((x)[0]*(y)[0] + (x)[1]*(y)[1] + (x)[2]*(y)[2])   /* M:2253 */
 
+/* sincosf of +-0 is (+-0, 1) exactly; most entities turn about one axis only, so the libm call is skipped there */
+static inline void sincos_angle(float angle, float *s, float *c)
+{
+    if (angle == 0.0f) { *s = angle; *c = 1.0f; }
+    else sincosf(angle, s, c);
+}
+
 /* AngleVectors, M:37566-37620 (PITCH = 0, YAW = 1, ROLL = 2) */
 void bq2_host_angle_vectors(const float angles[3], float forward[3], float right[3], float up[3])
 {
     if (angles[0] || angles[1] || angles[2]) {
         float angle, sp, sy, cp, cy, sr, cr;
         angle = angles[1] * (M_PI * 2 / 360);
-        sincosf(angle, &sy, &cy);
+        sincos_angle(angle, &sy, &cy);
         angle = angles[0] * (M_PI * 2 / 360);
-        sincosf(angle, &sp, &cp);
+        sincos_angle(angle, &sp, &cp);
         if (forward) { forward[0] = cp * cy; forward[1] = cp * sy; forward[2] = -sp; }
         if (right || up) {
             angle = angles[2] * (M_PI * 2 / 360);
-            sincosf(angle, &sr, &cr);
+            sincos_angle(angle, &sr, &cr);
             if (right) {
                 right[0] = (-sr * sp * cy + cr * sy);
                 right[1] = (-sr * sp * sy - cr * cy);
@@ -58,21 +65,6 @@ static void move_delta(const float origin[3], const float oldorigin[3], const fl
         move[0] = DOT(temp, f);
         move[1] = -DOT(temp, r);
         move[2] = DOT(temp, u);
-    }
-}
-
-/* the same with the entity's AngleVectors already evaluated (basis = forward, right, up; NULL = all angles zero) */
-static void move_delta_basis(const float origin[3], const float oldorigin[3], const float *basis, float move[3])
-{
-    move[0] = oldorigin[0] - origin[0];
-    move[1] = oldorigin[1] - origin[1];
-    move[2] = oldorigin[2] - origin[2];
-    if (basis) {
-        float temp[3];
-        temp[0] = move[0]; temp[1] = move[1]; temp[2] = move[2];
-        move[0] = DOT(temp, basis);
-        move[1] = -DOT(temp, basis + 3);
-        move[2] = DOT(temp, basis + 6);
     }
 }
 
@@ -222,71 +214,49 @@ void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *fi
 /* ---- the per-entity half of the world path (bq2_world_submit), one pass, plain C ---------------------- */
 #include "bq2_internal.h"
 int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
-                            const bq2_dev_mesh *meshes, bq2_dev_ent *he, bq2_dev_xform *hx,
-                            int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
+                            bq2_dev_xform *hx, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
 {
     uint32_t voff = 0;
-    int32_t e, k;
+    int32_t e;
     memset(st, 0, sizeof *st);
     for (e = 0; e < n; e++) {
         const bq2_world_entity *W = &ents[e];
         const bq2_model_row *mo;
-        const bq2_dev_mesh *me;
-        bq2_entity E;
-        bq2_dev_ent *d;
-        bq2_dev_xform *x;
+        bq2_dev_xform *x = &hx[e];
         uint32_t vpad, bitw;
-        int32_t rec, small, casts;
-        float mv[3];
+        int32_t rec, casts;
         if (W->model < 0 || W->model >= n_models) return -1;
         mo = &models[W->model];
         if (mo->n_mesh != 1) return -3;
         if (W->frame < 0 || W->frame >= mo->F || W->oldframe < 0 || W->oldframe >= mo->F) return -2;
-        me = &meshes[mo->first_mesh];
-        small = me->V <= BQ2_WARP_MAX_V && me->T <= BQ2_WARP_MAX_T;
-        if (small) {                                    /* warp-kernel records grow up from 0 ... */
+        x->nrm_off = 0;
+        if (mo->V <= BQ2_WARP_MAX_V && mo->T <= BQ2_WARP_MAX_T) {   /* warp-kernel records grow up from 0 ... */
             rec = st->n_warp++;
-            if (me->V > st->warp_max_V) st->warp_max_V = me->V;
-            if (me->T > st->warp_max_T) st->warp_max_T = me->T;
-            if (!(me->flags & BQ2_MESH_MD3)) st->warp_md2 = 1;
-        } else {                                        /* ... team-kernel records down from the end */
+            if (mo->V > st->warp_max_V) st->warp_max_V = mo->V;
+            if (mo->T > st->warp_max_T) st->warp_max_T = mo->T;
+            if (!(mo->mflags & BQ2_MESH_MD3)) st->warp_md2 = 1;
+        } else {                                                    /* ... team-kernel records down from the end */
             rec = n - 1 - st->n_team++;
-            if (me->V > st->team_max_V) st->team_max_V = me->V;
-            if (me->T > st->team_max_T) st->team_max_T = me->T;
-            if (!(me->flags & BQ2_MESH_MD3)) st->team_md2 = 1;
+            if (mo->V > st->team_max_V) st->team_max_V = mo->V;
+            if (mo->T > st->team_max_T) st->team_max_T = mo->T;
+            if (!(mo->mflags & BQ2_MESH_MD3)) st->team_md2 = 1;
+            x->nrm_off = st->team_normal_rows; st->team_normal_rows += (uint32_t)mo->Tp;
         }
         rec_of_ent[e] = rec;
         /* AngleVectors once per entity: the reference evaluates them again for the move delta and for every light
            (same inputs, same libm, same values) */
-        x = &hx[e];
         x->rotated = (uint32_t)bq2_host_entity_basis(W->angles, x->basis);
-        move_delta_basis(W->origin, W->oldorigin, x->rotated ? x->basis : NULL, mv);
-        if (mo->md3)
-            entity_md3_finish(mo->hdr + 3 * (size_t)W->frame, mo->hdr + 3 * (size_t)W->oldframe, W->frame, W->oldframe,
-                              W->backlerp, mv, &E);
-        else
-            entity_md2_finish(mo->hdr + 6 * (size_t)W->frame, mo->hdr + 6 * (size_t)W->oldframe, W->frame, W->oldframe,
-                              W->backlerp, mv, W->rf_flags, &E);
-        d = &he[rec];
-        d->cur = me->verts + (size_t)W->frame * me->vstride; d->old = me->verts + (size_t)W->oldframe * me->vstride;
-        d->tri = me->tri; d->V = me->V; d->T = me->T; d->Tp = me->Tp; d->mflags = me->flags; d->vstride = me->vstride; d->nrm_off = 0;
-        if (!small) { d->nrm_off = st->team_normal_rows; st->team_normal_rows += (uint32_t)me->Tp; }
-        d->mesh = mo->first_mesh; d->frame = W->frame; d->oldframe = W->oldframe; d->flags = E.flags;
-        d->backlerp = E.backlerp; d->frontlerp = E.frontlerp;
-        for (k = 0; k < 3; k++) { d->move[k] = E.move[k]; d->frontv[k] = E.frontv[k]; d->backv[k] = E.backv[k]; }
-        d->shell_scale = E.shell_scale;
-        d->vert_off = voff; d->tb_off = 0; d->pair_begin = 0; d->pair_count = 0;
-        ent_vert_off[e] = voff;
-        vpad = (uint32_t)(me->V + 3) & ~3u; bitw = (uint32_t)(me->T + 31) >> 5;
-        voff += vpad; st->total_verts += (uint64_t)me->V;
-        if (vpad > st->max_vpad) st->max_vpad = vpad;
-        if (bitw > st->max_bitw) st->max_bitw = bitw;
-        if (me->T > st->max_T) st->max_T = me->T;
         casts = bq2_host_casts_shadow(W->rf_flags, 0, 0.0f, 2.0f) &&
                 !(W->rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));                 /* M:63722-63727, 64089 */
-        x->origin[0] = W->origin[0]; x->origin[1] = W->origin[1]; x->origin[2] = W->origin[2];
-        x->rec = casts ? rec : -1;
+        x->rec = rec; x->pair_rec = casts ? rec : -1;
+        x->vert_off = voff;
+        ent_vert_off[e] = voff;
+        vpad = (uint32_t)(mo->V + 3) & ~3u; bitw = (uint32_t)(mo->T + 31) >> 5;
         x->vpad = vpad; x->bitw = bitw;
+        voff += vpad; st->total_verts += (uint64_t)mo->V;
+        if (vpad > st->max_vpad) st->max_vpad = vpad;
+        if (bitw > st->max_bitw) st->max_bitw = bitw;
+        if (mo->T > st->max_T) st->max_T = mo->T;
     }
     ent_vert_off[n] = voff;
     st->lerped_verts_padded = voff;

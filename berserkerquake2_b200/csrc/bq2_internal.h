@@ -73,17 +73,29 @@ typedef struct bq2_dev_pair {
  * AngleVectors basis -- libm trig) plus the raw light and pair lists; three small kernels turn that into the
  * per-pair records above: one kernel writes every pair's record (light moved to model space, M:63733-63745;
  * plain mul/add, bit-exact on the device) and files the pair under its entity (bucket + overflow chain). */
-typedef struct bq2_dev_xform {      /* one per world entity */
-    float    origin[3];
-    int32_t  rec;                   /* index of the entity's record, -1 = entity casts no volume          */
-    float    basis[9];              /* forward, right, up (AngleVectors M:37566) when rotated             */
+typedef struct bq2_dev_xform {      /* one per world entity: everything the HOST decides or needs libm for     */
+    float    basis[9];              /* forward, right, up (AngleVectors M:37566); written only when rotated  */
     uint32_t rotated;
-    uint32_t vpad;                  /* extruded row length of a pair of this entity (verts, multiple of 4) */
-    uint32_t bitw;                  /* facing words of a pair of this entity                               */
+    int32_t  rec;                   /* index of the entity's record (warp-kernel records first)              */
+    int32_t  pair_rec;              /* = rec, or -1 when the entity casts no volume (M:63722-63727, 64089)   */
+    uint32_t vert_off;              /* lerped row of the entity (vertices)                                    */
+    uint32_t nrm_off;               /* team kernel: row of the entity in the triangle-normal scratch          */
+    uint32_t vpad;                  /* extruded row length of a pair of this entity (verts, multiple of 4)    */
+    uint32_t bitw;                  /* facing words of a pair of this entity                                  */
 } bq2_dev_xform;                    /* 64 bytes */
 
+typedef struct bq2_dev_model {      /* device mirror of a single-mesh model, for the record-building kernel    */
+    const float *hdr;               /* MD2: F x {scale[3], translate[3]}; MD3: F x translate[3]               */
+    int32_t  first_mesh, md3;
+} bq2_dev_model;                    /* 16 bytes */
+
+struct bq2_world_entity;
 typedef struct bq2_world_launch {
     const bq2_dev_xform *xf;
+    const struct bq2_world_entity *wents;   /* the caller's entities, copied as they are                      */
+    const bq2_dev_model *models;
+    const bq2_dev_mesh  *meshes;
+    bq2_dev_ent    *ents_out;       /* [n_ents] entity records, written by the kernel (lerp constants M:63526-63553) */
     const float    *lights;         /* [n_lights][4]: origin, radius (bq2_world_light)                     */
     const int32_t  *pair_ent, *pair_light;
     int32_t  n_pairs, n_ents, n_lights, n_recs;
@@ -116,7 +128,9 @@ typedef struct bq2_launch {
 } bq2_launch;
 
 /* host-side flat model table for the per-entity loop in C (bq2_host.c) */
-typedef struct bq2_model_row { const float *hdr; int32_t F, md3, first_mesh, n_mesh; } bq2_model_row;
+typedef struct bq2_model_row {      /* host mirror of a model for the C entity loop (V, T, flags of its first mesh) */
+    int32_t F, md3, first_mesh, n_mesh, V, T, Tp; uint32_t mflags;
+} bq2_model_row;                    /* 32 bytes */
 typedef struct bq2_world_stats {
     int32_t n_warp, n_team;                 /* records [0, n_warp) -> warp kernel, [n - n_team, n) -> team kernel */
     int32_t warp_max_V, warp_max_T, warp_md2, team_max_V, team_max_T, team_md2;
@@ -129,12 +143,12 @@ typedef struct bq2_world_stats {
 extern "C" {
 #endif
 struct bq2_world_entity;
-/* One pass over the world entities: record (lerp constants M:63526-63553 / 63825-63856, frame pointers,
- * output offsets), transform (origin, AngleVectors basis, flag filter M:63722-63727) and kernel class.
- * Returns 0, -1 unknown model, -2 frame out of range, -3 a model of the frame is not single-mesh. */
+/* One pass over the world entities: validation, kernel class, record / output-row numbering, flag filter
+ * (M:63722-63727) and -- the one thing that needs the host's libm -- AngleVectors of rotated entities.  The lerp
+ * constants themselves (M:63526-63553 / 63825-63856) are computed by the record-building kernel from the caller's
+ * entities and these rows.  Returns 0, -1 unknown model, -2 frame out of range, -3 a model is not single-mesh. */
 int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
-                             const bq2_dev_mesh *meshes, bq2_dev_ent *he, bq2_dev_xform *hx,
-                             int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st);
+                             bq2_dev_xform *hx, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st);
 /* Two kernels share the records.  "warp" kernel: one warp per (entity, light) pair, one CTA per entity,
  * for meshes with V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T (an MD2 player model is ~500 triangles).
  * "team" kernel: the whole CTA works on one pair at a time; any mesh size, and the N/T/B + tangent-space
