@@ -282,8 +282,22 @@ def run_gpu(args):
 
     e2e_run(max(args.warmup, 12))      # every frame state of the ring has captured its graph before the timed frames
     barrier()
+    _, e2e_py_s = e2e_run(args.steps, timed=True)                  # the same loop driven from Python (ctypes per call)
+    # the frame loop as an engine runs it: C on top of the public ABI (csrc/bq2_frame_loop.c), same calls, same depth
+    loop = C.CDLL(os.path.join(ROOT, "berserkerquake2_b200", "libbq2loop.so"))
+    loop.bq2_frame_loop.restype = C.c_int
+    loop.bq2_frame_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    sec, tot64 = C.c_double(0), C.c_uint64(0)
+
+    def e2e_loop(k):
+        if loop.bq2_frame_loop(ctx._h, C.byref(wd), k, E2E_IN_FLIGHT, C.byref(sec), C.byref(tot64)) != 0:
+            raise RuntimeError(c.lib.bq2_last_error(ctx._h))
+        return int(tot64.value), float(sec.value)
+
+    e2e_loop(max(args.warmup, 12))
+    barrier()
     launches_e2e0 = ctx.kernel_launches
-    e2e_indices, e2e_s = e2e_run(args.steps, timed=True)
+    e2e_indices, e2e_s = e2e_loop(args.steps)
     launches_e2e = ctx.kernel_launches - launches_e2e0 - 2 * (E2E_IN_FLIGHT - 1)   # the frames that fill the pipeline
     barrier()
     t0 = time.perf_counter()                                      # one frame at a time (latency of a frame)
@@ -348,6 +362,7 @@ def run_gpu(args):
                        "timing": "CUDA events around each launch on the ctx stream, summed over K steps, max over ranks"},
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
+                    "ms_per_step_python_driver": e2e_py_s * 1e3 / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
                     "h2d_bytes_per_step": n_ents * (64 + 56) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
@@ -356,7 +371,9 @@ def run_gpu(args):
                             "fused kernel; D2H of per-pair index counts + totals) + "
                             "bq2_frame_wait, wall clock over K frames with %d frames in flight (each has its own records, "
                             "result arrays and stream; the clock runs over K submit+wait iterations of the full pipeline, K "
-                            "frames in and K frames out); ms_per_step_serial = one at a time; " % E2E_IN_FLIGHT +
+                            "frames in and K frames out); the loop itself is C on the public ABI (csrc/bq2_frame_loop.c), as "
+                            "an engine would run it; ms_per_step_python_driver = the same calls made from Python; "
+                            "ms_per_step_serial = one at a time; " % E2E_IN_FLIGHT +
                             
                             "vertex/index buffers stay in HBM for the draw"},
             "shared_model_variant": {

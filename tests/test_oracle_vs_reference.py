@@ -25,7 +25,8 @@ def test_constants(oracle, ref):
 
 def test_angle_vectors(oracle, ref):
     rng = np.random.RandomState(1)
-    for ang in [(0, 0, 0), (0, 90, 0), (30, 0, 0), (0, 0, 45), (-12.5, 333.25, 7)] + [tuple(rng.uniform(-360, 360, 3)) for _ in range(50)]:
+    for ang in [(0, 0, 0), (0, 90, 0), (30, 0, 0), (0, 0, 45), (-12.5, 333.25, 7), (-0.0, 45, 0), (0, -0.0, 10),
+                (-0.0, -0.0, 33), (1e-40, 20, 0), (0, 1e-44, -0.0), (360, 0, 0), (0, 180, 0)] + [tuple(rng.uniform(-360, 360, 3)) for _ in range(50)]:
         for x, y, z in zip(oracle.angle_vectors(ang), ref.angle_vectors(ang), host.angle_vectors(ang)):
             assert same(x, y) and same(y, z), ang
 
