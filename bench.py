@@ -38,7 +38,7 @@ WORKLOADS = {
 SLICES, RINGS, FRAMES = 16, 17, 198
 RADIUS = 300.0
 L2_FLUSH_BYTES = 256 << 20
-E2E_IN_FLIGHT = 3          # frames the e2e leg keeps in flight (the library allows three; results of each stay separate)
+E2E_IN_FLIGHT = 4          # frames the e2e leg keeps in flight (the library allows four; results of each stay separate)
 
 
 def peaks():
@@ -249,7 +249,10 @@ def run_gpu(args):
     kept = C.c_int32(0)
     fd = c.FrameDesc(); fo = c.FrameOut()
 
-    wd = ctx.world_desc(we_c, wl_c, pe, pl, None, bq2.WANT_SHADOW, 0)      # host arrays, as the engine holds them
+    # host arrays as the engine holds them, in page-locked memory from bq2_host_alloc (copied to the device from there)
+    we_p, wl_p, pe_p, pl_p = (ctx.host_array(a) for a in (we_c, wl_c, pe, pl))
+    wd = ctx.world_desc(we_p, wl_p, pe_p, pl_p, None, bq2.WANT_SHADOW, 0)
+    wd_pageable = ctx.world_desc(we_c, wl_c, pe, pl, None, bq2.WANT_SHADOW, 0); wd_pageable._keep = ctx._keep
 
     def e2e_submit():
         if c.lib.bq2_world_submit(ctx._h, C.byref(wd)) != 0:
@@ -289,8 +292,8 @@ def run_gpu(args):
     loop.bq2_frame_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     sec, tot64 = C.c_double(0), C.c_uint64(0)
 
-    def e2e_loop(k):
-        if loop.bq2_frame_loop(ctx._h, C.byref(wd), k, E2E_IN_FLIGHT, C.byref(sec), C.byref(tot64)) != 0:
+    def e2e_loop(k, desc=None):
+        if loop.bq2_frame_loop(ctx._h, C.byref(desc or wd), k, E2E_IN_FLIGHT, C.byref(sec), C.byref(tot64)) != 0:
             raise RuntimeError(c.lib.bq2_last_error(ctx._h))
         return int(tot64.value), float(sec.value)
 
@@ -300,6 +303,8 @@ def run_gpu(args):
     e2e_indices, e2e_s = e2e_loop(args.steps)
     launches_e2e = ctx.kernel_launches - launches_e2e0 - 2 * (E2E_IN_FLIGHT - 1)   # the frames that fill the pipeline
     barrier()
+    e2e_loop(max(args.warmup, 12), wd_pageable)                    # the same from pageable arrays (staged by the library)
+    _, e2e_pageable_s = e2e_loop(args.steps, wd_pageable)
     t0 = time.perf_counter()                                      # one frame at a time (latency of a frame)
     for _ in range(args.steps):
         e2e_submit(); e2e_wait()
@@ -363,11 +368,13 @@ def run_gpu(args):
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
                     "ms_per_step_python_driver": e2e_py_s * 1e3 / args.steps,
+                    "ms_per_step_pageable_inputs": e2e_pageable_s * 1e3 / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
                     "h2d_bytes_per_step": n_ents * (64 + 56) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
                     "what": "per frame: bq2_world_submit (host: per-entity validation, numbering and AngleVectors; "
-                            "pinned -> H2D of the caller's entities, lights, pairs; the record-building kernel + the "
+                            "H2D of the caller's entities, lights, pairs from page-locked memory (bq2_host_alloc) and of the "
+                            "host-built rows from the library's pinned buffer; the record-building kernel + the "
                             "fused kernel; D2H of per-pair index counts + totals) + "
                             "bq2_frame_wait, wall clock over K frames with %d frames in flight (each has its own records, "
                             "result arrays and stream; the clock runs over K submit+wait iterations of the full pipeline, K "

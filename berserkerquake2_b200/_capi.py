@@ -133,6 +133,8 @@ EXPORTS_GPU_H = [
     _sig("bq2_upload_brush", C.c_int, vp, i32, vp, vp, vp, vp, C.POINTER(i32)),
     _sig("bq2_brush_volumes", C.c_int, vp, vp, i32, vp, C.POINTER(BrushOut)),
     _sig("bq2_brush_download", C.c_int, vp, i32, vp, vp),
+    _sig("bq2_host_alloc", vp, vp, C.c_size_t),
+    _sig("bq2_host_free", None, vp, vp),
     _sig("bq2_world_submit", C.c_int, vp, C.POINTER(WorldDesc)),
     _sig("bq2_world_frame", C.c_int, vp, C.POINTER(WorldDesc), C.POINTER(FrameOut)),
     _sig("bq2_shard_entities", None, i32, i32, i32, C.POINTER(i32), C.POINTER(i32)),

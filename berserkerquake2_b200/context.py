@@ -205,6 +205,18 @@ class Context:
                          allow=(c.E_OVERFLOW,) if allow_overflow else ())
         return FrameResult(self, out, st)
 
+    def host_array(self, like):
+        """A copy of `like` in page-locked memory from bq2_host_alloc (numpy view; valid until close()).  World
+        descriptors whose arrays all come from here are copied to the device without the staging copy."""
+        like = np.ascontiguousarray(like)
+        p = c.lib.bq2_host_alloc(self._h, max(like.nbytes, 16))
+        if not p:
+            raise MemoryError(c.lib.bq2_last_error(self._h))
+        buf = (C.c_char * max(like.nbytes, 16)).from_address(p)
+        a = np.frombuffer(buf, dtype=like.dtype, count=like.size).reshape(like.shape)
+        a[...] = like
+        return a
+
     def world_submit(self, desc):
         """bq2_world_submit of a descriptor made by world_desc (keep it alive); pair with wait()."""
         self._check(c.lib.bq2_world_submit(self._h, C.byref(desc)))

@@ -201,15 +201,16 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
 /* Host records in, one fused launch per model family, per-slot counts back.  Equivalent to
  * bq2_frame_submit + bq2_frame_wait. */
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *desc, bq2_frame_out *out);
-/* Up to THREE frames may be in flight: bq2_frame_submit (or bq2_world_submit) for frames i+1 and i+2 may be
+/* Up to FOUR frames may be in flight: bq2_frame_submit (or bq2_world_submit) for frames i+1 .. i+3 may be
  * called before bq2_frame_wait for frame i, so the host packs the next frames while the GPU works; bq2_frame_wait
- * always completes the OLDEST submitted frame.  The ctx holds a ring of four complete frame states -- pinned host
+ * always completes the OLDEST submitted frame.  The ctx holds a ring of five complete frame states -- pinned host
  * buffers, device records, device RESULT arrays, host offset tables, stream, CUDA graph -- and a submit takes the
  * next one when a frame is in flight: the copies and kernels of consecutive frames overlap on the GPU, and what
  * bq2_frame_wait returned for frame i (device pointers, offset tables, bq2_download / bq2_expand_trisverts) stays
- * valid while the next frames are computed -- until the first submit after the NEXT bq2_frame_wait.  A caller that
- * never overlaps (bq2_frame / bq2_world_frame, or submit then wait) uses one state only: its results are valid
- * until the next submit, and no further set of arrays is allocated. */
+ * valid while the next frames are computed: if another frame was still in flight when the wait returned, until the
+ * first submit after the NEXT bq2_frame_wait; if that wait emptied the pipeline, until the next submit (which reuses
+ * the same state).  So a caller that never overlaps (bq2_frame / bq2_world_frame, or submit then wait) uses one
+ * state only -- results valid until the next submit, no further set of arrays allocated -- and bq2_stream is fixed. */
 bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *desc);   /* async on bq2_stream   */
 bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out);             /* sync + counts readback */
 /* Re-run the kernels of the last submitted frame on the records already resident in HBM
@@ -378,6 +379,15 @@ typedef struct bq2_world_desc {
     const float   *view_world;       /* [3] or NULL */
     uint32_t want, index_stride;
 } bq2_world_desc;
+/* Page-locked host memory for the arrays a bq2_world_desc points at.  When ents, lights, pair_ent and pair_light of a
+ * submit ALL lie inside blocks from bq2_host_alloc and together exceed 1 MiB, bq2_world_submit copies them to the
+ * device from where they are instead of staging them through its own pinned buffer (at 1M pairs the staging copy is
+ * half of the host's frame time; small frames are staged either way, one copy being cheaper than five); the caller must then leave them unchanged until that frame's bq2_frame_wait has returned (an engine keeps
+ * one set per frame in flight).  Any other memory works as before (borrowed only for the duration of the call).
+ * NULL when out of memory.  bq2_host_free waits for the frames in flight; bq2_destroy frees what is left. */
+void        *bq2_host_alloc(bq2_ctx *ctx, size_t bytes);
+void         bq2_host_free(bq2_ctx *ctx, void *p);
+
 bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *desc);     /* async; pair with bq2_frame_wait */
 bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *desc, bq2_frame_out *out);
 

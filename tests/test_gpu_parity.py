@@ -403,7 +403,7 @@ def test_world_frame_md3_and_tangent_space_take_the_host_route(gpu_ctx, oracle):
 
 def test_two_frames_in_flight(gpu_ctx, oracle):
     """bq2_world_submit for frame i+1 before bq2_frame_wait for frame i: waits complete the OLDEST frame and
-    every frame's counts/totals are its own; a fourth submit is refused."""
+    every frame's counts/totals are its own; a fifth submit is refused."""
     models = [Md2Model(oracle, frames=6, seed=70 + s) for s in range(4)]
     mids = [m.upload(gpu_ctx) for m in models]
     import ctypes as C
@@ -418,16 +418,16 @@ def test_two_frames_in_flight(gpu_ctx, oracle):
         scenes[-1]._keep = gpu_ctx._keep
     fo = c.FrameOut()
     got = []
-    assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[0])) == 0
-    assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[1])) == 0
-    for i in range(2, 5):
+    for i in range(3):
         assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
-        if i == 2:
-            assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[3])) == -1          # only three in flight
+    for i in range(3, 5):
+        assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
+        if i == 3:
+            assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[4])) == -1          # only four in flight
         assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
         cnt = np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()
         got.append((int(fo.total_indices), cnt))
-    for _ in range(2):
+    for _ in range(3):
         assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
         got.append((int(fo.total_indices), np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()))
     for (ta, ca), (tb, cb) in zip(serial, got):
@@ -474,6 +474,45 @@ def test_overlapped_frames_keep_their_own_device_results(gpu_ctx, oracle):
         for p, (a, b) in enumerate(zip(serial[k], got)):
             for x, y in zip(a, b):
                 assert np.array_equal(x, y), (rnd, p)
+
+
+def test_world_frame_from_page_locked_caller_arrays(gpu_ctx, oracle):
+    """Arrays from bq2_host_alloc are copied to the device from where they are (no staging copy, five copy nodes in
+    the captured graph): same results as pageable arrays, new contents are seen on every replay, and a descriptor that
+    mixes pinned and pageable arrays falls back to staging.  (The library takes this route from 1 MiB of input per
+    frame; BQ2_DIRECT_MIN=0, read at bq2_create, makes the small scene take it.)"""
+    import os
+    os.environ["BQ2_DIRECT_MIN"] = "0"
+    try:
+        own_ctx = bq2.Context(0)
+    finally:
+        del os.environ["BQ2_DIRECT_MIN"]
+    with own_ctx as gpu_ctx:
+        _pinned_arrays_body(gpu_ctx, oracle)
+
+
+def _pinned_arrays_body(gpu_ctx, oracle):
+    models = [Md2Model(oracle, s, r, frames=6, seed=120 + i) for i, (s, r) in enumerate([(8, 5), (16, 17)])]
+    mids = [m.upload(gpu_ctx) for m in models]
+    we, wl, pe, pl = world_scene(37, 3, 6, n_models=2, seed=4242)
+    we["model"] = np.array(mids)[we["model"]]
+    we["angles"][3] = (5, 50, -20)
+    pwe, pwl, ppe, ppl = (gpu_ctx.host_array(a) for a in (we, wl, pe, pl))
+    for rnd in range(4):                                         # rounds 2+ replay the captured graph
+        we["frame"] = (we["frame"] + rnd) % 6; we["backlerp"] = np.float32(0.125 * (rnd + 1))
+        wl["origin"][:, 2] += np.float32(3.0 * rnd)
+        pwe[...] = we; pwl[...] = wl
+        ref = check_world(gpu_ctx, oracle, models, mids, we, wl, pe, pl)         # pageable, oracle-checked
+        ref_counts = ref.index_counts.copy()
+        ref_idx = [ref.indices(p).copy() for p in range(len(pe))]
+        ref_ext = [bits(ref.extruded(p, models[mids.index(int(we["model"][pe[p]]))].V)).copy() for p in range(len(pe))]
+        for arrays in ((pwe, pwl, ppe, ppl), (pwe, wl, ppe, ppl)):               # all pinned / mixed
+            res = gpu_ctx.world_frame(*arrays)
+            assert np.array_equal(res.index_counts, ref_counts) and int(res.total_indices) == int(ref.total_indices)
+            for p in range(len(pe)):
+                m = models[mids.index(int(we["model"][pe[p]]))]
+                assert np.array_equal(res.indices(p), ref_idx[p]), (rnd, p)
+                assert np.array_equal(bits(res.extruded(p, m.V)), ref_ext[p]), (rnd, p)
 
 
 def test_world_frame_single_mesh_md3_and_many_lights(gpu_ctx, oracle):

@@ -43,7 +43,7 @@ for it in range(0 if os.environ.get('BQ2_WORLD_ONLY') else N + 20):
         t += (t1 - t0, t2 - t1, t3 - t2)
 wd = ctx.world_desc(we, wl, pe, pl, None, bq2.WANT_SHADOW, 0)
 tw = np.zeros(2)
-for it in range(N + 20):
+for it in range(0 if os.environ.get('BQ2_WORLD_ONLY') else N + 20):
     t0 = time.perf_counter()
     c.lib.bq2_world_submit(ctx._h, C.byref(wd))
     t1 = time.perf_counter()
@@ -54,7 +54,7 @@ for it in range(N + 20):
 print("world path us per step: submit %.1f  wait %.1f  total %.1f" % (*(tw / N * 1e6), tw.sum() / N * 1e6))
 print("us per step: build_records %.1f  frame_submit %.1f  frame_wait %.1f  total %.1f" % (*(t / N * 1e6), t.sum() / N * 1e6))
 # pipelined, as bench.py's e2e leg runs it: three frames in flight (submit frame i+2, then wait for frame i)
-for depth in (2, 3):
+for depth in ((3,) if os.environ.get('BQ2_WORLD_ONLY') else (2, 3)):
     tp = np.zeros(2)
     for _ in range(depth - 1):
         c.lib.bq2_world_submit(ctx._h, C.byref(wd))

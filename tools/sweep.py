@@ -45,7 +45,6 @@ def main():
         nb = host.md2_neighbours(blob) if nb is None else nb
         mids.append(ctx.upload_md2(blob, nb))
     mids = np.array(mids, np.int32)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     flush = torch.empty(bench.L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
     peak, _ = bench.peaks()
     rows = []
@@ -55,6 +54,7 @@ def main():
         we["model"] = mids[np.arange(n_ents) % len(mids)]
         ents, pairs = ctx.build_records(we, wl, pe, pl)
         res = ctx.frame(ents, pairs)
+        stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))   # of THIS frame's state
         tot = int(res.total_indices)
         steps = int(max(5, min(200, 2e9 // max(tot, 1))))
         for _ in range(3):
@@ -67,10 +67,11 @@ def main():
         torch.cuda.synchronize()
         k_ms = float(np.median([e0.elapsed_time(e1) for e0, e1 in evs]))
         # end to end like bench.py: bq2_world_submit + bq2_frame_wait from host arrays
-        wd = ctx.world_desc(we, wl, pe, pl, None, bq2.WANT_SHADOW, 0)
+        pin = [ctx.host_array(x) for x in (we, wl, pe, pl)]       # page-locked caller arrays (bq2_host_alloc)
+        wd = ctx.world_desc(*pin, None, bq2.WANT_SHADOW, 0)
         fo = c.FrameOut()
         k = max(6, steps // 4)
-        depth = 3 if n_pairs <= (1 << 18) else 2            # frames in flight (each owns its result arrays: memory)
+        depth = 4 if n_pairs <= (1 << 18) else 2            # frames in flight (each owns its result arrays: memory)
         for _ in range(depth - 1):
             assert c.lib.bq2_world_submit(ctx._h, C.byref(wd)) == 0
         for _ in range(3 * depth):                          # every frame state allocates and captures its graph
