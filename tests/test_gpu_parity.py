@@ -434,6 +434,40 @@ def test_two_frames_in_flight(gpu_ctx, oracle):
         assert ta == tb and np.array_equal(ca, cb)
 
 
+def test_host_built_frames_in_flight_and_host_alloc_edges(gpu_ctx, oracle):
+    """bq2_frame_submit (records built by the caller) through the same ring: four frames of different shapes in flight,
+    each wait returns the oldest frame's own counts and device arrays.  bq2_host_alloc / bq2_host_free edge cases."""
+    import ctypes as C
+    from berserkerquake2_b200 import _capi as c
+    models = [Md2Model(oracle, s, r, frames=5, seed=140 + i) for i, (s, r) in enumerate([(8, 5), (12, 9)])]
+    mids = [m.upload(gpu_ctx) for m in models]
+    frames = []
+    for i in range(6):
+        we, wl, pe, pl = world_scene(11 + 5 * i, 2, 5, n_models=2, seed=900 + i)
+        we["model"] = np.array(mids)[we["model"]]
+        ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+        r = gpu_ctx.frame(ents, pairs)
+        frames.append((ents, pairs, r.index_counts.copy(), [r.indices(p).copy() for p in range(r.n_pair_slots)]))
+    for i in range(3):
+        gpu_ctx.submit(frames[i][0], frames[i][1])
+    for i in range(3, 6 + 3):
+        if i < 6:
+            gpu_ctx.submit(frames[i][0], frames[i][1])
+        r = gpu_ctx.wait()
+        _, _, cnt, idx = frames[i - 3]
+        assert np.array_equal(r.index_counts, cnt), i
+        for p in range(r.n_pair_slots):
+            assert np.array_equal(r.indices(p), idx[p]), (i, p)
+    assert not c.lib.bq2_host_alloc(gpu_ctx._h, 0)                       # nothing to allocate
+    assert not c.lib.bq2_host_alloc(None, 64)
+    c.lib.bq2_host_free(gpu_ctx._h, None)                                # no-ops
+    c.lib.bq2_host_free(gpu_ctx._h, C.c_void_p(0x1000))
+    p = c.lib.bq2_host_alloc(gpu_ctx._h, 4096)
+    assert p
+    c.lib.bq2_host_free(gpu_ctx._h, p)
+    c.lib.bq2_host_free(gpu_ctx._h, p)                                   # already gone: ignored
+
+
 def test_overlapped_frames_keep_their_own_device_results(gpu_ctx, oracle):
     """Frame i+1 is submitted (and may run) before frame i is waited for: the vertex / facing / index arrays that
     bq2_frame_wait returns for frame i are still frame i's (each of the two frame states owns its result arrays),
