@@ -6,11 +6,15 @@ buffers) on BASELINE.json's configs[1]: 1,024 synthetic MD2 entities x 4 lights 
   python bench.py --impl reference [...]                          the reference's own CPU code, all host cores
 
 One "step" = one pass of the path over the whole batch = ONE launch of the fused kernel.
-  value     shadow-volume triangles/s (sum index_count / 3 / time), inputs resident in HBM, L2 flushed
-            between steps, CUDA events on the launching stream, max over ranks
-  e2e       the same metric through the C ABI with HOST records in: bq2_build_records (host trig) +
-            bq2_frame (pack, H2D, kernel, D2H of the per-pair counts), wall clock around K calls
-  roofline  SURVEY.md 8(d) algorithmic bytes per launch / mean kernel time, vs MEASURED_PEAKS.json
+  value     shadow-volume triangles/s (sum index_count / 3 / time) over EXACTLY K steps launched back to back between one
+            pair of CUDA events on the launching stream, max over ranks.  Inputs resident in HBM and larger than L2:
+            the steps cycle through a ring of resident frames (bq2_frame_keep), each drawing on its own device copy of
+            the models, so a cycle reads more key-frame / triangle-table / record bytes than the L2 holds (no flush).
+  e2e       the same metric through the C ABI from HOST arrays: bq2_world_submit (host: validation, numbering,
+            AngleVectors; H2D; record-building kernel + fused kernel; D2H of the per-pair counts) + bq2_frame_wait,
+            four frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
+  roofline  SURVEY.md 8(d) algorithmic bytes per launch / (timed region / K), vs MEASURED_PEAKS.json; the time of ONE
+            launch alone after an L2 flush is reported beside it (isolated_launch_ms)
   cpu_baseline  oracle/_ref (the unmodified reference, compiled headless) on the host cores, N=1 only
 
 The oracle (oracle/) is loaded ONLY by the cpu_baseline / --impl reference legs below, as the thing that
@@ -164,27 +168,39 @@ def run_gpu(args):
     ctx = bq2.Context(local)
     t0 = time.time()
     V, T = synth.sphere_dims(SLICES, RINGS)
+    # Inputs larger than L2 instead of a flush between steps: RING resident frames, each on its own device copy of the
+    # models (a frame reads 2 key-frame rows + the triangle table per entity and its records), so that a cycle through
+    # the ring reads more than the L2 holds and every launch finds its inputs in HBM.
+    l2_bytes = int(getattr(torch.cuda.get_device_properties(local), "L2_cache_size", 126 << 20))
+    step_input_bytes = n_ents * (2 * 4 * V + 12 * T + 128) + n_ents * lights * 48
+    ring = int(min(32, max(2, -(-int(1.1 * l2_bytes) // step_input_bytes))))
     nb = None
-    mids = np.zeros(n_ents, np.int32)
-    model_bytes = 0
+    blobs = []
     for e in range(n_ents):
-        blob = synth.md2(SLICES, RINGS, FRAMES, first + e)
+        blobs.append(synth.md2(SLICES, RINGS, FRAMES, first + e))
         if nb is None:
-            nb = host.md2_neighbours(blob)                                 # same topology for every sphere
-        mids[e] = ctx.upload_md2(blob, nb)
-        model_bytes += FRAMES * 4 * V + 12 * T
-    we, wl, pe, pl = make_scene(n_ents, lights, first, n_ents * world)
-    we["model"] = mids
+            nb = host.md2_neighbours(blobs[0])                             # same topology for every sphere
+    mids = np.zeros((ring, n_ents), np.int32)
+    model_bytes = 0
+    for r in range(ring):
+        for e in range(n_ents):
+            mids[r, e] = ctx.upload_md2(blobs[e], nb)
+            model_bytes += FRAMES * 4 * V + 12 * T
+    del blobs
     setup_s = time.time() - t0
 
-    ents, pairs = ctx.build_records(we, wl, pe, pl)
-    res = ctx.frame(ents, pairs, want=bq2.WANT_SHADOW)                     # records now resident
-    n_pairs = len(pairs)
-    total_indices = int(res.total_indices)
-    assert res.overflow_pairs == 0 and total_indices > 0
-
+    kept_frames, ring_indices = [], []
+    for r in range(ring):                              # frame r of the ring: scene step r on model copy r
+        we_r, wl_r, pe, pl = make_scene(n_ents, lights, first, n_ents * world, step=r)
+        we_r["model"] = mids[r]
+        ents_r, pairs_r = ctx.build_records(we_r, wl_r, pe, pl)
+        res = ctx.frame(ents_r, pairs_r, want=bq2.WANT_SHADOW)
+        assert res.overflow_pairs == 0 and int(res.total_indices) > 0
+        kept_frames.append(ctx.keep())                 # its records stay resident in HBM
+        ring_indices.append(int(res.total_indices))
+        if r == 0:
+            we, wl, n_pairs = we_r, wl_r, len(pairs_r)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
 
     def barrier():
         torch.cuda.synchronize()
@@ -192,55 +208,53 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_resident(ev0=None, ev1=None):
-        with torch.cuda.stream(stream):
-            flush.zero_()                                                  # evict the previous step from L2
-            if ev0 is not None:
-                ev0.record(stream)
-            ctx.replay()                                                   # ONE fused launch on ctx.stream
-            if ev1 is not None:
-                ev1.record(stream)
+    def steps_resident(k, start=0):
+        """k steps back to back on the ctx stream: ONE fused launch each, inputs resident, cycling through the ring"""
+        for i in range(k):
+            ctx.replay_kept(kept_frames[(start + i) % ring])
 
     clocks = ClockSampler(local) if rank == 0 else None
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
+    steps_resident(max(args.warmup, 3))
     t_spin = time.perf_counter()                       # idle GPUs sit at ~120 MHz: keep stepping until the
     while time.perf_counter() - t_spin < args.spinup:  # clocks have ramped, then start the timed region
-        step_resident()
+        steps_resident(ring)
         torch.cuda.synchronize()
     barrier()
     if clocks:
         clocks.mark()
     launches0 = ctx.kernel_launches
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in evs:
-        step_resident(a, b)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    steps_resident(args.steps)                         # EXACTLY K steps
+    ev1.record(stream)
     barrier()
-    kernel_ms = [a.elapsed_time(b) for a, b in evs]
+    ms_total = float(ev0.elapsed_time(ev1))
     launches = ctx.kernel_launches - launches0
+    total_indices = sum(ring_indices[i % ring] for i in range(args.steps))       # over the K timed steps
     if clocks:                                         # the timed region can be shorter than nvidia-smi's
-        t_more = time.perf_counter()                   # period: keep the SAME step running until it has
+        t_more = time.perf_counter()                   # period: keep the SAME steps running until it has
         while clocks.since_mark() < 4 and time.perf_counter() - t_more < 3.0:   # seen a few samples
-            step_resident()
+            steps_resident(ring)
             torch.cuda.synchronize()
         clocks.freeze()
     clock_info = clocks.stop() if clocks else None     # (the sampler polls the driver: not during the wall-clock leg)
-    ms_total = float(sum(kernel_ms))
-    # informational: the same step when L2 holds none of its data but no foreign DIRTY lines either (the memset is
-    # followed by a read of a second buffer, so the step's stores evict clean lines, as in back-to-back frames)
+    # informational: ONE launch alone between two events, L2 flushed before it by a 256 MiB memset (dirty lines), or by
+    # the memset followed by a read of a second buffer (clean lines) -- the latency of an isolated launch
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
     flush2 = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
-    evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-            for _ in range(min(args.steps, 50))]
-    for a, b in evs2:
-        with torch.cuda.stream(stream):
-            flush.zero_()
-            flush2.sum()
-            a.record(stream)
-            ctx.replay()
-            b.record(stream)
-    torch.cuda.synchronize()
-    kernel_ms_clean = float(np.mean([a.elapsed_time(b) for a, b in evs2]))
-    launches_extra = len(evs2)
+    iso = {}
+    for name, clean in (("dirty", False), ("clean", True)):
+        evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
+        for i, (a, b) in enumerate(evs2):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                if clean:
+                    flush2.sum()
+                a.record(stream)
+                ctx.replay_kept(kept_frames[i % ring])
+                b.record(stream)
+        torch.cuda.synchronize()
+        iso[name] = float(np.median([a.elapsed_time(b) for a, b in evs2]))
     del flush2
 
     # ---- e2e: HOST records in through the C ABI, counts back, wall clock -----------------------------
@@ -320,7 +334,7 @@ def run_gpu(args):
     e2e_host_s = time.perf_counter() - t0
 
     # ---- SURVEY 8(d) variant: every entity instantiates the SAME model (key frames come from L2 after first touch) --
-    we_s = we.copy(); we_s["model"] = mids[0]
+    we_s = we.copy(); we_s["model"] = mids[0, 0]
     ents_s, pairs_s = ctx.build_records(we_s, wl, pe, pl)
     res_s = ctx.frame(ents_s, pairs_s, want=bq2.WANT_SHADOW)
     shared_indices = int(res_s.total_indices)
@@ -340,31 +354,37 @@ def run_gpu(args):
     # ---- reduce: max time over ranks; NCCL all_gather of the per-shard counters (the only collective) --
     from berserkerquake2_b200 import shard
     dev = f"cuda:{local}"
-    per_rank = shard.gather_counters([n_pairs, n_ents * V, total_indices // 3, total_indices, e2e_indices // 3], dev, dist)
+    per_rank = shard.gather_counters([n_pairs * args.steps, n_ents * V * args.steps, total_indices // 3, total_indices,
+                                      e2e_indices // 3], dev, dist)           # summed over the K timed steps
     g_pairs, g_verts, g_tris, g_indices, g_e2e_tris = [int(x) for x in per_rank.sum(0)]
     ms_total_max, e2e_ms_max = shard.max_over_ranks([ms_total, e2e_s * 1e3], dev, dist)
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps
         peak, peak_src = peaks()
-        alg = algorithmic_bytes(n_ents, n_pairs, V, T, total_indices)       # per launch (this rank's)
-        mint = min_traffic_bytes(n_ents, n_pairs, V, T, total_indices)
-        k_ms = float(np.mean(kernel_ms))
+        alg = algorithmic_bytes(n_ents, n_pairs, V, T, total_indices / args.steps)     # per launch (this rank's mean)
+        mint = min_traffic_bytes(n_ents, n_pairs, V, T, total_indices / args.steps)
+        k_ms = ms_per_step                                                 # one launch per step
         out = {
             "metric": "shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/extrusion index "
                       "generation); lerped verts/s alongside",
-            "value": g_tris / (ms_per_step * 1e-3), "unit": "tris/s",
-            "lerped_verts_per_s": g_verts / (ms_per_step * 1e-3),
-            "pairs_per_s": g_pairs / (ms_per_step * 1e-3),
+            "value": g_tris / (ms_total_max * 1e-3), "unit": "tris/s",
+            "lerped_verts_per_s": g_verts / (ms_total_max * 1e-3),
+            "pairs_per_s": g_pairs / (ms_total_max * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc + " per GPU; one distinct model per entity; entity-major sharding, "
                                           "no data-path collective",
                        "entities_per_gpu": n_ents, "lights_per_entity": lights, "pairs_per_gpu": n_pairs,
                        "verts": V, "tris": T, "frames": FRAMES, "model_bytes_in_hbm_per_gpu": model_bytes,
-                       "mean_indices_per_pair": total_indices / n_pairs,
-                       "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset on the same stream, untimed)",
-                       "timing": "CUDA events around each launch on the ctx stream, summed over K steps, max over ranks"},
+                       "mean_indices_per_pair": total_indices / args.steps / n_pairs,
+                       "l2": f"not flushed: inputs larger than L2 -- the K steps cycle through a ring of {ring} resident frames "
+                             f"(scene steps 0..{ring - 1}), each on its own device copy of the {n_ents} models, so one cycle reads "
+                             f"{ring * step_input_bytes / 1e6:.0f} MB of key frames, triangle tables and records (L2: "
+                             f"{l2_bytes / 1e6:.0f} MB) besides streaming {ring} x the outputs through it",
+                       "resident_frames": ring, "input_bytes_per_step": step_input_bytes,
+                       "timing": "one pair of CUDA events on the ctx stream around the K back-to-back launches, max over ranks; "
+                                 "roofline.isolated_launch_ms = one launch alone between two events after an L2 flush"},
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
                     "ms_per_step_python_driver": e2e_py_s * 1e3 / args.steps,
@@ -397,7 +417,9 @@ def run_gpu(args):
                          "traffic": None,
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
                          "kernel": "bq2_frame_warp_kernel", "kernel_ms": k_ms,
-                         "kernel_ms_l2_clean_lines": kernel_ms_clean, "kernel_ms_median": float(np.median(kernel_ms)),
+                         "isolated_launch_ms": {"l2_flushed_by_memset": iso["dirty"], "l2_flushed_then_read": iso["clean"],
+                                                "what": "ONE launch between two events on an otherwise idle stream: adds "
+                                                        "the launch and completion latency that back-to-back steps hide"},
                          "min_traffic_bytes_per_launch": mint,
                          "achieved_min_traffic": mint / (k_ms * 1e-3) / 1e9,
                          "frac_min_traffic": mint / (k_ms * 1e-3) / 1e9 / peak},

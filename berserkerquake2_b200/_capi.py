@@ -102,6 +102,9 @@ EXPORTS_GPU_H = [
     _sig("bq2_frame_submit", C.c_int, vp, C.POINTER(FrameDesc)),
     _sig("bq2_frame_wait", C.c_int, vp, C.POINTER(FrameOut)),
     _sig("bq2_frame_replay", C.c_int, vp),
+    _sig("bq2_frame_keep", C.c_int, vp, C.POINTER(vp)),
+    _sig("bq2_resident_replay", C.c_int, vp, vp),
+    _sig("bq2_resident_free", None, vp, vp),
     _sig("bq2_download", C.c_int, vp, C.c_int, u64, u64, vp),
     _sig("bq2_host_index_counts", C.POINTER(u32), vp),
     _sig("bq2_expand_trisverts", C.c_int, vp, i32, vp, i32, C.POINTER(i32)),

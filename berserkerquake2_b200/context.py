@@ -225,6 +225,18 @@ class Context:
         """Re-launch the last frame's kernel on the records already in HBM (no copies, no sync)."""
         self._check(c.lib.bq2_frame_replay(self._h))
 
+    def keep(self):
+        """bq2_frame_keep: a handle to the last (host-built, completed) frame's records, for replay_kept()."""
+        h = C.c_void_p()
+        self._check(c.lib.bq2_frame_keep(self._h, C.byref(h)))
+        return h
+
+    def replay_kept(self, handle):
+        self._check(c.lib.bq2_resident_replay(self._h, handle))
+
+    def free_kept(self, handle):
+        c.lib.bq2_resident_free(self._h, handle)
+
     def download(self, which, first, count, dtype):
         buf = np.zeros(int(count), dtype)
         assert buf.itemsize == 4

@@ -122,6 +122,13 @@ struct FrameState {
 
 } // namespace
 
+struct bq2_resident {                   /* bq2_frame_keep: a frame's device records and launch parameters */
+    DevBuf<unsigned char> records;
+    int state = 0;
+    bq2_launch L{};
+    FrameState::KLaunch k_warp, k_team;
+};
+
 struct bq2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;                               /* = fs[0].stream: uploads, load-time kernels, brush pairs */
@@ -1306,6 +1313,59 @@ bq2_status bq2_frame_replay(bq2_ctx *ctx)
     if (F.world_mode)                                            /* the kernels add to the totals: start from zero */
         CK(cudaMemsetAsync(F.wlaunch.totals, 0, 2 * sizeof(unsigned long long), F.stream), "cudaMemset(totals)");
     return launch_kernels(ctx, F);
+}
+
+bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out)
+{
+    if (!ctx || !out) return BQ2_E_INVALID;
+    *out = nullptr;
+    FrameState &F = ctx->fs[ctx->cur];
+    if (!ctx->submitted || !F.n_ent_slots || ctx->submit_seq != ctx->wait_seq)
+        return fail(ctx, BQ2_E_INVALID, "bq2_frame_keep: no completed frame (submit and wait first)");
+    if (F.world_mode) return fail(ctx, BQ2_E_INVALID, "bq2_frame_keep: the frame must come from bq2_frame / bq2_frame_submit");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    const size_t bytes = (size_t)((const unsigned char *)(F.launch.pairs) - F.d_records.p) + (size_t)F.n_pair_slots * sizeof(bq2_dev_pair);
+    bq2_resident *r = new (std::nothrow) bq2_resident();
+    if (!r) return fail(ctx, BQ2_E_NOMEM, "bq2_frame_keep: out of host memory");
+    cudaError_t e = r->records.ensure(std::max<size_t>(bytes, 16));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r->records.p, F.d_records.p, bytes, cudaMemcpyDeviceToDevice, F.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(F.stream);
+    if (e != cudaSuccess) { r->records.release(); delete r; return fail_cuda(ctx, e, "bq2_frame_keep"); }
+    r->state = ctx->cur; r->L = F.launch; r->k_warp = F.k_warp; r->k_team = F.k_team;
+    r->L.ents = (const bq2_dev_ent *)r->records.p;
+    r->L.pairs = (const bq2_dev_pair *)(r->records.p + ((const unsigned char *)F.launch.pairs - F.d_records.p));
+    *out = r;
+    return BQ2_OK;
+}
+
+bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
+{
+    if (!ctx || !r) return BQ2_E_INVALID;
+    FrameState &F = ctx->fs[r->state];
+    if (r->L.lerped != F.lerped.p || r->L.extruded != F.extruded.p || r->L.indices != F.indices.p ||
+        r->L.index_count != F.index_count.p || r->L.facing_bits != F.facing_bits.p || r->L.tri_normals != F.tri_normals.p ||
+        r->L.meshes != ctx->d_meshes.p)
+        return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the result arrays of that frame state were re-allocated");
+    bq2_launch L = r->L;
+    if (r->k_warp.n) {
+        L.n_ent_slots = r->k_warp.n;
+        CK((cudaError_t)bq2_launch_frame_warp(&L, r->k_warp.max_V, r->k_warp.max_T, r->k_warp.any_md2, F.stream), "launch(bq2_frame_warp_kernel)");
+        ctx->launches++;
+    }
+    if (r->k_team.n) {
+        L.ents = r->L.ents + r->k_warp.n; L.rec_base = (uint32_t)r->k_warp.n; L.n_ent_slots = r->k_team.n;
+        CK((cudaError_t)bq2_launch_frame(&L, r->k_team.max_V, r->k_team.max_T, r->k_team.any_md2, F.stream), "launch(bq2_frame_kernel)");
+        ctx->launches++;
+    }
+    return BQ2_OK;
+}
+
+void bq2_resident_free(bq2_ctx *ctx, bq2_resident *r)
+{
+    if (!r) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->fs[r->state].stream); }
+    r->records.release();
+    delete r;
 }
 
 const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->fs[ctx->last_waited].hcnt.p : nullptr; }

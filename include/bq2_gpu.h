@@ -216,6 +216,15 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out);             /* sync
 /* Re-run the kernels of the last submitted frame on the records already resident in HBM
  * (no host->device or device->host traffic, no sync): the "inputs resident" measurement leg. */
 bq2_status bq2_frame_replay(bq2_ctx *ctx);
+/* Resident frames (measurement): bq2_frame_keep copies the device records of the most recently submitted frame --
+ * which must have come from bq2_frame / bq2_frame_submit and been waited for -- into an object of its own, so that a
+ * set of DIFFERENT frames can be re-run back to back with every input already in HBM (bench.py cycles through more
+ * of them than fit in L2).  bq2_resident_replay launches that frame's kernels on bq2_stream (async, no copies); the
+ * results go to the arrays of the frame state it was computed on, which must not have been re-allocated since. */
+typedef struct bq2_resident bq2_resident;
+bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out);
+bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r);
+void       bq2_resident_free(bq2_ctx *ctx, bq2_resident *r);
 
 /* ---- result download helpers (tests, the drop-in shim) --------------------------------------- */
 /* Copies `count` 32-bit words starting at word offset `first` of a device result array to host. */

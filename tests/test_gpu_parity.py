@@ -468,6 +468,41 @@ def test_host_built_frames_in_flight_and_host_alloc_edges(gpu_ctx, oracle):
     c.lib.bq2_host_free(gpu_ctx._h, p)                                   # already gone: ignored
 
 
+def test_kept_frames_replay_bit_identically(gpu_ctx, oracle):
+    """bq2_frame_keep / bq2_resident_replay (bench.py's ring of resident frames): re-running a kept frame reproduces
+    its results exactly, in any order, with other frames computed in between; world-path frames cannot be kept."""
+    import ctypes as C
+    from berserkerquake2_b200 import _capi as c
+    models = [Md2Model(oracle, s, r, frames=5, seed=160 + i) for i, (s, r) in enumerate([(8, 5), (16, 17)])]
+    mids = [m.upload(gpu_ctx) for m in models]
+    kept = []
+    for i in range(3):
+        we, wl, pe, pl = world_scene(40, 2, 5, n_models=2, seed=1000 + i)       # same shape: the result arrays are reused
+        we["model"] = np.array(mids)[we["model"]]
+        ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+        r = gpu_ctx.frame(ents, pairs)
+        snap = (r.index_counts.copy(), [r.indices(p).copy() for p in range(r.n_pair_slots)],
+                [bits(r.extruded(p, models[mids.index(int(we["model"][pe[p]]))].V)).copy() for p in range(len(pe))],
+                int(r.index_stride))
+        kept.append((gpu_ctx.keep(), snap))
+    for order in ((2, 0, 1), (1, 1, 0, 2)):
+        for k in order:
+            h, (cnt, idx, ext, stride) = kept[k]
+            gpu_ctx.replay_kept(h)
+            gpu_ctx.wait()                                                       # nothing pending: a stream sync
+            got = gpu_ctx.download(c.A_INDEX_COUNT, 0, len(cnt), np.uint32)
+            assert np.array_equal(got, cnt), k
+            for p in range(len(cnt)):
+                assert np.array_equal(gpu_ctx.download(c.A_INDICES, p * stride, cnt[p], np.uint32), idx[p]), (k, p)
+    for h, _ in kept:
+        gpu_ctx.free_kept(h)
+    we, wl, pe, pl = world_scene(10, 2, 5, n_models=2, seed=7)
+    we["model"] = np.array(mids)[we["model"]]
+    gpu_ctx.world_frame(we, wl, pe, pl)
+    h = C.c_void_p()
+    assert c.lib.bq2_frame_keep(gpu_ctx._h, C.byref(h)) == c.E_INVALID and not h
+
+
 def test_overlapped_frames_keep_their_own_device_results(gpu_ctx, oracle):
     """Frame i+1 is submitted (and may run) before frame i is waited for: the vertex / facing / index arrays that
     bq2_frame_wait returns for frame i are still frame i's (each of the two frame states owns its result arrays),
