@@ -4,7 +4,7 @@
 tag=${1:-x}
 CMD="python bench.py --steps 5 --warmup 3 --no-cpu --spinup 0"
 $CMD > gpurun_out/plain_launches.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches.log 2>&1
 echo launches=$?
 CMD3="python bench.py --workload c3shard --steps 3 --warmup 3 --no-cpu --spinup 0"
 $CMD3 > gpurun_out/plain_c3.log 2>&1 && \

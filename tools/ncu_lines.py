@@ -35,9 +35,11 @@ def sass_lines(so, kernel_sub):
             m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
             if m and cur_fn:
                 out[cur_fn][int(m.group(1), 16)] = (line, m.group(2).strip())
-    for fn, d in out.items():
-        if kernel_sub in fn and d:
-            return d
+    cands = [(fn, d) for fn, d in out.items() if kernel_sub in fn and d]
+    if len(cands) > 1:
+        print("# several kernels match %r, taking the first: %s" % (kernel_sub, ", ".join(fn for fn, _ in cands)), file=sys.stderr)
+    if cands:
+        return cands[0][1]
     raise SystemExit(f"no kernel matching {kernel_sub!r} in {so}")
 
 
