@@ -23,7 +23,9 @@ class Context:
     # -- lifetime ------------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            c.lib.bq2_destroy(self._h)
+            lib = getattr(c, "lib", None)          # module globals may already be gone at interpreter shutdown
+            if lib is not None:
+                lib.bq2_destroy(self._h)
             self._h = None
 
     __del__ = close
