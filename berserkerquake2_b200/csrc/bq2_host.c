@@ -216,31 +216,34 @@ void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *fi
 int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
                             bq2_dev_xform *hx, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
 {
+    /* the running numbers live in locals (the stores through hx / rec_of_ent could alias *st) */
+    bq2_world_stats s;
     uint32_t voff = 0;
     int32_t e;
+    memset(&s, 0, sizeof s);
     memset(st, 0, sizeof *st);
     for (e = 0; e < n; e++) {
         const bq2_world_entity *W = &ents[e];
         const bq2_model_row *mo;
         bq2_dev_xform *x = &hx[e];
-        uint32_t vpad, bitw;
-        int32_t rec, casts;
-        if (W->model < 0 || W->model >= n_models) return -1;
+        uint32_t vpad, bitw, nrm_off = 0;
+        int32_t rec, casts, V, T;
+        if ((uint32_t)W->model >= (uint32_t)n_models) return -1;
         mo = &models[W->model];
         if (mo->n_mesh != 1) return -3;
-        if (W->frame < 0 || W->frame >= mo->F || W->oldframe < 0 || W->oldframe >= mo->F) return -2;
-        x->nrm_off = 0;
-        if (mo->V <= BQ2_WARP_MAX_V && mo->T <= BQ2_WARP_MAX_T) {   /* warp-kernel records grow up from 0 ... */
-            rec = st->n_warp++;
-            if (mo->V > st->warp_max_V) st->warp_max_V = mo->V;
-            if (mo->T > st->warp_max_T) st->warp_max_T = mo->T;
-            if (!(mo->mflags & BQ2_MESH_MD3)) st->warp_md2 = 1;
+        if ((uint32_t)W->frame >= (uint32_t)mo->F || (uint32_t)W->oldframe >= (uint32_t)mo->F) return -2;
+        V = mo->V; T = mo->T;
+        if (V <= BQ2_WARP_MAX_V && T <= BQ2_WARP_MAX_T) {           /* warp-kernel records grow up from 0 ... */
+            rec = s.n_warp++;
+            if (V > s.warp_max_V) s.warp_max_V = V;
+            if (T > s.warp_max_T) s.warp_max_T = T;
+            s.warp_md2 |= !(mo->mflags & BQ2_MESH_MD3);
         } else {                                                    /* ... team-kernel records down from the end */
-            rec = n - 1 - st->n_team++;
-            if (mo->V > st->team_max_V) st->team_max_V = mo->V;
-            if (mo->T > st->team_max_T) st->team_max_T = mo->T;
-            if (!(mo->mflags & BQ2_MESH_MD3)) st->team_md2 = 1;
-            x->nrm_off = st->team_normal_rows; st->team_normal_rows += (uint32_t)mo->Tp;
+            rec = n - 1 - s.n_team++;
+            if (V > s.team_max_V) s.team_max_V = V;
+            if (T > s.team_max_T) s.team_max_T = T;
+            s.team_md2 |= !(mo->mflags & BQ2_MESH_MD3);
+            nrm_off = s.team_normal_rows; s.team_normal_rows += (uint32_t)mo->Tp;
         }
         rec_of_ent[e] = rec;
         /* AngleVectors once per entity: the reference evaluates them again for the move delta and for every light
@@ -248,18 +251,18 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         x->rotated = (uint32_t)bq2_host_entity_basis(W->angles, x->basis);
         casts = bq2_host_casts_shadow(W->rf_flags, 0, 0.0f, 2.0f) &&
                 !(W->rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));                 /* M:63722-63727, 64089 */
+        vpad = (uint32_t)(V + 3) & ~3u; bitw = (uint32_t)(T + 31) >> 5;
         x->rec = rec; x->pair_rec = casts ? rec : -1;
-        x->vert_off = voff;
+        x->vert_off = voff; x->nrm_off = nrm_off; x->vpad = vpad; x->bitw = bitw;
         ent_vert_off[e] = voff;
-        vpad = (uint32_t)(mo->V + 3) & ~3u; bitw = (uint32_t)(mo->T + 31) >> 5;
-        x->vpad = vpad; x->bitw = bitw;
-        voff += vpad; st->total_verts += (uint64_t)mo->V;
-        if (vpad > st->max_vpad) st->max_vpad = vpad;
-        if (bitw > st->max_bitw) st->max_bitw = bitw;
-        if (mo->T > st->max_T) st->max_T = mo->T;
+        voff += vpad; s.total_verts += (uint64_t)V;
+        if (vpad > s.max_vpad) s.max_vpad = vpad;
+        if (bitw > s.max_bitw) s.max_bitw = bitw;
+        if (T > s.max_T) s.max_T = T;
     }
     ent_vert_off[n] = voff;
-    st->lerped_verts_padded = voff;
+    s.lerped_verts_padded = voff;
+    *st = s;
     return 0;
 }
 
