@@ -81,7 +81,6 @@ struct PinBuf {
 #define BQ2_MAX_IN_FLIGHT  4
 struct FrameState {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev = nullptr;
     std::vector<int32_t>  ent_slot_first, pair_slot_first;
     std::vector<uint32_t> ent_vert_off, pair_vert_off, pair_bits_off, ent_tb_off, pair_ts_off;
     std::vector<uint32_t> cursor;                                /* scratch for the counting sort */
@@ -114,9 +113,8 @@ struct FrameState {
         d_records.release(); lerped.release(); extruded.release(); normals.release(); tangents.release(); binormals.release();
         lightp.release(); tsh.release(); tri_normals.release(); facing_bits.release(); indices.release(); index_count.release();
         d_world.release(); hrec.release(); hcnt.release();
-        if (ev) cudaEventDestroy(ev);
         if (stream) cudaStreamDestroy(stream);
-        ev = nullptr; stream = nullptr;
+        stream = nullptr;
     }
 };
 
@@ -279,9 +277,8 @@ bq2_status bq2_create(int device, bq2_ctx **out)
         delete ctx; return BQ2_E_NODEVICE;
     }
     for (int k = 0; k < BQ2_FRAME_STATES; k++) {
-        if ((e = cudaStreamCreateWithFlags(&ctx->fs[k].stream, cudaStreamNonBlocking)) != cudaSuccess ||
-            (e = cudaEventCreateWithFlags(&ctx->fs[k].ev, cudaEventDisableTiming)) != cudaSuccess) {
-            fail_cuda(nullptr, e, "cudaStreamCreate / cudaEventCreate");
+        if ((e = cudaStreamCreateWithFlags(&ctx->fs[k].stream, cudaStreamNonBlocking)) != cudaSuccess) {
+            fail_cuda(nullptr, e, "cudaStreamCreate");
             for (FrameState &f : ctx->fs) f.release();
             delete ctx; return BQ2_E_CUDA;
         }
@@ -310,7 +307,7 @@ void bq2_destroy(bq2_ctx *ctx)
     ctx->d_meshes.release(); ctx->d_models.release();
     ctx->d_brushes.release(); ctx->d_brush_in.release(); ctx->brush_vcache.release();
     ctx->brush_icache.release(); ctx->brush_counts.release();
-    for (FrameState &f : ctx->fs) f.release();                   /* streams and events included */
+    for (FrameState &f : ctx->fs) f.release();                   /* streams included */
     for (const bq2_ctx::HostRange &r : ctx->host_ranges) cudaFreeHost((void *)r.base);
     delete ctx;
 }

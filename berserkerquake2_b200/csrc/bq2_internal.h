@@ -69,10 +69,11 @@ typedef struct bq2_dev_pair {
 } bq2_dev_pair;             /* 48 bytes */
 
 /* ---- device-side record building ("world" path) ------------------------------------------------
- * The host ships what it alone can compute (per ENTITY: lerp constants and, for rotated entities, the
- * AngleVectors basis -- libm trig) plus the raw light and pair lists; three small kernels turn that into the
- * per-pair records above: one kernel writes every pair's record (light moved to model space, M:63733-63745;
- * plain mul/add, bit-exact on the device) and files the pair under its entity (bucket + overflow chain). */
+ * The host ships what it alone can decide (per ENTITY: validation, record and output-row numbering, the flag filter,
+ * and for rotated entities the AngleVectors basis -- libm trig) plus the caller's entity, light and pair lists as
+ * they are; ONE kernel turns that into the records above: an entity thread writes the entity record (lerp constants
+ * M:63526-63553 / 63825-63856), a pair thread writes the pair record (light moved to model space, M:63733-63745) and
+ * files the pair under its entity (bucket + overflow chain).  Plain mul/add in the reference's order: bit-exact. */
 typedef struct bq2_dev_xform {      /* one per world entity: everything the HOST decides or needs libm for     */
     float    basis[9];              /* forward, right, up (AngleVectors M:37566); written only when rotated  */
     uint32_t rotated;
