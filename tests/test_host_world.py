@@ -1,0 +1,104 @@
+"""CPU test of the host half of the world path (bq2_host_world_entities, csrc/bq2_host.c): what bq2_world_submit
+decides on the host before anything reaches the GPU -- validation, kernel class, record and output-row numbering,
+the flag filter M:63722-63727 / 64089, AngleVectors once per rotated entity.  No GPU, no compute call."""
+import ctypes as C
+
+import numpy as np
+
+import berserkerquake2_b200 as bq2
+from berserkerquake2_b200 import _capi as c, host
+
+MODEL_ROW = np.dtype([("F", "<i4"), ("md3", "<i4"), ("first_mesh", "<i4"), ("n_mesh", "<i4"), ("V", "<i4"), ("T", "<i4"),
+                      ("Tp", "<i4"), ("mflags", "<u4")])
+XFORM = np.dtype([("basis", "<f4", 9), ("rotated", "<u4"), ("rec", "<i4"), ("pair_rec", "<i4"), ("vert_off", "<u4"),
+                  ("nrm_off", "<u4"), ("vpad", "<u4"), ("bitw", "<u4")])
+STATS = np.dtype([("n_warp", "<i4"), ("n_team", "<i4"), ("warp_max_V", "<i4"), ("warp_max_T", "<i4"), ("warp_md2", "<i4"),
+                  ("team_max_V", "<i4"), ("team_max_T", "<i4"), ("team_md2", "<i4"), ("lerped_verts_padded", "<u4"),
+                  ("max_vpad", "<u4"), ("max_bitw", "<u4"), ("max_T", "<i4"), ("team_normal_rows", "<u4"), ("pad", "<u4"),
+                  ("total_verts", "<u8")])
+assert MODEL_ROW.itemsize == 32 and XFORM.itemsize == 64 and STATS.itemsize == 64
+MESH_MD3 = 0x1
+
+
+def run(we, rows):
+    fn = c.lib.bq2_host_world_entities
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    n = len(we)
+    hx = np.zeros(n, XFORM); rec = np.full(n + 1, -7, np.int32); voff = np.zeros(n + 1, np.uint32); st = np.zeros(1, STATS)
+    rc = fn(we.ctypes.data, n, rows.ctypes.data, len(rows), hx.ctypes.data, rec.ctypes.data, voff.ctypes.data, st.ctypes.data)
+    return rc, hx, rec[:n], voff, st[0]
+
+
+def rows_of(shapes):
+    rows = np.zeros(len(shapes), MODEL_ROW)
+    for i, (V, T, md3, n_mesh) in enumerate(shapes):
+        rows[i] = (6, md3, i, n_mesh, V, T, (T + 31) & ~31, MESH_MD3 if md3 else 0)
+    return rows
+
+
+def test_numbering_classes_and_stats():
+    rows = rows_of([(258, 512, 0, 1), (1026, 2048, 1, 1), (40, 60, 1, 1), (1024, 1024, 0, 1), (1025, 10, 0, 1)])
+    rng = np.random.RandomState(5)
+    n = 41
+    we = np.zeros(n, bq2.WORLD_ENTITY_DTYPE)
+    we["model"] = rng.randint(0, 5, n); we["frame"] = rng.randint(0, 6, n); we["oldframe"] = rng.randint(0, 6, n)
+    rc, hx, rec, voff, st = run(we, rows)
+    assert rc == 0
+    small = np.array([(rows["V"][m] <= 1024) and (rows["T"][m] <= 1024) for m in we["model"]])
+    # warp-kernel records count up from 0 in entity order, team-kernel records down from n-1
+    assert np.array_equal(rec[small], np.arange(small.sum()))
+    assert np.array_equal(rec[~small], n - 1 - np.arange((~small).sum()))
+    assert sorted(rec) == list(range(n)) and np.array_equal(hx["rec"], rec) and np.array_equal(hx["pair_rec"], rec)
+    V = rows["V"][we["model"]]; T = rows["T"][we["model"]]; Tp = rows["Tp"][we["model"]]
+    vpad = (V + 3) & ~3
+    assert np.array_equal(voff[:n], np.concatenate([[0], np.cumsum(vpad)[:-1]])) and voff[n] == vpad.sum()
+    assert np.array_equal(hx["vert_off"], voff[:n]) and np.array_equal(hx["vpad"], vpad)
+    assert np.array_equal(hx["bitw"], (T + 31) >> 5)
+    assert np.array_equal(hx["nrm_off"][~small], np.concatenate([[0], np.cumsum(Tp[~small])[:-1]]))
+    assert (hx["nrm_off"][small] == 0).all()
+    assert st["n_warp"] == small.sum() and st["n_team"] == (~small).sum()
+    assert st["warp_max_V"] == V[small].max() and st["warp_max_T"] == T[small].max()
+    assert st["team_max_V"] == V[~small].max() and st["team_max_T"] == T[~small].max()
+    assert st["warp_md2"] == int((rows["md3"][we["model"]][small] == 0).any())
+    assert st["team_md2"] == int((rows["md3"][we["model"]][~small] == 0).any())
+    assert st["lerped_verts_padded"] == vpad.sum() and st["max_vpad"] == vpad.max() and st["max_T"] == T.max()
+    assert st["max_bitw"] == ((T + 31) >> 5).max() and st["team_normal_rows"] == Tp[~small].sum()
+    assert st["total_verts"] == V.sum()
+
+
+def test_validation_codes():
+    rows = rows_of([(10, 12, 0, 1), (10, 12, 1, 3)])
+    we = np.zeros(3, bq2.WORLD_ENTITY_DTYPE)
+    assert run(we, rows)[0] == 0
+    for bad in (-1, 2, 1 << 30):
+        w = we.copy(); w["model"][1] = bad
+        assert run(w, rows)[0] == -1
+    for field in ("frame", "oldframe"):
+        for bad in (-1, 6):
+            w = we.copy(); w[field][2] = bad
+            assert run(w, rows)[0] == -2
+    w = we.copy(); w["model"][0] = 1                                  # multi-mesh model: the caller takes the host-built route
+    assert run(w, rows)[0] == -3
+    assert run(we[:0], rows)[0] == 0
+
+
+def test_flag_filter_and_basis():
+    rows = rows_of([(30, 40, 0, 1)])
+    flags = [0, 0x2, 0x4, 0x8, 0x20, 0x80, 0x400, 0x800, 0x1000, 0x80000, 0x10000000, 0x40, 0x100, 0x80000 | 0x400]
+    we = np.zeros(len(flags), bq2.WORLD_ENTITY_DTYPE)
+    we["rf_flags"] = flags
+    ang = np.zeros((len(flags), 3), np.float32)
+    ang[1] = (0, 90, 0); ang[2] = (10, 20, 30); ang[3] = (-0.0, 0, 0); ang[4] = (0, 0, -45); ang[5] = (1e-30, 0, 0)
+    we["angles"] = ang
+    rc, hx, rec, voff, st = run(we, rows)
+    assert rc == 0
+    for e, f in enumerate(flags):
+        casts = host.casts_shadow(f) and not (f & (0x80000 | 0x10000000))
+        assert hx["pair_rec"][e] == (rec[e] if casts else -1), hex(f)
+        rotated = bool(ang[e][0] or ang[e][1] or ang[e][2])             # -0.0 counts as zero, a denormal does not
+        assert bool(hx["rotated"][e]) == rotated, e
+        if rotated:
+            fwd, right, up = host.angle_vectors(ang[e])
+            got = hx["basis"][e].view(np.uint32)
+            assert np.array_equal(got, np.concatenate([fwd, right, up]).astype(np.float32).view(np.uint32)), e
