@@ -591,7 +591,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     tr.lap(0);
     /* which kernel takes each entity slot: small meshes -> one warp per pair; large meshes and the
        tangent-space outputs -> the whole CTA per pair */
-    const bool team_only = (want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT)) != 0;
+    const bool team_only = false;          /* both kernels write the tangent-space rows */
     F.slot_record.resize((size_t)nES);
     F.k_warp = FrameState::KLaunch(); F.k_team = FrameState::KLaunch();
     for (int e = 0; e < nE; e++) {
