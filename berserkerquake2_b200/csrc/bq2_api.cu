@@ -249,6 +249,61 @@ bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F)
     return BQ2_OK;
 }
 
+/* Enqueue a frame's stream operations on its state's stream.  A frame whose shape and buffers (the key) equal those of
+   the previous frame on this state goes through a CUDA graph: the second such frame is captured while it is enqueued,
+   later ones are one cudaGraphLaunch.  Anything else -- and every frame once a capture has failed -- is enqueued
+   directly.  enqueue() issues the operations and returns a status. */
+template <typename Enqueue>
+bq2_status enqueue_frame(bq2_ctx *ctx, FrameState &F, const FrameState::GraphKey *key, Enqueue enqueue)
+{
+    if (key && ctx->use_graphs) {
+        FrameState::GraphCache &g = F.gcache;
+        const bool same = g.have_key && memcmp(&g.key, key, sizeof *key) == 0;
+        if (same && g.exec) {
+            CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
+            ctx->launches += g.kernels;
+            return BQ2_OK;
+        }
+        if (same) {                                      /* second frame of this shape: capture it */
+            cudaGraph_t graph = nullptr;
+            const uint64_t l0 = ctx->launches;
+            if (cudaStreamBeginCapture(F.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                bq2_status es = enqueue();
+                cudaError_t ce = cudaStreamEndCapture(F.stream, &graph);
+                if (es == BQ2_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                    g.kernels = ctx->launches - l0;
+                    ctx->launches = l0;
+                    cudaGraphDestroy(graph);
+                    CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
+                    ctx->launches += g.kernels;
+                    return BQ2_OK;
+                }
+                if (graph) cudaGraphDestroy(graph);      /* capture is an optimisation only */
+                g.exec = nullptr; ctx->launches = l0; ctx->use_graphs = false;
+                cudaGetLastError();
+            }
+        } else {
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            g.key = *key; g.have_key = true;
+        }
+    }
+    return enqueue();
+}
+
+/* BQ2_TRACE: GPU time of the four stages of a world frame, direct launches, one frame at a time (diagnostics) */
+struct StageTimer {
+    cudaEvent_t ev[5]; bool init = false; double acc[4] = {0, 0, 0, 0}; long frames = 0;
+    void mark(int i, cudaStream_t s) { if (!init) { for (auto &e : ev) cudaEventCreate(&e); init = true; } cudaEventRecord(ev[i], s); }
+    void finish() {
+        cudaEventSynchronize(ev[4]);
+        for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms * 1e3; }
+        if (++frames % 100 == 0)
+            fprintf(stderr, "bq2 trace (GPU, us/frame): H2D %.1f  record-building kernel %.1f  frame kernel(s) %.1f  D2H %.1f\n",
+                    acc[0] / frames, acc[1] / frames, acc[2] / frames, acc[3] / frames);
+    }
+};
+StageTimer g_stage_timer;
+
 } // namespace
 
 extern "C" {
@@ -1191,7 +1246,9 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     F.slot_mesh_V.resize((size_t)nP); F.slot_mesh_T.resize((size_t)nP); F.pair_slot_entslot.resize((size_t)nP);
 
     /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals */
+    StageTimer *st = tr.gpu ? &g_stage_timer : nullptr;
     auto enqueue = [&]() -> bq2_status {
+        if (st) st->mark(0, F.stream);
         if (direct) {
             unsigned char *db = F.d_records.p;
             CK(cudaMemcpyAsync(db + off_xf, h_records.p + off_xf, off_lights - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(entity rows)");
@@ -1199,43 +1256,25 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
             CK(cudaMemcpyAsync(db + off_pe, wd->pair_ent, (size_t)nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_ent)");
             CK(cudaMemcpyAsync(db + off_pl, wd->pair_light, (size_t)nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_light)");
             CK(cudaMemcpyAsync(db + off_w, wd->ents, (size_t)nE * sizeof(bq2_world_entity), cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(entities)");
-        } else
-        if (rec_bytes > off_xf) CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, rec_bytes - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
+        } else if (rec_bytes > off_xf)
+            CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, rec_bytes - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
+        if (st) st->mark(1, F.stream);
         CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
         Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;         /* the entity records are always built */
         if (nP || nE) {
             CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
             ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
         }
+        if (st) st->mark(2, F.stream);
         bq2_status ls = launch_kernels(ctx, F);
         if (ls != BQ2_OK) return ls;
+        if (st) st->mark(3, F.stream);
         CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts + totals)");
+        if (st) { st->mark(4, F.stream); st->finish(); }
         return BQ2_OK;
     };
-    bool enqueued = false;
-    if (tr.gpu) {                                       /* BQ2_TRACE: GPU time of each stage of the frame, direct launches */
-        static cudaEvent_t ev[5]; static bool init = false; static double acc[4] = {0, 0, 0, 0}; static long nfr = 0;
-        if (!init) { for (auto &e : ev) cudaEventCreate(&e); init = true; }
-        cudaEventRecord(ev[0], F.stream);
-        if (rec_bytes > off_xf) cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, rec_bytes - off_xf, cudaMemcpyHostToDevice, F.stream);
-        cudaEventRecord(ev[1], F.stream);
-        cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream);
-        Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;
-        if (nP || nE) { bq2_launch_world_setup(&Wl, F.stream); ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl); }
-        cudaEventRecord(ev[2], F.stream);
-        launch_kernels(ctx, F);
-        cudaEventRecord(ev[3], F.stream);
-        cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, F.stream);
-        cudaEventRecord(ev[4], F.stream);
-        cudaEventSynchronize(ev[4]);
-        for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms * 1e3; }
-        if (++nfr % 100 == 0)
-            fprintf(stderr, "bq2 trace (GPU, us/frame): H2D %.1f  record-building kernels %.1f  frame kernel(s) %.1f  D2H %.1f\n",
-                    acc[0] / nfr, acc[1] / nfr, acc[2] / nfr, acc[3] / nfr);
-        enqueued = true;
-    }
-    if (!enqueued && ctx->use_graphs && !tables) {
-        FrameState::GraphKey key{};
+    FrameState::GraphKey key{};
+    {
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, 0, 0, 0, 0, 0};
         memcpy(key.v, kv, sizeof kv);
@@ -1244,38 +1283,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
                               F.d_records.p, F.d_world.p, h_records.p, h_counts.p, F.lerped.p, F.extruded.p, F.facing_bits.p,
                               F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, ctx->d_models.p};
         memcpy(key.p, kp, sizeof kp);
-        FrameState::GraphCache &g = F.gcache;
-        const bool same = g.have_key && memcmp(&g.key, &key, sizeof key) == 0;
-        if (same && g.exec) {
-            CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
-            ctx->launches += g.kernels;
-            enqueued = true;
-        } else if (same) {                               /* second frame of this shape: capture it */
-            cudaGraph_t graph = nullptr;
-            const uint64_t l0 = ctx->launches;
-            if (cudaStreamBeginCapture(F.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                bq2_status es = enqueue();
-                cudaError_t ce = cudaStreamEndCapture(F.stream, &graph);
-                if (es == BQ2_OK && ce == cudaSuccess && graph &&
-                    cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
-                    g.kernels = ctx->launches - l0;
-                    ctx->launches = l0;
-                    cudaGraphDestroy(graph);
-                    CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
-                    ctx->launches += g.kernels;
-                    enqueued = true;
-                } else {                                 /* capture is an optimisation only */
-                    if (graph) cudaGraphDestroy(graph);
-                    g.exec = nullptr; ctx->launches = l0; ctx->use_graphs = false;
-                    cudaGetLastError();
-                }
-            }
-        } else {
-            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
-            g.key = key; g.have_key = true;
-        }
     }
-    if (!enqueued) { bq2_status es = enqueue(); if (es != BQ2_OK) return es; }
+    { bq2_status es = enqueue_frame(ctx, F, (st || tables) ? nullptr : &key, enqueue); if (es != BQ2_OK) return es; }
     if (tables && nP) {
         F.world_pvoff.resize((size_t)nP + 1); F.world_pboff.resize((size_t)nP + 1);
         for (int p = 0; p <= nP; p++) { F.world_pvoff[p] = (uint32_t)p * maxVpad; F.world_pboff[p] = (uint32_t)p * maxBitw; }
