@@ -291,6 +291,60 @@ def test_c2_full_size_properties(gpu_ctx, oracle):
     assert np.array_equal(cnt2, cnt) and np.array_equal(res.indices(sample[3]), before)
 
 
+def test_c3_shard_full_size_properties(oracle):
+    """One GPU's share of BASELINE config 3 at full size (8,192 entities x 8 lights = 65,536 pairs, 1.1e8 index words):
+    the world path and the host-built path agree on every count, the totals are the sum of the counts, a checksum of
+    the whole index / extruded arrays is the same for both routes and for a second run, every silhouette of the sampled
+    pairs is a set of closed loops, and a sample of pairs matches the oracle."""
+    n_models = 48
+    with bq2.Context(0) as ctx:
+        models = [Md2Model(oracle, frames=8, seed=700 + s) for s in range(n_models)]
+        mids = [m.upload(ctx) for m in models]
+        n, L = 8192, 8
+        we, wl, pe, pl = world_scene(n, L, 8, n_models=n_models, seed=777)
+        we["model"] = np.array(mids)[we["model"]]
+        T, V = models[0].T, models[0].V
+        stride = 12 * T
+
+        def checksums(res):
+            cnt = res.index_counts.copy()
+            idx = ctx.download(c_api.A_INDICES, 0, len(pe) * stride, np.uint32).reshape(len(pe), stride)
+            wgt = np.arange(stride, dtype=np.uint64) % 251 + 1
+            h_idx = 0
+            for lo in range(0, len(pe), 4096):                           # position-weighted sum of the valid words
+                blk = idx[lo:lo + 4096]
+                mask = np.arange(stride)[None, :] < cnt[lo:lo + 4096, None]
+                h_idx += int(((blk * mask).astype(np.uint64) @ wgt).sum())
+            return cnt, h_idx, idx
+
+        from berserkerquake2_b200 import _capi as c_api
+        res_w = ctx.world_frame(we, wl, pe, pl)
+        cnt_w, h_w, idx_w = checksums(res_w)
+        assert res_w.overflow_pairs == 0 and int(res_w.total_indices) == int(cnt_w.sum())
+        assert (cnt_w % 6 == 0).all() and (cnt_w > 0).all()
+        ext_w = bits(ctx.download(c_api.A_EXTRUDED, 0, 3 * len(pe) * ((V + 3) & ~3), np.float32))
+        res_w2 = ctx.world_frame(we, wl, pe, pl)                         # again (graph path): idempotent
+        cnt_w2, h_w2, _ = checksums(res_w2)
+        assert np.array_equal(cnt_w, cnt_w2) and h_w == h_w2
+        ents, pairs = ctx.build_records(we, wl, pe, pl)
+        res_h = ctx.frame(ents, pairs)
+        cnt_h, h_h, _ = checksums(res_h)
+        assert np.array_equal(cnt_w, cnt_h) and h_w == h_h               # the two routes write the same index words
+        ext_h = bits(ctx.download(c_api.A_EXTRUDED, 0, 3 * len(pe) * ((V + 3) & ~3), np.float32))
+        rows_w = ext_w.reshape(len(pe), -1)[:, :3 * V]; rows_h = ext_h.reshape(len(pe), -1)[:, :3 * V]
+        assert np.array_equal(rows_w, rows_h)
+        sample = list(range(0, len(pe), 4099))
+        for p in sample:
+            e = int(pe[p]); W = we[e]; m = models[mids.index(int(W["model"]))]
+            w = oracle.md2_pair(m.blob, m.nb, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]), W["origin"],
+                                W["oldorigin"], W["angles"], wl["origin"][pl[p]], float(wl["radius"][pl[p]]), idx=m.idx)
+            ind = idx_w[p, :cnt_w[p]]
+            assert np.array_equal(ind, w["indices"]), p
+            nf = int(w["viss"].sum()); sides = (len(ind) - 6 * nf) // 6
+            quads = ind[:6 * sides].reshape(-1, 6)
+            assert np.array_equal(np.sort(quads[:, 0]), np.sort(quads[:, 4]))      # closed loops
+
+
 # ------------------------------------------------------------------------------------------------------
 # bq2_world_frame: per-pair records built on the device
 def check_world(ctx, o, models, mids, we, wl, pe, pl, view=None):
