@@ -65,6 +65,9 @@ typedef struct {
     int32_t ofs_skins, ofs_st, ofs_tris, ofs_frames, ofs_glcmds, ofs_end;
 } md2_header;
 
+extern uint8_t bq2_host_normal2index(const float v[3]);          /* bq2_synth.c: Normal2Index M:25206-25223 */
+extern const float *bq2_host_anorms(void);                      /* bq2_synth.c: the 162 x 4 anorms table */
+
 bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float scale, int invert,
                                   void *blob_out, size_t blob_capacity, float *st_out)
 {
@@ -96,6 +99,19 @@ bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float sca
         float *fo = (float *)(out + h->ofs_frames + (size_t)i * h->framesize);
         for (j = 0; j < 3; j++) { fo[j] = fi[j] * scale; fo[3 + j] = fi[3 + j] * scale; }
         if (invert) { fo[1] = -fo[1]; fo[4] = -fo[4]; }
+    }
+    if (invert) {                                           /* Mod_InvertNormal M:61850-61871, run by the loader at M:51657 */
+        const float *an = bq2_host_anorms();
+        uint8_t map[256];
+        for (i = 0; i < 256; i++) map[i] = (uint8_t)i;      /* indices past the table are not touched (the engine would read out of bounds) */
+        for (i = 0; i < 162; i++) {
+            float n[3] = { an[4*i], -an[4*i + 1], an[4*i + 2] };
+            map[i] = bq2_host_normal2index(n);
+        }
+        for (i = 0; i < h->num_frames; i++) {
+            uint8_t *v = out + h->ofs_frames + (size_t)i * h->framesize + 40;
+            for (j = 0; j < h->num_xyz; j++) v[4*j + 3] = map[v[4*j + 3]];
+        }
     }
     if (st_out) {                                           /* fstvert_t, M:51322-51329 */
         const int16_t *pst = (const int16_t *)(in + h->ofs_st);
@@ -214,7 +230,6 @@ typedef struct { int16_t point[3]; int16_t norm; } md3_file_vertex;             
 #define _GNU_SOURCE
 #include <math.h>
 extern void sincosf(float, float *, float *);
-extern uint8_t bq2_host_normal2index(const float v[3]);          /* bq2_synth.c: Normal2Index M:25206-25223 */
 
 static const md3_file_mesh *md3_mesh_at(const uint8_t *file, size_t bytes, const md3_file_header *h, int m, size_t *off_out)
 {

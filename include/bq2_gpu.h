@@ -317,7 +317,8 @@ bq2_status bq2_brush_download(bq2_ctx *ctx, int32_t pair, float *vcache /*[vb][2
 /* Com_BlockChecksum, M:40589-40602: the four words of an MD4 digest XOR-ed. */
 uint32_t   bq2_block_checksum(const void *buffer, size_t length);
 /* An MD2 FILE image -> the in-memory image the engine keeps (Mod_LoadAliasModel M:51216-51345: the load-time
- * checks, frame scale/translate multiplied by `scale`, winding inverted when `invert`) and its float st
+ * checks, frame scale/translate multiplied by `scale`; when `invert`: winding reversed, y mirrored and every
+ * lightnormalindex mapped to the anorm of its y-mirrored normal, Mod_InvertNormal M:61850) and its float st
  * (st_out = float[num_st][2], may be NULL).  blob_out needs header.ofs_end bytes. */
 bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float scale, int invert,
                                   void *blob_out, size_t blob_capacity, float *st_out);

@@ -512,3 +512,101 @@ unsigned Com_BlockChecksum(void *buffer, int length);                 /* M:40589
 unsigned bq2ref_block_checksum(void *buffer, int length) { return Com_BlockChecksum(buffer, length); }
 void bq2ref_angle_vectors(float *angles, float *f, float *r, float *u) { AngleVectors(angles, f, r, u); }
 float bq2ref_vector_normalize(float *v) { return VectorNormalize(v); }
+
+/* ---- the engine's model loaders, run whole ----------------------------------------------------
+ * Mod_LoadAliasModel (M:51217) and Mod_LoadAliasMD3Model (M:50584) with cache = true (no skins are looked up):
+ * file image -> in-memory image, neighbour tables, the assembled tangent / binormal / normal loops
+ * (M:51661-51804, 50956-51015) and the cache file they write under <gamedir>/cache/.  The caller passes a scratch
+ * directory; the loader runs with it as working directory, "./baseq2" as game directory and search path, so a
+ * models/.../tris.fx2 placed there ("unsmoothvecs") is honoured as in the engine (M:51363-51375). */
+#include <unistd.h>
+#include <stdlib.h>
+extern searchpath_t *fs_searchpaths;
+extern char          fs_gamedir[MAX_OSPATH];
+extern cvar_t       *r_simple, *developer;
+extern int           modfilelen;
+extern struct zlink { struct zlink *prev, *next; } z_chain;   /* the list head of M:2053-2061 (type private to main.c): its two links */
+bool  Mod_LoadAliasModel(model_t *, void *, float, bool, int, bool);
+void  Mod_LoadAliasMD3Model(model_t *, void *, float, bool, bool);
+void *Hunk_Begin(int, char *);
+void  Z_Free(void *);
+void  Swap_Init(void);
+
+static model_t       ld_mod;
+static void         *ld_base;
+static searchpath_t  ld_search;
+static cvar_t        cv_simple;
+
+static int loader_enter(const char *workdir, const char *modname, char *cwd, size_t cwd_len)
+{
+    bq2ref_init();
+    if (!getcwd(cwd, cwd_len) || chdir(workdir)) return -1;
+    memset(&cv_simple, 0, sizeof cv_simple); r_simple = &cv_simple; developer = NULL;
+    if (!z_chain.next) z_chain.next = z_chain.prev = &z_chain;      /* Qcommon_Init M:87900 */
+    Swap_Init();                                                    /* LittleLong & co. are function pointers, M:2227 */
+    strcpy(fs_gamedir, "./" BASEDIRNAME);
+    memset(&ld_search, 0, sizeof ld_search); strcpy(ld_search.filename, "./" BASEDIRNAME);
+    fs_searchpaths = &ld_search;
+    if (ld_base) { free(ld_base); ld_base = NULL; }
+    memset(&ld_mod, 0, sizeof ld_mod);
+    strncpy(ld_mod.name, modname, sizeof ld_mod.name - 1);
+    ld_base = Hunk_Begin(64 << 20, ld_mod.name);            /* as Mod_ForName does before it calls a loader (M:27000-27110) */
+    ld_mod.extradata = ld_base;
+    return 0;
+}
+
+/* returns 0, or -1 when the loader refused; *smooth = RF_SMOOTHVECS after the .fx2 was parsed.  image: ofs_end bytes. */
+int bq2ref_load_md2(void *file, int file_len, const char *workdir, const char *modname, float scale, int invert,
+                    void *image, int32_t *neighbours, uint8_t *tangents, uint8_t *binormals, uint8_t *normals, int *smooth)
+{
+    char cwd[4096];
+    if (loader_enter(workdir, modname, cwd, sizeof cwd)) return -2;
+    modfilelen = file_len;
+    bool ok = Mod_LoadAliasModel(&ld_mod, file, scale, invert != 0, 0, true);
+    if (chdir(cwd)) return -2;
+    if (ld_mod.st) { Z_Free(ld_mod.st); ld_mod.st = NULL; }
+    if (!ok) return -1;
+    dmdl_t *h = (dmdl_t *)ld_base;
+    *smooth = (ld_mod.flags & RF_SMOOTHVECS) != 0;
+    size_t rows = (size_t)(*smooth ? h->num_xyz : h->num_tris) * (size_t)h->num_frames;
+    memcpy(image, h, (size_t)h->ofs_end);
+    memcpy(neighbours, ld_mod.triangles, sizeof(neighbours_t) * (size_t)h->num_tris);
+    memcpy(tangents, ld_mod.tangents, rows);
+    memcpy(binormals, ld_mod.binormals, rows);
+    if (!*smooth) memcpy(normals, ld_mod.normals, rows);
+    return 0;
+}
+
+/* loads the whole .md3; returns the number of meshes, the model stays loaded for bq2ref_loaded_md3_mesh */
+int bq2ref_load_md3(void *file, int file_len, const char *workdir, const char *modname, float scale, int invert,
+                    int *num_frames)
+{
+    char cwd[4096];
+    if (loader_enter(workdir, modname, cwd, sizeof cwd)) return -2;
+    modfilelen = file_len;                                   /* the cache files carry the checksum of the whole file */
+    Mod_LoadAliasMD3Model(&ld_mod, file, scale, invert != 0, true);
+    if (chdir(cwd)) return -2;
+    maliasmodel_t *mm = (maliasmodel_t *)ld_base;
+    *num_frames = mm->num_frames;
+    return mm->num_meshes;
+}
+int bq2ref_loaded_md3_dims(int mesh, int *num_verts, int *num_tris)
+{
+    maliasmodel_t *mm = (maliasmodel_t *)ld_base;
+    if (!mm || mesh < 0 || mesh >= mm->num_meshes) return -1;
+    *num_verts = mm->meshes[mesh].num_verts; *num_tris = mm->meshes[mesh].num_tris;
+    return 0;
+}
+int bq2ref_loaded_md3_mesh(int mesh, void *verts, uint16_t *indexes, int32_t *neighbours, float *st, float *frame_translate)
+{
+    maliasmodel_t *mm = (maliasmodel_t *)ld_base;
+    if (!mm || mesh < 0 || mesh >= mm->num_meshes) return -1;
+    maliasmesh_t *m = &mm->meshes[mesh];
+    memcpy(verts, m->vertexes, sizeof(maliasvertex_t) * (size_t)mm->num_frames * (size_t)m->num_verts);
+    memcpy(indexes, m->indexes, sizeof(WORD) * 3 * (size_t)m->num_tris);
+    memcpy(neighbours, m->triangles, sizeof(neighbours_t) * (size_t)m->num_tris);
+    memcpy(st, m->stcoords, sizeof(maliascoord_t) * (size_t)m->num_verts);
+    for (int f = 0; f < mm->num_frames; f++)
+        for (int k = 0; k < 3; k++) frame_translate[3 * f + k] = mm->frames[f].translate[k];
+    return 0;
+}

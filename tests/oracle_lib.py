@@ -252,9 +252,56 @@ class Reference:
         L.bq2ref_tangent_for_tri_md3.argtypes = [vp] * 5
         L.bq2ref_angle_vectors.argtypes = [vp] * 4
         L.bq2ref_vector_normalize.argtypes = [vp]; L.bq2ref_vector_normalize.restype = f32
+        L.bq2ref_load_md2.argtypes = [vp, i32, C.c_char_p, C.c_char_p, f32, i32, vp, vp, vp, vp, vp, vp]
+        L.bq2ref_load_md3.argtypes = [vp, i32, C.c_char_p, C.c_char_p, f32, i32, vp]
+        L.bq2ref_loaded_md3_dims.argtypes = [i32, vp, vp]
+        L.bq2ref_loaded_md3_mesh.argtypes = [i32, vp, vp, vp, vp, vp]
 
     def smooth_cosine(self):
         return float(self.lib.bq2ref_smooth_cosine())
+
+    # ---- the engine's loaders run whole (cache = true: no skins), in a scratch game directory ----------
+    def load_md2(self, file, workdir, modname, scale=1.0, invert=False):
+        """Mod_LoadAliasModel M:51217 on a .md2 file image.  Returns the in-memory image, the neighbour table, the
+        tangent / binormal (/ normal) anorm bytes and the smooth flag; the loader's cache file is left under
+        <workdir>/baseq2/cache/[inv_]<modname>."""
+        file = np.ascontiguousarray(file, np.uint8).copy()
+        h = file[:68].view("<i4")
+        V, T, F, ofs_end = int(h[6]), int(h[8]), int(h[10]), int(h[16])
+        image = np.zeros(ofs_end, np.uint8); nb = np.zeros((T, 3), np.int32)
+        rows = max(V, T) * F
+        tan, bi, nm = (np.zeros(rows, np.uint8) for _ in range(3))
+        smooth = C.c_int(-1)
+        rc = self.lib.bq2ref_load_md2(P(file), file.nbytes, workdir.encode(), modname.encode(), scale, int(invert),
+                                      P(image), P(nb), P(tan), P(bi), P(nm), C.byref(smooth))
+        if rc != 0:
+            raise RuntimeError("bq2ref_load_md2 -> %d" % rc)
+        n = V if smooth.value else T
+        out = dict(image=image, neighbours=nb, smooth=bool(smooth.value), tangents=tan[:n * F].reshape(F, n).copy(),
+                   binormals=bi[:n * F].reshape(F, n).copy())
+        if not smooth.value:
+            out["normals"] = nm[:n * F].reshape(F, n).copy()
+        return out
+
+    def load_md3(self, file, workdir, modname, scale=1.0, invert=False):
+        """Mod_LoadAliasMD3Model M:50584 on a .md3 file image -> list of meshes (verts [F][V] maliasvertex_t, indexes,
+        neighbours, st) and the frame translations; cache files under <workdir>/baseq2/cache/[inv_]<modname>_<mesh>."""
+        from berserkerquake2_b200 import synth
+        file = np.ascontiguousarray(file, np.uint8).copy()
+        nf = C.c_int(0)
+        nm = self.lib.bq2ref_load_md3(P(file), file.nbytes, workdir.encode(), modname.encode(), scale, int(invert), C.byref(nf))
+        if nm < 0:
+            raise RuntimeError("bq2ref_load_md3 -> %d" % nm)
+        F = nf.value
+        meshes, tr = [], np.zeros((F, 3), np.float32)
+        for k in range(nm):
+            v, t = C.c_int(0), C.c_int(0)
+            assert self.lib.bq2ref_loaded_md3_dims(k, C.byref(v), C.byref(t)) == 0
+            verts = np.zeros((F, v.value), synth.MD3_VERTEX); idx = np.zeros((t.value, 3), np.uint16)
+            nb = np.zeros((t.value, 3), np.int32); st = np.zeros((v.value, 2), np.float32)
+            assert self.lib.bq2ref_loaded_md3_mesh(k, P(verts), P(idx), P(nb), P(st), P(tr)) == 0
+            meshes.append(dict(verts=verts, indexes=idx, neighbours=nb, st=st))
+        return meshes, tr
 
     def anorms(self):
         return np.ctypeslib.as_array(self.lib.bq2ref_anorms(), (162, 3)).copy()

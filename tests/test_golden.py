@@ -140,6 +140,79 @@ def test_host_trig_golden(oracle):
         assert same(np.concatenate(oracle.angle_vectors(a)), fru)
 
 
+# ---- the engine's loaders (vectors from Mod_LoadAliasModel / Mod_LoadAliasMD3Model run whole) -----------------------
+def loader_md2(kind, invert):
+    """file image -> in-memory image + st through the product's host C, and the engine's outputs for the same file"""
+    from berserkerquake2_b200 import _capi as c
+    file = np.ascontiguousarray(G["loader/md2/file"])
+    h = synth.md2_header(file)
+    blob = np.zeros(int(h["ofs_end"]), np.uint8); st = np.zeros((int(h["num_st"]), 2), np.float32)
+    assert c.lib.bq2_host_md2_from_file(c.ptr(file), file.nbytes, 1.0, invert, c.ptr(blob), blob.nbytes, c.ptr(st)) == 0
+    key = f"loader/md2/{kind}{invert}"
+    want = {k: G[f"{key}/{k}"] for k in ("image", "neighbours", "tangents", "binormals", "cache_file")}
+    if kind == "flat":
+        want["normals"] = G[f"{key}/normals"]
+    V, F, fs, of = int(h["num_xyz"]), int(h["num_frames"]), int(h["framesize"]), int(h["ofs_frames"])
+    for f in range(F):      # what the engine's loader writes of a frame: scale + translate, vertex bytes
+        o = of + f * fs
+        assert np.array_equal(blob[o:o + 24], want["image"][o:o + 24])
+        assert np.array_equal(blob[o + 40:o + 40 + 4 * V], want["image"][o + 40:o + 40 + 4 * V])
+    assert np.array_equal(synth.md2_tris(blob), synth.md2_tris(want["image"]))
+    return blob, st, want
+
+
+def loader_md3(invert, k):
+    from berserkerquake2_b200 import _capi as c
+    file = np.ascontiguousarray(G["loader/md3/file"])
+    key = f"loader/md3/inv{invert}/mesh{k}"
+    want = np.ascontiguousarray(G[f"{key}/verts"]).view(synth.MD3_VERTEX).reshape(G[f"{key}/verts"].shape[:2])
+    F, V = want.shape; T = len(G[f"{key}/indexes"])
+    verts = np.zeros((F, V), synth.MD3_VERTEX); idx = np.zeros((T, 3), np.uint16); st = np.zeros((V, 2), np.float32)
+    tr = np.zeros((F, 3), np.float32)
+    assert c.lib.bq2_host_md3_mesh_from_file(c.ptr(file), file.nbytes, k, 1.0, invert, c.ptr(tr), c.ptr(verts), c.ptr(idx), c.ptr(st)) == 0
+    assert same(verts["point"], want["point"]) and np.array_equal(verts["normal"], want["normal"])
+    assert np.array_equal(idx, G[f"{key}/indexes"]) and same(st, G[f"{key}/st"])
+    assert same(tr, G[f"loader/md3/inv{invert}/frame_translate"])
+    return file, verts, idx, st, want, G[f"{key}/neighbours"], G[f"{key}/cache_file"]
+
+
+@pytest.mark.parametrize("kind", ["smooth", "flat"])
+@pytest.mark.parametrize("invert", [0, 1])
+def test_oracle_md2_loader(oracle, kind, invert):
+    from berserkerquake2_b200 import _capi as c
+    blob, st, want = loader_md2(kind, invert)
+    assert np.array_equal(oracle.md2_neighbours(blob), want["neighbours"])
+    assert np.array_equal(host.md2_neighbours(blob), want["neighbours"])
+    cosine = float(G["loader/smooth_cosine"][0])
+    if kind == "smooth":
+        tn, bn = oracle.md2_tangents_smooth(blob, st, cosine); nm = None
+    else:
+        nm, tn, bn = oracle.md2_tangents_flat(blob, st)
+        assert np.array_equal(nm, want["normals"])
+    assert np.array_equal(tn, want["tangents"]) and np.array_equal(bn, want["binormals"])
+    F, rows = tn.shape; T = len(want["neighbours"])
+    buf = np.zeros(want["cache_file"].size, np.uint8)
+    assert c.lib.bq2_md2_cache_bytes(int(kind == "smooth"), T, rows, F) == buf.size
+    assert c.lib.bq2_md2_cache_write(c.ptr(buf), buf.size, int(kind == "smooth"), cosine, c.ptr(want["neighbours"]), T, rows, F,
+                                     c.ptr(bn), c.ptr(tn), c.ptr(nm)) == 0
+    assert np.array_equal(buf, want["cache_file"])          # the engine's cache file, byte for byte
+
+
+@pytest.mark.parametrize("invert", [0, 1])
+def test_oracle_md3_loader(oracle, invert):
+    from berserkerquake2_b200 import _capi as c
+    for k in range(2):
+        file, verts, idx, st, want, nb, cache = loader_md3(invert, k)
+        assert np.array_equal(oracle.md3_neighbours(idx), nb) and np.array_equal(host.md3_neighbours(idx), nb)
+        oracle.md3_tangents(verts, st, idx)
+        assert np.array_equal(verts["tangent"], want["tangent"]) and np.array_equal(verts["binormal"], want["binormal"])
+        F, V = verts.shape
+        buf = np.zeros(cache.size, np.uint8)
+        crc = int(c.lib.bq2_block_checksum(c.ptr(file), file.nbytes))
+        assert c.lib.bq2_md3_cache_write(c.ptr(buf), buf.size, crc, c.ptr(verts), F, V) == 0
+        assert np.array_equal(buf, cache)
+
+
 # ---------------------------------------------------------------- GPU: the CUDA library vs the same vectors
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["md2_small", "md2_c1"])
@@ -233,3 +306,26 @@ def test_gpu_md3(gpu_ctx):
             assert np.array_equal(res.facing(3 * p + k, T), G[f"md3/pair{p}/mesh{k}/viss"])
             assert same(res.trisverts(3 * p + k), G[f"md3/pair{p}/mesh{k}/tris_verts"])
         assert int(res.index_counts[3 * p + 1]) == 0            # the non-casting surface
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["smooth", "flat"])
+@pytest.mark.parametrize("invert", [0, 1])
+def test_gpu_md2_loader(gpu_ctx, kind, invert):
+    """the device's neighbour and tangent-space precompute against what the engine's loader produced"""
+    blob, st, want = loader_md2(kind, invert)
+    assert np.array_equal(gpu_ctx.gpu_md2_neighbours(blob), want["neighbours"])
+    nm, tn, bn = gpu_ctx.gpu_md2_tangents(blob, st, float(G["loader/smooth_cosine"][0]), smooth=(kind == "smooth"))
+    assert np.array_equal(tn, want["tangents"]) and np.array_equal(bn, want["binormals"])
+    if kind == "flat":
+        assert np.array_equal(nm, want["normals"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("invert", [0, 1])
+def test_gpu_md3_loader(gpu_ctx, invert):
+    for k in range(2):
+        file, verts, idx, st, want, nb, cache = loader_md3(invert, k)
+        assert np.array_equal(gpu_ctx.gpu_md3_neighbours(idx), nb)
+        gpu_ctx.gpu_md3_tangents(verts, st, idx)
+        assert np.array_equal(verts["tangent"], want["tangent"]) and np.array_equal(verts["binormal"], want["binormal"])
