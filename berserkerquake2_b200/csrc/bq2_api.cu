@@ -229,12 +229,12 @@ void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t 
 }
 
 /* the frame's kernels: warp-per-pair over the small-mesh records, CTA-per-pair over the rest */
-bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F)
+bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F, int overlap = 0)
 {
     bq2_launch L = F.launch;
     if (F.k_warp.n) {
         L.n_ent_slots = F.k_warp.n;
-        CK((cudaError_t)bq2_launch_frame_warp(&L, F.k_warp.max_V, F.k_warp.max_T, F.k_warp.any_md2, F.stream),
+        CK((cudaError_t)bq2_launch_frame_warp(&L, F.k_warp.max_V, F.k_warp.max_T, F.k_warp.any_md2, F.stream, overlap),
            "launch(bq2_frame_warp_kernel)");
         ctx->launches++;
     }
@@ -242,7 +242,7 @@ bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F)
         L.ents = F.launch.ents + F.k_warp.n;
         L.rec_base = (uint32_t)F.k_warp.n;
         L.n_ent_slots = F.k_team.n;
-        CK((cudaError_t)bq2_launch_frame(&L, F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2, F.stream),
+        CK((cudaError_t)bq2_launch_frame(&L, F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2, F.stream, overlap),
            "launch(bq2_frame_kernel)");
         ctx->launches++;
     }
@@ -1318,7 +1318,7 @@ bq2_status bq2_frame_replay(bq2_ctx *ctx)
     if (!ctx->submitted || !F.n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
     if (F.world_mode)                                            /* the kernels add to the totals: start from zero */
         CK(cudaMemsetAsync(F.wlaunch.totals, 0, 2 * sizeof(unsigned long long), F.stream), "cudaMemset(totals)");
-    return launch_kernels(ctx, F);
+    return launch_kernels(ctx, F, /*overlap=*/1);
 }
 
 bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out)
@@ -1355,12 +1355,12 @@ bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
     bq2_launch L = r->L;
     if (r->k_warp.n) {
         L.n_ent_slots = r->k_warp.n;
-        CK((cudaError_t)bq2_launch_frame_warp(&L, r->k_warp.max_V, r->k_warp.max_T, r->k_warp.any_md2, F.stream), "launch(bq2_frame_warp_kernel)");
+        CK((cudaError_t)bq2_launch_frame_warp(&L, r->k_warp.max_V, r->k_warp.max_T, r->k_warp.any_md2, F.stream, /*overlap=*/1), "launch(bq2_frame_warp_kernel)");
         ctx->launches++;
     }
     if (r->k_team.n) {
         L.ents = r->L.ents + r->k_warp.n; L.rec_base = (uint32_t)r->k_warp.n; L.n_ent_slots = r->k_team.n;
-        CK((cudaError_t)bq2_launch_frame(&L, r->k_team.max_V, r->k_team.max_T, r->k_team.any_md2, F.stream), "launch(bq2_frame_kernel)");
+        CK((cudaError_t)bq2_launch_frame(&L, r->k_team.max_V, r->k_team.max_T, r->k_team.any_md2, F.stream, /*overlap=*/1), "launch(bq2_frame_kernel)");
         ctx->launches++;
     }
     return BQ2_OK;

@@ -157,8 +157,10 @@ int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, con
 #define BQ2_WARP_MAX_V   1024
 #define BQ2_WARP_MAX_T   1024
 #define BQ2_WARP_WARPS   4
-int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);       /* team */
-int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream);  /* warp */
+/* overlap: launch with programmatic stream serialization (the kernel's prologue may run under the tail of the kernel
+   in front of it on the stream); never inside a graph capture */
+int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream, int overlap);       /* team */
+int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream, int overlap);  /* warp */
 int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* returns cudaError_t; one kernel */
 int  bq2_world_setup_launches(const bq2_world_launch *W);
 /* neighbour tables of one mesh on the device: idx = u16 vertex indices, in_stride u16s per triangle (6 for
