@@ -1023,6 +1023,7 @@ bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t 
     }
     const size_t o_lit = (((size_t)n_pairs * sizeof(bq2_brush_pair_dev_h)) + 15) & ~(size_t)15;
     CK(ctx->d_brush_in.ensure(o_lit + lit_bytes + 16), "cudaMalloc(brush pairs)");
+    istride = (istride + 1u) & ~1u;                      /* index rows start 8-byte aligned (the kernel stores index pairs) */
     CK(ctx->brush_vcache.ensure(6 * (size_t)n_pairs * vstride + 4), "cudaMalloc(brush vcache)");
     CK(ctx->brush_icache.ensure((size_t)n_pairs * istride + 4), "cudaMalloc(brush icache)");
     CK(ctx->brush_counts.ensure(2 * (size_t)n_pairs + 2), "cudaMalloc(brush counts)");
