@@ -10,6 +10,8 @@ One "step" = one pass of the path over the whole batch = ONE launch of the fused
             pair of CUDA events on the launching stream, max over ranks.  Inputs resident in HBM and larger than L2:
             the steps cycle through a ring of resident frames (bq2_frame_keep), each drawing on its own device copy of
             the models, so a cycle reads more key-frame / triangle-table / record bytes than the L2 holds (no flush).
+            The replays are launched with programmatic dependent launch: stream order of every write is kept, the
+            read-only front of the next step runs under the tail of the current one.
   e2e       the same metric through the C ABI from HOST arrays: bq2_world_submit (host: validation, numbering,
             AngleVectors; H2D; record-building kernel + fused kernel; D2H of the per-pair counts) + bq2_frame_wait,
             four frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
@@ -387,6 +389,9 @@ def run_gpu(args):
                              f"{l2_bytes / 1e6:.0f} MB) besides streaming {ring} x the outputs through it",
                        "resident_frames": ring, "input_bytes_per_step": step_input_bytes,
                        "timing": "one pair of CUDA events on the ctx stream around the K back-to-back launches, max over ranks; "
+                                 "the launches carry programmatic stream serialization: all K steps run in stream order and "
+                                 "complete inside the events, the read-only front of step N+1 (record load, TMA staging, lerp, "
+                                 "triangle normals) overlaps the tail of step N; "
                                  "roofline.isolated_launch_ms = one launch alone between two events after an L2 flush"},
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
