@@ -123,6 +123,7 @@ EXPORTS_GPU_H = [
     _sig("bq2_gpu_md3_neighbours", C.c_int, vp, vp, i32, vp),
     _sig("bq2_gpu_md2_tangents", C.c_int, vp, vp, C.c_size_t, vp, f32, C.c_int, vp, vp, vp),
     _sig("bq2_gpu_md3_tangents", C.c_int, vp, vp, i32, i32, vp, vp, i32),
+    _sig("bq2_selftest_ratio", C.c_int, vp, C.c_int, C.c_float, C.c_uint64, C.c_uint64, vp),
     _sig("bq2_block_checksum", C.c_uint32, vp, C.c_size_t),
     _sig("bq2_host_md2_from_file", C.c_int, vp, C.c_size_t, f32, C.c_int, vp, C.c_size_t, vp),
     _sig("bq2_md2_cache_bytes", C.c_size_t, C.c_int, i32, i32, i32),

@@ -120,6 +120,12 @@ class Context:
         st = np.ascontiguousarray(st, np.float32); ix = np.ascontiguousarray(indexes, np.uint16)
         self._check(c.lib.bq2_gpu_md3_tangents(self._h, c.ptr(verts), F, V, c.ptr(st), c.ptr(ix), ix.size // 3))
 
+    def selftest_ratio(self, mode, num=1.0, count=0, seed=0):
+        """bq2_selftest_ratio: mismatches between the kernels' num / sqrtf(len2) sequence and div.rn(sqrt.rn)."""
+        bad = C.c_uint64(0)
+        self._check(c.lib.bq2_selftest_ratio(self._h, int(mode), float(num), int(count), int(seed), C.byref(bad)))
+        return int(bad.value)
+
     # -- brush-model volumes (main.c:63326-63499) -------------------------------------------------------
     def upload_brush(self, numverts, verts, neighbours, fence=None):
         nv = np.ascontiguousarray(numverts, np.int32); v = np.ascontiguousarray(verts, np.float32)

@@ -890,6 +890,24 @@ bq2_status bq2_gpu_md2_neighbours(bq2_ctx *ctx, const int16_t *dtriangles, int32
 bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t num_tris, int32_t *out)
 { return gpu_neighbours(ctx, indexes, 3, num_tris, 1, out); }
 
+bq2_status bq2_selftest_ratio(bq2_ctx *ctx, int mode, float num, uint64_t count, uint64_t seed, uint64_t *mismatches)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    if (!mismatches || mode < 0 || mode > 2) return fail(ctx, BQ2_E_INVALID, "bq2_selftest_ratio: bad arguments");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (mode == 0) count = 1ull << 32;
+    unsigned long long *d = nullptr, h = 0;
+    CK(cudaMalloc(&d, sizeof h), "cudaMalloc(selftest)");
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof h, ctx->stream);
+    if (e == cudaSuccess) e = (cudaError_t)bq2_launch_selftest_ratio(mode, num, count, seed, d, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_selftest_ratio");
+    *mismatches = (uint64_t)h;
+    return BQ2_OK;
+}
+
 bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *blob, size_t blob_bytes, const float *st, float smooth_cosine,
                                 int smooth, uint8_t *normals, uint8_t *tangents, uint8_t *binormals)
 {

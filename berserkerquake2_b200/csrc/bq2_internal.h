@@ -165,6 +165,7 @@ int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* retur
 int  bq2_world_setup_launches(const bq2_world_launch *W);
 /* neighbour tables of one mesh on the device: idx = u16 vertex indices, in_stride u16s per triangle (6 for
    dtriangle_t, 3 for WORD indexes); out = int32[3*T] (device) */
+int  bq2_launch_selftest_ratio(int mode, float num, uint64_t count, uint64_t seed, unsigned long long *mismatches, void *stream);
 int  bq2_launch_neighbours(const uint16_t *idx, int in_stride, int T, int V, int md3, int32_t *out, void *stream);
 size_t bq2_neighbours_smem_bytes(int T, int V);
 /* tangent-space bytes of one mesh, one CTA per key-frame; device pointers; mode 0 MD2 smooth, 1 MD2 flat, 2 MD3 */

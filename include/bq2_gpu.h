@@ -292,6 +292,13 @@ bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *dmdl_blob, size_t blob
 bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t num_frames, int32_t num_verts,
                                 const float *st, const uint16_t *indexes, int32_t num_tris);
 
+/* Device self-test of the kernels' `num / sqrtf(len2)` sequence (`scale / VectorLength` M:63607, `1 / VectorLength`
+ * M:63620; DESIGN.md 5, Numerics) against div.rn(sqrt.rn) on the same device.  mode 0: every one of the 2^32 bit
+ * patterns of len2 with numerator `num` (count ignored); mode 1: `count` random pairs with exponents across the
+ * guarded ranges and their edges; mode 2: `count` raw random bit patterns.  *mismatches = results whose bits differ
+ * (two NaNs compare equal). */
+bq2_status bq2_selftest_ratio(bq2_ctx *ctx, int mode, float num, uint64_t count, uint64_t seed, uint64_t *mismatches);
+
 /* ---- brush-model dynamic volumes: R_DrawBrushModelVolumes M:63326-63499 ---------------- */
 /* A brush model as the renderer holds it for this function: polygon p has numverts[p] vertices (glpoly_t.verts,
  * x/y/z only) stored consecutively in verts, neighbours[slot] = polygon across edge j or -1 (glpoly_t.neighbours),

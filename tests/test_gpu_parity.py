@@ -807,3 +807,60 @@ def test_want_flag_combinations_and_many_lights(gpu_ctx, oracle):
             lp, ts = oracle.tslight(P, N, T_, B, pairs["light"][p], pairs["view"][p])
             gl, gt = res3.tslight(p, m.V)
             assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
+
+
+def test_ratio_sequence_is_exact(gpu_ctx):
+    """The straight-line `num / sqrtf(len2)` sequence of the kernels (scale / VectorLength M:63607, 1 / VectorLength
+    M:63620) against div.rn(sqrt.rn) on the device: EVERY bit pattern of len2 for the numerators the path uses most
+    (1.0 for the triangle normals, 32 * radius for the extrusion), then 2^31 random pairs across the guarded exponent
+    ranges and their edges, then raw random bit patterns (denormals, infinities, NaNs, negatives -> fallback)."""
+    for num in (1.0, 9600.0, 32.0 * 150.0, 32.0 * 87.5, -9600.0, 3.0e-12, 7.0e11):
+        assert gpu_ctx.selftest_ratio(0, num) == 0, num
+    assert gpu_ctx.selftest_ratio(1, count=1 << 31, seed=1) == 0
+    assert gpu_ctx.selftest_ratio(2, count=1 << 30, seed=2) == 0
+
+
+@pytest.mark.parametrize("want", [bq2.WANT_SHADOW, bq2.WANT_SHADOW | bq2.WANT_NTB | bq2.WANT_TSLIGHT])
+def test_back_to_back_replays_keep_stream_order(gpu_ctx, oracle, want):
+    """Replays are launched with programmatic dependent launch: the next frame's kernel starts under the tail of the
+    current one.  Kept frames of one shape SHARE their result arrays, so a kernel that wrote anything before the kernel
+    in front of it had finished would leave a mixture behind.  Many replays back to back without a sync in between,
+    then every result array must be exactly the last frame's."""
+    from berserkerquake2_b200 import _capi as c
+    m = Md2Model(oracle, 16, 17, frames=6, seed=77, tangent_space=True, smooth=True)
+    mid = m.upload(gpu_ctx)
+    n_ents, lights = 1024, 4
+    kept = []
+    view = np.array([40.0, -30.0, 25.0], np.float32)
+    for i in range(3):
+        we, wl, pe, pl = world_scene(n_ents, lights, 6, seed=3000 + i)
+        we["model"] = mid
+        ents, pairs = gpu_ctx.build_records(we, wl, pe, pl, view_world=view)
+        r = gpu_ctx.frame(ents, pairs, want=want)
+        arrays = {c.A_INDEX_COUNT: n_ents * lights, c.A_INDICES: n_ents * lights * int(r.index_stride),
+                  c.A_LERPED: 3 * n_ents * m.V, c.A_FACING_BITS: n_ents * lights * ((m.T + 31) // 32)}
+        if want & bq2.WANT_TSLIGHT:
+            arrays[c.A_NORMALS] = 3 * n_ents * m.V
+            arrays[c.A_LIGHTP] = 3 * n_ents * lights * m.V
+        snap = {a: gpu_ctx.download(a, 0, n, np.uint32) for a, n in arrays.items()}
+        ext = [bits(r.extruded(p, m.V)).copy() for p in (0, 1, 2047, 4095)]
+        kept.append((gpu_ctx.keep(), snap, ext, r))
+    assert not np.array_equal(kept[0][1][c.A_INDICES], kept[1][1][c.A_INDICES])
+    for last in (0, 1, 2):
+        for rep in range(40):
+            for k in (0, 1, 2):
+                gpu_ctx.replay_kept(kept[k][0])
+        gpu_ctx.replay_kept(kept[last][0])
+        gpu_ctx.wait()
+        h, snap, ext, r = kept[last]
+        cnt = snap[c.A_INDEX_COUNT]
+        live = np.arange(int(r.index_stride))[None, :] < cnt[:, None]           # beyond a pair's count the row holds leftovers
+        for a, want_arr in snap.items():
+            got = gpu_ctx.download(a, 0, len(want_arr), np.uint32)
+            if a == c.A_INDICES:
+                got, want_arr = got.reshape(live.shape)[live], want_arr.reshape(live.shape)[live]
+            assert np.array_equal(got, want_arr), (last, a)
+        for p, e in zip((0, 1, 2047, 4095), ext):
+            assert np.array_equal(bits(r.extruded(p, m.V)), e), (last, p)
+    for h, *_ in kept:
+        gpu_ctx.free_kept(h)
