@@ -111,6 +111,8 @@ typedef struct bq2_world_launch {
 } bq2_world_launch;
 #define BQ2_BUCKET 8                /* pairs per entity held in its bucket; further ones chain              */
 
+/* internal bit of bq2_launch.want, set by bq2_launch_frame: the team kernel runs with two sets of its per-light arrays */
+#define BQ2_WANT_TEAM_DOUBLE 0x40000000u
 typedef struct bq2_launch {
     const bq2_dev_mesh *meshes;
     const bq2_dev_ent  *ents;
