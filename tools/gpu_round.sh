@@ -22,3 +22,9 @@ CMD3="python bench.py --workload c3shard --steps 3 --warmup 3 --no-cpu --spinup 
 $CMD3 > gpurun_out/plain_c3.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:bq2_frame -s 4 -c 1 -o gpurun_out/prof_c3_$tag $CMD3 > gpurun_out/ncu_c3.log 2>&1
 echo c3full=$?
+CMD4="python tools/bench_c4.py --no-ntb --steps 3"
+ncu --set full --clock-control none --import-source on -k regex:bq2_frame_kernel -s 2 -c 1 -o gpurun_out/prof_c4_$tag $CMD4 > gpurun_out/ncu_c4.log 2>&1
+echo c4full=$?
+timeout 300 python bench.py > gpurun_out/bench_default_$tag.log 2> gpurun_out/bench_default_$tag.err; echo default=$?
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.log 2> gpurun_out/bench_ref_$tag.err; echo ref=$?
+tail -1 gpurun_out/bench_ref_$tag.log | cut -c1-300
