@@ -220,7 +220,10 @@ bq2_status bq2_frame_replay(bq2_ctx *ctx);
  * which must have come from bq2_frame / bq2_frame_submit and been waited for -- into an object of its own, so that a
  * set of DIFFERENT frames can be re-run back to back with every input already in HBM (bench.py cycles through more
  * of them than fit in L2).  bq2_resident_replay launches that frame's kernels on bq2_stream (async, no copies); the
- * results go to the arrays of the frame state it was computed on, which must not have been re-allocated since. */
+ * results go to the arrays of the frame state it was computed on, which must not have been re-allocated since.
+ * Replays (this one and bq2_frame_replay) are launched with programmatic stream serialization: every global write
+ * keeps its stream order -- frames that share result arrays may follow each other without a sync -- while the
+ * read-only front of a frame's kernel runs under the tail of the kernel in front of it. */
 typedef struct bq2_resident bq2_resident;
 bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out);
 bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r);
