@@ -262,6 +262,9 @@ def run_gpu(args):
 
     # ---- e2e: HOST records in through the C ABI, counts back, wall clock -----------------------------
     we_c = np.ascontiguousarray(we); wl_c = np.ascontiguousarray(wl)
+    # the AngleVectors bases of the rotated entities travel in steps of 64 rows of 36 bytes (bq2_world_submit)
+    n_rotated = int(np.count_nonzero((we_c["angles"] != 0).any(axis=1)))
+    h2d_basis_bytes = min(((n_rotated + 63) & ~63) * 36, (n_ents * 36 + 15) & ~15)
     ents_h = np.zeros(n_ents, c.ENTITY_DTYPE); pairs_h = np.zeros(n_pairs, c.PAIR_DTYPE)
     kept = C.c_int32(0)
     fd = c.FrameDesc(); fo = c.FrameOut()
@@ -400,10 +403,11 @@ def run_gpu(args):
                     "ms_per_step_pageable_inputs": e2e_pageable_s * 1e3 / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
-                    "h2d_bytes_per_step": n_ents * (64 + 56) + 16 + len(wl_c) * 16 + n_pairs * 8, "d2h_bytes_per_step": 4 * n_pairs + 24,
-                    "what": "per frame: bq2_world_submit (host: per-entity validation, numbering and AngleVectors; "
-                            "H2D of the caller's entities, lights, pairs from page-locked memory (bq2_host_alloc) and of the "
-                            "host-built rows from the library's pinned buffer; the record-building kernel + the "
+                    "h2d_bytes_per_step": n_ents * 64 + 16 + len(wl_c) * 16 + n_pairs * 8 + h2d_basis_bytes, "d2h_bytes_per_step": 4 * n_pairs + 24,
+                    "what": "per frame: bq2_world_submit (host: per-entity validation, numbering and AngleVectors into one 64-byte "
+                            "row per entity that also carries the caller's entity fields; H2D of those rows, the bases of the "
+                            "rotated entities and the caller's lights and pairs from the library's pinned buffer (the caller's "
+                            "own arrays are page-locked memory from bq2_host_alloc); the record-building kernel + the "
                             "fused kernel; D2H of per-pair index counts + totals) + "
                             "bq2_frame_wait, wall clock over K frames (median of %d such runs) with %d frames in flight (each has its own records, "
                             "result arrays and stream; the clock runs over K submit+wait iterations of the full pipeline, K "

@@ -1125,14 +1125,16 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
             ctx->model_rows[i] = bq2_model_row{mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2,
                                                me.V, me.T, me.Tp, me.flags};
+            bq2_model_row_derive(&ctx->model_rows[i]);
         }
     }
-    const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_xform),
+    const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_went),
                  off_lights = off_view + 16,
                  off_pe = off_lights + (size_t)nL * 16, off_pl = off_pe + (((size_t)nP * 4 + 15) & ~(size_t)15),
-                 off_w = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15),
-                 rec_bytes = off_w + (((size_t)nE * sizeof(bq2_world_entity) + 15) & ~(size_t)15);
-    /* [0, off_xf) = the entity records: device only, written by the record-building kernel; the copy starts at off_xf */
+                 off_b = off_pl + (((size_t)nP * 4 + 15) & ~(size_t)15),
+                 rec_bytes = off_b + (((size_t)nE * 36 + 15) & ~(size_t)15);
+    /* [0, off_xf) = the entity records: device only, written by the record-building kernel; the copy starts at off_xf.
+       [off_b, ..) = the AngleVectors bases of the rotated entities, room for all of them, copied as far as they go */
     Trace &tr = ctx->trace; tr.start(); tr.n++;
     bq2_world_stats ws{};
     int er = -3;
@@ -1140,8 +1142,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
         CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
         F.ent_slot_first.resize((size_t)nE + 1); F.ent_vert_off.resize((size_t)nE + 1); F.ent_tb_off.assign((size_t)nE + 1, 0u);
         F.slot_record.resize((size_t)nE + 1);
-        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, (bq2_dev_xform *)(h_records.p + off_xf),
-                                     F.slot_record.data(), F.ent_vert_off.data(), &ws);
+        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, (bq2_dev_went *)(h_records.p + off_xf),
+                                     (float *)(h_records.p + off_b), F.slot_record.data(), F.ent_vert_off.data(), &ws);
         if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
         if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
     }
@@ -1183,8 +1185,11 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     if (!direct) {
         if (nL) memcpy(h_records.p + off_lights, wd->lights, (size_t)nL * 16);
         if (nP) { memcpy(h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
-        if (nE) memcpy(h_records.p + off_w, wd->ents, (size_t)nE * sizeof(bq2_world_entity));
     }
+    /* the bases are copied in steps of 64 rows, so that frames whose number of rotated entities differs a little
+       still have the same copy sizes (the graph key below) */
+    const size_t basis_bytes = std::min((((size_t)ws.n_rotated + 63) & ~(size_t)63) * 36, rec_bytes - off_b);
+    const size_t copy_end = basis_bytes ? off_b + basis_bytes : off_b;
 
     tr.lap(3);
     uint32_t stride = wd->index_stride ? wd->index_stride : 12u * (uint32_t)maxT;
@@ -1234,8 +1239,8 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     /* (reading the pinned host records directly from the kernels instead of copying them was measured: the copy
        stage disappears but the record-building kernels and the frame kernel get 13 + 6 us slower at C2) */
     unsigned char *rb = F.d_records.p;
-    Wl.xf = (const bq2_dev_xform *)(rb + off_xf);
-    Wl.wents = (const bq2_world_entity *)(rb + off_w);
+    Wl.went = (const bq2_dev_went *)(rb + off_xf);
+    Wl.bases = (const float *)(rb + off_b);
     Wl.models = ctx->d_models.p; Wl.meshes = ctx->d_meshes.p; Wl.ents_out = (bq2_dev_ent *)rb;
     Wl.lights = (const float *)(rb + off_lights);
     Wl.pair_ent = (const int32_t *)(rb + off_pe); Wl.pair_light = (const int32_t *)(rb + off_pl);
@@ -1274,9 +1279,9 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
             CK(cudaMemcpyAsync(db + off_lights, wd->lights, (size_t)nL * 16, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(lights)");
             CK(cudaMemcpyAsync(db + off_pe, wd->pair_ent, (size_t)nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_ent)");
             CK(cudaMemcpyAsync(db + off_pl, wd->pair_light, (size_t)nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_light)");
-            CK(cudaMemcpyAsync(db + off_w, wd->ents, (size_t)nE * sizeof(bq2_world_entity), cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(entities)");
-        } else if (rec_bytes > off_xf)
-            CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, rec_bytes - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
+            if (basis_bytes) CK(cudaMemcpyAsync(db + off_b, h_records.p + off_b, basis_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(bases)");
+        } else if (copy_end > off_xf)
+            CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, copy_end - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
         if (st) st->mark(1, F.stream);
         CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
         Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;         /* the entity records are always built */
@@ -1295,7 +1300,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     FrameState::GraphKey key{};
     {
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
-                                ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, 0, 0, 0, 0, 0};
+                                ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, (int32_t)basis_bytes, 0, 0, 0, 0};
         memcpy(key.v, kv, sizeof kv);
         const void *kp[16] = {direct ? wd->ents : nullptr, direct ? wd->lights : nullptr, direct ? wd->pair_ent : nullptr,
                               direct ? wd->pair_light : nullptr,

@@ -11,6 +11,7 @@
 #include "bq2_gpu.h"
 #include <math.h>
 #include <string.h>
+#include <stddef.h>
 
 #define DOT(x, y) ((x)[0]*(y)[0] + (x)[1]*(y)[1] + (x)[2]*(y)[2])   /* M:2253 */
 
@@ -213,56 +214,97 @@ void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *fi
 
 /* ---- the per-entity half of the world path (bq2_world_submit), one pass, plain C ---------------------- */
 #include "bq2_internal.h"
-int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
-                            bq2_dev_xform *hx, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
+/* the flag filter of the shadow pass with its cvars at their defaults (r_mirror 0, r_playershadow 0, r_shadows 2):
+   bq2_host_casts_shadow above, M:63722-63727, plus the caller's own test M:64089 */
+#define BQ2_RF_NO_VOLUME (BQ2_RF_VIEWERMODEL | BQ2_RF_SHELL_GREEN | BQ2_RF_SHELL_RED | BQ2_RF_SHELL_BLUE | BQ2_RF_FULLBRIGHT | \
+                          BQ2_RF_BEAM | BQ2_RF_TRANSLUCENT | BQ2_RF_WEAPONMODEL | BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT)
+
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+/* the caller's entity and the first 44 bytes of its device row are the same fields */
+typedef char bq2_went_layout_check[(offsetof(bq2_dev_went, rec) == offsetof(bq2_world_entity, angles) &&
+                                    offsetof(bq2_dev_went, origin) == offsetof(bq2_world_entity, origin) &&
+                                    offsetof(bq2_dev_went, oldorigin) == offsetof(bq2_world_entity, oldorigin) &&
+                                    sizeof(bq2_dev_went) == 64 && sizeof(bq2_model_row) == 64) ? 1 : -1];
+
+void bq2_model_row_derive(bq2_model_row *r)
 {
-    /* the running numbers live in locals (the stores through hx / rec_of_ent could alias *st) */
-    bq2_world_stats s;
-    uint32_t voff = 0;
+    const int md2 = !(r->mflags & BQ2_MESH_MD3);
+    memset(r->cmax, 0, sizeof r->cmax); r->pad[0] = r->pad[1] = 0;
+    r->vpad = (uint32_t)(r->V + 3) & ~3u;
+    r->team = !(r->V <= BQ2_WARP_MAX_V && r->T <= BQ2_WARP_MAX_T);
+    r->cmax[2 * r->team] = (int16_t)r->V; r->cmax[2 * r->team + 1] = (int16_t)r->T; r->cmax[4 + r->team] = (int16_t)md2;
+}
+
+int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
+                            bq2_dev_went *rows, float *bases, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
+{
+    /* the running numbers live in locals (the stores through rows / rec_of_ent could alias *st); the six per-class
+       maxima are one 8 x int16 vector (bq2_model_row.cmax), what is a function of the largest mesh (row lengths) is
+       derived after the loop */
+    int32_t n_warp = 0, n_team = 0, n_rot = 0;
+    uint32_t voff = 0, team_rows = 0;
+    uint64_t total_verts = 0;
+    int16_t m[8];
     int32_t e;
-    memset(&s, 0, sizeof s);
+#if defined(__SSE2__)
+    __m128i mx = _mm_setzero_si128();
+#else
+    int k;
+    memset(m, 0, sizeof m);
+#endif
     memset(st, 0, sizeof *st);
     for (e = 0; e < n; e++) {
         const bq2_world_entity *W = &ents[e];
         const bq2_model_row *mo;
-        bq2_dev_xform *x = &hx[e];
-        uint32_t vpad, bitw, nrm_off = 0;
-        int32_t rec, casts, V, T;
+        bq2_dev_went *x = &rows[e];
+        uint32_t nrm_off = 0;
+        int32_t rec;
         if ((uint32_t)W->model >= (uint32_t)n_models) return -1;
         mo = &models[W->model];
         if (mo->n_mesh != 1) return -3;
         if ((uint32_t)W->frame >= (uint32_t)mo->F || (uint32_t)W->oldframe >= (uint32_t)mo->F) return -2;
-        V = mo->V; T = mo->T;
-        if (V <= BQ2_WARP_MAX_V && T <= BQ2_WARP_MAX_T) {           /* warp-kernel records grow up from 0 ... */
-            rec = s.n_warp++;
-            if (V > s.warp_max_V) s.warp_max_V = V;
-            if (T > s.warp_max_T) s.warp_max_T = T;
-            s.warp_md2 |= !(mo->mflags & BQ2_MESH_MD3);
-        } else {                                                    /* ... team-kernel records down from the end */
-            rec = n - 1 - s.n_team++;
-            if (V > s.team_max_V) s.team_max_V = V;
-            if (T > s.team_max_T) s.team_max_T = T;
-            s.team_md2 |= !(mo->mflags & BQ2_MESH_MD3);
-            nrm_off = s.team_normal_rows; s.team_normal_rows += (uint32_t)mo->Tp;
+#if defined(__SSE2__)
+        mx = _mm_max_epi16(mx, _mm_loadu_si128((const __m128i *)mo->cmax));
+#else
+        for (k = 0; k < 6; k++) if (mo->cmax[k] > m[k]) m[k] = mo->cmax[k];
+#endif
+        if (!mo->team) rec = n_warp++;                              /* warp-kernel records grow up from 0 ... */
+        else {                                                      /* ... team-kernel records down from the end */
+            rec = n - 1 - n_team++;
+            nrm_off = team_rows; team_rows += (uint32_t)mo->Tp;
         }
         rec_of_ent[e] = rec;
+        /* the caller's entity, without its angles (the device gets them as a basis): the first 44 bytes of both structs */
+        memcpy(x, W, offsetof(bq2_world_entity, angles));
         /* AngleVectors once per entity: the reference evaluates them again for the move delta and for every light
            (same inputs, same libm, same values) */
-        x->rotated = (uint32_t)bq2_host_entity_basis(W->angles, x->basis);
-        casts = bq2_host_casts_shadow(W->rf_flags, 0, 0.0f, 2.0f) &&
-                !(W->rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));                 /* M:63722-63727, 64089 */
-        vpad = (uint32_t)(V + 3) & ~3u; bitw = (uint32_t)(T + 31) >> 5;
-        x->rec = rec; x->pair_rec = casts ? rec : -1;
-        x->vert_off = voff; x->nrm_off = nrm_off; x->vpad = vpad; x->bitw = bitw;
+        if (W->angles[0] || W->angles[1] || W->angles[2]) {
+            float *b = bases + 9 * (size_t)n_rot;
+            bq2_host_angle_vectors(W->angles, b, b + 3, b + 6);
+            x->basis = n_rot++;
+        } else
+            x->basis = -1;
+        x->rec = rec; x->pair_rec = (W->rf_flags & BQ2_RF_NO_VOLUME) ? -1 : rec;        /* M:63722-63727, 64089 */
+        x->vert_off = voff; x->nrm_off = nrm_off;
         ent_vert_off[e] = voff;
-        voff += vpad; s.total_verts += (uint64_t)V;
-        if (vpad > s.max_vpad) s.max_vpad = vpad;
-        if (bitw > s.max_bitw) s.max_bitw = bitw;
-        if (T > s.max_T) s.max_T = T;
+        voff += mo->vpad; total_verts += (uint64_t)mo->V;
     }
     ent_vert_off[n] = voff;
-    s.lerped_verts_padded = voff;
-    *st = s;
+#if defined(__SSE2__)
+    _mm_storeu_si128((__m128i *)m, mx);
+#endif
+    st->n_warp = n_warp; st->n_team = n_team;
+    st->warp_max_V = m[0]; st->warp_max_T = m[1]; st->team_max_V = m[2]; st->team_max_T = m[3];
+    st->warp_md2 = m[4]; st->team_md2 = m[5];
+    {
+        const int32_t mV = m[0] > m[2] ? m[0] : m[2], mT = m[1] > m[3] ? m[1] : m[3];
+        st->max_vpad = (uint32_t)(mV + 3) & ~3u; st->max_bitw = (uint32_t)(mT + 31) >> 5; st->max_T = mT;
+    }
+    st->lerped_verts_padded = voff; st->team_normal_rows = team_rows; st->n_rotated = n_rot;
+    st->total_verts = total_verts;
     return 0;
 }
 

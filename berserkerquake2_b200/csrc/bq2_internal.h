@@ -70,20 +70,22 @@ typedef struct bq2_dev_pair {
 
 /* ---- device-side record building ("world" path) ------------------------------------------------
  * The host ships what it alone can decide (per ENTITY: validation, record and output-row numbering, the flag filter,
- * and for rotated entities the AngleVectors basis -- libm trig) plus the caller's entity, light and pair lists as
- * they are; ONE kernel turns that into the records above: an entity thread writes the entity record (lerp constants
+ * and for rotated entities the AngleVectors basis -- libm trig) in one row per entity that also carries the caller's
+ * entity fields, plus the caller's light and pair lists as they are; ONE kernel turns that into the records above: an entity thread writes the entity record (lerp constants
  * M:63526-63553 / 63825-63856), a pair thread writes the pair record (light moved to model space, M:63733-63745) and
  * files the pair under its entity (bucket + overflow chain).  Plain mul/add in the reference's order: bit-exact. */
-typedef struct bq2_dev_xform {      /* one per world entity: everything the HOST decides or needs libm for     */
-    float    basis[9];              /* forward, right, up (AngleVectors M:37566); written only when rotated  */
-    uint32_t rotated;
-    int32_t  rec;                   /* index of the entity's record (warp-kernel records first)              */
+typedef struct bq2_dev_went {       /* one per world entity, written by the host's entity loop                  */
+    int32_t  model, frame, oldframe;/* the caller's bq2_world_entity without its angles (44 bytes) ...         */
+    uint32_t rf_flags;
+    float    backlerp, origin[3], oldorigin[3];
+    int32_t  rec;                   /* ... and what the HOST decides: index of the entity's record (warp-kernel
+                                       records first)                                                          */
     int32_t  pair_rec;              /* = rec, or -1 when the entity casts no volume (M:63722-63727, 64089)   */
     uint32_t vert_off;              /* lerped row of the entity (vertices)                                    */
     uint32_t nrm_off;               /* team kernel: row of the entity in the triangle-normal scratch          */
-    uint32_t vpad;                  /* extruded row length of a pair of this entity (verts, multiple of 4)    */
-    uint32_t bitw;                  /* facing words of a pair of this entity                                  */
-} bq2_dev_xform;                    /* 64 bytes */
+    int32_t  basis;                 /* row of bases[] holding forward, right, up (AngleVectors M:37566: libm), or
+                                       -1 when all three angles are zero                                       */
+} bq2_dev_went;                     /* 64 bytes */
 
 typedef struct bq2_dev_model {      /* device mirror of a single-mesh model, for the record-building kernel    */
     const float *hdr;               /* MD2: F x {scale[3], translate[3]}; MD3: F x translate[3]               */
@@ -92,8 +94,8 @@ typedef struct bq2_dev_model {      /* device mirror of a single-mesh model, for
 
 struct bq2_world_entity;
 typedef struct bq2_world_launch {
-    const bq2_dev_xform *xf;
-    const struct bq2_world_entity *wents;   /* the caller's entities, copied as they are                      */
+    const bq2_dev_went *went;       /* [n_ents] the host's entity rows                                      */
+    const float    *bases;          /* [rotated entities][9]                                                */
     const bq2_dev_model *models;
     const bq2_dev_mesh  *meshes;
     bq2_dev_ent    *ents_out;       /* [n_ents] entity records, written by the kernel (lerp constants M:63526-63553) */
@@ -133,12 +135,20 @@ typedef struct bq2_launch {
 /* host-side flat model table for the per-entity loop in C (bq2_host.c) */
 typedef struct bq2_model_row {      /* host mirror of a model for the C entity loop (V, T, flags of its first mesh) */
     int32_t F, md3, first_mesh, n_mesh, V, T, Tp; uint32_t mflags;
-} bq2_model_row;                    /* 32 bytes */
+    /* derived by bq2_model_row_derive, so that the loop has nothing to decide per entity: */
+    uint32_t vpad;                  /* lerped row length, V rounded up to 4                                    */
+    int32_t  team;                  /* 0: warp-kernel mesh (V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T), 1: team kernel */
+    int32_t  pad[2];
+    int16_t  cmax[8];               /* the mesh's contribution to {warp max V, warp max T, team max V, team max T,
+                                       warp has an MD2, team has an MD2, 0, 0}: the frame's values are the
+                                       lane-wise maxima over its entities (V <= 4,096 and T <= 8,192 fit 16 bits) */
+} bq2_model_row;                    /* 64 bytes */
 typedef struct bq2_world_stats {
     int32_t n_warp, n_team;                 /* records [0, n_warp) -> warp kernel, [n - n_team, n) -> team kernel */
     int32_t warp_max_V, warp_max_T, warp_md2, team_max_V, team_max_T, team_md2;
     uint32_t lerped_verts_padded, max_vpad, max_bitw; int32_t max_T;
     uint32_t team_normal_rows;              /* sum of Tp over team-kernel records */
+    int32_t  n_rotated;                     /* rows of bases[] written */
     uint64_t total_verts;
 } bq2_world_stats;
 
@@ -150,8 +160,10 @@ struct bq2_world_entity;
  * (M:63722-63727) and -- the one thing that needs the host's libm -- AngleVectors of rotated entities.  The lerp
  * constants themselves (M:63526-63553 / 63825-63856) are computed by the record-building kernel from the caller's
  * entities and these rows.  Returns 0, -1 unknown model, -2 frame out of range, -3 a model is not single-mesh. */
+void bq2_model_row_derive(bq2_model_row *row);
 int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
-                             bq2_dev_xform *hx, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st);
+                             bq2_dev_went *rows, float *bases /* [n][9] */, int32_t *rec_of_ent, uint32_t *ent_vert_off,
+                             bq2_world_stats *st);
 /* Two kernels share the records.  "warp" kernel: one warp per (entity, light) pair, one CTA per entity,
  * for meshes with V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T (an MD2 player model is ~500 triangles).
  * "team" kernel: the whole CTA works on one pair at a time; any mesh size, and the N/T/B + tangent-space

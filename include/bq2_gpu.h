@@ -400,8 +400,9 @@ typedef struct bq2_world_desc {
     uint32_t want, index_stride;
 } bq2_world_desc;
 /* Page-locked host memory for the arrays a bq2_world_desc points at.  When ents, lights, pair_ent and pair_light of a
- * submit ALL lie inside blocks from bq2_host_alloc and together exceed 1 MiB, bq2_world_submit copies them to the
- * device from where they are instead of staging them through its own pinned buffer (at 1M pairs the staging copy is
+ * submit ALL lie inside blocks from bq2_host_alloc and together exceed 1 MiB, bq2_world_submit copies the light and
+ * pair arrays to the device from where they are instead of staging them through its own pinned buffer (the entities
+ * are read during the call either way: they travel inside the library's own per-entity rows; at 1M pairs the staging copy is
  * half of the host's frame time; small frames are staged either way, one copy being cheaper than five); the caller must then leave them unchanged until that frame's bq2_frame_wait has returned (an engine keeps
  * one set per frame in flight).  Any other memory works as before (borrowed only for the duration of the call).
  * NULL when out of memory.  bq2_host_free waits for the frames in flight; bq2_destroy frees what is left. */

@@ -9,31 +9,45 @@ import berserkerquake2_b200 as bq2
 from berserkerquake2_b200 import _capi as c, host
 
 MODEL_ROW = np.dtype([("F", "<i4"), ("md3", "<i4"), ("first_mesh", "<i4"), ("n_mesh", "<i4"), ("V", "<i4"), ("T", "<i4"),
-                      ("Tp", "<i4"), ("mflags", "<u4")])
-XFORM = np.dtype([("basis", "<f4", 9), ("rotated", "<u4"), ("rec", "<i4"), ("pair_rec", "<i4"), ("vert_off", "<u4"),
-                  ("nrm_off", "<u4"), ("vpad", "<u4"), ("bitw", "<u4")])
+                      ("Tp", "<i4"), ("mflags", "<u4"), ("vpad", "<u4"), ("team", "<i4"), ("pad", "<i4", 2), ("cmax", "<i2", 8)])
+# bq2_dev_went (csrc/bq2_internal.h): the caller's entity without its angles, then the host's numbering
+XFORM = np.dtype([("model", "<i4"), ("frame", "<i4"), ("oldframe", "<i4"), ("rf_flags", "<u4"), ("backlerp", "<f4"),
+                  ("origin", "<f4", 3), ("oldorigin", "<f4", 3), ("rec", "<i4"), ("pair_rec", "<i4"), ("vert_off", "<u4"),
+                  ("nrm_off", "<u4"), ("basis", "<i4")])
 STATS = np.dtype([("n_warp", "<i4"), ("n_team", "<i4"), ("warp_max_V", "<i4"), ("warp_max_T", "<i4"), ("warp_md2", "<i4"),
                   ("team_max_V", "<i4"), ("team_max_T", "<i4"), ("team_md2", "<i4"), ("lerped_verts_padded", "<u4"),
-                  ("max_vpad", "<u4"), ("max_bitw", "<u4"), ("max_T", "<i4"), ("team_normal_rows", "<u4"), ("pad", "<u4"),
+                  ("max_vpad", "<u4"), ("max_bitw", "<u4"), ("max_T", "<i4"), ("team_normal_rows", "<u4"), ("n_rotated", "<i4"),
                   ("total_verts", "<u8")])
-assert MODEL_ROW.itemsize == 32 and XFORM.itemsize == 64 and STATS.itemsize == 64
+assert MODEL_ROW.itemsize == 64 and XFORM.itemsize == 64 and STATS.itemsize == 64
 MESH_MD3 = 0x1
 
 
 def run(we, rows):
     fn = c.lib.bq2_host_world_entities
     fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     n = len(we)
     hx = np.zeros(n, XFORM); rec = np.full(n + 1, -7, np.int32); voff = np.zeros(n + 1, np.uint32); st = np.zeros(1, STATS)
-    rc = fn(we.ctypes.data, n, rows.ctypes.data, len(rows), hx.ctypes.data, rec.ctypes.data, voff.ctypes.data, st.ctypes.data)
+    bases = np.full((n + 1, 9), np.nan, np.float32)                # the loop may write rows [0, rotated entities) only
+    rc = fn(we.ctypes.data, n, rows.ctypes.data, len(rows), hx.ctypes.data, bases.ctypes.data, rec.ctypes.data,
+            voff.ctypes.data, st.ctypes.data)
+    if rc == 0:
+        assert np.isnan(bases[st[0]["n_rotated"]:]).all()
+        for f in ("model", "frame", "oldframe", "rf_flags", "backlerp", "origin", "oldorigin"):      # copied bit for bit
+            assert np.array_equal(hx[f].view(np.uint32), we[f].view(np.uint32)), f
+    run.bases = bases
     return rc, hx, rec[:n], voff, st[0]
 
 
 def rows_of(shapes):
     rows = np.zeros(len(shapes), MODEL_ROW)
     for i, (V, T, md3, n_mesh) in enumerate(shapes):
-        rows[i] = (6, md3, i, n_mesh, V, T, (T + 31) & ~31, MESH_MD3 if md3 else 0)
+        rows[i] = (6, md3, i, n_mesh, V, T, (T + 31) & ~31, MESH_MD3 if md3 else 0, 0xdead, 7, (7, 7), (7,) * 8)
+        c.lib.bq2_model_row_derive(C.c_void_p(rows[i:].ctypes.data))         # the fields the entity loop reads per entity
+        team = int(V > 1024 or T > 1024)
+        want = [0] * 8
+        want[2 * team] = V; want[2 * team + 1] = T; want[4 + team] = int(not md3)
+        assert rows["vpad"][i] == (V + 3) & ~3 and rows["team"][i] == team and list(rows["cmax"][i]) == want
     return rows
 
 
@@ -43,6 +57,7 @@ def test_numbering_classes_and_stats():
     n = 41
     we = np.zeros(n, bq2.WORLD_ENTITY_DTYPE)
     we["model"] = rng.randint(0, 5, n); we["frame"] = rng.randint(0, 6, n); we["oldframe"] = rng.randint(0, 6, n)
+    we["backlerp"] = rng.rand(n); we["origin"] = rng.randn(n, 3) * 500; we["oldorigin"] = we["origin"] + rng.randn(n, 3)
     rc, hx, rec, voff, st = run(we, rows)
     assert rc == 0
     small = np.array([(rows["V"][m] <= 1024) and (rows["T"][m] <= 1024) for m in we["model"]])
@@ -53,8 +68,8 @@ def test_numbering_classes_and_stats():
     V = rows["V"][we["model"]]; T = rows["T"][we["model"]]; Tp = rows["Tp"][we["model"]]
     vpad = (V + 3) & ~3
     assert np.array_equal(voff[:n], np.concatenate([[0], np.cumsum(vpad)[:-1]])) and voff[n] == vpad.sum()
-    assert np.array_equal(hx["vert_off"], voff[:n]) and np.array_equal(hx["vpad"], vpad)
-    assert np.array_equal(hx["bitw"], (T + 31) >> 5)
+    assert np.array_equal(hx["vert_off"], voff[:n])
+    assert (hx["basis"] == -1).all() and st["n_rotated"] == 0
     assert np.array_equal(hx["nrm_off"][~small], np.concatenate([[0], np.cumsum(Tp[~small])[:-1]]))
     assert (hx["nrm_off"][small] == 0).all()
     assert st["n_warp"] == small.sum() and st["n_team"] == (~small).sum()
@@ -93,12 +108,15 @@ def test_flag_filter_and_basis():
     we["angles"] = ang
     rc, hx, rec, voff, st = run(we, rows)
     assert rc == 0
+    n_rot = 0
     for e, f in enumerate(flags):
         casts = host.casts_shadow(f) and not (f & (0x80000 | 0x10000000))
         assert hx["pair_rec"][e] == (rec[e] if casts else -1), hex(f)
         rotated = bool(ang[e][0] or ang[e][1] or ang[e][2])             # -0.0 counts as zero, a denormal does not
-        assert bool(hx["rotated"][e]) == rotated, e
+        assert hx["basis"][e] == (n_rot if rotated else -1), e          # bases are numbered in entity order
         if rotated:
             fwd, right, up = host.angle_vectors(ang[e])
-            got = hx["basis"][e].view(np.uint32)
+            got = run.bases[n_rot].view(np.uint32)
             assert np.array_equal(got, np.concatenate([fwd, right, up]).astype(np.float32).view(np.uint32)), e
+            n_rot += 1
+    assert st["n_rotated"] == n_rot == 4
