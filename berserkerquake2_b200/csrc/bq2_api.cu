@@ -664,7 +664,8 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         if (F.slot_record[s] < 0) F.slot_record[s] = F.k_warp.n + (-1 - F.slot_record[s]);
 
     tr.lap(1);
-    uint32_t voff = 0, tboff = 0, team_rows = 0;
+    /* rows are numbered in 32 bits on the device: the running sums are kept in 64 and checked after the loops */
+    uint64_t voff = 0, tboff = 0, team_rows = 0;
     uint64_t total_verts = 0;
     for (int e = 0; e < nE; e++) {
         const bq2_entity &E = fd->ents[e];
@@ -677,13 +678,13 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             bq2_dev_ent &d = he[F.slot_record[s]];
             d.cur = me.verts + (size_t)E.frame * me.vstride; d.old = me.verts + (size_t)E.oldframe * me.vstride;
             d.tri = me.tri; d.V = me.V; d.T = me.T; d.Tp = me.Tp; d.mflags = me.flags; d.vstride = me.vstride; d.nrm_off = 0;
-            if (F.slot_record[s] >= F.k_warp.n) { d.nrm_off = team_rows; team_rows += (uint32_t)me.Tp; }
+            if (F.slot_record[s] >= F.k_warp.n) { d.nrm_off = (uint32_t)team_rows; team_rows += (uint32_t)me.Tp; }
             d.mesh = mo.first_mesh + m; d.frame = E.frame; d.oldframe = E.oldframe; d.flags = E.flags;
             d.backlerp = E.backlerp; d.frontlerp = E.frontlerp;
             for (int k = 0; k < 3; k++) { d.move[k] = E.move[k]; d.frontv[k] = E.frontv[k]; d.backv[k] = E.backv[k]; }
             d.shell_scale = E.shell_scale;
-            d.vert_off = voff; d.tb_off = tboff; d.pair_begin = 0; d.pair_count = 0;
-            F.ent_vert_off[s] = voff; F.ent_tb_off[s] = tboff;
+            d.vert_off = (uint32_t)voff; d.tb_off = (uint32_t)tboff; d.pair_begin = 0; d.pair_count = 0;
+            F.ent_vert_off[s] = (uint32_t)voff; F.ent_tb_off[s] = (uint32_t)tboff;
             voff += (uint32_t)(me.V + 3) & ~3u;
             tboff += (uint32_t)(((me.flags & BQ2_MESH_SMOOTH) ? me.V : me.T) + 3) & ~3u;
             total_verts += (uint64_t)me.V;
@@ -691,12 +692,13 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             if (!(me.flags & BQ2_MESH_MD3)) anyMd2 = 1;
         }
     }
-    F.ent_vert_off[nES] = voff; F.ent_tb_off[nES] = tboff;
-    const uint32_t ent_verts = voff, tb_rows = tboff;
+    if ((voff | tboff | team_rows) >> 32) return fail(ctx, BQ2_E_LIMIT, "bq2_frame: more than 2^32 output rows, split the frame");
+    F.ent_vert_off[nES] = (uint32_t)voff; F.ent_tb_off[nES] = (uint32_t)tboff;
+    const uint32_t ent_verts = (uint32_t)voff, tb_rows = (uint32_t)tboff;
 
     tr.lap(2);
     /* pair slots: offsets in caller order, then a counting sort by entity slot for the kernel */
-    uint32_t pvoff = 0, pboff = 0, ptsoff = 0;
+    uint64_t pvoff = 0, pboff = 0, ptsoff = 0;
     for (int p = 0; p < nP; p++) {
         int e = fd->pairs[p].entity;
         const bool dead = e < 0;
@@ -705,7 +707,7 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
         for (int m = 0; m < mo.n_mesh; m++) {
             int ps = F.pair_slot_first[p] + m, es = F.ent_slot_first[e] + m;
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh + m];
-            F.pair_vert_off[ps] = pvoff; F.pair_bits_off[ps] = pboff; F.pair_ts_off[ps] = ptsoff;
+            F.pair_vert_off[ps] = (uint32_t)pvoff; F.pair_bits_off[ps] = (uint32_t)pboff; F.pair_ts_off[ps] = (uint32_t)ptsoff;
             /* LightP / tsH rows: per vertex, or per triangle corner for a non-smooth MD2 (M:64943-65017) */
             ptsoff += (uint32_t)(((me.flags & BQ2_MESH_SMOOTH) ? me.V : 3 * me.T) + 3) & ~3u;
             F.slot_mesh_V[ps] = me.V; F.slot_mesh_T[ps] = me.T; F.pair_slot_entslot[ps] = es;
@@ -714,7 +716,8 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
             if (mo.casts[m] && !dead) F.cursor[es]++;
         }
     }
-    F.pair_vert_off[nPS] = pvoff; F.pair_bits_off[nPS] = pboff; F.pair_ts_off[nPS] = ptsoff;
+    if ((pvoff | pboff | ptsoff) >> 32) return fail(ctx, BQ2_E_LIMIT, "bq2_frame: more than 2^32 output rows, split the frame");
+    F.pair_vert_off[nPS] = (uint32_t)pvoff; F.pair_bits_off[nPS] = (uint32_t)pboff; F.pair_ts_off[nPS] = (uint32_t)ptsoff;
     uint32_t n_dev_pairs = 0;
     {
         uint32_t run = 0;
@@ -1146,6 +1149,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
                                      (float *)(h_records.p + off_b), F.slot_record.data(), F.ent_vert_off.data(), &ws);
         if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
         if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
+        if (er == -4) return fail(ctx, BQ2_E_LIMIT, "bq2_world: more than 2^32 output rows, split the frame");
     }
     if (er != 0) {
         /* multi-mesh models or tangent-space outputs: host-built records, same slot numbering (filtered pairs
@@ -1167,6 +1171,9 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     F.k_warp.n = ws.n_warp; F.k_warp.max_V = ws.warp_max_V; F.k_warp.max_T = ws.warp_max_T; F.k_warp.any_md2 = ws.warp_md2;
     F.k_team.n = ws.n_team; F.k_team.max_V = ws.team_max_V; F.k_team.max_T = ws.team_max_T; F.k_team.any_md2 = ws.team_md2;
     const uint32_t voff = ws.lerped_verts_padded, maxVpad = ws.max_vpad, maxBitw = ws.max_bitw;
+    /* rows are numbered in 32 bits on the device (pair p's rows start at p * stride) */
+    if (((uint64_t)nP * maxVpad | (uint64_t)nP * maxBitw) >> 32)
+        return fail(ctx, BQ2_E_LIMIT, "bq2_world: more than 2^32 output rows, split the frame");
     const int maxT = ws.max_T;
     const uint64_t total_verts = ws.total_verts;
     {

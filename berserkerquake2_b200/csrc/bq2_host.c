@@ -245,7 +245,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
        maxima are one 8 x int16 vector (bq2_model_row.cmax), what is a function of the largest mesh (row lengths) is
        derived after the loop */
     int32_t n_warp = 0, n_team = 0, n_rot = 0;
-    uint32_t voff = 0, team_rows = 0;
+    uint64_t voff = 0, team_rows = 0;          /* stored as 32-bit row numbers; checked after the loop */
     uint64_t total_verts = 0;
     int16_t m[8];
     int32_t e;
@@ -274,7 +274,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         if (!mo->team) rec = n_warp++;                              /* warp-kernel records grow up from 0 ... */
         else {                                                      /* ... team-kernel records down from the end */
             rec = n - 1 - n_team++;
-            nrm_off = team_rows; team_rows += (uint32_t)mo->Tp;
+            nrm_off = (uint32_t)team_rows; team_rows += (uint32_t)mo->Tp;
         }
         rec_of_ent[e] = rec;
         /* the caller's entity, without its angles (the device gets them as a basis): the first 44 bytes of both structs */
@@ -288,11 +288,12 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         } else
             x->basis = -1;
         x->rec = rec; x->pair_rec = (W->rf_flags & BQ2_RF_NO_VOLUME) ? -1 : rec;        /* M:63722-63727, 64089 */
-        x->vert_off = voff; x->nrm_off = nrm_off;
-        ent_vert_off[e] = voff;
+        x->vert_off = (uint32_t)voff; x->nrm_off = nrm_off;
+        ent_vert_off[e] = (uint32_t)voff;
         voff += mo->vpad; total_verts += (uint64_t)mo->V;
     }
-    ent_vert_off[n] = voff;
+    if ((voff | team_rows) >> 32) return -4;
+    ent_vert_off[n] = (uint32_t)voff;
 #if defined(__SSE2__)
     _mm_storeu_si128((__m128i *)m, mx);
 #endif
@@ -303,7 +304,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         const int32_t mV = m[0] > m[2] ? m[0] : m[2], mT = m[1] > m[3] ? m[1] : m[3];
         st->max_vpad = (uint32_t)(mV + 3) & ~3u; st->max_bitw = (uint32_t)(mT + 31) >> 5; st->max_T = mT;
     }
-    st->lerped_verts_padded = voff; st->team_normal_rows = team_rows; st->n_rotated = n_rot;
+    st->lerped_verts_padded = (uint32_t)voff; st->team_normal_rows = (uint32_t)team_rows; st->n_rotated = n_rot;
     st->total_verts = total_verts;
     return 0;
 }

@@ -159,7 +159,8 @@ struct bq2_world_entity;
 /* One pass over the world entities: validation, kernel class, record / output-row numbering, flag filter
  * (M:63722-63727) and -- the one thing that needs the host's libm -- AngleVectors of rotated entities.  The lerp
  * constants themselves (M:63526-63553 / 63825-63856) are computed by the record-building kernel from the caller's
- * entities and these rows.  Returns 0, -1 unknown model, -2 frame out of range, -3 a model is not single-mesh. */
+ * entities and these rows.  Returns 0, -1 unknown model, -2 frame out of range, -3 a model is not single-mesh,
+ * -4 the frame's rows do not fit 32-bit row numbers. */
 void bq2_model_row_derive(bq2_model_row *row);
 int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
                              bq2_dev_went *rows, float *bases /* [n][9] */, int32_t *rec_of_ent, uint32_t *ent_vert_off,

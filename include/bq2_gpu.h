@@ -45,6 +45,7 @@ typedef enum bq2_status {
     BQ2_E_CUDA      = -2,   /* CUDA runtime error, text in bq2_last_error                           */
     BQ2_E_NOMEM     = -3,   /* host or device allocation failed                                     */
     BQ2_E_LIMIT     = -4,   /* exceeds a reference limit (MAX_VERTS 2048, MAX_TRIANGLES 4096, ...)   */
+                            /* ... or a frame whose output rows do not fit 32-bit row numbers (2^32 vertex rows) */
     BQ2_E_OVERFLOW  = -5,   /* some pair produced more indices than index_stride holds              */
     BQ2_E_NODEVICE  = -6    /* no usable CUDA device: there is no CPU path                          */
 } bq2_status;

@@ -98,6 +98,18 @@ def test_validation_codes():
     assert run(we[:0], rows)[0] == 0
 
 
+def test_row_numbers_must_fit_32_bits():
+    """Output rows are numbered in 32 bits on the device: a frame whose lerped rows exceed 2^32 vertices is refused
+    (-4 -> BQ2_E_LIMIT), one entity short of it is accepted."""
+    rows = rows_of([(4096, 10, 1, 1)])
+    n = (1 << 32) // 4096
+    we = np.zeros(n + 1, bq2.WORLD_ENTITY_DTYPE)
+    rc, hx, rec, voff, st = run(we[:n - 1], rows)
+    assert rc == 0 and int(voff[n - 1]) == 4096 * (n - 1) and int(hx["vert_off"][-1]) == 4096 * (n - 2)
+    assert run(we[:n], rows)[0] == -4                             # the total itself (2^32) is kept in 32 bits too
+    assert run(we, rows)[0] == -4
+
+
 def test_flag_filter_and_basis():
     rows = rows_of([(30, 40, 0, 1)])
     flags = [0, 0x2, 0x4, 0x8, 0x20, 0x80, 0x400, 0x800, 0x1000, 0x80000, 0x10000000, 0x40, 0x100, 0x80000 | 0x400]
