@@ -47,7 +47,8 @@ L2_FLUSH_BYTES = 256 << 20
 E2E_REPEATS = 9            # the K-frame wall-clock measurement is repeated at least this often, and for at least
 E2E_MIN_SECONDS = 0.5      # this long (nine 100-frame runs last 20 ms: one hiccup of the host would cover them all);
 E2E_MAX_REPEATS = 999      # the median run is reported, min/max alongside
-E2E_IN_FLIGHT = 4          # frames the e2e leg keeps in flight (the library allows four; results of each stay separate)
+E2E_IN_FLIGHT = int(os.environ.get("BQ2_BENCH_IN_FLIGHT", "4"))   # frames the e2e leg keeps in flight (the library allows
+                           # four; results of each stay separate; the variable is for experiment builds of the library)
 
 
 def peaks():

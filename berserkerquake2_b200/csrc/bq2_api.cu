@@ -77,8 +77,11 @@ struct PinBuf {
 
 /* everything that belongs to ONE frame */
 #define BQ2_DIRECT_MIN_BYTES (1u << 20)
+#ifndef BQ2_FRAME_STATES        /* (overridable for experiments: make EXTRA="-DBQ2_FRAME_STATES=8 -DBQ2_MAX_IN_FLIGHT=7") */
 #define BQ2_FRAME_STATES   5
 #define BQ2_MAX_IN_FLIGHT  4
+#endif
+static_assert(BQ2_MAX_IN_FLIGHT < BQ2_FRAME_STATES, "the state bq2_frame_wait returned last must not be the one taken next");
 struct FrameState {
     cudaStream_t stream = nullptr;
     std::vector<int32_t>  ent_slot_first, pair_slot_first;
