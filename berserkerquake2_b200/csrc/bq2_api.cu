@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -182,6 +183,19 @@ bq2_status fail_cuda(bq2_ctx *c, cudaError_t e, const char *where)
 #define CK(call, where) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(ctx, e_, where); } while (0)
 
 /* bump allocation out of 64 MiB slabs; 256-byte aligned so every array is TMA/128-bit friendly */
+/* The C ABI never lets a C++ exception out (std::bad_alloc from a host-side table is the one that can occur):
+   every entry point that builds host tables is a function-try-block ending here. */
+bq2_status guard_exception(bq2_ctx *ctx) noexcept
+{
+    bq2_status s = BQ2_E_INVALID;
+    const char *what = "internal error (C++ exception)";
+    try { throw; }
+    catch (const std::bad_alloc &) { s = BQ2_E_NOMEM; what = "out of host memory"; }
+    catch (...) {}
+    try { if (ctx) ctx->err = what; } catch (...) {}
+    return s;
+}
+
 bq2_status arena_alloc(bq2_ctx *ctx, size_t bytes, unsigned char **out)
 {
     const size_t kSlab = 64u << 20;
@@ -380,7 +394,7 @@ static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, 
 bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, const int32_t *neighbours,
                           const uint8_t *tangents, const uint8_t *binormals, const uint8_t *normals,
                           uint32_t model_flags, int32_t *model_id)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!blob || !model_id || blob_bytes < sizeof(md2_header)) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: bad arguments");
     const md2_header *h = (const md2_header *)blob;
@@ -457,11 +471,11 @@ bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, con
     ctx->meshes.push_back(m); ctx->models.push_back(mo); ctx->meshes_dirty = true;
     *model_id = (int32_t)ctx->models.size() - 1;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate, const bq2_md3_mesh *meshes,
                           int32_t num_meshes, int32_t *model_id)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!meshes || !model_id || !frame_translate || F <= 0 || num_meshes <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md3: bad arguments");
     if (num_meshes > BQ2_MD3_MAX_MESHES) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: too many meshes");
@@ -515,7 +529,7 @@ bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate,
     ctx->models.push_back(mo); ctx->meshes_dirty = true;
     *model_id = (int32_t)ctx->models.size() - 1;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t id, int32_t *is_md3, int32_t *num_frames,
                           int32_t *num_meshes, int32_t *num_verts, int32_t *num_tris)
@@ -538,10 +552,10 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
                              const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
                              const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
                              int32_t *n_pairs_out)
-{
+try {
     return build_records_impl(ctx, ents, n_ents, lights, n_lights, pair_ent, pair_light, n_pairs, view_world,
                               out_ents, out_pairs, n_pairs_out, false);
-}
+} catch (...) { return guard_exception(ctx); }
 
 static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
                              const bq2_world_light *lights, int32_t n_lights,
@@ -598,7 +612,7 @@ static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents,
 }
 
 bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!fd || fd->n_ents < 0 || fd->n_pairs < 0 || (fd->n_ents > 0 && !fd->ents) || (fd->n_pairs > 0 && !fd->pairs))
         return fail(ctx, BQ2_E_INVALID, "bq2_frame: bad descriptor");
@@ -811,10 +825,10 @@ bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
     ctx->submit_seq++; ctx->cur = slot_k;
     tr.lap(6);
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_frame_wait: nothing submitted");
     int k;
@@ -860,7 +874,7 @@ bq2_status bq2_frame_wait(bq2_ctx *ctx, bq2_frame_out *out)
     if (out) *out = o;
     if (o.overflow_pairs) return fail(ctx, BQ2_E_OVERFLOW, "bq2_frame: index_stride too small for at least one pair (counts are exact, indices truncated)");
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
 {
@@ -871,7 +885,7 @@ bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
 }
 
 static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, int32_t T, int md3, int32_t *out)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!idx || !out || T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_neighbours: bad arguments");
     if (T > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_neighbours: too many triangles");
@@ -889,7 +903,7 @@ static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, 
     buf.release();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_neighbours");
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_gpu_md2_neighbours(bq2_ctx *ctx, const int16_t *dtriangles, int32_t num_tris, int32_t *out)
 { return gpu_neighbours(ctx, (const uint16_t *)dtriangles, 6, num_tris, 0, out); }
@@ -897,7 +911,7 @@ bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t
 { return gpu_neighbours(ctx, indexes, 3, num_tris, 1, out); }
 
 bq2_status bq2_selftest_ratio(bq2_ctx *ctx, int mode, float num, uint64_t count, uint64_t seed, uint64_t *mismatches)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!mismatches || mode < 0 || mode > 2) return fail(ctx, BQ2_E_INVALID, "bq2_selftest_ratio: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -912,11 +926,11 @@ bq2_status bq2_selftest_ratio(bq2_ctx *ctx, int mode, float num, uint64_t count,
     if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_selftest_ratio");
     *mismatches = (uint64_t)h;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *blob, size_t blob_bytes, const float *st, float smooth_cosine,
                                 int smooth, uint8_t *normals, uint8_t *tangents, uint8_t *binormals)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!blob || blob_bytes < sizeof(md2_header) || !st || !tangents || !binormals || (!smooth && !normals))
         return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: bad arguments");
@@ -957,11 +971,11 @@ bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *blob, size_t blob_byte
     buf.release();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_md2_tangents");
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t F, int32_t V, const float *st,
                                 const uint16_t *indexes, int32_t T)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!vertexes || !st || !indexes || F <= 0 || V <= 0 || T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md3_tangents: bad arguments");
     if (V > BQ2_MD3_MAX_VERTS || T > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md3_tangents: mesh outside the MD3 limits");
@@ -983,11 +997,11 @@ bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t F, int32_t
     buf.release();
     if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_gpu_md3_tangents");
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numverts, const float *verts,
                             const int32_t *neighbours, const uint8_t *fence, int32_t *brush_id)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (n_polys <= 0 || !numverts || !verts || !neighbours || !brush_id) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: bad arguments");
     if (n_polys > BQ2_BRUSH_MAX_POLYS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_brush: too many polygons");
@@ -1027,10 +1041,10 @@ bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numver
     CK(cudaMemcpy(ctx->d_brushes.p, ctx->brush_dev.data(), ctx->brush_dev.size() * sizeof(bq2_brush_dev_h), cudaMemcpyHostToDevice), "cudaMemcpy(brush table)");
     *brush_id = (int32_t)ctx->brushes.size() - 1;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t n_pairs, const uint8_t *lit, bq2_brush_out *out)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (n_pairs < 0 || (n_pairs && (!pairs || !lit)) || !out) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -1065,10 +1079,10 @@ bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t 
     out->vcache = ctx->brush_vcache.p; out->icache = ctx->brush_icache.p; out->counts = ctx->h_brush_counts.data();
     out->vert_stride = vstride; out->index_stride = istride;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_brush_download(bq2_ctx *ctx, int32_t pair, float *vcache, uint32_t *icache)
-{
+try {
     if (!ctx || !vcache || !icache) return BQ2_E_INVALID;
     if (pair < 0 || pair >= ctx->brush_pairs) return fail(ctx, BQ2_E_INVALID, "bq2_brush_download: bad pair");
     const uint32_t vb = ctx->h_brush_counts[2 * (size_t)pair], ib = ctx->h_brush_counts[2 * (size_t)pair + 1];
@@ -1076,7 +1090,7 @@ bq2_status bq2_brush_download(bq2_ctx *ctx, int32_t pair, float *vcache, uint32_
     if (vb) CK(cudaMemcpy(vcache, ctx->brush_vcache.p + 6 * (size_t)pair * ctx->brush_vstride, 24 * (size_t)vb, cudaMemcpyDeviceToHost), "cudaMemcpy(vcache)");
     if (ib) CK(cudaMemcpy(icache, ctx->brush_icache.p + (size_t)pair * ctx->brush_istride, 4 * (size_t)ib, cudaMemcpyDeviceToHost), "cudaMemcpy(icache)");
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 void *bq2_host_alloc(bq2_ctx *ctx, size_t bytes)
 {
@@ -1085,7 +1099,8 @@ void *bq2_host_alloc(bq2_ctx *ctx, size_t bytes)
     void *p = nullptr;
     cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
     if (e != cudaSuccess) { fail_cuda(ctx, e, "cudaHostAlloc"); return nullptr; }
-    ctx->host_ranges.push_back(bq2_ctx::HostRange{(const unsigned char *)p, bytes});
+    try { ctx->host_ranges.push_back(bq2_ctx::HostRange{(const unsigned char *)p, bytes}); }
+    catch (...) { cudaFreeHost(p); guard_exception(ctx); return nullptr; }
     return p;
 }
 
@@ -1110,7 +1125,7 @@ static bool host_pinned(const bq2_ctx *ctx, const void *p, size_t bytes)
 }
 
 bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     if (!wd || wd->n_ents < 0 || wd->n_pairs < 0 || wd->n_lights < 0 || (wd->n_ents > 0 && !wd->ents) ||
         (wd->n_pairs > 0 && (!wd->pair_ent || !wd->pair_light || !wd->lights)))
@@ -1335,7 +1350,7 @@ bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
     ctx->submit_seq++; ctx->cur = slot_k;
     tr.lap(6);
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *wd, bq2_frame_out *out)
 {
@@ -1346,17 +1361,17 @@ bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *wd, bq2_frame_out
 }
 
 bq2_status bq2_frame_replay(bq2_ctx *ctx)
-{
+try {
     if (!ctx) return BQ2_E_INVALID;
     FrameState &F = ctx->fs[ctx->cur];
     if (!ctx->submitted || !F.n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
     if (F.world_mode)                                            /* the kernels add to the totals: start from zero */
         CK(cudaMemsetAsync(F.wlaunch.totals, 0, 2 * sizeof(unsigned long long), F.stream), "cudaMemset(totals)");
     return launch_kernels(ctx, F, /*overlap=*/1);
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out)
-{
+try {
     if (!ctx || !out) return BQ2_E_INVALID;
     *out = nullptr;
     FrameState &F = ctx->fs[ctx->cur];
@@ -1376,10 +1391,10 @@ bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out)
     r->L.pairs = (const bq2_dev_pair *)(r->records.p + ((const unsigned char *)F.launch.pairs - F.d_records.p));
     *out = r;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
-{
+try {
     if (!ctx || !r) return BQ2_E_INVALID;
     FrameState &F = ctx->fs[r->state];
     if (r->L.lerped != F.lerped.p || r->L.extruded != F.extruded.p || r->L.indices != F.indices.p ||
@@ -1398,7 +1413,7 @@ bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
         ctx->launches++;
     }
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 void bq2_resident_free(bq2_ctx *ctx, bq2_resident *r)
 {
@@ -1411,7 +1426,7 @@ void bq2_resident_free(bq2_ctx *ctx, bq2_resident *r)
 const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->fs[ctx->last_waited].hcnt.p : nullptr; }
 
 bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host)
-{
+try {
     if (!ctx || !host) return BQ2_E_INVALID;
     FrameState &F = ctx->fs[ctx->last_waited];                   /* the frame bq2_frame_wait returned last */
     const void *src = nullptr; size_t cap = 0;
@@ -1433,10 +1448,10 @@ bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t 
     CK(cudaMemcpyAsync(host, (const uint32_t *)src + first, count * 4, cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(download)");
     CK(cudaStreamSynchronize(F.stream), "cudaStreamSynchronize(download)");
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t ps, float *tris_verts, int32_t max_verts, int32_t *tris_counter)
-{
+try {
     if (!ctx || !tris_verts || !tris_counter) return BQ2_E_INVALID;
     FrameState &F = ctx->fs[ctx->last_waited];
     if (!ctx->submitted || ps < 0 || ps >= F.n_pair_slots) return fail(ctx, BQ2_E_INVALID, "bq2_expand_trisverts: bad pair slot");
@@ -1459,6 +1474,6 @@ bq2_status bq2_expand_trisverts(bq2_ctx *ctx, int32_t ps, float *tris_verts, int
     for (uint32_t k = 0; k < cnt; k++) memcpy(tris_verts + 3 * (size_t)k, &pool[3 * (size_t)idx[k]], 12);
     *tris_counter = (int32_t)cnt;
     return BQ2_OK;
-}
+} catch (...) { return guard_exception(ctx); }
 
 } // extern "C"
