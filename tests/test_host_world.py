@@ -132,3 +132,54 @@ def test_flag_filter_and_basis():
             assert np.array_equal(got, np.concatenate([fwd, right, up]).astype(np.float32).view(np.uint32)), e
             n_rot += 1
     assert st["n_rotated"] == n_rot == 4
+
+
+def test_rows_and_bases_carry_what_the_record_kernel_needs():
+    """The record-building kernel (bq2_world_link_kernel, csrc/bq2_kernels.cu) sees only the 64-byte rows, the bases of
+    the rotated entities, the frame headers and the lights.  Its arithmetic restated here in numpy float32, one
+    rounding per operation and in its order, must give the lerp constants of bq2_host_entity_md2 (M:63526-63553) and
+    the model-space light of bq2_host_point_to_model (M:63733-63745) bit for bit -- i.e. the rows lose nothing."""
+    from berserkerquake2_b200 import synth
+    f32 = np.float32
+    F = 6
+    blob = synth.md2(8, 5, F, 3)
+    h = blob[:68].view("<i4"); fsz, ofs = int(h[4]), int(h[14])
+    hdr = np.stack([blob[ofs + f * fsz: ofs + f * fsz + 24].view("<f4") for f in range(F)])   # scale[3], translate[3]
+    rows = rows_of([(int(h[6]), int(h[8]), 0, 1)]); rows["F"] = F
+    rng = np.random.RandomState(11)
+    n = 64
+    we = np.zeros(n, bq2.WORLD_ENTITY_DTYPE)
+    we["frame"] = rng.randint(0, F, n); we["oldframe"] = rng.randint(0, F, n); we["backlerp"] = rng.rand(n)
+    we["origin"] = rng.randn(n, 3) * 300; we["oldorigin"] = we["origin"] + rng.randn(n, 3) * 2
+    ang = np.zeros((n, 3), np.float32)
+    for e in range(n):
+        k = rng.randint(4)
+        if k == 1: ang[e, 1] = rng.uniform(-180, 180)
+        elif k == 2: ang[e] = rng.uniform(-180, 180, 3)
+        elif k == 3: ang[e, rng.randint(3)] = -0.0
+    we["angles"] = ang
+    rc, hx, rec, voff, st = run(we, rows)
+    assert rc == 0 and st["n_rotated"] == np.count_nonzero((ang != 0).any(axis=1))
+
+    def dot3(t, b):                                               # DotProduct M:2253: (x0*y0 + x1*y1) + x2*y2
+        return f32(f32(f32(t[0] * b[0]) + f32(t[1] * b[1])) + f32(t[2] * b[2]))
+
+    def to_model(basis, t):
+        return t if basis is None else np.array([dot3(t, basis[0:3]), -dot3(t, basis[3:6]), dot3(t, basis[6:9])], f32)
+
+    light = (rng.randn(3) * 400).astype(f32)
+    for e in range(n):
+        x = hx[e]
+        basis = run.bases[x["basis"]] if x["basis"] >= 0 else None
+        bl = f32(x["backlerp"]); fl = f32(np.float64(1.0) - np.float64(bl))
+        mv = to_model(basis, (x["oldorigin"] - x["origin"]).astype(f32))
+        fr, ofr = hdr[x["frame"]], hdr[x["oldframe"]]
+        move = np.array([f32(f32(bl * f32(mv[k] + ofr[3 + k])) + f32(fl * fr[3 + k])) for k in range(3)], f32)
+        frontv = np.array([f32(fl * fr[k]) for k in range(3)], f32); backv = np.array([f32(bl * ofr[k]) for k in range(3)], f32)
+        want = host.entity_md2(blob, int(we["frame"][e]), int(we["oldframe"][e]), float(we["backlerp"][e]), we["origin"][e],
+                               we["oldorigin"][e], we["angles"][e])
+        for name, got in (("move", move), ("frontv", frontv), ("backv", backv)):
+            assert np.array_equal(got.view(np.uint32), np.asarray(want[name]).view(np.uint32)), (e, name)
+        assert f32(want["frontlerp"]) == fl
+        got = to_model(basis, (light - x["origin"]).astype(f32))
+        assert np.array_equal(got.view(np.uint32), host.point_to_model(light, we["origin"][e], we["angles"][e]).view(np.uint32)), e
