@@ -11,6 +11,7 @@
  */
 #include "bq2_gpu.h"
 #include <string.h>
+#include <stddef.h>
 
 /* ---- MD4 (RFC 1320), folded to 32 bits as Com_BlockChecksum does --------------------------------------- */
 #define ROL(x, n) (((x) << (n)) | ((x) >> (32 - (n))))
@@ -68,14 +69,22 @@ typedef struct {
 extern uint8_t bq2_host_normal2index(const float v[3]);          /* bq2_synth.c: Normal2Index M:25206-25223 */
 extern const float *bq2_host_anorms(void);                      /* bq2_synth.c: the 162 x 4 anorms table */
 
+/* a file's offsets need not be aligned: multi-byte fields are read and written through memcpy */
+static float   rd_f32(const uint8_t *p) { float v; memcpy(&v, p, 4); return v; }
+static int16_t rd_i16(const uint8_t *p) { int16_t v; memcpy(&v, p, 2); return v; }
+static void    wr_f32(uint8_t *p, float v) { memcpy(p, &v, 4); }
+static void    wr_i16(uint8_t *p, int16_t v) { memcpy(p, &v, 2); }
+
 bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float scale, int invert,
                                   void *blob_out, size_t blob_capacity, float *st_out)
 {
-    const md2_header *h = (const md2_header *)file;
+    md2_header hdr;
+    const md2_header *h = &hdr;
     const uint8_t *in = (const uint8_t *)file;
     uint8_t *out = (uint8_t *)blob_out;
     int i, j;
     if (!file || !blob_out || file_bytes < sizeof *h) return BQ2_E_INVALID;
+    memcpy(&hdr, file, sizeof hdr);
     if (scale <= 0.001) return BQ2_E_INVALID;                                   /* "invalid scale" */
     if (h->version != 8) return BQ2_E_INVALID;                                  /* ALIAS_VERSION */
     if (h->num_xyz <= 0 || h->num_st <= 0 || h->num_tris <= 0 || h->num_frames <= 0) return BQ2_E_INVALID;
@@ -88,17 +97,22 @@ bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float sca
         return BQ2_E_INVALID;
     memcpy(out, in, (size_t)h->ofs_end);                    /* little-endian host: LittleLong/LittleShort are identities */
     {
-        const int16_t *pin = (const int16_t *)(in + h->ofs_tris);
-        int16_t *pout = (int16_t *)(out + h->ofs_tris);
+        const uint8_t *pin = in + h->ofs_tris;
+        uint8_t *pout = out + h->ofs_tris;
         if (invert)                                         /* invert the index sequence, M:51274-51281 */
             for (i = 0; i < h->num_tris; i++)
-                for (j = 0; j < 3; j++) { pout[6*i + j] = pin[6*i + 2 - j]; pout[6*i + 3 + j] = pin[6*i + 3 + 2 - j]; }
+                for (j = 0; j < 3; j++) {
+                    wr_i16(pout + 2 * (6*i + j), rd_i16(pin + 2 * (6*i + 2 - j)));
+                    wr_i16(pout + 2 * (6*i + 3 + j), rd_i16(pin + 2 * (6*i + 3 + 2 - j)));
+                }
     }
     for (i = 0; i < h->num_frames; i++) {
-        const float *fi = (const float *)(in + h->ofs_frames + (size_t)i * h->framesize);
-        float *fo = (float *)(out + h->ofs_frames + (size_t)i * h->framesize);
-        for (j = 0; j < 3; j++) { fo[j] = fi[j] * scale; fo[3 + j] = fi[3 + j] * scale; }
-        if (invert) { fo[1] = -fo[1]; fo[4] = -fo[4]; }
+        const uint8_t *fi = in + h->ofs_frames + (size_t)i * h->framesize;
+        uint8_t *fo = out + h->ofs_frames + (size_t)i * h->framesize;
+        for (j = 0; j < 6; j++) {                           /* scale[3], translate[3]; y mirrored when inverted */
+            float v = rd_f32(fi + 4 * j) * scale;
+            wr_f32(fo + 4 * j, (invert && (j == 1 || j == 4)) ? -v : v);
+        }
     }
     if (invert) {                                           /* Mod_InvertNormal M:61850-61871, run by the loader at M:51657 */
         const float *an = bq2_host_anorms();
@@ -114,10 +128,10 @@ bq2_status bq2_host_md2_from_file(const void *file, size_t file_bytes, float sca
         }
     }
     if (st_out) {                                           /* fstvert_t, M:51322-51329 */
-        const int16_t *pst = (const int16_t *)(in + h->ofs_st);
+        const uint8_t *pst = in + h->ofs_st;
         float iw = 1.0 / h->skinwidth, ih = 1.0 / h->skinheight;
         for (i = 0; i < h->num_st; i++) {
-            float s = pst[2*i], t = pst[2*i + 1];
+            float s = rd_i16(pst + 4*i), t = rd_i16(pst + 4*i + 2);
             st_out[2*i] = (s - 0.5) * iw;
             st_out[2*i + 1] = (t - 0.5) * ih;
         }
@@ -231,17 +245,21 @@ typedef struct { int16_t point[3]; int16_t norm; } md3_file_vertex;             
 #include <math.h>
 extern void sincosf(float, float *, float *);
 
-static const md3_file_mesh *md3_mesh_at(const uint8_t *file, size_t bytes, const md3_file_header *h, int m, size_t *off_out)
+/* header of mesh m (a copy: the offsets of a file need not be aligned) and its offset; NULL when the chain of
+   meshsize fields leaves the file */
+static const md3_file_mesh *md3_mesh_at(const uint8_t *file, size_t bytes, const md3_file_header *h, int m,
+                                        md3_file_mesh *copy, size_t *off_out)
 {
-    size_t off = (size_t)h->ofs_meshes;
+    size_t off;
     int i;
+    if (h->ofs_meshes < 0) return NULL;
+    off = (size_t)h->ofs_meshes;
     for (i = 0;; i++) {
-        const md3_file_mesh *pm;
-        if (off + sizeof(md3_file_mesh) > bytes) return NULL;
-        pm = (const md3_file_mesh *)(file + off);
-        if (i == m) { if (off_out) *off_out = off; return pm; }
-        if (pm->meshsize <= 0) return NULL;
-        off += (size_t)pm->meshsize;
+        if (off > bytes || bytes - off < sizeof(md3_file_mesh)) return NULL;
+        memcpy(copy, file + off, sizeof *copy);
+        if (i == m) { if (off_out) *off_out = off; return copy; }
+        if (copy->meshsize <= 0) return NULL;
+        off += (size_t)copy->meshsize;
     }
 }
 
@@ -250,16 +268,19 @@ static const md3_file_mesh *md3_mesh_at(const uint8_t *file, size_t bytes, const
 bq2_status bq2_md3_file_info(const void *file, size_t bytes, int32_t *num_frames, int32_t *num_meshes,
                              int32_t *num_verts, int32_t *num_tris)
 {
-    const md3_file_header *h = (const md3_file_header *)file;
+    md3_file_header hdr;
+    const md3_file_header *h = &hdr;
+    md3_file_mesh mesh_copy;
     int m;
     if (!file || bytes < sizeof *h) return BQ2_E_INVALID;
+    memcpy(&hdr, file, sizeof hdr);
     if (h->version != 15) return BQ2_E_INVALID;                                   /* MD3_ALIAS_VERSION */
     if (h->num_frames <= 0 || h->num_meshes <= 0) return BQ2_E_INVALID;
     if (h->num_frames > 1024 || h->num_meshes > BQ2_MD3_MAX_MESHES) return BQ2_E_LIMIT;
     if (h->ofs_frames < 0 || (size_t)h->ofs_frames + (size_t)h->num_frames * sizeof(md3_file_frame) > bytes) return BQ2_E_INVALID;
     for (m = 0; m < h->num_meshes; m++) {
         size_t off;
-        const md3_file_mesh *pm = md3_mesh_at((const uint8_t *)file, bytes, h, m, &off);
+        const md3_file_mesh *pm = md3_mesh_at((const uint8_t *)file, bytes, h, m, &mesh_copy, &off);
         if (!pm || memcmp(pm->id, "IDP3", 4)) return BQ2_E_INVALID;               /* "wrong id" */
         if (pm->num_skins <= 0 || pm->num_tris <= 0 || pm->num_verts <= 0) return BQ2_E_INVALID;
         if (pm->num_skins > 32 || pm->num_tris > BQ2_MD3_MAX_TRIANGLES || pm->num_verts > BQ2_MD3_MAX_VERTS) return BQ2_E_LIMIT;
@@ -282,28 +303,33 @@ bq2_status bq2_md3_file_info(const void *file, size_t bytes, int32_t *num_frames
 bq2_status bq2_host_md3_mesh_from_file(const void *file, size_t bytes, int32_t mesh, float scale, int invert,
                                        float *frame_translate, void *vertexes, uint16_t *indexes, float *st)
 {
-    const md3_file_header *h = (const md3_file_header *)file;
+    md3_file_header hdr;
+    const md3_file_header *h = &hdr;
     const uint8_t *base = (const uint8_t *)file;
+    md3_file_mesh mesh_copy;
     const md3_file_mesh *pm;
     size_t off = 0;
     float invscale[3];
     int i, j, l, y;
     bq2_status s = bq2_md3_file_info(file, bytes, NULL, NULL, NULL, NULL);
     if (s != BQ2_OK) return s;
+    memcpy(&hdr, file, sizeof hdr);
     if (scale <= 0.001 || mesh < 0 || mesh >= h->num_meshes || !vertexes || !indexes) return BQ2_E_INVALID;
-    pm = md3_mesh_at(base, bytes, h, mesh, &off);
+    pm = md3_mesh_at(base, bytes, h, mesh, &mesh_copy, &off);
     if (!pm) return BQ2_E_INVALID;
     invscale[0] = (1.0 / 64) * scale; invscale[1] = invert ? -(1.0 / 64) * scale : (1.0 / 64) * scale; invscale[2] = (1.0 / 64) * scale;
     if (frame_translate) {
-        const md3_file_frame *pf = (const md3_file_frame *)(base + h->ofs_frames);
+        const uint8_t *pf = base + h->ofs_frames + offsetof(md3_file_frame, translate);
         for (i = 0; i < h->num_frames; i++) {
-            for (j = 0; j < 3; j++) frame_translate[3*i + j] = pf[i].translate[j] * scale;           /* M:50672 */
+            for (j = 0; j < 3; j++) frame_translate[3*i + j] = rd_f32(pf + sizeof(md3_file_frame) * (size_t)i + 4 * j) * scale;   /* M:50672 */
             if (invert) frame_translate[3*i + 1] = -frame_translate[3*i + 1];
         }
     }
     {
-        const uint32_t *pin = (const uint32_t *)(base + off + pm->ofs_tris);
-        for (j = 0; j < pm->num_tris; j++, pin += 3) {
+        const uint8_t *ptri = base + off + pm->ofs_tris;
+        for (j = 0; j < pm->num_tris; j++, ptri += 12) {
+            uint32_t pin[3];
+            memcpy(pin, ptri, 12);
             if (pin[0] >= (uint32_t)pm->num_verts || pin[1] >= (uint32_t)pm->num_verts || pin[2] >= (uint32_t)pm->num_verts) return BQ2_E_INVALID;
             indexes[3*j + 0] = (uint16_t)(invert ? pin[2] : pin[0]);
             indexes[3*j + 1] = (uint16_t)pin[1];
@@ -312,14 +338,15 @@ bq2_status bq2_host_md3_mesh_from_file(const void *file, size_t bytes, int32_t m
     }
     if (st) memcpy(st, base + off + pm->ofs_tcs, 8u * (size_t)pm->num_verts);
     {
-        const md3_file_vertex *pv = (const md3_file_vertex *)(base + off + pm->ofs_verts);
+        const uint8_t *pvb = base + off + pm->ofs_verts;
         uint8_t *out = (uint8_t *)vertexes;
         for (l = 0; l < h->num_frames; l++)
-            for (j = 0; j < pm->num_verts; j++, pv++, out += 16) {
-                float *pt = (float *)out, lat, lng, norma[3], slat, clat, slng, clng;
-                for (y = 0; y < 3; y++) pt[y] = (float)pv->point[y] * invscale[y];
-                lat = (pv->norm >> 8) & 0xff;
-                lng = (pv->norm & 0xff);
+            for (j = 0; j < pm->num_verts; j++, pvb += sizeof(md3_file_vertex), out += 16) {
+                float lat, lng, norma[3], slat, clat, slng, clng;
+                const int16_t norm = rd_i16(pvb + 6);
+                for (y = 0; y < 3; y++) wr_f32(out + 4 * y, (float)rd_i16(pvb + 2 * y) * invscale[y]);
+                lat = (norm >> 8) & 0xff;
+                lng = (norm & 0xff);
                 lat *= M_PI / 128;
                 lng *= M_PI / 128;
                 sincosf(lat, &slat, &clat);

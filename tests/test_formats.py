@@ -238,6 +238,53 @@ def test_md3_file_to_memory(oracle):
     assert L.bq2_md3_file_info(c.ptr(file), 300, None, None, None, None) == -1                  # truncated
 
 
+def test_malformed_and_unaligned_file_images(oracle):
+    """File images are untrusted bytes: offsets that leave the file (negative ones included) are refused, and a file
+    whose sections sit at odd offsets -- which the engine's x86 loader reads without complaint -- converts to the same
+    arrays as its aligned twin (the parsers read multi-byte fields through memcpy; tools/fuzz_host_parsers.py runs
+    them under ASan / UBSan)."""
+    rng = np.random.RandomState(3)
+    F, V, T = 2, 6, 4
+    mesh = dict(points=rng.randint(-3000, 3000, (F, V, 3)), norm=rng.randint(-32768, 32767, (F, V)),
+                tris=rng.randint(0, V, (T, 3)), st=rng.rand(V, 2).astype(np.float32))
+    file = build_md3_file([mesh, mesh], rng.randn(F, 3).astype(np.float32))
+    info = lambda f, n=None: L.bq2_md3_file_info(c.ptr(f), f.nbytes if n is None else n, None, None, None, None)
+    assert info(file) == 0
+    for field_ofs, value in ((100, -100), (100, -(1 << 31)), (100, file.nbytes - 50), (92, -8), (92, file.nbytes)):   # ofs_meshes, ofs_frames
+        bad = file.copy(); bad[field_ofs:field_ofs + 4].view("<i4")[0] = value
+        assert info(bad) == -1, (field_ofs, value)
+    m0 = 108 + F * 56                                              # first mesh header: ... num_verts +80, num_tris +84, ofs_tris +88, meshsize +104
+    for field_ofs, value in ((m0 + 88, -4), (m0 + 88, file.nbytes), (m0 + 96, 1 << 30), (m0 + 104, 0), (m0 + 104, -5), (m0 + 104, 1 << 30)):
+        bad = file.copy(); bad[field_ofs:field_ofs + 4].view("<i4")[0] = value
+        assert info(bad) == -1, (field_ofs, value)
+    # the same file with one byte inserted in front of the frames: every later section sits at an odd offset
+    odd = np.concatenate([file[:108], np.zeros(1, np.uint8), file[108:]])
+    h = odd[:108].view("<i4"); h[23] += 1; h[24] += 1; h[25] += 1; h[26] += 1      # ofs_frames, ofs_tags, ofs_meshes, ofs_end
+    assert info(odd) == 0
+    for k in range(2):
+        got = []
+        for f in (file, odd):
+            verts = np.zeros((F, V), synth.MD3_VERTEX); idx = np.zeros((T, 3), np.uint16); st = np.zeros((V, 2), np.float32)
+            tr = np.zeros((F, 3), np.float32)
+            assert L.bq2_host_md3_mesh_from_file(c.ptr(f), f.nbytes, k, 0.75, 1, c.ptr(tr), c.ptr(verts), c.ptr(idx), c.ptr(st)) == 0
+            got.append((verts.tobytes(), idx.tobytes(), st.tobytes(), tr.tobytes()))
+        assert got[0] == got[1]
+    # MD2: sections at odd offsets, and offsets that leave the file
+    blob = synth.md2(6, 5, 3, 9)
+    hdr = blob[:68].view("<i4").copy()
+    out = np.zeros(blob.nbytes + 8, np.uint8); st = np.zeros((int(hdr[7]), 2), np.float32)
+    conv = lambda f, o, s: L.bq2_host_md2_from_file(c.ptr(f), f.nbytes, 0.5, 1, c.ptr(o), o.nbytes, c.ptr(s))
+    assert conv(blob, out, st) == 0
+    odd2 = np.concatenate([blob[:68], np.zeros(1, np.uint8), blob[68:]])
+    odd2[:68].view("<i4")[11:17] += 1                                             # every ofs_* field
+    out2 = np.zeros_like(out); st2 = np.zeros_like(st)
+    assert conv(odd2, out2, st2) == 0
+    assert np.array_equal(out[68:blob.nbytes], out2[69:blob.nbytes + 1]) and np.array_equal(bits(st), bits(st2))
+    for field, value in ((13, -12), (14, -40), (12, -4), (16, blob.nbytes + 1), (14, blob.nbytes - 10), (4, -1), (10, 1 << 28)):
+        bad = blob.copy(); bad[:68].view("<i4")[field] = value
+        assert conv(bad, out, st) in (-1, -4), (field, value)
+
+
 @pytest.mark.gpu
 def test_md3_file_to_shadow_volume(gpu_ctx, oracle):
     """.md3 bytes -> meshes -> neighbours + tangent bytes on the device -> upload -> frame, against the oracle."""
