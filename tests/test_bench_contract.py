@@ -1,0 +1,45 @@
+"""bench.py's reference arm (`--impl reference`: the reference's own CPU path from oracle/_ref on the host cores)
+runs without a GPU, so its JSON line -- the keys the driver reads on both arms -- is checked here.  The b200 arm needs
+a device; on a box without one it must fail loudly, not fall back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "libbq2ref.so")
+
+
+def run_bench(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=300)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libbq2ref.so not built (needs /root/reference at build time)")
+def test_reference_arm_line():
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1                                         # ONE JSON line
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "tris/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "f32" and d["scaling"] == "weak"
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    assert d["gpu_launches"] == 0
+    # throughput is consistent with the step time: 4,096 pairs per step
+    assert abs(d["pairs_per_s"] * d["ms_per_step"] * 1e-3 - 4096) < 1
+
+
+def test_b200_arm_needs_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the b200 arm is what tests/ -m gpu and the driver's bench run exercise")
+    r = run_bench("--steps", "1", "--warmup", "0", "--no-cpu")
+    assert r.returncode != 0                                       # no CPU fallback: the run fails, it prints no result line
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{") and '"value"' in l]
