@@ -68,10 +68,10 @@ def algorithmic_bytes(n_ents, n_pairs, V, T, total_indices):
 
 
 def min_traffic_bytes(n_ents, n_pairs, V, T, total_indices):
-    """What THIS layout has to move at minimum: per entity two 4V-byte frames + an 80-byte record + the
+    """What THIS layout has to move at minimum: per entity two 4V-byte frames + the 128-byte record + the
     12T-byte index/neighbour table (read once per entity, not per pair) + 12V out; per pair a 48-byte
     record in, 12V + 4*ceil(T/32) + 4 + 4*I out."""
-    per_ent = 2 * 4 * V + 80 + 12 * T + 12 * V
+    per_ent = 2 * 4 * V + 128 + 12 * T + 12 * V
     per_pair = 48 + 12 * V + 4 * ((T + 31) // 32) + 4
     return n_ents * per_ent + n_pairs * per_pair + 4 * total_indices
 

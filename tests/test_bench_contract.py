@@ -43,3 +43,18 @@ def test_b200_arm_needs_a_gpu():
     r = run_bench("--steps", "1", "--warmup", "0", "--no-cpu")
     assert r.returncode != 0                                       # no CPU fallback: the run fails, it prints no result line
     assert not [l for l in r.stdout.splitlines() if l.startswith("{") and '"value"' in l]
+
+
+def test_byte_formulas_match_survey_8d():
+    """SURVEY.md 8(d) at C1 / C2 (V=258, T=512): entity 2,180 R + 3,096 W; pair 9,232 R + 3,096 + 64 + 4 + 4*I W;
+    `bytes = E*5,276 + E*L*(9,232 + 3,160 + 4*I + 4)`.  The layout's own minimum moves the 12-byte-per-triangle table
+    once per entity and a 48-byte pair record."""
+    sys.path.insert(0, ROOT)
+    import bench
+    E, Lt, V, T, I = 1024, 4, 258, 512, 2156
+    assert bench.algorithmic_bytes(1, 0, V, T, 0) == 2180 + 3096
+    assert bench.algorithmic_bytes(0, 1, V, T, I) == 9232 + 3096 + 64 + 4 * I + 4
+    assert bench.algorithmic_bytes(E, E * Lt, V, T, E * Lt * I) == E * 5276 + E * Lt * (9232 + 3160 + 4 * I + 4)
+    assert bench.min_traffic_bytes(1, 0, V, T, 0) == 2 * 4 * V + 128 + 12 * T + 12 * V
+    assert bench.min_traffic_bytes(0, 1, V, T, I) == 48 + 12 * V + 64 + 4 + 4 * I
+    assert bench.min_traffic_bytes(E, E * Lt, V, T, E * Lt * I) < bench.algorithmic_bytes(E, E * Lt, V, T, E * Lt * I)
