@@ -6,17 +6,23 @@ buffers) on BASELINE.json's configs[1]: 1,024 synthetic MD2 entities x 4 lights 
   python bench.py --impl reference [...]                          the reference's own CPU code, all host cores
 
 One "step" = one pass of the path over the whole batch = ONE launch of the fused kernel.
-  value     shadow-volume triangles/s (sum index_count / 3 / time) over EXACTLY K steps launched back to back between one
-            pair of CUDA events on the launching stream, max over ranks.  Inputs resident in HBM and larger than L2:
-            the steps cycle through a ring of resident frames (bq2_frame_keep), each drawing on its own device copy of
-            the models, so a cycle reads more key-frame / triangle-table / record bytes than the L2 holds (no flush).
-            The replays are launched with programmatic dependent launch: stream order of every write is kept, the
-            read-only front of the next step runs under the tail of the current one.
+  value     shadow-volume triangles/s (sum index_count / 3 / time) over EXACTLY K steps launched back to back FROM C
+            (bq2_resident_run) between one pair of CUDA events on the launching stream, max over ranks; the K-step
+            region is repeated (a barrier in front of each) and the median repeat is reported.  Inputs AND outputs are
+            resident in HBM and larger than L2: the steps cycle through a ring of resident frames (bq2_frame_keep_own),
+            each drawing on its own device copy of the models and writing its OWN result arrays, so a cycle reads and
+            writes several times what the L2 holds (no flush).  The replays carry programmatic dependent launch:
+            stream order of every write is kept, the read-only front of the next step runs under the tail of the
+            current one.
+  roofline  bound = HBM.  frac = UNIQUE bytes per launch (SURVEY 8(d) in its unique-input form: what the launch must
+            read and write once) / (timed region / K) / MEASURED_PEAKS hbm_gbs; SURVEY 8(d)'s per-pair form (table
+            bytes charged per pair) beside it; traffic = dram__bytes_read + dram__bytes_write per step, MEASURED IN
+            THIS RUN by a child process under ncu's range replay over the same K back-to-back steps.
   e2e       the same metric through the C ABI from HOST arrays: bq2_world_submit (host: validation, numbering,
             AngleVectors; H2D; record-building kernel + fused kernel; D2H of the per-pair counts) + bq2_frame_wait,
             four frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
-  roofline  SURVEY.md 8(d) algorithmic bytes per launch / (timed region / K), vs MEASURED_PEAKS.json; the time of ONE
-            launch alone after an L2 flush is reported beside it (isolated_launch_ms)
+  c3_strong BASELINE configs[2] as written: 65,536 entities x 8 lights sharded entity-major over the N GPUs
+            (strong scaling), same timing rules
   cpu_baseline  oracle/_ref (the unmodified reference, compiled headless) on the host cores, N=1 only
 
 The oracle (oracle/) is loaded ONLY by the cpu_baseline / --impl reference legs below, as the thing that
@@ -151,10 +157,179 @@ def make_scene(n_ents, lights, first_global_ent=0, total_ents=None, step=0):
     return we, wl, pe, pl
 
 
+METRIC = ("shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/extrusion index generation); "
+          "lerped verts/s alongside")
+
+
+def workload_config(name):
+    """The keys that define the workload -- identical on both arms (the driver compares them)."""
+    n_ents, lights, desc = WORKLOADS[name]
+    return {"workload": desc + " per GPU; one distinct model per entity; entity-major sharding, no data-path collective",
+            "entities_per_gpu": n_ents, "lights_per_entity": lights, "pairs_per_gpu": n_ents * lights,
+            "verts": 258, "tris": 512, "frames": FRAMES}
+
+
+def ring_size(l2_bytes, n_ents, lights, V, T, cap=32):
+    """Resident frames in the ring: enough that one cycle READS more than the L2 holds (outputs come on top)."""
+    step_input_bytes = n_ents * (2 * 4 * V + 12 * T + 128) + n_ents * lights * 48
+    return int(min(cap, max(1, -(-int(1.1 * l2_bytes) // step_input_bytes)))), step_input_bytes
+
+
+def build_ring(ctx, n_ents, lights, first, total_ents, ring, own_results, threads=8, chunk=1024):
+    """`ring` resident frames of n_ents entities x lights (scene steps 0..ring-1 of the global entity list, this
+    rank's entities [first, first + n_ents)), frame r drawing on its own device copy of the models and, with
+    own_results, writing its own result arrays.  Models are generated by `threads` host threads (C generator, GIL
+    released) a chunk at a time, so that 65,536 of them never sit in host memory at once."""
+    import berserkerquake2_b200 as bq2
+    from berserkerquake2_b200 import synth, host
+    from concurrent.futures import ThreadPoolExecutor
+    V, T = synth.sphere_dims(SLICES, RINGS)
+    t0 = time.time()
+    mids = np.zeros((ring, n_ents), np.int32)
+    nb, model_bytes = None, 0
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as pool:
+        for lo in range(0, n_ents, chunk):
+            hi = min(n_ents, lo + chunk)
+            blobs = list(pool.map(lambda e: synth.md2(SLICES, RINGS, FRAMES, first + e), range(lo, hi)))
+            if nb is None:
+                nb = host.md2_neighbours(blobs[0])                         # same topology for every sphere
+            for r in range(ring):
+                for e in range(lo, hi):
+                    mids[r, e] = ctx.upload_md2(blobs[e - lo], nb)
+                    model_bytes += FRAMES * 4 * V + 12 * T
+            del blobs
+    kept, ring_indices, scene0 = [], [], None
+    for r in range(ring):                              # frame r of the ring: scene step r on model copy r
+        we_r, wl_r, pe, pl = make_scene(n_ents, lights, first, total_ents, step=r)
+        we_r["model"] = mids[r]
+        ents_r, pairs_r = ctx.build_records(we_r, wl_r, pe, pl)
+        res = ctx.frame(ents_r, pairs_r, want=bq2.WANT_SHADOW)
+        assert res.overflow_pairs == 0 and int(res.total_indices) > 0
+        kept.append(ctx.keep(own_results=own_results))  # its records (and result arrays) stay resident in HBM
+        ring_indices.append(int(res.total_indices))
+        if r == 0:
+            scene0 = (we_r, wl_r, pe, pl, len(pairs_r))
+    return {"kept": kept, "indices": ring_indices, "scene0": scene0, "mids": mids, "model_bytes": model_bytes,
+            "setup_s": time.time() - t0, "V": V, "T": T}
+
+
+def timed_regions(ctx, kept, steps, repeats, barrier, dev, dist):
+    """`repeats` device-timed regions of EXACTLY `steps` back-to-back launches each (bq2_resident_run: launched from
+    C between two CUDA events on the launching stream), a barrier + synchronize in front of each; every region's time
+    is the MAX over ranks.  Returns (median region ms, all region ms)."""
+    from berserkerquake2_b200 import shard
+    ms = []
+    for r in range(repeats):
+        barrier()
+        ms.append(ctx.run_ring(kept, (r * steps) % len(kept), steps, timed=True))
+    barrier()
+    ms = shard.max_over_ranks(ms, dev, dist)
+    return float(np.median(ms)), [float(x) for x in ms]
+
+
+def roofline_block(n_ents, n_pairs, V, T, indices_per_launch, kernel_ms, kernel="bq2_frame_warp_kernel"):
+    peak, peak_src = peaks()
+    uniq = min_traffic_bytes(n_ents, n_pairs, V, T, indices_per_launch)
+    alg = algorithmic_bytes(n_ents, n_pairs, V, T, indices_per_launch)
+    sec = kernel_ms * 1e-3
+    return {"bound": "hbm", "achieved": uniq / sec / 1e9, "peak": peak, "unit": "GB/s", "frac": uniq / sec / 1e9 / peak,
+            "traffic": None, "peak_source": peak_src, "kernel": kernel, "kernel_ms": kernel_ms,
+            "bytes_per_launch": uniq,
+            "bytes_definition": "UNIQUE bytes of one launch = SURVEY 8(d) in its unique-input form: per entity read two "
+                                "4V-byte key-frame rows + the 128-byte record + the 12T-byte index/neighbour table "
+                                "(once per entity, as the kernel stages it), write 12V; per pair read the 48-byte "
+                                "record, write 12V + 4*ceil(T/32) + 4 + 4*I (I = measured index count)",
+            "frac_of_spec_8000": uniq / sec / 1e9 / 8000.0,
+            "survey_8d_per_pair_form": {"bytes_per_launch": alg, "achieved": alg / sec / 1e9, "frac": alg / sec / 1e9 / peak,
+                                        "note": "8(d) as tabulated charges 18T table bytes per PAIR; the kernel reads the "
+                                                "table once per entity, so this figure can exceed 1 and is not an HBM "
+                                                "fraction -- kept for continuity with round 1"}}
+
+
+# ---- DRAM traffic of the timed region, measured in this run ---------------------------------------------
+def traffic_probe(args):
+    """Child of measure_traffic(), run UNDER ncu: the same ring, the same K back-to-back launches, bracketed by
+    cudaProfilerStart/Stop.  Prints nothing the parent parses; ncu writes the counters."""
+    import torch
+    import berserkerquake2_b200 as bq2
+    from berserkerquake2_b200 import synth
+    n_ents, lights, _ = WORKLOADS[args.workload]
+    ctx = bq2.Context(0)
+    V, T = synth.sphere_dims(SLICES, RINGS)
+    l2 = int(getattr(torch.cuda.get_device_properties(0), "L2_cache_size", 126 << 20))
+    ring, _ = ring_size(l2, n_ents, lights, V, T)
+    R = build_ring(ctx, n_ents, lights, 0, n_ents, ring, own_results=ring > 1, threads=args.threads)
+    ctx.run_ring(R["kept"], 0, max(args.warmup, 3) + ring)
+    ctx.profiler_range(True)                            # range replay measures the range as one unit; application replay
+    ctx.run_ring(R["kept"], 0, args.steps)              # profiles the launches inside it one by one
+    ctx.profiler_range(False)
+    ctx.close()
+
+
+def measure_traffic(args, log_dir):
+    """dram__bytes_read.sum + dram__bytes_write.sum over the K back-to-back steps of the timed region, per step.
+    A child process repeats the region under ncu (a number TIMED under a profiler is never reported; byte counters are
+    not timings): first as one range (range replay over cudaProfilerStart/Stop: the launches overlap as they do in
+    the timed region), else per kernel (application replay: launches serialised, cache state natural)."""
+    import csv
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    os.makedirs(log_dir, exist_ok=True)
+    base = [sys.executable, os.path.abspath(__file__), "--_traffic_probe", "--workload", args.workload,
+            "--steps", str(args.steps), "--warmup", str(args.warmup), "--threads", str(args.threads)]
+    metrics = "dram__bytes_read.sum,dram__bytes_write.sum"
+    tries = [
+        ("range", "ncu --replay-mode app-range over cudaProfilerStart/Stop around the K back-to-back launches",
+         [ncu, "--replay-mode", "app-range", "--profile-from-start", "off", "--metrics", metrics, "--print-units", "base",
+          "--csv", "--clock-control", "none"]),
+        ("kernel", "ncu --replay-mode application, one pass, the K launches of the region profiled one by one",
+         [ncu, "--replay-mode", "application", "--profile-from-start", "off", "--metrics", metrics, "--print-units", "base",
+          "--csv", "--clock-control", "none", "-k", "regex:bq2_frame"]),
+    ]
+    why = []
+    for mode, how, cmd in tries:
+        log = os.path.join(log_dir, f"traffic_{args.workload}_{mode}.csv")
+        try:
+            r = subprocess.run(cmd + ["--log-file", log] + base + ["--probe-mode", mode], capture_output=True, text=True,
+                               timeout=args.traffic_timeout)
+        except (subprocess.TimeoutExpired, OSError) as e:
+            why.append(f"{mode}: {type(e).__name__}")
+            continue
+        if r.returncode != 0 or not os.path.exists(log):
+            why.append(f"{mode}: rc={r.returncode} {r.stderr.strip()[-200:]}")
+            continue
+        rd = wr = 0.0
+        rows = 0
+        with open(log, newline="") as f:
+            lines = [l for l in f if not l.startswith("==")]
+        hdr = None
+        for row in csv.reader(lines):
+            if hdr is None:
+                if "Metric Name" in row and "Metric Value" in row:
+                    hdr = {k: i for i, k in enumerate(row)}
+                continue
+            try:
+                name, val = row[hdr["Metric Name"]], float(row[hdr["Metric Value"]].replace(",", ""))
+            except (IndexError, ValueError):
+                continue
+            if name == "dram__bytes_read.sum":
+                rd += val; rows += 1
+            elif name == "dram__bytes_write.sum":
+                wr += val
+        if rows == 0:
+            why.append(f"{mode}: no counter rows in {os.path.basename(log)}")
+            continue
+        return {"bytes_per_step": (rd + wr) / args.steps, "read_per_step": rd / args.steps, "write_per_step": wr / args.steps,
+                "steps": args.steps, "rows": rows, "how": how}, None
+    return None, "; ".join(why)
+
+
 def run_gpu(args):
     import torch
     import berserkerquake2_b200 as bq2
-    from berserkerquake2_b200 import synth, host, _capi as c
+    from berserkerquake2_b200 import synth, host, shard, _capi as c
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -163,50 +338,22 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback "
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
     dist = None
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    n_ents, lights, desc = WORKLOADS[args.workload]
-    first, _ = host.shard_entities(n_ents * world, rank, world)           # weak scaling: n_ents per GPU
-    ctx = bq2.Context(local)
-    t0 = time.time()
-    V, T = synth.sphere_dims(SLICES, RINGS)
-    # Inputs larger than L2 instead of a flush between steps: RING resident frames, each on its own device copy of the
-    # models (a frame reads 2 key-frame rows + the triangle table per entity and its records), so that a cycle through
-    # the ring reads more than the L2 holds and every launch finds its inputs in HBM.
-    l2_bytes = int(getattr(torch.cuda.get_device_properties(local), "L2_cache_size", 126 << 20))
-    step_input_bytes = n_ents * (2 * 4 * V + 12 * T + 128) + n_ents * lights * 48
-    ring = int(min(32, max(2, -(-int(1.1 * l2_bytes) // step_input_bytes))))
-    nb = None
-    blobs = []
-    for e in range(n_ents):
-        blobs.append(synth.md2(SLICES, RINGS, FRAMES, first + e))
-        if nb is None:
-            nb = host.md2_neighbours(blobs[0])                             # same topology for every sphere
-    mids = np.zeros((ring, n_ents), np.int32)
-    model_bytes = 0
-    for r in range(ring):
-        for e in range(n_ents):
-            mids[r, e] = ctx.upload_md2(blobs[e], nb)
-            model_bytes += FRAMES * 4 * V + 12 * T
-    del blobs
-    setup_s = time.time() - t0
-
-    kept_frames, ring_indices = [], []
-    for r in range(ring):                              # frame r of the ring: scene step r on model copy r
-        we_r, wl_r, pe, pl = make_scene(n_ents, lights, first, n_ents * world, step=r)
-        we_r["model"] = mids[r]
-        ents_r, pairs_r = ctx.build_records(we_r, wl_r, pe, pl)
-        res = ctx.frame(ents_r, pairs_r, want=bq2.WANT_SHADOW)
-        assert res.overflow_pairs == 0 and int(res.total_indices) > 0
-        kept_frames.append(ctx.keep())                 # its records stay resident in HBM
-        ring_indices.append(int(res.total_indices))
-        if r == 0:
-            we, wl, n_pairs = we_r, wl_r, len(pairs_r)
-    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    if hasattr(os, "sched_setaffinity"):               # one host core per rank for the launching thread's neighbourhood:
+        cpus = sorted(os.sched_getaffinity(0))         # ranks share the box, the clock sampler and torchrun too
+        per = max(1, len(cpus) // max(world, 1))
+        mine = cpus[local * per:(local + 1) * per] or cpus
+        try:
+            os.sched_setaffinity(0, mine)
+        except OSError:
+            pass
+    threads = args.threads or max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
+    args.threads = threads
 
     def barrier():
         torch.cuda.synchronize()
@@ -214,10 +361,23 @@ def run_gpu(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    n_ents, lights, desc = WORKLOADS[args.workload]
+    first, _ = host.shard_entities(n_ents * world, rank, world)           # weak scaling: n_ents per GPU
+    ctx = bq2.Context(local)
+    V, T = synth.sphere_dims(SLICES, RINGS)
+    # Inputs AND outputs larger than L2 instead of a flush between steps: a ring of resident frames, each on its own
+    # device copy of the models and with its own result arrays.
+    l2_bytes = int(getattr(torch.cuda.get_device_properties(local), "L2_cache_size", 126 << 20))
+    ring, step_input_bytes = ring_size(l2_bytes, n_ents, lights, V, T)
+    R = build_ring(ctx, n_ents, lights, first, n_ents * world, ring, own_results=ring > 1, threads=threads)
+    kept_frames, ring_indices = R["kept"], R["indices"]
+    we, wl, pe, pl, n_pairs = R["scene0"]
+    mids, model_bytes, setup_s = R["mids"], R["model_bytes"], R["setup_s"]
+    result_bytes_per_frame = int(c.lib.bq2_resident_result_bytes(kept_frames[0]))
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+
     def steps_resident(k, start=0):
-        """k steps back to back on the ctx stream: ONE fused launch each, inputs resident, cycling through the ring"""
-        for i in range(k):
-            ctx.replay_kept(kept_frames[(start + i) % ring])
+        ctx.run_ring(kept_frames, start % ring, k)
 
     clocks = ClockSampler(local) if rank == 0 else None
     steps_resident(max(args.warmup, 3))
@@ -225,29 +385,24 @@ def run_gpu(args):
     while time.perf_counter() - t_spin < args.spinup:  # clocks have ramped, then start the timed region
         steps_resident(ring)
         torch.cuda.synchronize()
-    barrier()
     if clocks:
         clocks.mark()
     launches0 = ctx.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    steps_resident(args.steps)                         # EXACTLY K steps
-    ev1.record(stream)
-    barrier()
-    ms_total = float(ev0.elapsed_time(ev1))
-    launches = ctx.kernel_launches - launches0
-    total_indices = sum(ring_indices[i % ring] for i in range(args.steps))       # over the K timed steps
-    if clocks:                                         # the timed region can be shorter than nvidia-smi's
-        t_more = time.perf_counter()                   # period: keep the SAME steps running until it has
-        while clocks.since_mark() < 4 and time.perf_counter() - t_more < 3.0:   # seen a few samples
+    ms_total_max, region_ms = timed_regions(ctx, kept_frames, args.steps, args.repeats, barrier, dev, dist)
+    launches = (ctx.kernel_launches - launches0) // args.repeats
+    med_r = int(np.argsort(region_ms)[len(region_ms) // 2])               # the repeat that is reported
+    total_indices = sum(ring_indices[(med_r * args.steps + i) % ring] for i in range(args.steps))   # over its K steps
+    if clocks:                                         # the timed regions are shorter than nvidia-smi's period:
+        t_more = time.perf_counter()                   # keep the SAME steps running until it has seen a few samples
+        while clocks.since_mark() < 4 and time.perf_counter() - t_more < 3.0:
             steps_resident(ring)
             torch.cuda.synchronize()
         clocks.freeze()
     clock_info = clocks.stop() if clocks else None     # (the sampler polls the driver: not during the wall-clock leg)
     # informational: ONE launch alone between two events, L2 flushed before it by a 256 MiB memset (dirty lines), or by
     # the memset followed by a read of a second buffer (clean lines) -- the latency of an isolated launch
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
-    flush2 = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=f"cuda:{local}")
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    flush2 = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     iso = {}
     for name, clean in (("dirty", False), ("clean", True)):
         evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 50))]
@@ -287,12 +442,7 @@ def run_gpu(args):
         return fo.total_indices
 
     def e2e_run(k, timed=False):
-        """k frames through the public C ABI from HOST data.  Each frame: bq2_world_submit (host: per-entity
-        validation, numbering and AngleVectors -> pinned -> H2D; the record-building kernel + the fused kernel; D2H of
-        the per-pair index counts and totals) and bq2_frame_wait.  E2E_IN_FLIGHT frames in flight (the library's
-        documented mode: each frame has its own records, result arrays and stream, so frames i+1, i+2 are packed,
-        copied and computed while frame i is on the GPU and every frame's results stay valid for the consumer).
-        timed: the clock runs over k submit+wait iterations of the full pipeline (k frames in, k frames out)."""
+        """k frames through the public C ABI from HOST data, driven from Python (two ctypes calls per frame)."""
         tot = 0
         depth = E2E_IN_FLIGHT
         for _ in range(depth - 1):
@@ -364,44 +514,52 @@ def run_gpu(args):
                 evs3[i - 3][1].record(stream_s)
     torch.cuda.synchronize()
     shared_ms = float(np.median([a.elapsed_time(b) for a, b in evs3]))
+    del flush
 
-    # ---- reduce: max time over ranks; NCCL all_gather of the per-shard counters (the only collective) --
-    from berserkerquake2_b200 import shard
-    dev = f"cuda:{local}"
+    # ---- reduce: NCCL all_gather of the per-shard counters (the only collective of the path) ----------
     per_rank = shard.gather_counters([n_pairs * args.steps, n_ents * V * args.steps, total_indices // 3, total_indices,
                                       e2e_indices // 3], dev, dist)           # summed over the K timed steps
     g_pairs, g_verts, g_tris, g_indices, g_e2e_tris = [int(x) for x in per_rank.sum(0)]
-    ms_total_max, e2e_ms_max = shard.max_over_ranks([ms_total, e2e_s * 1e3], dev, dist)
+    (e2e_ms_max,) = shard.max_over_ranks([e2e_s * 1e3], dev, dist)
+
+    # ---- BASELINE configs[2] as written: 65,536 x 8 sharded entity-major over the N GPUs (strong scaling) ----------
+    for h in kept_frames:
+        ctx.free_kept(h)
+    ctx.close()
+    torch.cuda.empty_cache()
+    c3 = None
+    if not args.no_c3:
+        c3 = c3_strong_leg(args, local, rank, world, barrier, dev, dist, l2_bytes)
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps
-        peak, peak_src = peaks()
-        alg = algorithmic_bytes(n_ents, n_pairs, V, T, total_indices / args.steps)     # per launch (this rank's mean)
-        mint = min_traffic_bytes(n_ents, n_pairs, V, T, total_indices / args.steps)
-        k_ms = ms_per_step                                                 # one launch per step
         out = {
-            "metric": "shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/extrusion index "
-                      "generation); lerped verts/s alongside",
+            "metric": METRIC,
             "value": g_tris / (ms_total_max * 1e-3), "unit": "tris/s",
             "lerped_verts_per_s": g_verts / (ms_total_max * 1e-3),
             "pairs_per_s": g_pairs / (ms_total_max * 1e-3),
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc + " per GPU; one distinct model per entity; entity-major sharding, "
-                                          "no data-path collective",
-                       "entities_per_gpu": n_ents, "lights_per_entity": lights, "pairs_per_gpu": n_pairs,
-                       "verts": V, "tris": T, "frames": FRAMES, "model_bytes_in_hbm_per_gpu": model_bytes,
-                       "mean_indices_per_pair": total_indices / args.steps / n_pairs,
-                       "l2": f"not flushed: inputs larger than L2 -- the K steps cycle through a ring of {ring} resident frames "
-                             f"(scene steps 0..{ring - 1}), each on its own device copy of the {n_ents} models, so one cycle reads "
-                             f"{ring * step_input_bytes / 1e6:.0f} MB of key frames, triangle tables and records (L2: "
-                             f"{l2_bytes / 1e6:.0f} MB) besides streaming {ring} x the outputs through it",
-                       "resident_frames": ring, "input_bytes_per_step": step_input_bytes,
-                       "timing": "one pair of CUDA events on the ctx stream around the K back-to-back launches, max over ranks; "
-                                 "the launches carry programmatic stream serialization: all K steps run in stream order and "
-                                 "complete inside the events, the read-only front of step N+1 (record load, TMA staging, lerp, "
-                                 "triangle normals) overlaps the tail of step N; "
-                                 "roofline.isolated_launch_ms = one launch alone between two events after an L2 flush"},
+            "config": workload_config(args.workload),
+            "measurement": {
+                "model_bytes_in_hbm_per_gpu": model_bytes,
+                "mean_indices_per_pair": total_indices / args.steps / n_pairs,
+                "l2": f"not flushed: inputs and outputs larger than L2 -- the K steps cycle through a ring of {ring} resident "
+                      f"frames (scene steps 0..{ring - 1}), each on its own device copy of the {n_ents} models and, "
+                      f"{'with' if result_bytes_per_frame else 'WITHOUT'} result arrays of its own: one cycle reads "
+                      f"{ring * step_input_bytes / 1e6:.0f} MB of key frames, triangle tables and records and writes "
+                      f"{ring * (min_traffic_bytes(n_ents, n_pairs, V, T, total_indices / args.steps) - step_input_bytes) / 1e6:.0f}"
+                      f" MB of results to {ring} different sets of arrays (L2: {l2_bytes / 1e6:.0f} MB)",
+                "resident_frames": ring, "input_bytes_per_step": step_input_bytes,
+                "result_array_bytes_owned_per_frame": result_bytes_per_frame,
+                "timed_regions_ms": region_ms, "repeats": args.repeats,
+                "timing": f"EXACTLY K = {args.steps} launches back to back from C (bq2_resident_run) between one pair of CUDA "
+                          f"events on the launching stream; the region is run {args.repeats} times with a barrier + "
+                          "synchronize in front of each, each region's time is the max over ranks, the MEDIAN region is "
+                          "reported (all of them in timed_regions_ms).  The launches carry programmatic stream "
+                          "serialization: all K steps run in stream order and complete inside the events, the read-only "
+                          "front of step N+1 (record load, TMA staging, lerp, triangle normals) overlaps the tail of step "
+                          "N; roofline.isolated_launch_ms = one launch alone between two events after an L2 flush"},
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
                     "repeats": e2e_repeats, "ms_per_step_min_max_rank0": e2e_spread,
@@ -420,45 +578,86 @@ def run_gpu(args):
                             "frames in and K frames out); the loop itself is C on the public ABI (csrc/bq2_frame_loop.c), as "
                             "an engine would run it; ms_per_step_python_driver = the same calls made from Python; "
                             "ms_per_step_serial = one at a time; " % (e2e_repeats, E2E_IN_FLIGHT) +
-                            
                             "vertex/index buffers stay in HBM for the draw"},
             "shared_model_variant": {
-                "what": "SURVEY 8(d): the same frame with every entity instantiating ONE model; scored with the unique-"
-                        "input form of the byte formula (the model's frames and tables counted once)",
+                "what": "SURVEY 8(d): the same frame with every entity instantiating ONE model (one launch alone after an "
+                        "L2 flush); scored on its unique bytes (the model's frames and table counted once)",
                 "ms_per_step": shared_ms, "tris_per_s": shared_indices / 3 / (shared_ms * 1e-3),
-                "algorithmic_bytes_unique_input": algorithmic_bytes(n_ents, n_pairs, V, T, shared_indices)
-                    - (n_ents - 1) * 2 * (40 + 4 * V) - (n_pairs - 1) * 18 * T,
-                "frac": (algorithmic_bytes(n_ents, n_pairs, V, T, shared_indices) - (n_ents - 1) * 2 * (40 + 4 * V)
-                         - (n_pairs - 1) * 18 * T) / (shared_ms * 1e-3) / 1e9 / peak},
+                "unique_bytes": min_traffic_bytes(n_ents, n_pairs, V, T, shared_indices) - (n_ents - 1) * (2 * 4 * V + 12 * T),
+                "frac": (min_traffic_bytes(n_ents, n_pairs, V, T, shared_indices) - (n_ents - 1) * (2 * 4 * V + 12 * T))
+                        / (shared_ms * 1e-3) / 1e9 / peaks()[0]},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": alg / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (k_ms * 1e-3) / 1e9 / peak, "frac_of_spec_8000": alg / (k_ms * 1e-3) / 1e9 / 8000.0,
-                         "traffic": None,
-                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
-                         "kernel": "bq2_frame_warp_kernel", "kernel_ms": k_ms,
-                         "isolated_launch_ms": {"l2_flushed_by_memset": iso["dirty"], "l2_flushed_then_read": iso["clean"],
-                                                "what": "ONE launch between two events on an otherwise idle stream: adds "
-                                                        "the launch and completion latency that back-to-back steps hide"},
-                         "min_traffic_bytes_per_launch": mint,
-                         "achieved_min_traffic": mint / (k_ms * 1e-3) / 1e9,
-                         "frac_min_traffic": mint / (k_ms * 1e-3) / 1e9 / peak},
+            "roofline": roofline_block(n_ents, n_pairs, V, T, total_indices / args.steps, ms_per_step),
             "clocks": clock_info,
             "setup_s": setup_s,
         }
-        prof = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(prof):
-            try:
-                with open(prof) as f:
-                    out["roofline"]["traffic"] = json.load(f).get(args.workload)
-            except (OSError, ValueError):
-                pass
+        out["roofline"]["isolated_launch_ms"] = {
+            "l2_flushed_by_memset": iso["dirty"], "l2_flushed_then_read": iso["clean"],
+            "what": "ONE launch between two events on an otherwise idle stream: adds the launch and completion latency "
+                    "that back-to-back steps hide"}
+        if c3 is not None:
+            out["c3_strong"] = c3
+        if world == 1 and not args.no_traffic:
+            t, why = measure_traffic(args, os.path.join(ROOT, "gpurun_out"))
+            if t is not None:
+                out["roofline"]["traffic"] = t["bytes_per_step"]
+                out["roofline"]["traffic_detail"] = t
+                out["roofline"]["traffic_over_bytes"] = t["bytes_per_step"] / out["roofline"]["bytes_per_launch"]
+            else:
+                out["roofline"]["traffic_unmeasured"] = why
+        if out["roofline"]["traffic"] is None:          # not measured in this run: the committed capture, marked as such
+            prof = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(prof):
+                try:
+                    with open(prof) as f:
+                        out["roofline"]["traffic"] = json.load(f).get(args.workload)
+                        out["roofline"]["traffic_source"] = "profiles/traffic.json (a committed ncu capture, NOT this run)"
+                except (OSError, ValueError):
+                    pass
         if world == 1 and not args.no_cpu:
             out["cpu_baseline"] = cpu_arm(WORKLOADS["c2"][0], WORKLOADS["c2"][1], steps=None, warmup=1,
                                           budget_s=args.cpu_seconds)
         print(json.dumps(out), flush=True)
-    ctx.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def c3_strong_leg(args, local, rank, world, barrier, dev, dist, l2_bytes):
+    """BASELINE configs[2]: 65,536 entities x 8 lights, the global entity list sharded entity-major over the N ranks
+    (rank r owns a contiguous block of entities with all their lights; nothing crosses devices)."""
+    import berserkerquake2_b200 as bq2
+    from berserkerquake2_b200 import host, shard
+    E, Lt = args.c3_entities, 8
+    first, count = host.shard_entities(E, rank, world)
+    ctx = bq2.Context(local)
+    V, T = 258, 512
+    ring, step_input_bytes = ring_size(l2_bytes, count, Lt, V, T, cap=4)
+    R = build_ring(ctx, count, Lt, first, E, ring, own_results=ring > 1, threads=args.threads)
+    kept = R["kept"]
+    n_pairs = R["scene0"][4]
+    steps = args.steps
+    ctx.run_ring(kept, 0, max(3, min(args.warmup, 5)))
+    ms_max, region_ms = timed_regions(ctx, kept, steps, max(3, min(args.repeats, 5)), barrier, dev, dist)
+    med_r = int(np.argsort(region_ms)[len(region_ms) // 2])
+    idx = sum(R["indices"][(med_r * steps + i) % ring] for i in range(steps))
+    per_rank = shard.gather_counters([n_pairs * steps, count * V * steps, idx // 3, idx, count], dev, dist)
+    g_pairs, g_verts, g_tris, g_idx, g_ents = [int(x) for x in per_rank.sum(0)]
+    for h in kept:
+        ctx.free_kept(h)
+    ctx.close()
+    if rank != 0:
+        return None
+    ms_per_step = ms_max / steps
+    # roofline of the slowest rank's launch ~ the mean rank's bytes (shards are equal to within one entity)
+    rf = roofline_block(g_ents / world, g_pairs / steps / world, V, T, g_idx / steps / world, ms_per_step)
+    return {"workload": f"BASELINE configs[2]: {E} synthetic MD2 entities (V=258,T=512,198 frames) x {Lt} lights, one distinct model "
+                        f"per entity, sharded entity-major over {world} GPU(s): {g_ents // world} entities x {Lt} lights per GPU",
+            "scaling": "strong", "n_gpus": world, "entities_total": g_ents, "lights_per_entity": Lt, "pairs_total": g_pairs // steps,
+            "value": g_tris / (ms_max * 1e-3), "unit": "tris/s", "pairs_per_s": g_pairs / (ms_max * 1e-3),
+            "lerped_verts_per_s": g_verts / (ms_max * 1e-3), "ms_per_step": ms_per_step, "steps": steps,
+            "timed_regions_ms": region_ms, "resident_frames": ring, "setup_s": R["setup_s"],
+            "roofline": rf}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -470,6 +669,11 @@ def cpu_worker(args):
     from berserkerquake2_b200 import synth, host
     n_ents, lights = args.cpu_ents, args.cpu_lights
     lo, hi = args.cpu_lo, args.cpu_hi                                      # pair range of this worker
+    if args.cpu_pin >= 0 and hasattr(os, "sched_setaffinity"):
+        try:
+            os.sched_setaffinity(0, {args.cpu_pin})
+        except OSError:
+            pass
     ref_so = os.path.join(ROOT, "oracle", "_ref", "libbq2ref.so")
     if os.path.exists(ref_so):
         lib = C.CDLL(ref_so); fn = lib.bq2ref_md2_world_bench; lib.bq2ref_init()
@@ -506,8 +710,11 @@ def cpu_worker(args):
 
 
 def cpu_arm(n_ents, lights, steps, warmup, budget_s=12.0, cores=None):
-    """Each step = the whole batch (n_ents x lights pairs) once, split over one process per core."""
-    cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    """Each step = the whole batch (n_ents x lights pairs) once, split over one process per core, every process
+    pinned to its own core.  A measurement = one batch of `passes` back-to-back passes on all workers at once; at
+    least five batches are run (more until the budget is spent), the MEDIAN batch is reported with the min / max."""
+    cpus = sorted(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else list(range(os.cpu_count() or 1))
+    cores = cores or len(cpus)
     n_pairs = n_ents * lights
     cores = max(1, min(cores, n_pairs))
     kind = "reference" if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libbq2ref.so")) else "port"
@@ -515,7 +722,8 @@ def cpu_arm(n_ents, lights, steps, warmup, budget_s=12.0, cores=None):
     for w in range(cores):
         lo, hi = n_pairs * w // cores, n_pairs * (w + 1) // cores
         procs.append(subprocess.Popen([sys.executable, os.path.abspath(__file__), "--_cpu_worker", "--cpu-ents", str(n_ents),
-                                       "--cpu-lights", str(lights), "--cpu-lo", str(lo), "--cpu-hi", str(hi)],
+                                       "--cpu-lights", str(lights), "--cpu-lo", str(lo), "--cpu-hi", str(hi),
+                                       "--cpu-pin", str(cpus[w % len(cpus)])],
                                       stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1))
     for p in procs:
         assert p.stdout.readline().strip() == "ready"
@@ -532,24 +740,23 @@ def cpu_arm(n_ents, lights, steps, warmup, budget_s=12.0, cores=None):
     run(max(warmup, 1))
     while time.perf_counter() - t_warm < 0.5:
         run(max(warmup, 1))
-    if steps is not None:
-        k = steps
-        s_per_step, tot = run(k)
-    else:                                               # bounded sample: batches of 20 passes until the budget is spent
-        times, k, t_begin = [], 0, time.perf_counter()
-        while time.perf_counter() - t_begin < budget_s and k < 20000:
-            dt, tot = run(20)
-            times.append(dt); k += 20
-        s_per_step = float(np.mean(times))
+    passes = steps if steps is not None else 20         # a FIXED number of passes per batch
+    times, t_begin = [], time.perf_counter()
+    while len(times) < 5 or (time.perf_counter() - t_begin < budget_s and len(times) < 400):
+        dt, tot = run(passes)
+        times.append(dt)
     for p in procs:
         p.stdin.write("quit\n"); p.stdin.flush(); p.wait(timeout=10)
+    s_per_step = float(np.median(times))
     V, T = 258, 512
     return {"value": tot / 3 / s_per_step, "unit": "tris/s", "cores": cores, "kind": kind,
             "lerped_verts_per_s": n_pairs * V / s_per_step, "pairs_per_s": n_pairs / s_per_step,
-            "ms_per_step": s_per_step * 1e3, "steps": k,
-            "sample": f"{k} passes over the whole {n_ents} x {lights} batch ({n_pairs} pairs, {tot // 3} tris per pass), "
-                      f"one process per core, each looping the reference's R_DrawAliasShadowVolume over its slice, no "
-                      f"synchronisation between passes (time per pass = the slowest process's total / passes)"}
+            "ms_per_step": s_per_step * 1e3, "steps": passes, "batches": len(times),
+            "ms_per_step_min_max": [min(times) * 1e3, max(times) * 1e3],
+            "sample": f"{len(times)} batches of {passes} passes over the whole {n_ents} x {lights} batch ({n_pairs} pairs, "
+                      f"{tot // 3} tris per pass), one process per core, each pinned to its core and looping the reference's "
+                      f"R_DrawAliasShadowVolume over its slice, no synchronisation between passes (time per pass = the "
+                      f"slowest process's total / passes); the median batch is reported, min / max beside it"}
 
 
 def run_reference(args):
@@ -557,16 +764,17 @@ def run_reference(args):
     if rank != 0:
         return
     n_ents, lights, desc = WORKLOADS["c2"]
-    r = cpu_arm(n_ents, lights, steps=args.steps, warmup=max(args.warmup, 1))
-    out = {"impl": "reference", "metric": "shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/"
-                                          "extrusion index generation); lerped verts/s alongside",
+    r = cpu_arm(n_ents, lights, steps=args.steps, warmup=max(args.warmup, 1), budget_s=min(args.cpu_seconds, 6.0))
+    out = {"impl": "reference", "metric": METRIC,
            "value": r["value"], "unit": "tris/s", "lerped_verts_per_s": r["lerped_verts_per_s"],
            "pairs_per_s": r["pairs_per_s"], "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(args.warmup, 1),
            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": desc + "; the reference's CPU path (R_DrawAliasShadowVolume per pair) on the host "
-                                         "cores; the reference lerps once per PAIR, so lerped verts/s counts V per pair",
-                      "entities": n_ents, "lights_per_entity": lights},
+           "config": workload_config("c2"),
+           "measurement": {"what": "the reference's CPU path (the whole R_DrawAliasShadowVolume per pair) on the host cores; the "
+                                   "reference lerps once per PAIR, so lerped verts/s counts V per pair; the same batch whatever "
+                                   "--gpus says (the reference has one process image per core, not per GPU)",
+                           "batches": r["batches"], "ms_per_step_min_max": r["ms_per_step_min_max"]},
            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
            "e2e": {"value": r["value"], "unit": "tris/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -588,9 +796,20 @@ def main():
     ap.add_argument("--cpu-lights", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-lo", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--cpu-hi", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-pin", type=int, default=-1, help=argparse.SUPPRESS)
+    ap.add_argument("--repeats", type=int, default=11, help="device-timed regions of K steps each; the median is reported")
+    ap.add_argument("--threads", type=int, default=0, help="host threads generating the synthetic models (0 = this rank's cores)")
+    ap.add_argument("--no-c3", action="store_true", help="skip the strong-scaling leg (BASELINE configs[2])")
+    ap.add_argument("--c3-entities", type=int, default=65536)
+    ap.add_argument("--no-traffic", action="store_true", help="skip the in-run DRAM traffic measurement (ncu child)")
+    ap.add_argument("--traffic-timeout", type=float, default=240.0)
+    ap.add_argument("--_traffic_probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--probe-mode", default="range", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args._cpu_worker:
         return cpu_worker(args)
+    if args._traffic_probe:
+        return traffic_probe(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

@@ -5,7 +5,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "libbq2gpu.so")
+# BQ2_LIB: a diagnostic build of the SAME library (make TIMELINE=1 / CHECK=1 into another file) for tools/ -- still the
+# CUDA library, still no fallback
+lib_path = os.environ.get("BQ2_LIB") or os.path.join(_HERE, "libbq2gpu.so")
 if not os.path.exists(lib_path):
     raise ImportError(
         f"{lib_path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
@@ -103,7 +105,13 @@ EXPORTS_GPU_H = [
     _sig("bq2_frame_wait", C.c_int, vp, C.POINTER(FrameOut)),
     _sig("bq2_frame_replay", C.c_int, vp),
     _sig("bq2_frame_keep", C.c_int, vp, C.POINTER(vp)),
+    _sig("bq2_frame_keep_own", C.c_int, vp, C.POINTER(vp)),
+    _sig("bq2_resident_result_bytes", u64, vp),
     _sig("bq2_resident_replay", C.c_int, vp, vp),
+    _sig("bq2_resident_run", C.c_int, vp, C.POINTER(vp), i32, i32, i32, C.POINTER(f32)),
+    _sig("bq2_resident_download", C.c_int, vp, vp, C.c_int, u64, u64, vp),
+    _sig("bq2_hash_results", C.c_int, vp, vp, vp, i32),
+    _sig("bq2_profiler_range", C.c_int, vp, C.c_int),
     _sig("bq2_resident_free", None, vp, vp),
     _sig("bq2_download", C.c_int, vp, C.c_int, u64, u64, vp),
     _sig("bq2_host_index_counts", C.POINTER(u32), vp),

@@ -233,14 +233,38 @@ class Context:
         """Re-launch the last frame's kernel on the records already in HBM (no copies, no sync)."""
         self._check(c.lib.bq2_frame_replay(self._h))
 
-    def keep(self):
-        """bq2_frame_keep: a handle to the last (host-built, completed) frame's records, for replay_kept()."""
+    def keep(self, own_results=False):
+        """bq2_frame_keep / bq2_frame_keep_own: a handle to the last (host-built, completed) frame's records, for
+        replay_kept() / run_ring(); own_results: the kept frame gets result arrays of its own."""
         h = C.c_void_p()
-        self._check(c.lib.bq2_frame_keep(self._h, C.byref(h)))
+        self._check((c.lib.bq2_frame_keep_own if own_results else c.lib.bq2_frame_keep)(self._h, C.byref(h)))
         return h
 
     def replay_kept(self, handle):
         self._check(c.lib.bq2_resident_replay(self._h, handle))
+
+    def run_ring(self, handles, start, k, timed=False):
+        """bq2_resident_run: k replays launched from C, handles[(start + i) % len]; timed: returns the milliseconds
+        between two CUDA events on the stream around the k launches (the call waits for the second)."""
+        arr = (C.c_void_p * len(handles))(*[h.value if isinstance(h, C.c_void_p) else h for h in handles])
+        ms = C.c_float(0.0)
+        self._check(c.lib.bq2_resident_run(self._h, arr, len(handles), int(start), int(k), C.byref(ms) if timed else None))
+        return float(ms.value) if timed else None
+
+    def download_kept(self, handle, which, first, count, dtype):
+        buf = np.zeros(int(count), dtype)
+        if count:
+            self._check(c.lib.bq2_resident_download(self._h, handle, which, int(first), int(count), c.ptr(buf)))
+        return buf
+
+    def hash_results(self, n_pair_slots, handle=None):
+        """bq2_hash_results: one uint64 per pair slot over the frame's lerped / extruded / facing / count / stream."""
+        out = np.zeros(int(n_pair_slots), np.uint64)
+        self._check(c.lib.bq2_hash_results(self._h, handle, c.ptr(out), int(n_pair_slots)))
+        return out
+
+    def profiler_range(self, on):
+        self._check(c.lib.bq2_profiler_range(self._h, 1 if on else 0))
 
     def free_kept(self, handle):
         c.lib.bq2_resident_free(self._h, handle)

@@ -11,6 +11,7 @@
  * returns an error.
  */
 #include <cuda_runtime.h>
+#include <cuda_profiler_api.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -129,6 +130,16 @@ struct bq2_resident {                   /* bq2_frame_keep: a frame's device reco
     int state = 0;
     bq2_launch L{};
     FrameState::KLaunch k_warp, k_team;
+    /* bq2_frame_keep_own: the frame's result arrays are its own (a ring of such frames writes a different set of
+       output lines on every step instead of overwriting one set that stays in L2) */
+    bool own = false;
+    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
+    DevBuf<uint32_t> facing_bits, indices, index_count;
+    size_t result_bytes = 0;
+    void release() {
+        records.release(); lerped.release(); extruded.release(); normals.release(); tangents.release(); binormals.release();
+        lightp.release(); tsh.release(); facing_bits.release(); indices.release(); index_count.release();
+    }
 };
 
 struct bq2_ctx {
@@ -231,6 +242,27 @@ struct md2_header {
 
 inline uint32_t up16(uint32_t x) { return (x + 15u) & ~15u; }
 
+/* The reference's load-time checks on a dmdl_t image (M:51247-51264) plus the bounds of the two sections this
+   library reads; shared by every entry point that takes an MD2 blob.  Returns NULL when the image is fine. */
+const char *md2_header_problem(const md2_header *h, size_t blob_bytes, bq2_status *st)
+{
+    const int V = h->num_xyz, T = h->num_tris, F = h->num_frames;
+    *st = BQ2_E_INVALID;
+    if (h->version != 8) return "wrong version number";
+    if (V <= 0) return "model has no vertices";
+    if (T <= 0) return "model has no triangles";
+    if (F <= 0) return "model has no frames";
+    *st = BQ2_E_LIMIT;
+    if (V > BQ2_MD2_MAX_VERTS) return "model has too many vertices";
+    if (T > BQ2_MD2_MAX_TRIANGLES) return "model has too many triangles";
+    *st = BQ2_E_INVALID;
+    if (h->framesize < 40 + 4 * V || h->ofs_tris < 0 || h->ofs_frames < 0 ||
+        (size_t)h->ofs_tris + 12u * (size_t)T > blob_bytes ||
+        (size_t)h->ofs_frames + (size_t)F * (size_t)h->framesize > blob_bytes)
+        return "offsets run past the blob";
+    return nullptr;
+}
+
 /* index + neighbour table -> Tp records {a, b, c, n0+1} (8 B) followed by Tp records {n1+1, n2+1} (4 B);
    neighbour + 1 so that 0 means "open edge" and no sign extension is needed on the device */
 void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t *nb /*[T][3] or null*/, int16_t *dst)
@@ -249,6 +281,7 @@ void pack_tri_table(int T, int Tp, const int32_t *idx /*[T][3]*/, const int32_t 
 bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F, int overlap = 0)
 {
     bq2_launch L = F.launch;
+    L.seq = (uint32_t)ctx->launches;
     if (F.k_warp.n) {
         L.n_ent_slots = F.k_warp.n;
         CK((cudaError_t)bq2_launch_frame_warp(&L, F.k_warp.max_V, F.k_warp.max_T, F.k_warp.any_md2, F.stream, overlap),
@@ -399,17 +432,10 @@ try {
     if (!blob || !model_id || blob_bytes < sizeof(md2_header)) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: bad arguments");
     const md2_header *h = (const md2_header *)blob;
     const int V = h->num_xyz, T = h->num_tris, F = h->num_frames;
-    /* the reference's load-time checks, M:51247-51264 */
-    if (h->version != 8) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: wrong version number");
-    if (V <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: model has no vertices");
-    if (V > BQ2_MD2_MAX_VERTS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md2: model has too many vertices");
-    if (T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: model has no triangles");
-    if (T > BQ2_MD2_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md2: model has too many triangles");
-    if (F <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: model has no frames");
-    if (h->framesize < 40 + 4 * V || h->ofs_tris < 0 || h->ofs_frames < 0 ||
-        (size_t)h->ofs_tris + 12u * (size_t)T > blob_bytes ||
-        (size_t)h->ofs_frames + (size_t)F * (size_t)h->framesize > blob_bytes)
-        return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: offsets run past the blob");
+    {   /* the reference's load-time checks, M:51247-51264 */
+        bq2_status hs; const char *why = md2_header_problem(h, blob_bytes, &hs);
+        if (why) { static thread_local std::string msg; msg = std::string("bq2_upload_md2: ") + why; return fail(ctx, hs, msg.c_str()); }
+    }
     const unsigned char *base = (const unsigned char *)blob;
     const int16_t *tri = (const int16_t *)(base + h->ofs_tris);
     std::vector<int32_t> idx(3 * (size_t)T);
@@ -623,7 +649,8 @@ try {
     PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
     const int nE = fd->n_ents, nP = fd->n_pairs;
     const int nModels = (int)ctx->models.size();
-    const uint32_t want = fd->want;
+    if (fd->want & ~BQ2_WANT_PUBLIC_MASK) return fail(ctx, BQ2_E_INVALID, "bq2_frame: unknown bits in want");
+    const uint32_t want = fd->want & ~BQ2_WANT_TABLES;
     Trace &tr = ctx->trace; tr.start(); tr.n++;
 
     /* ---- entity slots ------------------------------------------------------------------------- */
@@ -798,8 +825,9 @@ try {
     tr.lap(5);
     if (rec_bytes)
         CK(cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(records)");
-    /* slots of non-casting MD3 meshes are never written by a kernel: only then is the clear needed */
-    if (nPS && n_dev_pairs != (uint32_t)nPS)
+    /* slots of non-casting MD3 meshes are never written by a kernel, and a frame without BQ2_WANT_SHADOW writes no
+       count at all: only then is the clear needed */
+    if (nPS && (n_dev_pairs != (uint32_t)nPS || !(want & BQ2_WANT_SHADOW)))
         CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * (size_t)nPS, F.stream), "cudaMemset(index_count)");
 
     bq2_launch &L = F.launch;
@@ -936,11 +964,11 @@ try {
         return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: bad arguments");
     const md2_header *h = (const md2_header *)blob;
     const int V = h->num_xyz, T = h->num_tris, F = h->num_frames, NS = h->num_st;
-    if (V <= 0 || T <= 0 || F <= 0 || NS <= 0 || V > BQ2_MD2_MAX_VERTS || T > BQ2_MD2_MAX_TRIANGLES)
-        return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md2_tangents: model outside the MD2 limits");
-    if (h->framesize < 40 + 4 * V || (size_t)h->ofs_tris + 12u * (size_t)T > blob_bytes ||
-        (size_t)h->ofs_frames + (size_t)F * (size_t)h->framesize > blob_bytes)
-        return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: offsets run past the blob");
+    {
+        bq2_status hs; const char *why = md2_header_problem(h, blob_bytes, &hs);
+        if (why) { static thread_local std::string msg; msg = std::string("bq2_gpu_md2_tangents: ") + why; return fail(ctx, hs, msg.c_str()); }
+        if (NS <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: model has no texture coordinates");
+    }
     const unsigned char *base = (const unsigned char *)blob;
     const int16_t *tri = (const int16_t *)(base + h->ofs_tris);
     for (int t = 0; t < T; t++) for (int k = 0; k < 3; k++)
@@ -1137,6 +1165,7 @@ try {
     PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
     const int nE = wd->n_ents, nP = wd->n_pairs, nL = wd->n_lights;
     const int nModels = (int)ctx->models.size();
+    if (wd->want & ~BQ2_WANT_PUBLIC_MASK) return fail(ctx, BQ2_E_INVALID, "bq2_world: unknown bits in want");
     const uint32_t want = wd->want;
 
     if (ctx->model_rows.size() != ctx->models.size()) {
@@ -1308,8 +1337,11 @@ try {
         } else if (copy_end > off_xf)
             CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, copy_end - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
         if (st) st->mark(1, F.stream);
-        CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
         Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;         /* the entity records are always built */
+        if (Wl.n_pairs)
+            CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
+        else        /* no pair thread runs: nothing writes the per-pair counts, clear them with the rest */
+            CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * (cnt_word + 2 * (size_t)nE), F.stream), "cudaMemset(counts, totals, pair lists)");
         if (nP || nE) {
             CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
             ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
@@ -1365,13 +1397,14 @@ try {
     if (!ctx) return BQ2_E_INVALID;
     FrameState &F = ctx->fs[ctx->cur];
     if (!ctx->submitted || !F.n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (F.world_mode)                                            /* the kernels add to the totals: start from zero */
         CK(cudaMemsetAsync(F.wlaunch.totals, 0, 2 * sizeof(unsigned long long), F.stream), "cudaMemset(totals)");
     return launch_kernels(ctx, F, /*overlap=*/1);
 } catch (...) { return guard_exception(ctx); }
 
-bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out)
-try {
+static bq2_status frame_keep_impl(bq2_ctx *ctx, bq2_resident **out, bool own)
+{
     if (!ctx || !out) return BQ2_E_INVALID;
     *out = nullptr;
     FrameState &F = ctx->fs[ctx->cur];
@@ -1384,24 +1417,40 @@ try {
     if (!r) return fail(ctx, BQ2_E_NOMEM, "bq2_frame_keep: out of host memory");
     cudaError_t e = r->records.ensure(std::max<size_t>(bytes, 16));
     if (e == cudaSuccess) e = cudaMemcpyAsync(r->records.p, F.d_records.p, bytes, cudaMemcpyDeviceToDevice, F.stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(F.stream);
-    if (e != cudaSuccess) { r->records.release(); delete r; return fail_cuda(ctx, e, "bq2_frame_keep"); }
     r->state = ctx->cur; r->L = F.launch; r->k_warp = F.k_warp; r->k_team = F.k_team;
     r->L.ents = (const bq2_dev_ent *)r->records.p;
     r->L.pairs = (const bq2_dev_pair *)(r->records.p + ((const unsigned char *)F.launch.pairs - F.d_records.p));
+    if (own) {
+        /* a set of result arrays of the frame's own, as large as the state's, holding the same results */
+        r->own = true;
+        #define BQ2_OWN(field) do { if (e == cudaSuccess && F.field.p) { e = r->field.ensure(F.field.cap); \
+            if (e == cudaSuccess) e = cudaMemcpyAsync(r->field.p, F.field.p, F.field.cap * sizeof(*F.field.p), cudaMemcpyDeviceToDevice, F.stream); \
+            r->L.field = r->field.p; r->result_bytes += F.field.cap * sizeof(*F.field.p); } } while (0)
+        BQ2_OWN(lerped); BQ2_OWN(extruded); BQ2_OWN(facing_bits); BQ2_OWN(indices); BQ2_OWN(index_count);
+        BQ2_OWN(normals); BQ2_OWN(tangents); BQ2_OWN(binormals); BQ2_OWN(lightp); BQ2_OWN(tsh);
+        #undef BQ2_OWN
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(F.stream);
+    if (e != cudaSuccess) { r->release(); delete r; return fail_cuda(ctx, e, "bq2_frame_keep"); }
     *out = r;
     return BQ2_OK;
-} catch (...) { return guard_exception(ctx); }
+}
 
-bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
-try {
-    if (!ctx || !r) return BQ2_E_INVALID;
+bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out)
+try { return frame_keep_impl(ctx, out, false); } catch (...) { return guard_exception(ctx); }
+bq2_status bq2_frame_keep_own(bq2_ctx *ctx, bq2_resident **out)
+try { return frame_keep_impl(ctx, out, true); } catch (...) { return guard_exception(ctx); }
+
+static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r)
+{
     FrameState &F = ctx->fs[r->state];
-    if (r->L.lerped != F.lerped.p || r->L.extruded != F.extruded.p || r->L.indices != F.indices.p ||
-        r->L.index_count != F.index_count.p || r->L.facing_bits != F.facing_bits.p || r->L.tri_normals != F.tri_normals.p ||
-        r->L.meshes != ctx->d_meshes.p)
+    if (!r->own && (r->L.lerped != F.lerped.p || r->L.extruded != F.extruded.p || r->L.indices != F.indices.p ||
+        r->L.index_count != F.index_count.p || r->L.facing_bits != F.facing_bits.p))
         return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the result arrays of that frame state were re-allocated");
+    if (r->L.tri_normals != F.tri_normals.p || r->L.meshes != ctx->d_meshes.p)
+        return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the mesh table or the scratch rows of that frame state were re-allocated");
     bq2_launch L = r->L;
+    L.seq = (uint32_t)ctx->launches;
     if (r->k_warp.n) {
         L.n_ent_slots = r->k_warp.n;
         CK((cudaError_t)bq2_launch_frame_warp(&L, r->k_warp.max_V, r->k_warp.max_T, r->k_warp.any_md2, F.stream, /*overlap=*/1), "launch(bq2_frame_warp_kernel)");
@@ -1413,14 +1462,91 @@ try {
         ctx->launches++;
     }
     return BQ2_OK;
+}
+
+bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
+try {
+    if (!ctx || !r) return BQ2_E_INVALID;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    return resident_launch(ctx, r);
 } catch (...) { return guard_exception(ctx); }
+
+/* k replays launched from C: ring[(start + i) % n_ring] for i = 0 .. k-1, all on the stream of the ring's frame state.
+   ms != NULL: the launches are bracketed by two CUDA events on that stream and the call returns their distance after
+   waiting for the second (the device-timed region of bench.py: no Python between the launches). */
+bq2_status bq2_resident_run(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k, float *ms)
+try {
+    if (!ctx || !ring || n_ring <= 0 || k < 0 || start < 0) return BQ2_E_INVALID;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    for (int i = 0; i < n_ring; i++) {
+        if (!ring[i]) return fail(ctx, BQ2_E_INVALID, "bq2_resident_run: NULL frame in the ring");
+        if (ring[i]->state != ring[0]->state) return fail(ctx, BQ2_E_INVALID, "bq2_resident_run: the frames of a ring must come from one frame state (one stream)");
+    }
+    cudaStream_t s = ctx->fs[ring[0]->state].stream;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms) {
+        CK(cudaEventCreate(&e0), "cudaEventCreate"); 
+        cudaError_t ce = cudaEventCreate(&e1);
+        if (ce != cudaSuccess) { cudaEventDestroy(e0); return fail_cuda(ctx, ce, "cudaEventCreate"); }
+        cudaEventRecord(e0, s);
+    }
+    bq2_status st = BQ2_OK;
+    for (int i = 0; i < k && st == BQ2_OK; i++) st = resident_launch(ctx, ring[(start + i) % n_ring]);
+    if (ms) {
+        cudaError_t ce = cudaEventRecord(e1, s);
+        if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+        if (ce == cudaSuccess) ce = cudaEventElapsedTime(ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        if (st == BQ2_OK && ce != cudaSuccess) return fail_cuda(ctx, ce, "bq2_resident_run(events)");
+    }
+    return st;
+} catch (...) { return guard_exception(ctx); }
+
+uint64_t bq2_resident_result_bytes(const bq2_resident *r) { return r ? (uint64_t)r->result_bytes : 0; }
 
 void bq2_resident_free(bq2_ctx *ctx, bq2_resident *r)
 {
     if (!r) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->fs[r->state].stream); }
-    r->records.release();
+    r->release();
     delete r;
+}
+
+/* One 64-bit hash per pair slot over everything the frame produced for it (bq2_hash_kernel); r == NULL: the frame
+   bq2_frame_wait returned last.  Both kernel classes, host-built and device-built records. */
+bq2_status bq2_hash_results(bq2_ctx *ctx, const bq2_resident *r, uint64_t *host_hashes, int32_t n_pair_slots)
+try {
+    if (!ctx || !host_hashes || n_pair_slots < 0) return BQ2_E_INVALID;
+    if (!r && !ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_hash_results: nothing submitted");
+    FrameState &F = ctx->fs[r ? r->state : ctx->last_waited];
+    const int32_t nPS = F.n_pair_slots;       /* (a kept frame has the shape of the frame it was kept from) */
+    if (!r && n_pair_slots != nPS) return fail(ctx, BQ2_E_INVALID, "bq2_hash_results: n_pair_slots does not match the frame");
+    if (!(( r ? r->L.want : F.launch.want) & BQ2_WANT_SHADOW)) return fail(ctx, BQ2_E_INVALID, "bq2_hash_results: the frame has no shadow volumes");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    if (n_pair_slots == 0) return BQ2_OK;
+    unsigned long long *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(unsigned long long) * (size_t)n_pair_slots), "cudaMalloc(hashes)");
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)n_pair_slots, F.stream);
+    bq2_launch L = r ? r->L : F.launch;
+    const FrameState::KLaunch &kw = r ? r->k_warp : F.k_warp, &kt = r ? r->k_team : F.k_team;
+    const bq2_dev_ent *ents0 = L.ents;
+    if (e == cudaSuccess && kw.n) { L.n_ent_slots = kw.n; L.rec_base = 0; e = (cudaError_t)bq2_launch_hash(&L, d, F.stream); ctx->launches++; }
+    if (e == cudaSuccess && kt.n) { L.ents = ents0 + kw.n; L.rec_base = (uint32_t)kw.n; L.n_ent_slots = kt.n; e = (cudaError_t)bq2_launch_hash(&L, d, F.stream); ctx->launches++; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_hashes, d, sizeof(unsigned long long) * (size_t)n_pair_slots, cudaMemcpyDeviceToHost, F.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(F.stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail_cuda(ctx, e, "bq2_hash_results");
+    return BQ2_OK;
+} catch (...) { return guard_exception(ctx); }
+
+/* cudaProfilerStart / Stop around a measured region (bench.py's DRAM-traffic probe runs under ncu's range replay) */
+bq2_status bq2_profiler_range(bq2_ctx *ctx, int on)
+{
+    if (!ctx) return BQ2_E_INVALID;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    CK(on ? cudaProfilerStart() : cudaProfilerStop(), "cudaProfilerStart/Stop");
+    return BQ2_OK;
 }
 
 const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const uint32_t *)ctx->fs[ctx->last_waited].hcnt.p : nullptr; }
@@ -1444,6 +1570,32 @@ try {
     default: return fail(ctx, BQ2_E_INVALID, "bq2_download: unknown array");
     }
     if (!src || first + count > cap) return fail(ctx, BQ2_E_INVALID, "bq2_download: range outside the array");
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaMemcpyAsync(host, (const uint32_t *)src + first, count * 4, cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(download)");
+    CK(cudaStreamSynchronize(F.stream), "cudaStreamSynchronize(download)");
+    return BQ2_OK;
+} catch (...) { return guard_exception(ctx); }
+
+/* the same from the result arrays a kept frame writes to (its own, or those of its frame state) */
+bq2_status bq2_resident_download(bq2_ctx *ctx, const bq2_resident *r, bq2_array which, uint64_t first, uint64_t count, void *host)
+try {
+    if (!ctx || !r || !host) return BQ2_E_INVALID;
+    const FrameState &F = ctx->fs[r->state];
+    const void *src = nullptr; size_t cap = 0;
+    switch (which) {
+    case BQ2_A_LERPED:      src = r->L.lerped;      cap = r->own ? r->lerped.cap : F.lerped.cap; break;
+    case BQ2_A_EXTRUDED:    src = r->L.extruded;    cap = r->own ? r->extruded.cap : F.extruded.cap; break;
+    case BQ2_A_FACING_BITS: src = r->L.facing_bits; cap = r->own ? r->facing_bits.cap : F.facing_bits.cap; break;
+    case BQ2_A_INDICES:     src = r->L.indices;     cap = r->own ? r->indices.cap : F.indices.cap; break;
+    case BQ2_A_INDEX_COUNT: src = r->L.index_count; cap = r->own ? r->index_count.cap : F.index_count.cap; break;
+    case BQ2_A_NORMALS:     src = r->L.normals;     cap = r->own ? r->normals.cap : F.normals.cap; break;
+    case BQ2_A_TANGENTS:    src = r->L.tangents;    cap = r->own ? r->tangents.cap : F.tangents.cap; break;
+    case BQ2_A_BINORMALS:   src = r->L.binormals;   cap = r->own ? r->binormals.cap : F.binormals.cap; break;
+    case BQ2_A_LIGHTP:      src = r->L.lightp;      cap = r->own ? r->lightp.cap : F.lightp.cap; break;
+    case BQ2_A_TSH:         src = r->L.tsh;         cap = r->own ? r->tsh.cap : F.tsh.cap; break;
+    default: return fail(ctx, BQ2_E_INVALID, "bq2_resident_download: unknown array");
+    }
+    if (!src || first + count > cap) return fail(ctx, BQ2_E_INVALID, "bq2_resident_download: range outside the array");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     CK(cudaMemcpyAsync(host, (const uint32_t *)src + first, count * 4, cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(download)");
     CK(cudaStreamSynchronize(F.stream), "cudaStreamSynchronize(download)");

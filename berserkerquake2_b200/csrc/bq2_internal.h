@@ -130,6 +130,7 @@ typedef struct bq2_launch {
     /* device-built pair lists (world path), NULL for host-built records */
     const uint32_t *bucket_cnt, *bucket, *ohead, *onext;
     uint32_t rec_base;              /* record index of this launch's first CTA                                */
+    uint32_t seq;                   /* launch sequence number (diagnostic builds: make TIMELINE=1)            */
 } bq2_launch;
 
 /* host-side flat model table for the per-entity loop in C (bq2_host.c) */
@@ -198,6 +199,8 @@ typedef struct bq2_brush_pair_dev_h { int32_t brush; float light[3]; float scale
 int  bq2_launch_brush(const void *brushes, const void *pairs, const uint8_t *lit, float *vcache, uint32_t *icache,
                       uint32_t *counts, uint32_t vert_stride, uint32_t index_stride, int n_pairs, int max_polys, int max_slots,
                       void *stream);
+/* one 64-bit hash per pair slot over the frame's results (verification; out = device [n_pair_slots], zeroed by the caller) */
+int  bq2_launch_hash(const bq2_launch *L, unsigned long long *out, void *stream);
 int  bq2_kernel_prepare(void);   /* opt in to large dynamic shared memory once per process */
 size_t bq2_kernel_smem_bytes(int max_V, int max_T, int md2);
 size_t bq2_kernel_warp_smem_bytes(int max_V, int max_T, int md2);

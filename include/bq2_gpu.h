@@ -112,6 +112,9 @@ typedef struct bq2_pair {
 #define BQ2_WANT_NTB      0x2u  /* lerped normal / tangent / binormal per entity (a10)            */
 #define BQ2_WANT_TSLIGHT  0x4u  /* tangent-space light vector LightP and half vector tsH per pair */
 #define BQ2_WANT_NOLERPOUT 0x8u /* do not write lerped[] to memory (shadow-only callers)          */
+/* every bit a caller may set (BQ2_WANT_TABLES 0x10 is declared with bq2_world_desc below); anything else in
+   `want` is refused with BQ2_E_INVALID */
+#define BQ2_WANT_PUBLIC_MASK 0x1fu
 
 typedef struct bq2_frame_desc {
     const bq2_entity *ents;    int32_t n_ents;
@@ -163,8 +166,8 @@ bq2_status   bq2_create(int device, bq2_ctx **out);
 void         bq2_destroy(bq2_ctx *ctx);
 const char  *bq2_last_error(const bq2_ctx *ctx);          /* ctx may be NULL: last create error   */
 void        *bq2_stream(bq2_ctx *ctx);                     /* cudaStream_t of the most recently submitted frame (each of
-                                                              the two frame states has its own; fixed for callers that
-                                                              never overlap frames) */
+                                                              the five frame states has its own -- up to four frames in
+                                                              flight; fixed for callers that never overlap frames) */
 int          bq2_device(const bq2_ctx *ctx);
 uint64_t     bq2_kernel_launches(const bq2_ctx *ctx);      /* kernels launched by this ctx so far  */
 
@@ -227,8 +230,18 @@ bq2_status bq2_frame_replay(bq2_ctx *ctx);
  * read-only front of a frame's kernel runs under the tail of the kernel in front of it. */
 typedef struct bq2_resident bq2_resident;
 bq2_status bq2_frame_keep(bq2_ctx *ctx, bq2_resident **out);
+/* The same, with a set of RESULT arrays of the kept frame's own (a copy of the state's, same sizes): a ring of such
+ * frames writes a different set of output lines on every step, so that a measurement cycling through more result
+ * bytes than the L2 holds streams its outputs to HBM instead of overwriting one L2-resident set. */
+bq2_status bq2_frame_keep_own(bq2_ctx *ctx, bq2_resident **out);
+uint64_t   bq2_resident_result_bytes(const bq2_resident *r);   /* bytes of result arrays owned by the frame (0: shared) */
 bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r);
+/* k replays launched from C, ring[(start + i) % n_ring] for i = 0 .. k-1 (all kept on one frame state).  ms != NULL:
+ * two CUDA events on the stream bracket the k launches; the call waits for the second and returns their distance. */
+bq2_status bq2_resident_run(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k, float *ms);
 void       bq2_resident_free(bq2_ctx *ctx, bq2_resident *r);
+/* cudaProfilerStart (on != 0) / cudaProfilerStop after a device synchronize: the range ncu's range replay measures */
+bq2_status bq2_profiler_range(bq2_ctx *ctx, int on);
 
 /* ---- result download helpers (tests, the drop-in shim) --------------------------------------- */
 /* Copies `count` 32-bit words starting at word offset `first` of a device result array to host. */
@@ -237,7 +250,17 @@ typedef enum bq2_array {
     BQ2_A_NORMALS, BQ2_A_TANGENTS, BQ2_A_BINORMALS, BQ2_A_LIGHTP, BQ2_A_TSH
 } bq2_array;
 bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host);
+/* the same from the arrays a kept frame writes to (its own after bq2_frame_keep_own) */
+bq2_status bq2_resident_download(bq2_ctx *ctx, const bq2_resident *r, bq2_array which, uint64_t first, uint64_t count, void *host);
 const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx);  /* pinned host copy, n_pair_slots      */
+
+/* Verification at full size: one 64-bit hash per pair slot over everything the path produced for it -- the entity's
+ * lerped row, the pair's extruded row, the facing words, index_count and the expanded stream pool[indices[k]] (the
+ * reference's tempVertexArray, extrudedVerts, viss, TrisCounter, TrisVerts) -- computed on the device, so that every
+ * pair of a 65,536-pair frame can be compared with the reference without downloading the geometry.  The definition is
+ * in csrc/bq2_kernels.cu (bq2_hash_kernel); the test harness computes the same number from the engine's globals.  r == NULL: the frame bq2_frame_wait returned last; n_pair_slots must match it.  Slots that cast nothing
+ * hash to 0. */
+bq2_status bq2_hash_results(bq2_ctx *ctx, const bq2_resident *r, uint64_t *host_hashes, int32_t n_pair_slots);
 
 /* Expand one pair slot into the reference's non-indexed stream: TrisVerts[3*k..] =
  * pool[indices[k]] with pool = lerped ++ extruded (M:63661-63708).  Host-side, for the shim. */

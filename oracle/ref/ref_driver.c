@@ -273,6 +273,53 @@ long long bq2ref_md2_world_bench(void *const *blobs, void *const *neighbours, in
     return total;
 }
 
+/* Full-size parity: the per-pair 64-bit hash the product computes on the device (csrc/bq2_kernels.cu, bq2_hash_kernel;
+ * include/bq2_gpu.h bq2_hash_results), here from the engine's own globals after the WHOLE R_DrawAliasShadowVolume ran
+ * for the pair: tempVertexArray, extrudedVerts, viss packed into 32-bit words, TrisCounter, TrisVerts.  The hash is test
+ * plumbing (a sum of mixed (section, position, word) triples); no arithmetic of the path is restated.  Every vertex of
+ * the model must be referenced by a triangle (the engine extrudes per triangle corner), which holds for the
+ * generators' closed meshes. */
+static uint64_t hash_word(uint32_t section, uint32_t i, uint32_t w)
+{
+    uint64_t x = ((uint64_t)section << 56) ^ ((uint64_t)i << 32) ^ (uint64_t)w;
+    x += 0x9e3779b97f4a7c15ull; x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull; x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+static uint64_t hash_globals(int V, int T)
+{
+    uint64_t h = 0;
+    const uint32_t *lp = (const uint32_t *)tempVertexArray, *ep = (const uint32_t *)extrudedVerts, *tv = (const uint32_t *)TrisVerts;
+    for (int i = 0; i < 3 * V; i++) { h += hash_word(1, (uint32_t)i, lp[i]); h += hash_word(2, (uint32_t)i, ep[i]); }
+    for (int c = 0; c < (T + 31) / 32; c++) {
+        uint32_t w = 0;
+        for (int b = 0; b < 32 && 32 * c + b < T; b++) if (viss[32 * c + b]) w |= 1u << b;
+        h += hash_word(3, (uint32_t)c, w);
+    }
+    h += hash_word(4, 0, (uint32_t)TrisCounter);
+    for (int i = 0; i < 3 * TrisCounter; i++) h += hash_word(5, (uint32_t)i, tv[i]);
+    return h;
+}
+long long bq2ref_md2_world_hash(void *const *blobs, void *const *neighbours, int n_pairs,
+                                const int32_t *frames, const int32_t *oldframes, const float *backlerps,
+                                const float *origins, const float *oldorigins, const float *angles,
+                                const float *lights_world, const float *radii, uint64_t *hashes)
+{
+    bq2ref_init();
+    long long total = 0;
+    for (int p = 0; p < n_pairs; p++) {
+        dmdl_t *h = (dmdl_t *)blobs[p];
+        memset(&mdl, 0, sizeof mdl); mdl.type = mod_alias; mdl.extradata = blobs[p];
+        mdl.triangles = (neighbours_t *)neighbours[p];
+        set_entity(frames[p], oldframes[p], backlerps[p], origins + 3 * p, oldorigins + 3 * p, angles + 3 * p, 0);
+        set_light(lights_world + 3 * p, radii[p]);
+        TrisCounter = 0;
+        R_DrawAliasShadowVolume();
+        total += TrisCounter;
+        hashes[p] = hash_globals(h->num_xyz, h->num_tris);
+    }
+    return total;
+}
+
 /* MD2 light-lerp family.  which: 0 = ..LightARB (LightP on TMU1, tsH on TMU3, expanded verts on
  * TMU2), 1 = ..LightARB_vp (tangent TMU1? see below).  We record every TMU; callers pick. */
 int bq2ref_md2_light(void *blob, const uint8_t *tangents, const uint8_t *binormals, const uint8_t *normals,

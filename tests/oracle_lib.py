@@ -482,3 +482,83 @@ class Reference:
         self.lib.bq2ref_md3_light(P(mv), V, frame, oldframe, backlerp, P(np.ascontiguousarray(lerped, np.float32)),
                                   P(f3(light_model)), P(f3(view_model)), int(vp_variant), P(tmu), P(sizes))
         return {t: tmu[t, :sizes[t] * V].reshape(V, sizes[t]).copy() for t in range(8) if sizes[t]}
+
+
+# ------------------------------------------------------------------------------------------------------
+# Full-size parity: the per-pair 64-bit hash (csrc/bq2_kernels.cu bq2_hash_kernel == oracle/ref/ref_driver.c
+# hash_globals), here in numpy for outputs that are already arrays, and a fan-out over the host cores that runs the
+# reference's own R_DrawAliasShadowVolume for EVERY pair of a frame.
+def _mix64(x):
+    x = x + np.uint64(0x9e3779b97f4a7c15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+    return x ^ (x >> np.uint64(31))
+
+
+def _hash_section(section, words):
+    w = np.ascontiguousarray(words).view(np.uint32).reshape(-1).astype(np.uint64)
+    i = np.arange(len(w), dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        return _mix64((np.uint64(section) << np.uint64(56)) ^ (i << np.uint64(32)) ^ w).sum(dtype=np.uint64)
+
+
+def pair_hash(lerped, extruded, viss, tris_verts, lerped_out=True):
+    """The hash of one pair slot from reference-style outputs (lerped [V][3], extruded [V][3], viss [T] bytes,
+    tris_verts [TrisCounter][3])."""
+    T = len(viss)
+    bits_ = np.zeros(((T + 31) // 32) * 32, np.uint8); bits_[:T] = np.asarray(viss) != 0
+    words = (bits_.reshape(-1, 32).astype(np.uint32) << np.arange(32, dtype=np.uint32)[None, :]).sum(1, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        h = np.uint64(0)
+        if lerped_out:
+            h = h + _hash_section(1, np.asarray(lerped, np.float32))
+        h = h + _hash_section(2, np.asarray(extruded, np.float32)) + _hash_section(3, words)
+        h = h + _hash_section(4, np.array([len(tris_verts)], np.uint32)) + _hash_section(5, np.asarray(tris_verts, np.float32))
+    return np.uint64(h)
+
+
+_HASH_JOB = {}
+
+
+def _hash_worker(rng):
+    lo, hi = rng
+    J = _HASH_JOB
+    lib = C.CDLL(REF_SO)
+    lib.bq2ref_init()
+    fn = lib.bq2ref_md2_world_hash
+    fn.restype = C.c_longlong
+    fn.argtypes = [vp] * 2 + [i32] + [vp] * 9
+    we, wl, pe, pl = J["we"], J["wl"], J["pe"][lo:hi], J["pl"][lo:hi]
+    n = hi - lo
+    if n == 0:
+        return np.zeros(0, np.uint64), 0
+    model_of = we["model"][pe]
+    bp = (vp * n)(*[J["blobs"][int(m)].ctypes.data for m in model_of])
+    nbp = (vp * n)(*[J["nbs"][int(m)].ctypes.data for m in model_of])
+    a = [np.ascontiguousarray(x) for x in (we["frame"][pe].astype(np.int32), we["oldframe"][pe].astype(np.int32),
+                                           we["backlerp"][pe].astype(np.float32), we["origin"][pe], we["oldorigin"][pe],
+                                           we["angles"][pe], wl["origin"][pl], wl["radius"][pl].astype(np.float32))]
+    out = np.zeros(n, np.uint64)
+    tot = fn(bp, nbp, n, *[P(x) for x in a], P(out))
+    return out, int(tot)
+
+
+def reference_pair_hashes(blobs, nbs, we, wl, pe, pl, procs=None):
+    """hash of every pair (pe[k], pl[k]) computed by the unmodified reference (whole R_DrawAliasShadowVolume per pair),
+    fanned out over forked processes (the engine keeps its state in globals).  blobs / nbs: per MODEL id (we["model"]
+    indexes them): MD2 images and int32 neighbour tables.  Returns (uint64 [n_pairs], total index count)."""
+    import multiprocessing as mp
+    procs = procs or max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
+    n = len(pe)
+    procs = max(1, min(procs, n))
+    _HASH_JOB.clear()
+    _HASH_JOB.update(blobs=[np.ascontiguousarray(b) for b in blobs], nbs=[np.ascontiguousarray(x, np.int32) for x in nbs],
+                     we=we, wl=wl, pe=np.ascontiguousarray(pe, np.int32), pl=np.ascontiguousarray(pl, np.int32))
+    ranges = [(n * w // procs, n * (w + 1) // procs) for w in range(procs)]
+    if procs == 1:
+        res = [_hash_worker(ranges[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_hash_worker, ranges)
+    _HASH_JOB.clear()
+    return np.concatenate([r[0] for r in res]), sum(r[1] for r in res)

@@ -132,6 +132,24 @@ def test_md3_cache_roundtrip(oracle):
 
 
 @pytest.mark.gpu
+def test_md2_blob_entry_points_refuse_malformed_headers(gpu_ctx):
+    """bq2_upload_md2 and bq2_gpu_md2_tangents share one header check: negative section offsets (which wrap to small
+    numbers in unsigned arithmetic and used to pass the bounds test of the tangent entry point), a wrong version, a
+    frame size too small for the vertex count -- all refused, none read."""
+    rc, blob, st = md2_from_file(synth.md2(8, 5, 2, 1), scale=1.0)
+    assert rc == 0
+    h = synth.md2_header(blob); V, T, F = int(h["num_xyz"]), int(h["num_tris"]), int(h["num_frames"])
+    tn = np.zeros((F, V), np.uint8); bn = np.zeros((F, V), np.uint8); mid = C.c_int32(-1)
+    for field, value in (("ofs_tris", -12), ("ofs_frames", -40), ("ofs_tris", -(2 ** 31)), ("version", 7), ("framesize", 8),
+                         ("num_frames", 0), ("num_xyz", 4096), ("ofs_frames", 2 ** 30)):
+        bad = blob.copy()
+        bad[:68].view(synth.MD2_HEADER)[0][field] = value
+        assert L.bq2_gpu_md2_tangents(gpu_ctx._h, c.ptr(bad), bad.nbytes, c.ptr(st), SMOOTH_COSINE, 1, None, c.ptr(tn), c.ptr(bn)) < 0, field
+        assert L.bq2_upload_md2(gpu_ctx._h, c.ptr(bad), bad.nbytes, None, None, None, None, 0, C.byref(mid)) < 0, field
+    assert L.bq2_gpu_md2_tangents(gpu_ctx._h, c.ptr(blob), blob.nbytes, c.ptr(st), SMOOTH_COSINE, 1, None, c.ptr(tn), c.ptr(bn)) == 0
+
+
+@pytest.mark.gpu
 def test_file_to_shadow_volume_with_device_precompute(gpu_ctx, oracle):
     """file bytes -> bq2_host_md2_from_file -> neighbours + tangent bytes on the device -> cache file -> read back
     -> upload -> frame: the same index buffers and N/T/B rows as the oracle on the oracle's own tables."""

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import berserkerquake2_b200 as bq2
+from berserkerquake2_b200 import synth as synth_mod
 from scenes import Md2Model, Md3Model, world_scene, bits
 
 pytestmark = pytest.mark.gpu
@@ -794,6 +795,7 @@ def test_want_flag_combinations_and_many_lights(gpu_ctx, oracle):
         assert np.array_equal(res2.indices(p), want[p]["indices"]) and np.array_equal(bits(res2.extruded(p, m.V)), bits(want[p]["extruded"]))
     # tangent space only
     res3 = gpu_ctx.frame(ents, pairs, want=bq2.WANT_NTB | bq2.WANT_TSLIGHT)
+    assert int(res3.total_indices) == 0 and not res3.index_counts.any()         # no volumes asked for: no stale counts
     from berserkerquake2_b200 import synth
     for e in range(2):
         f, of = int(we["frame"][e]), int(we["oldframe"][e]); bl = float(we["backlerp"][e]); fl = float(ents["frontlerp"][e])
@@ -807,6 +809,60 @@ def test_want_flag_combinations_and_many_lights(gpu_ctx, oracle):
             lp, ts = oracle.tslight(P, N, T_, B, pairs["light"][p], pairs["view"][p])
             gl, gt = res3.tslight(p, m.V)
             assert np.array_equal(bits(gl), bits(lp)) and np.array_equal(bits(gt), bits(ts))
+
+
+def test_counts_are_cleared_without_shadow_and_unknown_want_bits_are_refused(oracle):
+    """A frame without BQ2_WANT_SHADOW reports zero indices on a FRESH context (nothing stale to read back), on both
+    routes; bits outside the public mask (the team kernel's internal one among them) are refused."""
+    m = Md2Model(oracle, 10, 7, frames=4, seed=6, tangent_space=True, smooth=True)
+    we, wl, pe, pl = world_scene(3, 2, 4, seed=10)
+    with bq2.Context(0) as ctx:
+        we["model"] = m.upload(ctx)
+        ents, pairs = ctx.build_records(we, wl, pe, pl)
+        r = ctx.frame(ents, pairs, want=bq2.WANT_NTB)
+        assert int(r.total_indices) == 0 and not r.index_counts.any()
+        r = ctx.world_frame(we, wl, pe, pl, want=bq2.WANT_TABLES)          # lerp only through the world route
+        assert int(r.total_indices) == 0 and not r.index_counts.any()
+        for bad in (0x40000000, 0x20, 0x80000000):
+            with pytest.raises(bq2.Bq2Error):
+                ctx.frame(ents, pairs, want=bq2.WANT_SHADOW | bad)
+            with pytest.raises(bq2.Bq2Error):
+                ctx.world_frame(we, wl, pe, pl, want=bq2.WANT_SHADOW | bad)
+        r = ctx.frame(ents, pairs)                                           # the context is still usable
+        assert int(r.total_indices) > 0
+
+
+def test_anorm_bytes_beyond_the_table_decode_to_zero(oracle):
+    """Bytes >= 162 (never produced by Normal2Index; the reference reads past r_avertexnormals) are DEFINED here: the
+    device table has 256 rows, the extra ones zero -- a shell push-out along such a "normal" moves nothing, and a basis
+    row decoded from it is the zero vector."""
+    m = Md2Model(oracle, 10, 7, frames=3, seed=8, tangent_space=True, smooth=True)
+    blob = m.blob.copy()
+    V = m.V
+    for f in range(3):
+        synth_rows = synth_mod.md2_frame_verts(blob, f)
+        synth_rows[::2, 3] = np.arange(len(synth_rows[::2]), dtype=np.uint8) % 94 + 162      # 162..255 on even vertices
+    tang = m.tangents.copy(); tang[:, 1::3] = 255
+    with bq2.Context(0) as ctx:
+        mid = ctx.upload_md2(blob, m.nb, tang, m.binormals, None, smooth=True)
+        mid0 = ctx.upload_md2(m.blob, m.nb, m.tangents, m.binormals, None, smooth=True)
+        we, wl, pe, pl = world_scene(1, 1, 3, seed=3)
+        we["rf_flags"] = 0x400                                              # RF_SHELL_RED: the push-out path
+        ents = []
+        for mm in (mid, mid0):
+            we["model"] = mm
+            e, p = ctx.build_records(we, wl, pe, pl)
+            ents.append(e)
+        bad = ctx.frame(ents[0], None, want=bq2.WANT_NTB)
+        lerped_bad = bad.lerped(0, V); N, T_, _ = bad.ntb(0, V)
+        ok = ctx.frame(ents[1], None, want=bq2.WANT_NTB)
+        lerped_ok = ok.lerped(0, V); N0, T0, _ = ok.ntb(0, V)
+        noshell = ents[1].copy(); noshell["flags"] = 0
+        plain = ctx.frame(noshell, None).lerped(0, V)
+        assert np.array_equal(bits(lerped_bad[::2]), bits(plain[::2]))       # zero normal: no push-out on those vertices
+        assert np.array_equal(bits(lerped_bad[1::2]), bits(lerped_ok[1::2]))  # the others as before
+        assert not N[::2].any() and np.array_equal(bits(N[1::2]), bits(N0[1::2]))
+        assert not T_[1::3].any() and np.array_equal(bits(T_[0::3]), bits(T0[0::3]))
 
 
 def test_ratio_sequence_is_exact(gpu_ctx):
