@@ -283,10 +283,10 @@ def measure_traffic(args, log_dir):
     tries = [
         ("range", "ncu --replay-mode app-range over cudaProfilerStart/Stop around the K back-to-back launches",
          [ncu, "--replay-mode", "app-range", "--profile-from-start", "off", "--metrics", metrics, "--print-units", "base",
-          "--csv", "--clock-control", "none"]),
+          "--csv", "--clock-control", "none", "--cache-control", "none"]),
         ("kernel", "ncu --replay-mode application, one pass, the K launches of the region profiled one by one",
          [ncu, "--replay-mode", "application", "--profile-from-start", "off", "--metrics", metrics, "--print-units", "base",
-          "--csv", "--clock-control", "none", "-k", "regex:bq2_frame"]),
+          "--csv", "--clock-control", "none", "--cache-control", "none", "-k", "regex:bq2_frame"]),
     ]
     why = []
     for mode, how, cmd in tries:
@@ -297,6 +297,8 @@ def measure_traffic(args, log_dir):
         except (subprocess.TimeoutExpired, OSError) as e:
             why.append(f"{mode}: {type(e).__name__}")
             continue
+        with open(log + ".stderr", "w") as f:
+            f.write(r.stdout[-4000:] + "\n" + r.stderr[-4000:])
         if r.returncode != 0 or not os.path.exists(log):
             why.append(f"{mode}: rc={r.returncode} {r.stderr.strip()[-200:]}")
             continue
@@ -322,7 +324,9 @@ def measure_traffic(args, log_dir):
             why.append(f"{mode}: no counter rows in {os.path.basename(log)}")
             continue
         return {"bytes_per_step": (rd + wr) / args.steps, "read_per_step": rd / args.steps, "write_per_step": wr / args.steps,
-                "steps": args.steps, "rows": rows, "how": how}, None
+                "steps": args.steps, "rows": rows, "how": how + " (--cache-control none: ncu neither flushes nor invalidates "
+                "the caches around a launch, the L2 holds what the steps in front left in it)",
+                "not_available": why}, None
     return None, "; ".join(why)
 
 

@@ -64,7 +64,17 @@ class FrameOut(C.Structure):
 class WorldDesc(C.Structure):
     _fields_ = [("ents", C.c_void_p), ("n_ents", C.c_int32), ("lights", C.c_void_p), ("n_lights", C.c_int32),
                 ("pair_ent", C.c_void_p), ("pair_light", C.c_void_p), ("n_pairs", C.c_int32),
-                ("view_world", C.c_void_p), ("want", C.c_uint32), ("index_stride", C.c_uint32)]
+                ("view_world", C.c_void_p), ("want", C.c_uint32), ("index_stride", C.c_uint32), ("opts", C.c_void_p)]
+
+
+class RenderOpts(C.Structure):
+    """bq2_render_opts: the cvars / r_mirror / pass of the caller loops (main.c:64041-64133, 63722-63727)"""
+    _fields_ = [("r_mirror", C.c_int32), ("r_mirror_shadows", C.c_float), ("r_mirror_models", C.c_float),
+                ("r_playershadow", C.c_float), ("r_shadows", C.c_float), ("r_drawentities", C.c_float), ("pass_", C.c_int32)]
+
+
+PASS_ALL, PASS_SELF, PASS_NOSELF = 0, 1, 2
+RF_NOSELFSHADOW, RF_NOCASTSHADOW, RF_DISTORT, RF_VIEWERMODEL = 0x2000, 0x80000, 0x10000000, 0x2
 
 
 class BrushOut(C.Structure):
@@ -99,6 +109,10 @@ EXPORTS_GPU_H = [
     _sig("bq2_kernel_launches", u64, vp),
     _sig("bq2_upload_md2", C.c_int, vp, vp, C.c_size_t, vp, vp, vp, vp, u32, C.POINTER(i32)),
     _sig("bq2_upload_md3", C.c_int, vp, i32, vp, C.POINTER(Md3Mesh), i32, C.POINTER(i32)),
+    _sig("bq2_model_set_rf_flags", C.c_int, vp, i32, u32),
+    _sig("bq2_render_opts_default", None, vp),
+    _sig("bq2_host_entity_casts", C.c_int, u32, u32, C.c_int, vp),
+    _sig("bq2_build_records_opts", C.c_int, vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, vp, vp, C.POINTER(i32)),
     _sig("bq2_model_info", C.c_int, vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp, vp),
     _sig("bq2_frame", C.c_int, vp, C.POINTER(FrameDesc), C.POINTER(FrameOut)),
     _sig("bq2_frame_submit", C.c_int, vp, C.POINTER(FrameDesc)),

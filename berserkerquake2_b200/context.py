@@ -150,17 +150,35 @@ class Context:
         return res
 
     # -- per frame -----------------------------------------------------------------------------------
-    def build_records(self, world_ents, world_lights, pair_ent, pair_light, view_world=None):
+    def set_model_rf_flags(self, model_id, rf_flags):
+        """model_t.flags bits the caller loop reads (RF_NOCASTSHADOW, RF_DISTORT, RF_NOSELFSHADOW)."""
+        self._check(c.lib.bq2_model_set_rf_flags(self._h, int(model_id), int(rf_flags)))
+
+    @staticmethod
+    def render_opts(**kw):
+        """bq2_render_opts at the engine's defaults, fields overridden by keyword (pass_ = PASS_ALL / SELF / NOSELF)."""
+        o = c.RenderOpts()
+        c.lib.bq2_render_opts_default(C.byref(o))
+        for k, v in kw.items():
+            setattr(o, k, v)
+        return o
+
+    def build_records(self, world_ents, world_lights, pair_ent, pair_light, view_world=None, opts=None):
         """The renderer's (light x entity) loop nest flattened into bq2_entity / bq2_pair records, on the
-        host in C (bq2_build_records)."""
+        host in C (bq2_build_records / bq2_build_records_opts)."""
         we = np.ascontiguousarray(world_ents, c.WORLD_ENTITY_DTYPE)
         wl = np.ascontiguousarray(world_lights, c.WORLD_LIGHT_DTYPE)
         pe = np.ascontiguousarray(pair_ent, np.int32); pl = np.ascontiguousarray(pair_light, np.int32)
         vw = None if view_world is None else np.ascontiguousarray(view_world, np.float32)
         ents = np.zeros(len(we), c.ENTITY_DTYPE); pairs = np.zeros(len(pe), c.PAIR_DTYPE)
         kept = C.c_int32(0)
-        self._check(c.lib.bq2_build_records(self._h, c.ptr(we), len(we), c.ptr(wl), len(wl), c.ptr(pe), c.ptr(pl),
-                                            len(pe), c.ptr(vw), c.ptr(ents), c.ptr(pairs), C.byref(kept)))
+        if opts is None:
+            self._check(c.lib.bq2_build_records(self._h, c.ptr(we), len(we), c.ptr(wl), len(wl), c.ptr(pe), c.ptr(pl),
+                                                len(pe), c.ptr(vw), c.ptr(ents), c.ptr(pairs), C.byref(kept)))
+        else:
+            self._check(c.lib.bq2_build_records_opts(self._h, c.ptr(we), len(we), c.ptr(wl), len(wl), c.ptr(pe), c.ptr(pl),
+                                                     len(pe), c.ptr(vw), C.cast(C.byref(opts), C.c_void_p), c.ptr(ents),
+                                                     c.ptr(pairs), C.byref(kept)))
         return ents, pairs[:kept.value]
 
     def _desc(self, ents, pairs, want, index_stride):
@@ -190,13 +208,14 @@ class Context:
         return FrameResult(self, out, st)
 
     def world_desc(self, world_ents, world_lights, pair_ent, pair_light, view_world=None, want=c.WANT_SHADOW,
-                   index_stride=0):
+                   index_stride=0, opts=None):
         we = np.ascontiguousarray(world_ents, c.WORLD_ENTITY_DTYPE)
         wl = np.ascontiguousarray(world_lights, c.WORLD_LIGHT_DTYPE)
         pe = np.ascontiguousarray(pair_ent, np.int32); pl = np.ascontiguousarray(pair_light, np.int32)
         vw = None if view_world is None else np.ascontiguousarray(view_world, np.float32)
-        self._keep = [we, wl, pe, pl, vw]
+        self._keep = [we, wl, pe, pl, vw, opts]
         d = c.WorldDesc()
+        d.opts = None if opts is None else C.addressof(opts)
         d.ents = we.ctypes.data if len(we) else None; d.n_ents = len(we)
         d.lights = wl.ctypes.data if len(wl) else None; d.n_lights = len(wl)
         d.pair_ent = pe.ctypes.data if len(pe) else None; d.pair_light = pl.ctypes.data if len(pl) else None
@@ -205,9 +224,9 @@ class Context:
         return d
 
     def world_frame(self, world_ents, world_lights, pair_ent, pair_light, view_world=None,
-                    want=c.WANT_SHADOW | c.WANT_TABLES, index_stride=0, allow_overflow=False):
+                    want=c.WANT_SHADOW | c.WANT_TABLES, index_stride=0, allow_overflow=False, opts=None):
         """bq2_world_frame: records built on the device; pair slot p is caller pair p."""
-        d = self.world_desc(world_ents, world_lights, pair_ent, pair_light, view_world, want, index_stride)
+        d = self.world_desc(world_ents, world_lights, pair_ent, pair_light, view_world, want, index_stride, opts)
         out = c.FrameOut()
         st = self._check(c.lib.bq2_world_frame(self._h, C.byref(d), C.byref(out)),
                          allow=(c.E_OVERFLOW,) if allow_overflow else ())

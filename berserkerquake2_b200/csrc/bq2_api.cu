@@ -44,6 +44,7 @@ struct Model {
     int  F = 0;
     int  first_mesh = 0, n_mesh = 0;
     uint32_t flags = 0;
+    uint32_t rf_flags = 0;       /* model_t.flags bits of the caller loop's filter (bq2_model_set_rf_flags) */
     std::vector<int> V, T, casts;
     std::vector<float> hdr;      /* MD2: F x {scale[3], translate[3]} (daliasframe_t header);
                                     MD3: F x translate[3] (maliasframe_t.translate)            */
@@ -570,8 +571,26 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t id, int32_t *is_md3, int32
 static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
                              const bq2_world_light *lights, int32_t n_lights,
                              const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
-                             const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
+                             const float *view_world, const bq2_render_opts *opts, bq2_entity *out_ents, bq2_pair *out_pairs,
                              int32_t *n_pairs_out, bool keep_dead);
+
+bq2_status bq2_model_set_rf_flags(bq2_ctx *ctx, int32_t id, uint32_t model_rf_flags)
+{
+    if (!ctx || id < 0 || id >= (int32_t)ctx->models.size()) return ctx ? fail(ctx, BQ2_E_INVALID, "bq2_model_set_rf_flags: unknown model") : BQ2_E_INVALID;
+    ctx->models[id].rf_flags = model_rf_flags;
+    if ((size_t)id < ctx->model_rows.size()) ctx->model_rows[id].pad[0] = (int32_t)model_rf_flags;
+    return BQ2_OK;
+}
+
+bq2_status bq2_build_records_opts(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
+                                  const bq2_world_light *lights, int32_t n_lights,
+                                  const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
+                                  const float *view_world, const bq2_render_opts *opts,
+                                  bq2_entity *out_ents, bq2_pair *out_pairs, int32_t *n_pairs_out)
+try {
+    return build_records_impl(ctx, ents, n_ents, lights, n_lights, pair_ent, pair_light, n_pairs, view_world, opts,
+                              out_ents, out_pairs, n_pairs_out, false);
+} catch (...) { return guard_exception(ctx); }
 
 bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
                              const bq2_world_light *lights, int32_t n_lights,
@@ -579,17 +598,19 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
                              const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
                              int32_t *n_pairs_out)
 try {
-    return build_records_impl(ctx, ents, n_ents, lights, n_lights, pair_ent, pair_light, n_pairs, view_world,
+    return build_records_impl(ctx, ents, n_ents, lights, n_lights, pair_ent, pair_light, n_pairs, view_world, nullptr,
                               out_ents, out_pairs, n_pairs_out, false);
 } catch (...) { return guard_exception(ctx); }
 
 static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
                              const bq2_world_light *lights, int32_t n_lights,
                              const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
-                             const float *view_world, bq2_entity *out_ents, bq2_pair *out_pairs,
+                             const float *view_world, const bq2_render_opts *opts, bq2_entity *out_ents, bq2_pair *out_pairs,
                              int32_t *n_pairs_out, bool keep_dead)
 {
     if (!ctx) return BQ2_E_INVALID;
+    int f_off, f_brush; uint32_t f_em, f_mm, f_mx;
+    bq2_host_filter_masks(opts, &f_off, &f_em, &f_mm, &f_mx, &f_brush);
     if (n_ents < 0 || n_pairs < 0 || (n_ents && (!ents || !out_ents)) ||
         (n_pairs && (!lights || !pair_ent || !pair_light || !out_pairs)) || !n_pairs_out)
         return fail(ctx, BQ2_E_INVALID, "bq2_build_records: bad arguments");
@@ -610,8 +631,7 @@ static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents,
                                     W.backlerp, W.origin, W.oldorigin, W.angles, W.rf_flags, &out_ents[e]);
         out_ents[e].model = W.model;
         float *b = &ctx->ent_basis[10 * (size_t)e];
-        const bool casts = bq2_host_casts_shadow(W.rf_flags, 0, 0.0f, 2.0f) &&
-                           !(W.rf_flags & (BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT));             /* M:64089 */
+        const bool casts = !(f_off || (W.rf_flags & f_em) || ((mo.rf_flags ^ f_mx) & f_mm));   /* M:63722-63727, 64041-64089 */
         b[9] = !casts ? -1.0f : (float)bq2_host_entity_basis(W.angles, b);
     }
     int kept = 0;
@@ -1176,6 +1196,7 @@ try {
             ctx->model_rows[i] = bq2_model_row{mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2,
                                                me.V, me.T, me.Tp, me.flags};
             bq2_model_row_derive(&ctx->model_rows[i]);
+            ctx->model_rows[i].pad[0] = (int32_t)mo.rf_flags;
         }
     }
     const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_went),
@@ -1192,7 +1213,7 @@ try {
         CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
         F.ent_slot_first.resize((size_t)nE + 1); F.ent_vert_off.resize((size_t)nE + 1); F.ent_tb_off.assign((size_t)nE + 1, 0u);
         F.slot_record.resize((size_t)nE + 1);
-        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, (bq2_dev_went *)(h_records.p + off_xf),
+        er = bq2_host_world_entities(wd->ents, nE, ctx->model_rows.data(), nModels, wd->opts, (bq2_dev_went *)(h_records.p + off_xf),
                                      (float *)(h_records.p + off_b), F.slot_record.data(), F.ent_vert_off.data(), &ws);
         if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
         if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
@@ -1204,7 +1225,7 @@ try {
         ctx->tmp_ents.resize((size_t)nE + 1); ctx->tmp_pairs.resize((size_t)nP + 1);
         int32_t kept = 0;
         bq2_status s = build_records_impl(ctx, wd->ents, nE, wd->lights, nL, wd->pair_ent, wd->pair_light, nP, wd->view_world,
-                                          ctx->tmp_ents.data(), ctx->tmp_pairs.data(), &kept, true);
+                                          wd->opts, ctx->tmp_ents.data(), ctx->tmp_pairs.data(), &kept, true);
         if (s != BQ2_OK) return s;
         bq2_frame_desc fd{};
         fd.ents = ctx->tmp_ents.data(); fd.n_ents = nE; fd.pairs = ctx->tmp_pairs.data(); fd.n_pairs = kept;

@@ -200,6 +200,46 @@ int bq2_host_casts_shadow(uint32_t rf_flags, int r_mirror, float r_playershadow,
     return 1;
 }
 
+/* ---- the caller loops' switches (M:64041-64133 + M:63722-63727), reduced to three masks so that the per-entity loop
+ *      below tests an entity with two ANDs ------------------------------------------------------------------------ */
+void bq2_render_opts_default(bq2_render_opts *o)
+{
+    o->r_mirror = 0; o->r_mirror_shadows = 2.0f; o->r_mirror_models = 1.0f; o->r_playershadow = 0.0f;
+    o->r_shadows = 2.0f; o->r_drawentities = 1.0f; o->pass = BQ2_PASS_ALL;
+}
+/* off: nothing alias casts under these options; ent_mask: entity flags that reject; an alias model is rejected when
+   ((model flags ^ model_xor) & model_mask) != 0; brush: the loop draws brush models in this pass */
+void bq2_host_filter_masks(const bq2_render_opts *opts, int *off, uint32_t *ent_mask, uint32_t *model_mask, uint32_t *model_xor, int *brush)
+{
+    bq2_render_opts d;
+    const bq2_render_opts *o = opts;
+    int alias_on, loop_on, nomdl;
+    if (!o) { bq2_render_opts_default(&d); o = &d; }
+    /* M:64046-64060: the loop runs at all */
+    if (o->r_mirror) { loop_on = o->r_drawentities != 0.0f && o->r_mirror_shadows != 0.0f; nomdl = !(o->r_mirror_models != 0.0f); }
+    else             { loop_on = o->r_drawentities != 0.0f && o->r_shadows != 0.0f; nomdl = 0; }
+    /* M:64072-64079: alias volumes only with r_shadows (r_mirror_shadows in the mirror) > 1, and not with nomdl */
+    alias_on = loop_on && !nomdl && (o->r_mirror ? o->r_mirror_shadows > 1.0f : o->r_shadows > 1.0f);
+    *off = !alias_on;
+    *brush = loop_on && (o->pass == BQ2_PASS_ALL || o->pass == BQ2_PASS_SELF);                    /* M:64068-64070 */
+    /* M:64089 (entity side) + M:63725-63726 */
+    *ent_mask = BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT | BQ2_RF_SHELL_GREEN | BQ2_RF_SHELL_RED | BQ2_RF_SHELL_BLUE |
+                BQ2_RF_FULLBRIGHT | BQ2_RF_BEAM | BQ2_RF_TRANSLUCENT | BQ2_RF_WEAPONMODEL;
+    /* M:63722-63724: the player's own model casts only in the mirror, or with r_playershadow and r_shadows > 1 */
+    if (!o->r_mirror && !(o->r_playershadow != 0.0f && o->r_shadows > 1.0f)) *ent_mask |= BQ2_RF_VIEWERMODEL;
+    /* M:64089 (model side) and the self-shadow split M:64081-64087 */
+    *model_mask = BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT; *model_xor = 0u;
+    if (o->pass == BQ2_PASS_SELF) *model_mask |= BQ2_RF_NOSELFSHADOW;
+    else if (o->pass == BQ2_PASS_NOSELF) { *model_mask |= BQ2_RF_NOSELFSHADOW; *model_xor = BQ2_RF_NOSELFSHADOW; }
+}
+int bq2_host_entity_casts(uint32_t ent_rf_flags, uint32_t model_rf_flags, int model_kind, const bq2_render_opts *opts)
+{
+    int off, brush; uint32_t em, mm, mx;
+    bq2_host_filter_masks(opts, &off, &em, &mm, &mx, &brush);
+    if (model_kind == 1) return brush;
+    return !(off || (ent_rf_flags & em) || ((model_rf_flags ^ mx) & mm));
+}
+
 /* entity-major sharding: contiguous, sizes differ by at most one */
 void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *first, int32_t *count)
 {
@@ -214,10 +254,7 @@ void bq2_shard_entities(int32_t n_ents, int32_t rank, int32_t world, int32_t *fi
 
 /* ---- the per-entity half of the world path (bq2_world_submit), one pass, plain C ---------------------- */
 #include "bq2_internal.h"
-/* the flag filter of the shadow pass with its cvars at their defaults (r_mirror 0, r_playershadow 0, r_shadows 2):
-   bq2_host_casts_shadow above, M:63722-63727, plus the caller's own test M:64089 */
-#define BQ2_RF_NO_VOLUME (BQ2_RF_VIEWERMODEL | BQ2_RF_SHELL_GREEN | BQ2_RF_SHELL_RED | BQ2_RF_SHELL_BLUE | BQ2_RF_FULLBRIGHT | \
-                          BQ2_RF_BEAM | BQ2_RF_TRANSLUCENT | BQ2_RF_WEAPONMODEL | BQ2_RF_NOCASTSHADOW | BQ2_RF_DISTORT)
+/* the flag filter of the shadow pass (bq2_host_filter_masks above: M:63722-63727, 64041-64089) arrives as masks */
 
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -239,8 +276,10 @@ void bq2_model_row_derive(bq2_model_row *r)
 }
 
 int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
+                            const bq2_render_opts *opts,
                             bq2_dev_went *rows, float *bases, int32_t *rec_of_ent, uint32_t *ent_vert_off, bq2_world_stats *st)
 {
+    int f_off, f_brush; uint32_t f_em, f_mm, f_mx;
     /* the running numbers live in locals (the stores through rows / rec_of_ent could alias *st); the six per-class
        maxima are one 8 x int16 vector (bq2_model_row.cmax), what is a function of the largest mesh (row lengths) is
        derived after the loop */
@@ -256,6 +295,8 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
     memset(m, 0, sizeof m);
 #endif
     memset(st, 0, sizeof *st);
+    bq2_host_filter_masks(opts, &f_off, &f_em, &f_mm, &f_mx, &f_brush);
+    if (f_off) f_em = 0xffffffffu, f_mm = 0xffffffffu, f_mx = 0xffffffffu;      /* nothing casts: every entity is rejected below */
     for (e = 0; e < n; e++) {
         const bq2_world_entity *W = &ents[e];
         const bq2_model_row *mo;
@@ -287,7 +328,8 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
             x->basis = n_rot++;
         } else
             x->basis = -1;
-        x->rec = rec; x->pair_rec = (W->rf_flags & BQ2_RF_NO_VOLUME) ? -1 : rec;        /* M:63722-63727, 64089 */
+        x->rec = rec;
+        x->pair_rec = (f_off | (W->rf_flags & f_em) | (((uint32_t)mo->pad[0] ^ f_mx) & f_mm)) ? -1 : rec;   /* M:63722-63727, 64041-64089 */
         x->vert_off = (uint32_t)voff; x->nrm_off = nrm_off;
         ent_vert_off[e] = (uint32_t)voff;
         voff += mo->vpad; total_verts += (uint64_t)mo->V;

@@ -139,7 +139,7 @@ typedef struct bq2_model_row {      /* host mirror of a model for the C entity l
     /* derived by bq2_model_row_derive, so that the loop has nothing to decide per entity: */
     uint32_t vpad;                  /* lerped row length, V rounded up to 4                                    */
     int32_t  team;                  /* 0: warp-kernel mesh (V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T), 1: team kernel */
-    int32_t  pad[2];
+    int32_t  pad[2];                /* [0] = model_t.flags bits of the caller loop's filter (bq2_model_set_rf_flags) */
     int16_t  cmax[8];               /* the mesh's contribution to {warp max V, warp max T, team max V, team max T,
                                        warp has an MD2, team has an MD2, 0, 0}: the frame's values are the
                                        lane-wise maxima over its entities (V <= 4,096 and T <= 8,192 fit 16 bits) */
@@ -163,8 +163,10 @@ struct bq2_world_entity;
  * entities and these rows.  Returns 0, -1 unknown model, -2 frame out of range, -3 a model is not single-mesh,
  * -4 the frame's rows do not fit 32-bit row numbers. */
 void bq2_model_row_derive(bq2_model_row *row);
+struct bq2_render_opts;
+void bq2_host_filter_masks(const struct bq2_render_opts *opts, int *off, uint32_t *ent_mask, uint32_t *model_mask, uint32_t *model_xor, int *brush);
 int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
-                             bq2_dev_went *rows, float *bases /* [n][9] */, int32_t *rec_of_ent, uint32_t *ent_vert_off,
+                             const struct bq2_render_opts *opts, bq2_dev_went *rows, float *bases /* [n][9] */, int32_t *rec_of_ent, uint32_t *ent_vert_off,
                              bq2_world_stats *st);
 /* Two kernels share the records.  "warp" kernel: one warp per (entity, light) pair, one CTA per entity,
  * for meshes with V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T (an MD2 player model is ~500 triangles).

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BQ2_ABI_VERSION 1
+#define BQ2_ABI_VERSION 2      /* 2: bq2_world_desc.opts (render options of the caller loops) */
 
 typedef enum bq2_status {
     BQ2_OK          = 0,
@@ -67,8 +67,31 @@ typedef enum bq2_status {
 #define BQ2_RF_SHELL_RED     0x00000400u
 #define BQ2_RF_SHELL_GREEN   0x00000800u
 #define BQ2_RF_SHELL_BLUE    0x00001000u
-#define BQ2_RF_NOCASTSHADOW  0x00080000u   /* filtered by the caller loop, M:64089 */
-#define BQ2_RF_DISTORT       0x10000000u
+#define BQ2_RF_NOSELFSHADOW  0x00002000u   /* model_t.flags: which of the two self-shadow passes draws it, M:64078-64083 */
+#define BQ2_RF_NOCASTSHADOW  0x00080000u   /* entity OR model flag, filtered by the caller loop, M:64089 */
+#define BQ2_RF_DISTORT       0x10000000u   /* entity OR model flag, M:64089 */
+
+/* ---- the caller loops' switches: R_DrawEntsShadowVolumes M:64041-64133 and the early-outs of
+ *      R_DrawAliasShadowVolume / R_DrawMD3AliasShadowVolume M:63722-63727, 63811-63816 -------------------------- */
+typedef enum bq2_pass {
+    BQ2_PASS_ALL    = 0,    /* R_DrawEntsShadowVolumes(false, true): every caster                                 */
+    BQ2_PASS_SELF   = 1,    /* (true, false): brush models + alias models WITHOUT RF_NOSELFSHADOW (M:64078-64080) */
+    BQ2_PASS_NOSELF = 2     /* (false, false): alias models WITH RF_NOSELFSHADOW only (M:64081-64082)             */
+} bq2_pass;
+typedef struct bq2_render_opts {
+    int32_t r_mirror;               /* data.h r_mirror: the mirrored scene is being drawn                        */
+    float   r_mirror_shadows;       /* cvar, default 2 (M:4536)                                                   */
+    float   r_mirror_models;        /* cvar, default 1 (M:4525)                                                   */
+    float   r_playershadow;         /* cvar, default 0 (M:4390)                                                   */
+    float   r_shadows;              /* cvar, default 2 (M:4383): alias volumes only when > 1                      */
+    float   r_drawentities;         /* cvar, default 1 (M:4556)                                                   */
+    int32_t pass;                   /* bq2_pass                                                                   */
+} bq2_render_opts;
+void bq2_render_opts_default(bq2_render_opts *o);       /* the engine's defaults above, r_mirror 0, BQ2_PASS_ALL */
+/* 1 = the loop reaches the entity's volume builder and the builder does not return early.  model_kind: 0 alias
+ * (MD2 / MD3; the per-mesh skin filter M:63862-63880 is bq2_md3_mesh.casts_shadow), 1 brush model (M:64066-64071:
+ * entity / model flags are not looked at).  model_rf_flags = model_t.flags.  opts NULL = defaults. */
+int  bq2_host_entity_casts(uint32_t ent_rf_flags, uint32_t model_rf_flags, int model_kind, const bq2_render_opts *opts);
 
 /* bq2_entity.flags (ours) */
 #define BQ2_ENT_SHELL        0x1u   /* add anorm[cur.lightnormalindex]*shell_scale  (M:63565-63572) */
@@ -196,6 +219,10 @@ typedef struct bq2_md3_mesh {
 
 bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t num_frames, const float *frame_translate /*[F][3]*/,
                           const bq2_md3_mesh *meshes, int32_t num_meshes, int32_t *model_id);
+
+/* model_t.flags of an uploaded model: the bits the caller loop reads (BQ2_RF_NOCASTSHADOW, BQ2_RF_DISTORT,
+ * BQ2_RF_NOSELFSHADOW; M:64078-64089); 0 after upload. */
+bq2_status bq2_model_set_rf_flags(bq2_ctx *ctx, int32_t model_id, uint32_t model_rf_flags);
 
 bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
                           int32_t *num_frames, int32_t *num_meshes,
@@ -404,6 +431,14 @@ bq2_status bq2_build_records(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t
                              const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
                              const float *view_world /* [3] or NULL */,
                              bq2_entity *out_ents, bq2_pair *out_pairs, int32_t *n_pairs_out);
+/* The same under explicit render options (cvars, r_mirror, pass) and the models' own flags (bq2_model_set_rf_flags):
+ * a pair is kept exactly when the engine's loop would have produced a volume for it.  opts NULL = defaults, which is
+ * what bq2_build_records uses. */
+bq2_status bq2_build_records_opts(bq2_ctx *ctx, const bq2_world_entity *ents, int32_t n_ents,
+                                  const bq2_world_light *lights, int32_t n_lights,
+                                  const int32_t *pair_ent, const int32_t *pair_light, int32_t n_pairs,
+                                  const float *view_world, const bq2_render_opts *opts,
+                                  bq2_entity *out_ents, bq2_pair *out_pairs, int32_t *n_pairs_out);
 
 /* ---- the same, fused, with the per-pair records built ON THE DEVICE ----------------------------------- */
 /* bq2_build_records + bq2_frame in one call.  The host does only what needs libm or the model table (per
@@ -422,6 +457,7 @@ typedef struct bq2_world_desc {
     const int32_t *pair_ent, *pair_light;  int32_t n_pairs;
     const float   *view_world;       /* [3] or NULL */
     uint32_t want, index_stride;
+    const bq2_render_opts *opts;     /* NULL = the engine's defaults (bq2_render_opts_default) */
 } bq2_world_desc;
 /* Page-locked host memory for the arrays a bq2_world_desc points at.  When ents, lights, pair_ent and pair_light of a
  * submit ALL lie inside blocks from bq2_host_alloc and together exceed 1 MiB, bq2_world_submit copies the light and

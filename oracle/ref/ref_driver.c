@@ -112,11 +112,16 @@ void glDrawElements(GLenum mode, GLsizei count, GLenum type, const GLvoid *indic
 /* R_RotateForEntity (M:26670) is called right after the light went to model space (M:63747):
    snapshot what the compute functions will see. */
 static float snap_light[3], snap_view[3];
+/* R_DrawEntsShadowVolumes run whole (bq2ref_ents_shadow_volumes below): each of the three volume builders calls
+   R_RotateForEntity exactly once, after its own early-outs -- the entity that got this far is recorded here */
+static entity_t *sink_ents; static int sink_n, *sink_order, sink_count;
 void glTranslatef(GLfloat x, GLfloat y, GLfloat z)
 {
     (void)x; (void)y; (void)z;
     if (currentshadowlight) for (int k = 0; k < 3; k++) snap_light[k] = currentshadowlight->origin[k];
     for (int k = 0; k < 3; k++) snap_view[k] = r_origin[k];
+    if (sink_order && currententity >= sink_ents && currententity < sink_ents + sink_n)
+        sink_order[sink_count++] = (int)(currententity - sink_ents);
 }
 
 /* ---- set-up ---------------------------------------------------------------------------------- */
@@ -318,6 +323,55 @@ long long bq2ref_md2_world_hash(void *const *blobs, void *const *neighbours, int
         hashes[p] = hash_globals(h->num_xyz, h->num_tris);
     }
     return total;
+}
+
+/* ---- the caller loop: R_DrawEntsShadowVolumes M:64041-64133 whole ---------------------- */
+extern int        cl_numlightvisedicts;                          /* data.h:2728 */
+extern entity_t  *cl_lightvisedicts[];                           /* data.h:2729 */
+extern cvar_t    *r_mirror_shadows, *r_mirror_models, *r_drawentities;
+void R_DrawEntsShadowVolumes(bool SelfShadow, bool all);
+
+/* n entities of kind 0 (MD2: md2_blob / md2_nb), 1 (MD3: an empty mesh list -- only the early-outs and the transform
+ * run) or 2 (brush model without surfaces), each with entity flags and MODEL flags; the cvars and r_mirror as given.
+ * Runs the engine's loop and returns how many entities reached their volume builder; order_out = their indices in
+ * call order.  Nothing of the loop's logic is restated. */
+int bq2ref_ents_shadow_volumes(int n, const int *kinds, const int *ent_flags, const int *model_flags,
+                               void *md2_blob, const int32_t *md2_nb,
+                               int mirror, float mirror_shadows, float mirror_models, float playershadow, float shadows,
+                               float drawentities, int self_shadow, int all, int *order_out)
+{
+    static cvar_t cv_ms, cv_mm, cv_de;
+    static maliasmodel_t mm; static maliasframe_t mframes[1];
+    static const float org[3] = {10, 20, 30}, lorg[3] = {100, 50, 80};
+    bq2ref_init();
+    if (n > 256) return -1;
+    entity_t *es = calloc((size_t)n, sizeof *es);
+    model_t *ms = calloc((size_t)n, sizeof *ms);
+    if (!es || !ms) { free(es); free(ms); return -1; }
+    memset(&mm, 0, sizeof mm); memset(mframes, 0, sizeof mframes); mm.num_frames = 1; mm.frames = mframes; mm.num_meshes = 0;
+    memset(&cv_ms, 0, sizeof cv_ms); memset(&cv_mm, 0, sizeof cv_mm); memset(&cv_de, 0, sizeof cv_de);
+    cv_ms.value = mirror_shadows; cv_mm.value = mirror_models; cv_de.value = drawentities;
+    r_mirror_shadows = &cv_ms; r_mirror_models = &cv_mm; r_drawentities = &cv_de;
+    const float keep_shadows = cv_shadows.value, keep_ps = cv_playershadow.value;
+    cv_shadows.value = shadows; cv_playershadow.value = playershadow; r_mirror = mirror ? true : false;
+    for (int i = 0; i < n; i++) {
+        model_t *m = &ms[i];
+        m->flags = model_flags[i];
+        if (kinds[i] == 0) { m->type = mod_alias; m->extradata = md2_blob; m->triangles = (neighbours_t *)md2_nb; }
+        else if (kinds[i] == 1) { m->type = mod_alias_md3; m->extradata = &mm; }
+        else { m->type = mod_brush; m->nummodelsurfaces = 0; m->firstmodelsurface = 0; }
+        es[i].model = m; es[i].flags = ent_flags[i]; es[i].frame = 0; es[i].oldframe = 0; es[i].backlerp = 0.25f;
+        for (int k = 0; k < 3; k++) { es[i].origin[k] = org[k] + i; es[i].oldorigin[k] = org[k] + i; }
+        cl_lightvisedicts[i] = &es[i];
+    }
+    cl_numlightvisedicts = n;
+    set_light(lorg, 300.0f);
+    sink_ents = es; sink_n = n; sink_order = order_out; sink_count = 0;
+    R_DrawEntsShadowVolumes(self_shadow ? true : false, all ? true : false);
+    sink_order = 0; cl_numlightvisedicts = 0;
+    cv_shadows.value = keep_shadows; cv_playershadow.value = keep_ps; r_mirror = false;
+    free(es); free(ms);
+    return sink_count;
 }
 
 /* MD2 light-lerp family.  which: 0 = ..LightARB (LightP on TMU1, tsH on TMU3, expanded verts on

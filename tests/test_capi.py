@@ -31,7 +31,7 @@ def test_every_declared_symbol_is_exported(header):
 
 
 def test_abi_version_and_record_sizes():
-    assert _capi.lib.bq2_abi_version() == 1
+    assert _capi.lib.bq2_abi_version() == 2
     assert bq2.ENTITY_DTYPE.itemsize == 64 and bq2.PAIR_DTYPE.itemsize == 32
     assert bq2.WORLD_ENTITY_DTYPE.itemsize == 56 and bq2.WORLD_LIGHT_DTYPE.itemsize == 16
 
