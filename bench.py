@@ -501,6 +501,37 @@ def run_gpu(args):
         c.lib.bq2_frame(ctx._h, C.byref(fd), C.byref(fo))
     e2e_host_s = time.perf_counter() - t0
 
+    # ---- the route that DELIVERS geometry to host memory: per frame bq2_world_submit + bq2_frame_wait, then the frame's
+    # lerped rows, extruded rows and index buffers (every pair's first max-count words, one strided copy) to page-locked
+    # host memory -- what a renderer that draws from host arrays (the reference ends in glDrawArrays over TrisVerts,
+    # M:63778-63788) would consume.  Four frames in flight; the copies of frame i run while frames i+1.. compute.
+    cnt_max = int(max(ring_indices) / n_pairs * 1.35) + 64              # words per pair brought back (>= every count: checked)
+    vrow = (V + 3) & ~3
+    g_l = ctx.host_array(np.zeros(3 * n_ents * vrow, np.float32)); g_e = ctx.host_array(np.zeros(3 * n_pairs * vrow, np.float32))
+    g_i = ctx.host_array(np.zeros(n_pairs * cnt_max, np.uint32))
+
+    def geometry_frames(k):
+        for _ in range(E2E_IN_FLIGHT - 1):
+            e2e_submit()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_submit(); e2e_wait()
+            for which, buf in ((c.A_LERPED, g_l), (c.A_EXTRUDED, g_e)):
+                if c.lib.bq2_download(ctx._h, which, 0, buf.size, c.ptr(buf)) != 0:
+                    raise RuntimeError(c.lib.bq2_last_error(ctx._h))
+            if c.lib.bq2_download_indices(ctx._h, 0, n_pairs, cnt_max, c.ptr(g_i)) != 0:
+                raise RuntimeError(c.lib.bq2_last_error(ctx._h))
+        dt = time.perf_counter() - t0
+        for _ in range(E2E_IN_FLIGHT - 1):
+            e2e_wait()
+        return dt
+    geometry_frames(3)
+    k_geo = max(5, min(args.steps, 40))
+    e2e_geo_s = geometry_frames(k_geo) / k_geo
+    counts_h = np.ctypeslib.as_array(c.lib.bq2_host_index_counts(ctx._h), (n_pairs,))
+    assert int(counts_h.max()) <= cnt_max, "geometry leg: a pair has more indices than were brought back"
+    geo_bytes = 4 * (g_l.size + g_e.size + g_i.size)
+
     # ---- SURVEY 8(d) variant: every entity instantiates the SAME model (key frames come from L2 after first touch) --
     we_s = we.copy(); we_s["model"] = mids[0, 0]
     ents_s, pairs_s = ctx.build_records(we_s, wl, pe, pl)
@@ -534,6 +565,10 @@ def run_gpu(args):
     c3 = None
     if not args.no_c3:
         c3 = c3_strong_leg(args, local, rank, world, barrier, dev, dist, l2_bytes)
+
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_dropin:
+        dropin = dropin_leg(args)
 
     if rank == 0:
         ms_per_step = ms_total_max / args.steps
@@ -571,6 +606,11 @@ def run_gpu(args):
                     "ms_per_step_pageable_inputs": e2e_pageable_s * 1e3 / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
+                    "geometry_d2h": {"ms_per_step": e2e_geo_s * 1e3, "tris_per_s": e2e_indices / args.steps / 3 / e2e_geo_s,
+                                     "d2h_bytes_per_step": geo_bytes, "d2h_gb_per_s": geo_bytes / e2e_geo_s / 1e9,
+                                     "what": "the same frames, and every frame's lerped rows, extruded rows and index buffers "
+                                             f"(the first {cnt_max} words of each pair's row, one strided copy) copied to "
+                                             "page-locked host memory: the route for a renderer that draws from host arrays"},
                     "h2d_bytes_per_step": n_ents * 64 + 16 + len(wl_c) * 16 + n_pairs * 8 + h2d_basis_bytes, "d2h_bytes_per_step": 4 * n_pairs + 24,
                     "what": "per frame: bq2_world_submit (host: per-entity validation, numbering and AngleVectors into one 64-byte "
                             "row per entity that also carries the caller's entity fields; H2D of those rows, the bases of the "
@@ -601,6 +641,8 @@ def run_gpu(args):
                     "that back-to-back steps hide"}
         if c3 is not None:
             out["c3_strong"] = c3
+        if dropin is not None:
+            out["e2e"]["dropin"] = dropin
         if world == 1 and not args.no_traffic:
             t, why = measure_traffic(args, os.path.join(ROOT, "gpurun_out"))
             if t is not None:
@@ -625,6 +667,57 @@ def run_gpu(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def dropin_worker(args):
+    """The reference's own R_DrawAliasShadowVolume (unmodified object code) with integration/bq2_dropin.c linked in front of
+    it (oracle/_ref/libbq2ref_dropin.so): the three compute functions it calls are the CUDA-backed ones, a batch of one
+    per call, results copied back into the engine's globals (TrisVerts filled)."""
+    from berserkerquake2_b200 import synth, host
+    so = os.path.join(ROOT, "oracle", "_ref", "libbq2ref_dropin.so")
+    lib = C.CDLL(so); fn = lib.bq2ref_md2_world_bench; lib.bq2ref_init()
+    fn.restype = C.c_longlong
+    fn.argtypes = [C.c_void_p] * 2 + [C.c_int] + [C.c_void_p] * 8
+    n_ents, lights = args.cpu_ents, args.cpu_lights
+    we, wl, pe, pl = make_scene(n_ents, lights)
+    n = len(pe)
+    blobs = [synth.md2(SLICES, RINGS, FRAMES, e) for e in range(n_ents)]
+    nb = host.md2_neighbours(blobs[0])
+    bp = (C.c_void_p * n)(*[blobs[int(e)].ctypes.data for e in pe])
+    np_ = (C.c_void_p * n)(*[nb.ctypes.data] * n)
+    a = dict(frames=we["frame"][pe].astype(np.int32), oldframes=we["oldframe"][pe].astype(np.int32),
+             backlerps=we["backlerp"][pe].astype(np.float32), origins=np.ascontiguousarray(we["origin"][pe]),
+             oldorigins=np.ascontiguousarray(we["oldorigin"][pe]), angles=np.ascontiguousarray(we["angles"][pe]),
+             lights=np.ascontiguousarray(wl["origin"][pl]), radii=np.ascontiguousarray(wl["radius"][pl]))
+    P = lambda x: x.ctypes.data_as(C.c_void_p)
+    call = lambda: fn(bp, np_, n, P(a["frames"]), P(a["oldframes"]), P(a["backlerps"]), P(a["origins"]),
+                      P(a["oldorigins"]), P(a["angles"]), P(a["lights"]), P(a["radii"]))
+    call(); call()                                       # models become resident, clocks ramp
+    times = []
+    for _ in range(5):
+        t0 = time.perf_counter(); tot = call(); times.append(time.perf_counter() - t0)
+    lib.bq2_dropin_kernel_launches.restype = C.c_int
+    print(json.dumps({"pairs": n, "indices": int(tot), "s": float(np.median(times)), "s_min_max": [min(times), max(times)],
+                      "launches": int(lib.bq2_dropin_kernel_launches())}), flush=True)
+
+
+def dropin_leg(args):
+    so = os.path.join(ROOT, "oracle", "_ref", "libbq2ref_dropin.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libbq2ref_dropin.so not built (needs the reference tree at build time)"}
+    n_ents, lights = 64, 4                               # a bounded sample of the C2 scene: its first 64 entities
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--_dropin_worker", "--cpu-ents", str(n_ents),
+                            "--cpu-lights", str(lights)], capture_output=True, text=True, timeout=180)
+        d = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    except (subprocess.TimeoutExpired, OSError, IndexError, ValueError) as e:
+        return {"unavailable": f"{type(e).__name__}"}
+    return {"ms_per_pair": d["s"] * 1e3 / d["pairs"], "tris_per_s": d["indices"] / 3 / d["s"], "pairs_per_s": d["pairs"] / d["s"],
+            "sample": f"the first {n_ents} entities x {lights} lights of the C2 scene, 5 passes, median; one process, one pair per call",
+            "what": "the signature-keeping route: the reference's own, unmodified R_DrawAliasShadowVolume (M:63713) calls "
+                    "R_CalcAliasFrameLerpShadow / R_CalcAliasFrameShadowVolume, which integration/bq2_dropin.c implements as a "
+                    "batch of ONE on the C ABI (submit, wait, lerped / extruded / facing / TrisVerts copied back into the "
+                    "engine's globals); the cost of one synchronous round trip per pair -- the batched routes above are the product"}
 
 
 def c3_strong_leg(args, local, rank, world, barrier, dev, dist, l2_bytes):
@@ -808,12 +901,16 @@ def main():
     ap.add_argument("--no-traffic", action="store_true", help="skip the in-run DRAM traffic measurement (ncu child)")
     ap.add_argument("--traffic-timeout", type=float, default=240.0)
     ap.add_argument("--_traffic_probe", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--_dropin_worker", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in (signature-keeping) e2e leg")
     ap.add_argument("--probe-mode", default="range", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args._cpu_worker:
         return cpu_worker(args)
     if args._traffic_probe:
         return traffic_probe(args)
+    if args._dropin_worker:
+        return dropin_worker(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_gpu(args)

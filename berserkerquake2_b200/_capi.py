@@ -128,6 +128,7 @@ EXPORTS_GPU_H = [
     _sig("bq2_profiler_range", C.c_int, vp, C.c_int),
     _sig("bq2_resident_free", None, vp, vp),
     _sig("bq2_download", C.c_int, vp, C.c_int, u64, u64, vp),
+    _sig("bq2_download_indices", C.c_int, vp, i32, i32, u32, vp),
     _sig("bq2_host_index_counts", C.POINTER(u32), vp),
     _sig("bq2_expand_trisverts", C.c_int, vp, i32, vp, i32, C.POINTER(i32)),
     _sig("bq2_host_angle_vectors", None, vp, vp, vp, vp),

@@ -1597,6 +1597,24 @@ try {
     return BQ2_OK;
 } catch (...) { return guard_exception(ctx); }
 
+/* The first `words_per_slot` index words of pair slots [first_slot, first_slot + n_slots) of the frame bq2_frame_wait
+   returned last, packed into host[n_slots][words_per_slot] by ONE strided copy (a consumer that draws from host memory
+   brings a frame's index buffers back with this and bq2_download of the two vertex arrays). */
+bq2_status bq2_download_indices(bq2_ctx *ctx, int32_t first_slot, int32_t n_slots, uint32_t words_per_slot, uint32_t *host)
+try {
+    if (!ctx || !host || first_slot < 0 || n_slots < 0) return BQ2_E_INVALID;
+    FrameState &F = ctx->fs[ctx->last_waited];
+    const uint32_t stride = F.launch.index_stride;
+    if (!ctx->submitted || !F.indices.p || first_slot + n_slots > F.n_pair_slots || words_per_slot > stride)
+        return fail(ctx, BQ2_E_INVALID, "bq2_download_indices: range outside the frame");
+    if (n_slots == 0 || words_per_slot == 0) return BQ2_OK;
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    CK(cudaMemcpy2DAsync(host, (size_t)words_per_slot * 4, F.indices.p + (size_t)first_slot * stride, (size_t)stride * 4,
+                         (size_t)words_per_slot * 4, (size_t)n_slots, cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy2D(indices)");
+    CK(cudaStreamSynchronize(F.stream), "cudaStreamSynchronize(download)");
+    return BQ2_OK;
+} catch (...) { return guard_exception(ctx); }
+
 /* the same from the result arrays a kept frame writes to (its own, or those of its frame state) */
 bq2_status bq2_resident_download(bq2_ctx *ctx, const bq2_resident *r, bq2_array which, uint64_t first, uint64_t count, void *host)
 try {

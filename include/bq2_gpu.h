@@ -277,6 +277,9 @@ typedef enum bq2_array {
     BQ2_A_NORMALS, BQ2_A_TANGENTS, BQ2_A_BINORMALS, BQ2_A_LIGHTP, BQ2_A_TSH
 } bq2_array;
 bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host);
+/* The first words_per_slot index words of pair slots [first_slot, first_slot + n_slots), packed into
+ * host[n_slots][words_per_slot] by one strided copy (host memory from bq2_host_alloc makes it a DMA). */
+bq2_status bq2_download_indices(bq2_ctx *ctx, int32_t first_slot, int32_t n_slots, uint32_t words_per_slot, uint32_t *host);
 /* the same from the arrays a kept frame writes to (its own after bq2_frame_keep_own) */
 bq2_status bq2_resident_download(bq2_ctx *ctx, const bq2_resident *r, bq2_array which, uint64_t first, uint64_t count, void *host);
 const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx);  /* pinned host copy, n_pair_slots      */
