@@ -282,7 +282,7 @@ def measure_traffic(args, log_dir):
     metrics = "dram__bytes_read.sum,dram__bytes_write.sum"
     tries = [
         ("range", "ncu --replay-mode app-range over cudaProfilerStart/Stop around the K back-to-back launches",
-         [ncu, "--replay-mode", "app-range", "--profile-from-start", "off", "--metrics", metrics, "--print-units", "base",
+         [ncu, "--replay-mode", "app-range", "--metrics", metrics, "--print-units", "base",
           "--csv", "--clock-control", "none", "--cache-control", "none"]),
         ("kernel", "ncu --replay-mode application, one pass, the K launches of the region profiled one by one",
          [ncu, "--replay-mode", "application", "--profile-from-start", "off", "--metrics", metrics, "--print-units", "base",
