@@ -521,6 +521,7 @@ _HASH_JOB = {}
 
 
 def _hash_worker(rng):
+    import time
     lo, hi = rng
     J = _HASH_JOB
     lib = C.CDLL(REF_SO)
@@ -528,6 +529,9 @@ def _hash_worker(rng):
     fn = lib.bq2ref_md2_world_hash
     fn.restype = C.c_longlong
     fn.argtypes = [vp] * 2 + [i32] + [vp] * 9
+    bench = lib.bq2ref_md2_world_bench
+    bench.restype = C.c_longlong
+    bench.argtypes = [vp] * 2 + [i32] + [vp] * 8
     we, wl, pe, pl = J["we"], J["wl"], J["pe"][lo:hi], J["pl"][lo:hi]
     n = hi - lo
     if n == 0:
@@ -540,10 +544,16 @@ def _hash_worker(rng):
                                            we["angles"][pe], wl["origin"][pl], wl["radius"][pl].astype(np.float32))]
     out = np.zeros(n, np.uint64)
     tot = fn(bp, nbp, n, *[P(x) for x in a], P(out))
-    return out, int(tot)
+    secs = 0.0
+    if J.get("timed_passes"):                            # the same slice again, without the hashing, timed
+        t0 = time.perf_counter()
+        for _ in range(J["timed_passes"]):
+            bench(bp, nbp, n, *[P(x) for x in a])
+        secs = (time.perf_counter() - t0) / J["timed_passes"]
+    return out, int(tot), secs
 
 
-def reference_pair_hashes(blobs, nbs, we, wl, pe, pl, procs=None):
+def reference_pair_hashes(blobs, nbs, we, wl, pe, pl, procs=None, timed_passes=0, want_seconds=False):
     """hash of every pair (pe[k], pl[k]) computed by the unmodified reference (whole R_DrawAliasShadowVolume per pair),
     fanned out over forked processes (the engine keeps its state in globals).  blobs / nbs: per MODEL id (we["model"]
     indexes them): MD2 images and int32 neighbour tables.  Returns (uint64 [n_pairs], total index count)."""
@@ -553,7 +563,8 @@ def reference_pair_hashes(blobs, nbs, we, wl, pe, pl, procs=None):
     procs = max(1, min(procs, n))
     _HASH_JOB.clear()
     _HASH_JOB.update(blobs=[np.ascontiguousarray(b) for b in blobs], nbs=[np.ascontiguousarray(x, np.int32) for x in nbs],
-                     we=we, wl=wl, pe=np.ascontiguousarray(pe, np.int32), pl=np.ascontiguousarray(pl, np.int32))
+                     we=we, wl=wl, pe=np.ascontiguousarray(pe, np.int32), pl=np.ascontiguousarray(pl, np.int32),
+                     timed_passes=int(timed_passes))
     ranges = [(n * w // procs, n * (w + 1) // procs) for w in range(procs)]
     if procs == 1:
         res = [_hash_worker(ranges[0])]
@@ -561,4 +572,6 @@ def reference_pair_hashes(blobs, nbs, we, wl, pe, pl, procs=None):
         with mp.get_context("fork").Pool(procs) as pool:
             res = pool.map(_hash_worker, ranges)
     _HASH_JOB.clear()
+    if want_seconds:        # seconds per pass over the whole list = the slowest process's (timed_passes > 0), and the process count
+        return np.concatenate([r[0] for r in res]), sum(r[1] for r in res), max(r[2] for r in res), procs
     return np.concatenate([r[0] for r in res]), sum(r[1] for r in res)
