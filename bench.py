@@ -20,7 +20,7 @@ One "step" = one pass of the path over the whole batch = ONE launch of the fused
             THIS RUN by a child process under ncu's range replay over the same K back-to-back steps.
   e2e       the same metric through the C ABI from HOST arrays: bq2_world_submit (host: validation, numbering,
             AngleVectors; H2D; record-building kernel + fused kernel; D2H of the per-pair counts) + bq2_frame_wait,
-            four frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
+            eight frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
   c3_strong BASELINE configs[2] as written: 65,536 entities x 8 lights sharded entity-major over the N GPUs
             (strong scaling), same timing rules
   cpu_baseline  oracle/_ref (the unmodified reference, compiled headless) on the host cores, N=1 only
@@ -53,8 +53,8 @@ L2_FLUSH_BYTES = 256 << 20
 E2E_REPEATS = 9            # the K-frame wall-clock measurement is repeated at least this often, and for at least
 E2E_MIN_SECONDS = 0.5      # this long (nine 100-frame runs last 20 ms: one hiccup of the host would cover them all);
 E2E_MAX_REPEATS = 999      # the median run is reported, min/max alongside
-E2E_IN_FLIGHT = int(os.environ.get("BQ2_BENCH_IN_FLIGHT", "4"))   # frames the e2e leg keeps in flight (the library allows
-                           # four; results of each stay separate; the variable is for experiment builds of the library)
+E2E_IN_FLIGHT = int(os.environ.get("BQ2_BENCH_IN_FLIGHT", "8"))   # frames the e2e leg keeps in flight (the library allows
+                           # eight, bq2_max_frames_in_flight; the results of each stay separate)
 
 
 def peaks():
@@ -460,7 +460,7 @@ def run_gpu(args):
             e2e_wait()
         return (tot, dt) if timed else tot
 
-    e2e_run(max(args.warmup, 12))      # every frame state of the ring has captured its graph before the timed frames
+    e2e_run(max(args.warmup, 30))      # every frame state of the ring has captured its graph before the timed frames
     barrier()
     _, e2e_py_s = e2e_run(args.steps, timed=True)                  # the same loop driven from Python (ctypes per call)
     # the frame loop as an engine runs it: C on top of the public ABI (csrc/bq2_frame_loop.c), same calls, same depth
@@ -469,12 +469,12 @@ def run_gpu(args):
     loop.bq2_frame_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     sec, tot64 = C.c_double(0), C.c_uint64(0)
 
-    def e2e_loop(k, desc=None):
-        if loop.bq2_frame_loop(ctx._h, C.byref(desc or wd), k, E2E_IN_FLIGHT, C.byref(sec), C.byref(tot64)) != 0:
+    def e2e_loop(k, desc=None, depth=E2E_IN_FLIGHT):
+        if loop.bq2_frame_loop(ctx._h, C.byref(desc or wd), k, depth, C.byref(sec), C.byref(tot64)) != 0:
             raise RuntimeError(c.lib.bq2_last_error(ctx._h))
         return int(tot64.value), float(sec.value)
 
-    e2e_loop(max(args.warmup, 12))
+    e2e_loop(max(args.warmup, 30))
     barrier()
     launches_e2e0 = ctx.kernel_launches
     e2e_runs, t_e2e0 = [], time.perf_counter()                     # K frames each; the median run is reported
@@ -485,8 +485,12 @@ def run_gpu(args):
     e2e_indices, e2e_s = sorted(e2e_runs, key=lambda r: r[1])[e2e_repeats // 2]
     e2e_spread = [min(r[1] for r in e2e_runs) * 1e3 / args.steps, max(r[1] for r in e2e_runs) * 1e3 / args.steps]
     barrier()
-    e2e_loop(max(args.warmup, 12), wd_pageable)                    # the same from pageable arrays (staged by the library)
+    e2e_loop(max(args.warmup, 30), wd_pageable)                    # the same from pageable arrays (staged by the library)
     _, e2e_pageable_s = e2e_loop(args.steps, wd_pageable)
+    e2e_by_depth = {}
+    for d in (2, 4):                                               # fewer frames in flight: less latency, lower rate
+        e2e_loop(20, None, d)
+        e2e_by_depth[d] = float(np.median([e2e_loop(args.steps, None, d)[1] for _ in range(9)]))
     t0 = time.perf_counter()                                      # one frame at a time (latency of a frame)
     for _ in range(args.steps):
         e2e_submit(); e2e_wait()
@@ -504,7 +508,7 @@ def run_gpu(args):
     # ---- the route that DELIVERS geometry to host memory: per frame bq2_world_submit + bq2_frame_wait, then the frame's
     # lerped rows, extruded rows and index buffers (every pair's first max-count words, one strided copy) to page-locked
     # host memory -- what a renderer that draws from host arrays (the reference ends in glDrawArrays over TrisVerts,
-    # M:63778-63788) would consume.  Four frames in flight; the copies of frame i run while frames i+1.. compute.
+    # M:63778-63788) would consume.  Frames in flight as above; the copies of frame i run while frames i+1.. compute.
     cnt_max = int(max(ring_indices) / n_pairs * 1.35) + 64              # words per pair brought back (>= every count: checked)
     vrow = (V + 3) & ~3
     g_l = ctx.host_array(np.zeros(3 * n_ents * vrow, np.float32)); g_e = ctx.host_array(np.zeros(3 * n_pairs * vrow, np.float32))
@@ -605,6 +609,9 @@ def run_gpu(args):
                     "ms_per_step_python_driver": e2e_py_s * 1e3 / args.steps,
                     "ms_per_step_pageable_inputs": e2e_pageable_s * 1e3 / args.steps,
                     "ms_per_step_serial": e2e_serial_s * 1e3 / args.steps,
+                    "frames_in_flight": E2E_IN_FLIGHT,
+                    "ms_per_step_2_in_flight": e2e_by_depth[2] * 1e3 / args.steps,
+                    "ms_per_step_4_in_flight": e2e_by_depth[4] * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
                     "geometry_d2h": {"ms_per_step": e2e_geo_s * 1e3, "tris_per_s": e2e_indices / args.steps / 3 / e2e_geo_s,
                                      "d2h_bytes_per_step": geo_bytes, "d2h_gb_per_s": geo_bytes / e2e_geo_s / 1e9,

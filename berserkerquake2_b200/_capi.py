@@ -101,6 +101,7 @@ vp, i32, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_floa
 # every symbol include/bq2_gpu.h declares
 EXPORTS_GPU_H = [
     _sig("bq2_abi_version", C.c_int),
+    _sig("bq2_max_frames_in_flight", C.c_int),
     _sig("bq2_create", C.c_int, C.c_int, C.POINTER(vp)),
     _sig("bq2_destroy", None, vp),
     _sig("bq2_last_error", C.c_char_p, vp),

@@ -19,6 +19,11 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <chrono>
 #include "bq2_gpu.h"
 #include "bq2_internal.h"
 
@@ -80,9 +85,13 @@ struct PinBuf {
 
 /* everything that belongs to ONE frame */
 #define BQ2_DIRECT_MIN_BYTES (1u << 20)
-#ifndef BQ2_FRAME_STATES        /* (overridable for experiments: make EXTRA="-DBQ2_FRAME_STATES=8 -DBQ2_MAX_IN_FLIGHT=7") */
-#define BQ2_FRAME_STATES   5
-#define BQ2_MAX_IN_FLIGHT  4
+/* Eight frames in flight: a world frame is a chain of five dependent stream operations (copy in, clear, two kernels,
+   copy out) whose END-TO-END LATENCY is 50-60 us on a B200 even when the kernels are trivial (copy-engine and graph-node
+   latencies), so the frame rate of a pipelined caller is latency / frames in flight until the host or the SMs become the
+   limit: C2 measured 21.3 / 17.1 / 14.8 us per frame with 4 / 6 / 8 in flight (profiles/r02_history.md). */
+#ifndef BQ2_FRAME_STATES        /* (overridable for experiments: make EXTRA="-DBQ2_FRAME_STATES=5 -DBQ2_MAX_IN_FLIGHT=4") */
+#define BQ2_FRAME_STATES   9
+#define BQ2_MAX_IN_FLIGHT  8
 #endif
 static_assert(BQ2_MAX_IN_FLIGHT < BQ2_FRAME_STATES, "the state bq2_frame_wait returned last must not be the one taken next");
 struct FrameState {
@@ -106,6 +115,17 @@ struct FrameState {
     DevBuf<unsigned char> d_world;                               /* world path: dpairs | buckets | overflow chain */
     bq2_world_launch wlaunch{};
     bool world_mode = false, world_tables = false;
+    /* what the stream operations of a world frame need, so that they can be enqueued by the ctx's submit worker
+       (bq2_world_submit returns after the per-entity loop; bq2_frame_wait meets the worker before it meets the GPU) */
+    struct WorldJob {
+        const void *lights = nullptr, *pair_ent = nullptr, *pair_light = nullptr;   /* caller arrays the worker still reads */
+        bool direct = false, stage = false, use_key = false;
+        size_t off_xf = 0, off_lights = 0, off_pe = 0, off_pl = 0, off_b = 0, basis_bytes = 0, copy_end = 0, tot_word = 0, cnt_word = 0;
+        int nE = 0, nL = 0, nP = 0; uint32_t want = 0;
+        GraphKey key{};
+        bq2_status status = BQ2_OK; std::string err;
+    } job;
+    std::atomic<uint64_t> job_posted{0}, job_done{0};
     bq2_launch launch{};
     /* entity-slot records are grouped by kernel: [0, n_warp) -> warp kernel, [n_warp, n_ent_slots) -> team kernel */
     struct KLaunch { int n = 0, max_V = 0, max_T = 0, any_md2 = 0; } k_warp, k_team;
@@ -147,8 +167,17 @@ struct bq2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;                               /* = fs[0].stream: uploads, load-time kernels, brush pairs */
     std::string err;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     Trace trace;
+    /* submit worker: one thread per ctx that issues the stream operations of world frames (staging copy of the caller's
+       page-locked arrays, graph launch), so that the caller's thread pays for the per-entity loop only */
+    std::thread worker;
+    std::mutex wmx; std::condition_variable wcv;
+    std::atomic<int> wq[BQ2_FRAME_STATES + 1];              /* ring of frame-state numbers */
+    std::atomic<uint64_t> wq_head{0}, wq_tail{0};
+    std::atomic<bool> wstop{false}, wsleeping{false};
+    bool use_worker = getenv("BQ2_NO_SUBMIT_THREAD") == nullptr;
+    double last_submit_us = -1e18;
 
     std::vector<Slab> slabs;
     std::vector<Model> models;
@@ -164,7 +193,7 @@ struct bq2_ctx {
     /* Complete frame states (host tables, pinned buffers, device records AND device result arrays, stream, event,
        graph) used as a ring: frames i+1, i+2 are packed, copied and computed while frame i is still on the GPU or
        being consumed.  A submit takes the next state of the ring when a frame is in flight, the same one otherwise;
-       with at most BQ2_MAX_IN_FLIGHT (four) in flight the state bq2_frame_wait returned last is never the one taken next. */
+       with at most BQ2_MAX_IN_FLIGHT (eight) in flight the state bq2_frame_wait returned last is never the one taken next. */
     FrameState fs[BQ2_FRAME_STATES];
     int cur = 0;                                                 /* state of the most recently submitted frame */
     uint64_t submit_seq = 0, wait_seq = 0;
@@ -183,12 +212,17 @@ struct bq2_ctx {
 
 namespace {
 
+/* kernels issued while a stream is being captured are not launched: they are counted aside and added per graph launch */
+thread_local uint64_t *tl_capture_count = nullptr;
+#define COUNT_LAUNCH(ctx, n) do { if (tl_capture_count) *tl_capture_count += (uint64_t)(n); else (ctx)->launches += (uint64_t)(n); } while (0)
+/* the submit worker (below) reports into its job: ctx->err belongs to the caller's thread */
+thread_local std::string *tl_err_sink = nullptr;
 bq2_status fail(bq2_ctx *c, bq2_status s, const char *what)
-{ if (c) c->err = what; else g_create_error = what; return s; }
+{ if (tl_err_sink) *tl_err_sink = what; else if (c) c->err = what; else g_create_error = what; return s; }
 bq2_status fail_cuda(bq2_ctx *c, cudaError_t e, const char *where)
 {
     std::string m = std::string(where) + ": " + cudaGetErrorString(e);
-    if (c) c->err = m; else g_create_error = m;
+    if (tl_err_sink) *tl_err_sink = m; else if (c) c->err = m; else g_create_error = m;
     cudaGetLastError();                      /* a launch error must not be reported again by the next call */
     return BQ2_E_CUDA;
 }
@@ -287,7 +321,7 @@ bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F, int overlap = 0)
         L.n_ent_slots = F.k_warp.n;
         CK((cudaError_t)bq2_launch_frame_warp(&L, F.k_warp.max_V, F.k_warp.max_T, F.k_warp.any_md2, F.stream, overlap),
            "launch(bq2_frame_warp_kernel)");
-        ctx->launches++;
+        COUNT_LAUNCH(ctx, 1);
     }
     if (F.k_team.n) {
         L.ents = F.launch.ents + F.k_warp.n;
@@ -295,7 +329,7 @@ bq2_status launch_kernels(bq2_ctx *ctx, FrameState &F, int overlap = 0)
         L.n_ent_slots = F.k_team.n;
         CK((cudaError_t)bq2_launch_frame(&L, F.k_team.max_V, F.k_team.max_T, F.k_team.any_md2, F.stream, overlap),
            "launch(bq2_frame_kernel)");
-        ctx->launches++;
+        COUNT_LAUNCH(ctx, 1);
     }
     return BQ2_OK;
 }
@@ -317,20 +351,21 @@ bq2_status enqueue_frame(bq2_ctx *ctx, FrameState &F, const FrameState::GraphKey
         }
         if (same) {                                      /* second frame of this shape: capture it */
             cudaGraph_t graph = nullptr;
-            const uint64_t l0 = ctx->launches;
             if (cudaStreamBeginCapture(F.stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                uint64_t captured = 0;
+                tl_capture_count = &captured;
                 bq2_status es = enqueue();
+                tl_capture_count = nullptr;
                 cudaError_t ce = cudaStreamEndCapture(F.stream, &graph);
                 if (es == BQ2_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
-                    g.kernels = ctx->launches - l0;
-                    ctx->launches = l0;
+                    g.kernels = captured;
                     cudaGraphDestroy(graph);
                     CK(cudaGraphLaunch(g.exec, F.stream), "cudaGraphLaunch(frame)");
                     ctx->launches += g.kernels;
                     return BQ2_OK;
                 }
                 if (graph) cudaGraphDestroy(graph);      /* capture is an optimisation only */
-                g.exec = nullptr; ctx->launches = l0; ctx->use_graphs = false;
+                g.exec = nullptr; ctx->use_graphs = false;
                 cudaGetLastError();
             }
         } else {
@@ -359,7 +394,15 @@ StageTimer g_stage_timer;
 
 extern "C" {
 
+static void worker_drain(bq2_ctx *ctx);
+static bq2_status worker_join_frame(bq2_ctx *ctx, FrameState &F);
+static bq2_status worker_post(bq2_ctx *ctx, int k);
+static void worker_wake(bq2_ctx *ctx);
+static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F);
+static void stage_caller_arrays(FrameState &F);
+
 int bq2_abi_version(void) { return BQ2_ABI_VERSION; }
+int bq2_max_frames_in_flight(void) { return BQ2_MAX_IN_FLIGHT; }
 
 bq2_status bq2_create(int device, bq2_ctx **out)
 {
@@ -402,6 +445,12 @@ bq2_status bq2_create(int device, bq2_ctx **out)
 void bq2_destroy(bq2_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->worker.joinable()) {
+        worker_drain(ctx);
+        ctx->wstop.store(true, std::memory_order_seq_cst);
+        { std::lock_guard<std::mutex> lk(ctx->wmx); ctx->wcv.notify_all(); }
+        ctx->worker.join();
+    }
     cudaSetDevice(ctx->device);
     for (FrameState &f : ctx->fs) if (f.stream) cudaStreamSynchronize(f.stream);
     if (ctx->trace.on && ctx->trace.n > 64) {
@@ -421,7 +470,7 @@ void bq2_destroy(bq2_ctx *ctx)
 const char *bq2_last_error(const bq2_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 void *bq2_stream(bq2_ctx *ctx) { return ctx ? (void *)ctx->fs[ctx->cur].stream : nullptr; }   /* of the last submitted frame */
 int bq2_device(const bq2_ctx *ctx) { return ctx ? ctx->device : -1; }
-uint64_t bq2_kernel_launches(const bq2_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t bq2_kernel_launches(const bq2_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, int32_t T, int md3, int32_t *out);
 
@@ -430,6 +479,7 @@ bq2_status bq2_upload_md2(bq2_ctx *ctx, const void *blob, size_t blob_bytes, con
                           uint32_t model_flags, int32_t *model_id)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!blob || !model_id || blob_bytes < sizeof(md2_header)) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md2: bad arguments");
     const md2_header *h = (const md2_header *)blob;
     const int V = h->num_xyz, T = h->num_tris, F = h->num_frames;
@@ -504,6 +554,7 @@ bq2_status bq2_upload_md3(bq2_ctx *ctx, int32_t F, const float *frame_translate,
                           int32_t num_meshes, int32_t *model_id)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!meshes || !model_id || !frame_translate || F <= 0 || num_meshes <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_upload_md3: bad arguments");
     if (num_meshes > BQ2_MD3_MAX_MESHES) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: too many meshes");
     if (F > 1024) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_md3: too many frames");
@@ -660,10 +711,11 @@ static bq2_status build_records_impl(bq2_ctx *ctx, const bq2_world_entity *ents,
 bq2_status bq2_frame_submit(bq2_ctx *ctx, const bq2_frame_desc *fd)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!fd || fd->n_ents < 0 || fd->n_pairs < 0 || (fd->n_ents > 0 && !fd->ents) || (fd->n_pairs > 0 && !fd->pairs))
         return fail(ctx, BQ2_E_INVALID, "bq2_frame: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: four frames are already in flight, call bq2_frame_wait first");
+    if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: the maximum number of frames is already in flight (bq2_max_frames_in_flight), call bq2_frame_wait first");
     const int slot_k = (ctx->submit_seq != ctx->wait_seq) ? (ctx->cur + 1) % BQ2_FRAME_STATES : ctx->cur;   /* ring */
     FrameState &F = ctx->fs[slot_k];
     PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
@@ -881,12 +933,14 @@ try {
     if (!ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_frame_wait: nothing submitted");
     int k;
     if (ctx->submit_seq == ctx->wait_seq) {                      /* nothing pending (e.g. after bq2_frame_replay) */
+        worker_drain(ctx);
         CK(cudaStreamSynchronize(ctx->fs[ctx->cur].stream), "cudaStreamSynchronize(frame)");
         k = ctx->last_waited;
     } else {                                                     /* the OLDEST frame in flight */
         k = (ctx->cur + BQ2_FRAME_STATES - (int)(ctx->submit_seq - ctx->wait_seq - 1)) % BQ2_FRAME_STATES;
+        ctx->wait_seq++; ctx->last_waited = k;                   /* the frame is consumed whatever happens below */
+        { bq2_status js = worker_join_frame(ctx, ctx->fs[k]); if (js != BQ2_OK) return js; }   /* the submit worker has issued it */
         CK(cudaStreamSynchronize(ctx->fs[k].stream), "cudaStreamSynchronize(frame)");   /* one frame per state and stream */
-        ctx->wait_seq++; ctx->last_waited = k;
     }
     FrameState &F = ctx->fs[k];
     const FrameState::Meta &m = F.meta;
@@ -935,6 +989,7 @@ bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *fd, bq2_frame_out *out)
 static bq2_status gpu_neighbours(bq2_ctx *ctx, const uint16_t *idx, int stride, int32_t T, int md3, int32_t *out)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!idx || !out || T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_neighbours: bad arguments");
     if (T > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_neighbours: too many triangles");
     int V = 0;
@@ -961,6 +1016,7 @@ bq2_status bq2_gpu_md3_neighbours(bq2_ctx *ctx, const uint16_t *indexes, int32_t
 bq2_status bq2_selftest_ratio(bq2_ctx *ctx, int mode, float num, uint64_t count, uint64_t seed, uint64_t *mismatches)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!mismatches || mode < 0 || mode > 2) return fail(ctx, BQ2_E_INVALID, "bq2_selftest_ratio: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (mode == 0) count = 1ull << 32;
@@ -980,6 +1036,7 @@ bq2_status bq2_gpu_md2_tangents(bq2_ctx *ctx, const void *blob, size_t blob_byte
                                 int smooth, uint8_t *normals, uint8_t *tangents, uint8_t *binormals)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!blob || blob_bytes < sizeof(md2_header) || !st || !tangents || !binormals || (!smooth && !normals))
         return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md2_tangents: bad arguments");
     const md2_header *h = (const md2_header *)blob;
@@ -1025,6 +1082,7 @@ bq2_status bq2_gpu_md3_tangents(bq2_ctx *ctx, void *vertexes, int32_t F, int32_t
                                 const uint16_t *indexes, int32_t T)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!vertexes || !st || !indexes || F <= 0 || V <= 0 || T <= 0) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md3_tangents: bad arguments");
     if (V > BQ2_MD3_MAX_VERTS || T > BQ2_MD3_MAX_TRIANGLES) return fail(ctx, BQ2_E_LIMIT, "bq2_gpu_md3_tangents: mesh outside the MD3 limits");
     for (int i = 0; i < 3 * T; i++) if (indexes[i] >= V) return fail(ctx, BQ2_E_INVALID, "bq2_gpu_md3_tangents: index out of range");
@@ -1051,6 +1109,7 @@ bq2_status bq2_upload_brush(bq2_ctx *ctx, int32_t n_polys, const int32_t *numver
                             const int32_t *neighbours, const uint8_t *fence, int32_t *brush_id)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (n_polys <= 0 || !numverts || !verts || !neighbours || !brush_id) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: bad arguments");
     if (n_polys > BQ2_BRUSH_MAX_POLYS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_brush: too many polygons");
     std::vector<uint32_t> first((size_t)n_polys + 1);
@@ -1094,6 +1153,7 @@ try {
 bq2_status bq2_brush_volumes(bq2_ctx *ctx, const bq2_brush_pair *pairs, int32_t n_pairs, const uint8_t *lit, bq2_brush_out *out)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (n_pairs < 0 || (n_pairs && (!pairs || !lit)) || !out) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     std::vector<bq2_brush_pair_dev_h> hp((size_t)n_pairs + 1);
@@ -1155,6 +1215,7 @@ void *bq2_host_alloc(bq2_ctx *ctx, size_t bytes)
 void bq2_host_free(bq2_ctx *ctx, void *p)
 {
     if (!ctx || !p) return;
+    worker_drain(ctx);
     for (size_t i = 0; i < ctx->host_ranges.size(); i++)
         if (ctx->host_ranges[i].base == (const unsigned char *)p) {
             for (FrameState &f : ctx->fs) if (f.stream) cudaStreamSynchronize(f.stream);    /* a copy may still read it */
@@ -1172,6 +1233,146 @@ static bool host_pinned(const bq2_ctx *ctx, const void *p, size_t bytes)
     return false;
 }
 
+/* ---- the stream operations of a world frame, from what bq2_world_submit left in F.job ---------------------- */
+static void stage_caller_arrays(FrameState &F)
+{
+    const FrameState::WorldJob &J = F.job;
+    unsigned char *h = F.hrec.p;
+    if (J.nL) memcpy(h + J.off_lights, J.lights, (size_t)J.nL * 16);
+    if (J.nP) { memcpy(h + J.off_pe, J.pair_ent, (size_t)J.nP * 4); memcpy(h + J.off_pl, J.pair_light, (size_t)J.nP * 4); }
+}
+
+static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F)
+{
+    const FrameState::WorldJob &J = F.job;
+    bq2_world_launch &Wl = F.wlaunch;
+    PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
+    StageTimer *st = (ctx->trace.gpu && !tl_err_sink) ? &g_stage_timer : nullptr;
+    auto enqueue = [&]() -> bq2_status {
+        if (st) st->mark(0, F.stream);
+        if (J.direct) {
+            unsigned char *db = F.d_records.p;
+            CK(cudaMemcpyAsync(db + J.off_xf, h_records.p + J.off_xf, J.off_lights - J.off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(entity rows)");
+            CK(cudaMemcpyAsync(db + J.off_lights, J.lights, (size_t)J.nL * 16, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(lights)");
+            CK(cudaMemcpyAsync(db + J.off_pe, J.pair_ent, (size_t)J.nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_ent)");
+            CK(cudaMemcpyAsync(db + J.off_pl, J.pair_light, (size_t)J.nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_light)");
+            if (J.basis_bytes) CK(cudaMemcpyAsync(db + J.off_b, h_records.p + J.off_b, J.basis_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(bases)");
+        } else if (J.copy_end > J.off_xf)
+            CK(cudaMemcpyAsync(F.d_records.p + J.off_xf, h_records.p + J.off_xf, J.copy_end - J.off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
+        if (st) st->mark(1, F.stream);
+        Wl.n_pairs = (J.want & BQ2_WANT_SHADOW) ? J.nP : 0;         /* the entity records are always built */
+        if (Wl.n_pairs)
+            CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)J.nE), F.stream), "cudaMemset(totals, pair lists)");
+        else        /* no pair thread runs: nothing writes the per-pair counts, clear them with the rest */
+            CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * (J.cnt_word + 2 * (size_t)J.nE), F.stream), "cudaMemset(counts, totals, pair lists)");
+        if (J.nP || J.nE) {
+            CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
+            COUNT_LAUNCH(ctx, bq2_world_setup_launches(&Wl));
+        }
+        if (st) st->mark(2, F.stream);
+        bq2_status ls = launch_kernels(ctx, F);
+        if (ls != BQ2_OK) return ls;
+        if (st) st->mark(3, F.stream);
+        CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (J.tot_word + 6), cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts + totals)");
+        if (st) { st->mark(4, F.stream); st->finish(); }
+        return BQ2_OK;
+    };
+    return enqueue_frame(ctx, F, J.use_key ? &J.key : nullptr, enqueue);
+}
+
+/* ---- submit worker ------------------------------------------------------------------------------------------
+ * One thread per ctx, started by the first world frame that can use it.  The caller's thread posts the number of a
+ * frame state whose job is complete; the worker stages the caller's page-locked arrays into the state's pinned record
+ * buffer and issues the frame's stream operations (a graph launch in the steady state).  bq2_frame_wait -- and every
+ * other entry point that touches frame states or CUDA objects of the ctx -- first waits for the worker to have
+ * finished what was posted.  The worker spins for a short while between frames (a frame loop posts every few
+ * microseconds) and then sleeps on a condition variable. */
+static void worker_main(bq2_ctx *ctx)
+{
+    cudaSetDevice(ctx->device);
+    uint64_t tail = 0;
+    for (;;) {
+        int spins = 0;
+        while (ctx->wq_head.load(std::memory_order_acquire) == tail) {
+            if (ctx->wstop.load(std::memory_order_acquire)) return;
+            if (++spins < 20000) {
+#if defined(__x86_64__) || defined(__i386__)
+                __builtin_ia32_pause();
+#endif
+                continue;
+            }
+            std::unique_lock<std::mutex> lk(ctx->wmx);
+            ctx->wsleeping.store(true, std::memory_order_seq_cst);
+            if (ctx->wq_head.load(std::memory_order_seq_cst) == tail && !ctx->wstop.load())
+                ctx->wcv.wait_for(lk, std::chrono::milliseconds(50));
+            ctx->wsleeping.store(false, std::memory_order_seq_cst);
+            spins = 0;
+        }
+        const int k = ctx->wq[tail % (BQ2_FRAME_STATES + 1)].load(std::memory_order_relaxed);
+        FrameState &F = ctx->fs[k];
+        tl_err_sink = &F.job.err;
+        bq2_status st = BQ2_OK;
+        try {
+            if (F.job.stage) stage_caller_arrays(F);
+            st = world_enqueue(ctx, F);
+        } catch (...) { st = BQ2_E_NOMEM; F.job.err = "submit worker: out of host memory"; }
+        tl_err_sink = nullptr;
+        F.job.status = st;
+        tail++;
+        ctx->wq_tail.store(tail, std::memory_order_release);
+        F.job_done.store(F.job_posted.load(std::memory_order_relaxed), std::memory_order_release);
+    }
+}
+
+/* start the worker, or end its sleep, so that the frames that follow find it spinning */
+static void worker_wake(bq2_ctx *ctx)
+{
+    if (!ctx->worker.joinable()) {
+        try { ctx->worker = std::thread(worker_main, ctx); } catch (...) { ctx->use_worker = false; }
+        return;
+    }
+    std::lock_guard<std::mutex> lk(ctx->wmx);
+    ctx->wcv.notify_one();
+}
+
+static bq2_status worker_post(bq2_ctx *ctx, int k)
+{
+    FrameState &F = ctx->fs[k];
+    F.job.err.clear();
+    F.job_posted.store(F.job_posted.load(std::memory_order_relaxed) + 1, std::memory_order_relaxed);
+    const uint64_t head = ctx->wq_head.load(std::memory_order_relaxed);
+    ctx->wq[head % (BQ2_FRAME_STATES + 1)].store(k, std::memory_order_relaxed);
+    ctx->wq_head.store(head + 1, std::memory_order_seq_cst);
+    if (ctx->wsleeping.load(std::memory_order_seq_cst)) { std::lock_guard<std::mutex> lk(ctx->wmx); ctx->wcv.notify_one(); }
+    return BQ2_OK;
+}
+
+/* the worker has issued everything that was posted (entry points that touch frame states call this first) */
+static void worker_drain(bq2_ctx *ctx)
+{
+    if (!ctx || !ctx->worker.joinable()) return;
+    const uint64_t head = ctx->wq_head.load(std::memory_order_acquire);
+    while (ctx->wq_tail.load(std::memory_order_acquire) != head) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+
+/* ... for ONE frame state: bq2_frame_wait meets the worker here; an error of the job becomes the caller's */
+static bq2_status worker_join_frame(bq2_ctx *ctx, FrameState &F)
+{
+    if (!ctx->worker.joinable()) return BQ2_OK;
+    const uint64_t posted = F.job_posted.load(std::memory_order_relaxed);
+    while (F.job_done.load(std::memory_order_acquire) != posted) {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (F.job.status != BQ2_OK) { ctx->err = F.job.err; const bq2_status st = F.job.status; F.job.status = BQ2_OK; return st; }
+    return BQ2_OK;
+}
+
 bq2_status bq2_world_submit(bq2_ctx *ctx, const bq2_world_desc *wd)
 try {
     if (!ctx) return BQ2_E_INVALID;
@@ -1179,7 +1380,7 @@ try {
         (wd->n_pairs > 0 && (!wd->pair_ent || !wd->pair_light || !wd->lights)))
         return fail(ctx, BQ2_E_INVALID, "bq2_world: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_world_submit: four frames are already in flight, call bq2_frame_wait first");
+    if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_world_submit: the maximum number of frames is already in flight (bq2_max_frames_in_flight), call bq2_frame_wait first");
     const int slot_k = (ctx->submit_seq != ctx->wait_seq) ? (ctx->cur + 1) % BQ2_FRAME_STATES : ctx->cur;   /* ring */
     FrameState &F = ctx->fs[slot_k];
     PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
@@ -1257,9 +1458,18 @@ try {
                         (size_t)nL * 16 + (size_t)nP * 8 + (size_t)nE * sizeof(bq2_world_entity) >= ctx->direct_min_bytes &&
                         host_pinned(ctx, wd->ents, (size_t)nE * sizeof(bq2_world_entity)) && host_pinned(ctx, wd->lights, (size_t)nL * 16) &&
                         host_pinned(ctx, wd->pair_ent, (size_t)nP * 4) && host_pinned(ctx, wd->pair_light, (size_t)nP * 4);
+    /* staged: by the submit worker when the caller's arrays are page-locked memory of this ctx (they stay valid and
+       unchanged until bq2_frame_wait, as for the direct copies), by this thread otherwise */
+    const bool caller_arrays_stay = !direct && nL && nP && !ctx->host_ranges.empty() &&
+                                    host_pinned(ctx, wd->lights, (size_t)nL * 16) && host_pinned(ctx, wd->pair_ent, (size_t)nP * 4) &&
+                                    host_pinned(ctx, wd->pair_light, (size_t)nP * 4);
+    F.job.stage = false;
     if (!direct) {
-        if (nL) memcpy(h_records.p + off_lights, wd->lights, (size_t)nL * 16);
-        if (nP) { memcpy(h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
+        if (caller_arrays_stay && ctx->use_worker && !tr.gpu && !(want & BQ2_WANT_TABLES)) F.job.stage = true;
+        else {
+            if (nL) memcpy(h_records.p + off_lights, wd->lights, (size_t)nL * 16);
+            if (nP) { memcpy(h_records.p + off_pe, wd->pair_ent, (size_t)nP * 4); memcpy(h_records.p + off_pl, wd->pair_light, (size_t)nP * 4); }
+        }
     }
     /* the bases are copied in steps of 64 rows, so that frames whose number of rotated entities differs a little
        still have the same copy sizes (the graph key below) */
@@ -1344,49 +1554,48 @@ try {
     /* per-slot host tables used by bq2_expand_trisverts */
     F.slot_mesh_V.resize((size_t)nP); F.slot_mesh_T.resize((size_t)nP); F.pair_slot_entslot.resize((size_t)nP);
 
-    /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals */
-    StageTimer *st = tr.gpu ? &g_stage_timer : nullptr;
-    auto enqueue = [&]() -> bq2_status {
-        if (st) st->mark(0, F.stream);
-        if (direct) {
-            unsigned char *db = F.d_records.p;
-            CK(cudaMemcpyAsync(db + off_xf, h_records.p + off_xf, off_lights - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(entity rows)");
-            CK(cudaMemcpyAsync(db + off_lights, wd->lights, (size_t)nL * 16, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(lights)");
-            CK(cudaMemcpyAsync(db + off_pe, wd->pair_ent, (size_t)nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_ent)");
-            CK(cudaMemcpyAsync(db + off_pl, wd->pair_light, (size_t)nP * 4, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(pair_light)");
-            if (basis_bytes) CK(cudaMemcpyAsync(db + off_b, h_records.p + off_b, basis_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(bases)");
-        } else if (copy_end > off_xf)
-            CK(cudaMemcpyAsync(F.d_records.p + off_xf, h_records.p + off_xf, copy_end - off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
-        if (st) st->mark(1, F.stream);
-        Wl.n_pairs = (want & BQ2_WANT_SHADOW) ? nP : 0;         /* the entity records are always built */
-        if (Wl.n_pairs)
-            CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)nE), F.stream), "cudaMemset(totals, pair lists)");
-        else        /* no pair thread runs: nothing writes the per-pair counts, clear them with the rest */
-            CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * (cnt_word + 2 * (size_t)nE), F.stream), "cudaMemset(counts, totals, pair lists)");
-        if (nP || nE) {
-            CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
-            ctx->launches += (uint64_t)bq2_world_setup_launches(&Wl);
-        }
-        if (st) st->mark(2, F.stream);
-        bq2_status ls = launch_kernels(ctx, F);
-        if (ls != BQ2_OK) return ls;
-        if (st) st->mark(3, F.stream);
-        CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (tot_word + 6), cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts + totals)");
-        if (st) { st->mark(4, F.stream); st->finish(); }
-        return BQ2_OK;
-    };
-    FrameState::GraphKey key{};
+    /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals -- issued by the
+       submit worker when the ctx has one and the caller's arrays may be read after this call returns (page-locked
+       memory from bq2_host_alloc: the contract already says they stay unchanged until bq2_frame_wait), else here */
     {
+        FrameState::WorldJob &J = F.job;
+        J.direct = direct; J.lights = wd->lights; J.pair_ent = wd->pair_ent; J.pair_light = wd->pair_light;
+        J.off_xf = off_xf; J.off_lights = off_lights; J.off_pe = off_pe; J.off_pl = off_pl; J.off_b = off_b;
+        J.basis_bytes = basis_bytes; J.copy_end = copy_end; J.tot_word = tot_word; J.cnt_word = cnt_word;
+        J.nE = nE; J.nL = nL; J.nP = nP; J.want = want; J.status = BQ2_OK;
+        J.use_key = !(tr.gpu || tables);
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, (int32_t)basis_bytes, 0, 0, 0, 0};
-        memcpy(key.v, kv, sizeof kv);
+        memset(&J.key, 0, sizeof J.key);
+        memcpy(J.key.v, kv, sizeof kv);
         const void *kp[16] = {direct ? wd->ents : nullptr, direct ? wd->lights : nullptr, direct ? wd->pair_ent : nullptr,
                               direct ? wd->pair_light : nullptr,
                               F.d_records.p, F.d_world.p, h_records.p, h_counts.p, F.lerped.p, F.extruded.p, F.facing_bits.p,
                               F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, ctx->d_models.p};
-        memcpy(key.p, kp, sizeof kp);
+        memcpy(J.key.p, kp, sizeof kp);
+        /* to the worker unless it is asleep (an engine that submits once per 16 ms frame would pay the wake-up latency on
+           every frame: it is woken for the frames that follow only when submits come in quick succession) */
+        /* ... and only for a caller that overlaps frames: with nothing in flight there is nothing for the hand-over to
+           overlap with, it would only add its latency to the frame's */
+        bool to_worker = ctx->use_worker && !tr.gpu && !tables && ctx->submit_seq != ctx->wait_seq;
+        if (to_worker) {
+            const double now = Trace::now();
+            const bool quick = now - ctx->last_submit_us < 300.0;
+            ctx->last_submit_us = now;
+            if (!ctx->worker.joinable() || ctx->wsleeping.load(std::memory_order_seq_cst)) {
+                to_worker = false;
+                if (quick) worker_wake(ctx);
+            }
+        }
+        if (to_worker) {
+            bq2_status ws_ = worker_post(ctx, slot_k);
+            if (ws_ != BQ2_OK) return ws_;
+        } else {
+            if (J.stage) { stage_caller_arrays(F); J.stage = false; }
+            bq2_status es = world_enqueue(ctx, F);
+            if (es != BQ2_OK) return es;
+        }
     }
-    { bq2_status es = enqueue_frame(ctx, F, (st || tables) ? nullptr : &key, enqueue); if (es != BQ2_OK) return es; }
     if (tables && nP) {
         F.world_pvoff.resize((size_t)nP + 1); F.world_pboff.resize((size_t)nP + 1);
         for (int p = 0; p <= nP; p++) { F.world_pvoff[p] = (uint32_t)p * maxVpad; F.world_pboff[p] = (uint32_t)p * maxBitw; }
@@ -1416,6 +1625,7 @@ bq2_status bq2_world_frame(bq2_ctx *ctx, const bq2_world_desc *wd, bq2_frame_out
 bq2_status bq2_frame_replay(bq2_ctx *ctx)
 try {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     FrameState &F = ctx->fs[ctx->cur];
     if (!ctx->submitted || !F.n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
@@ -1427,6 +1637,7 @@ try {
 static bq2_status frame_keep_impl(bq2_ctx *ctx, bq2_resident **out, bool own)
 {
     if (!ctx || !out) return BQ2_E_INVALID;
+    worker_drain(ctx);
     *out = nullptr;
     FrameState &F = ctx->fs[ctx->cur];
     if (!ctx->submitted || !F.n_ent_slots || ctx->submit_seq != ctx->wait_seq)
@@ -1488,6 +1699,7 @@ static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r)
 bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r)
 try {
     if (!ctx || !r) return BQ2_E_INVALID;
+    worker_drain(ctx);
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     return resident_launch(ctx, r);
 } catch (...) { return guard_exception(ctx); }
@@ -1498,6 +1710,7 @@ try {
 bq2_status bq2_resident_run(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k, float *ms)
 try {
     if (!ctx || !ring || n_ring <= 0 || k < 0 || start < 0) return BQ2_E_INVALID;
+    worker_drain(ctx);
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     for (int i = 0; i < n_ring; i++) {
         if (!ring[i]) return fail(ctx, BQ2_E_INVALID, "bq2_resident_run: NULL frame in the ring");
@@ -1528,6 +1741,7 @@ uint64_t bq2_resident_result_bytes(const bq2_resident *r) { return r ? (uint64_t
 void bq2_resident_free(bq2_ctx *ctx, bq2_resident *r)
 {
     if (!r) return;
+    worker_drain(ctx);
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->fs[r->state].stream); }
     r->release();
     delete r;
@@ -1538,6 +1752,7 @@ void bq2_resident_free(bq2_ctx *ctx, bq2_resident *r)
 bq2_status bq2_hash_results(bq2_ctx *ctx, const bq2_resident *r, uint64_t *host_hashes, int32_t n_pair_slots)
 try {
     if (!ctx || !host_hashes || n_pair_slots < 0) return BQ2_E_INVALID;
+    worker_drain(ctx);
     if (!r && !ctx->submitted) return fail(ctx, BQ2_E_INVALID, "bq2_hash_results: nothing submitted");
     FrameState &F = ctx->fs[r ? r->state : ctx->last_waited];
     const int32_t nPS = F.n_pair_slots;       /* (a kept frame has the shape of the frame it was kept from) */
@@ -1564,6 +1779,7 @@ try {
 bq2_status bq2_profiler_range(bq2_ctx *ctx, int on)
 {
     if (!ctx) return BQ2_E_INVALID;
+    worker_drain(ctx);
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     CK(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
     CK(on ? cudaProfilerStart() : cudaProfilerStop(), "cudaProfilerStart/Stop");
@@ -1575,6 +1791,7 @@ const uint32_t *bq2_host_index_counts(const bq2_ctx *ctx) { return ctx ? (const 
 bq2_status bq2_download(bq2_ctx *ctx, bq2_array which, uint64_t first, uint64_t count, void *host)
 try {
     if (!ctx || !host) return BQ2_E_INVALID;
+    worker_drain(ctx);
     FrameState &F = ctx->fs[ctx->last_waited];                   /* the frame bq2_frame_wait returned last */
     const void *src = nullptr; size_t cap = 0;
     switch (which) {
@@ -1603,6 +1820,7 @@ try {
 bq2_status bq2_download_indices(bq2_ctx *ctx, int32_t first_slot, int32_t n_slots, uint32_t words_per_slot, uint32_t *host)
 try {
     if (!ctx || !host || first_slot < 0 || n_slots < 0) return BQ2_E_INVALID;
+    worker_drain(ctx);
     FrameState &F = ctx->fs[ctx->last_waited];
     const uint32_t stride = F.launch.index_stride;
     if (!ctx->submitted || !F.indices.p || first_slot + n_slots > F.n_pair_slots || words_per_slot > stride)
@@ -1619,6 +1837,7 @@ try {
 bq2_status bq2_resident_download(bq2_ctx *ctx, const bq2_resident *r, bq2_array which, uint64_t first, uint64_t count, void *host)
 try {
     if (!ctx || !r || !host) return BQ2_E_INVALID;
+    worker_drain(ctx);
     const FrameState &F = ctx->fs[r->state];
     const void *src = nullptr; size_t cap = 0;
     switch (which) {

@@ -17,7 +17,7 @@ static double now_s(void)
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-/* k submit+wait iterations with `depth` (1..4) frames in flight; the clock runs over the k iterations (k frames in,
+/* k submit+wait iterations with `depth` frames in flight (the library refuses more than it has frame states for); the clock runs over the k iterations (k frames in,
  * k frames out), the frames that fill and drain the pipeline are outside it.  Returns 0 or the first error status;
  * *seconds = wall clock of the k iterations, *total_indices = sum of the k waited frames' index counts. */
 int bq2_frame_loop(bq2_ctx *ctx, const bq2_world_desc *wd, int k, int depth, double *seconds, uint64_t *total_indices)
@@ -27,7 +27,7 @@ int bq2_frame_loop(bq2_ctx *ctx, const bq2_world_desc *wd, int k, int depth, dou
     uint64_t tot = 0;
     double t0;
     int i;
-    if (!ctx || !wd || k < 0 || depth < 1 || depth > 4 || !seconds || !total_indices) return BQ2_E_INVALID;
+    if (!ctx || !wd || k < 0 || depth < 1 || depth > 16 || !seconds || !total_indices) return BQ2_E_INVALID;
     for (i = 0; i < depth - 1; i++)
         if ((s = bq2_world_submit(ctx, wd)) != BQ2_OK) return s;
     t0 = now_s();

@@ -150,7 +150,7 @@ typedef struct bq2_frame_desc {
 } bq2_frame_desc;
 
 /* Where the results of the last frame live.  All pointers are DEVICE pointers owned by the ctx,
- * valid until the next bq2_frame*(ctx) (see "two frames in flight" below) or bq2_destroy.  "Slots": MD2 entities/pairs occupy one
+ * valid until the next bq2_frame*(ctx) (see "frames in flight" below) or bq2_destroy.  "Slots": MD2 entities/pairs occupy one
  * slot; an MD3 entity/pair occupies one slot per mesh (the reference draws per mesh, M:63858).
  *   ent_slot_first[e]  .. +n meshes : slots of entity e        (n_ents + 1 entries, host array)
  *   pair_slot_first[p] .. +n meshes : slots of pair p          (n_pairs + 1 entries, host array)
@@ -185,11 +185,12 @@ typedef struct bq2_frame_out {
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
 int          bq2_abi_version(void);
+int          bq2_max_frames_in_flight(void);               /* submits that may precede the wait for the oldest frame */
 bq2_status   bq2_create(int device, bq2_ctx **out);
 void         bq2_destroy(bq2_ctx *ctx);
 const char  *bq2_last_error(const bq2_ctx *ctx);          /* ctx may be NULL: last create error   */
 void        *bq2_stream(bq2_ctx *ctx);                     /* cudaStream_t of the most recently submitted frame (each of
-                                                              the five frame states has its own -- up to four frames in
+                                                              the nine frame states has its own -- up to eight frames in
                                                               flight; fixed for callers that never overlap frames) */
 int          bq2_device(const bq2_ctx *ctx);
 uint64_t     bq2_kernel_launches(const bq2_ctx *ctx);      /* kernels launched by this ctx so far  */
@@ -232,9 +233,11 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
 /* Host records in, one fused launch per model family, per-slot counts back.  Equivalent to
  * bq2_frame_submit + bq2_frame_wait. */
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *desc, bq2_frame_out *out);
-/* Up to FOUR frames may be in flight: bq2_frame_submit (or bq2_world_submit) for frames i+1 .. i+3 may be
- * called before bq2_frame_wait for frame i, so the host packs the next frames while the GPU works; bq2_frame_wait
- * always completes the OLDEST submitted frame.  The ctx holds a ring of five complete frame states -- pinned host
+/* Up to EIGHT frames may be in flight (bq2_max_frames_in_flight): bq2_frame_submit (or bq2_world_submit) for frames
+ * i+1 .. i+7 may be called before bq2_frame_wait for frame i, so the host packs the next frames while the GPU works;
+ * bq2_frame_wait always completes the OLDEST submitted frame.  (A frame is a chain of dependent stream operations with
+ * 50-60 us of latency end to end; a pipelined caller's frame rate is that latency / frames in flight until the host or
+ * the SMs become the limit.)  The ctx holds a ring of nine complete frame states -- pinned host
  * buffers, device records, device RESULT arrays, host offset tables, stream, CUDA graph -- and a submit takes the
  * next one when a frame is in flight: the copies and kernels of consecutive frames overlap on the GPU, and what
  * bq2_frame_wait returned for frame i (device pointers, offset tables, bq2_download / bq2_expand_trisverts) stays

@@ -458,13 +458,15 @@ def test_world_frame_md3_and_tangent_space_take_the_host_route(gpu_ctx, oracle):
 
 def test_two_frames_in_flight(gpu_ctx, oracle):
     """bq2_world_submit for frame i+1 before bq2_frame_wait for frame i: waits complete the OLDEST frame and
-    every frame's counts/totals are its own; a fifth submit is refused."""
+    every frame's counts/totals are its own; one submit more than the library keeps in flight is refused."""
     models = [Md2Model(oracle, frames=6, seed=70 + s) for s in range(4)]
     mids = [m.upload(gpu_ctx) for m in models]
     import ctypes as C
     from berserkerquake2_b200 import _capi as c
     scenes, serial = [], []
-    for i in range(5):
+    depth = c.lib.bq2_max_frames_in_flight()
+    assert depth == 8
+    for i in range(depth + 1):
         we, wl, pe, pl = world_scene(40 + 7 * i, 3, 6, n_models=4, seed=500 + i)
         we["model"] = np.array(mids)[we["model"]]
         r = gpu_ctx.world_frame(we, wl, pe, pl)
@@ -473,18 +475,18 @@ def test_two_frames_in_flight(gpu_ctx, oracle):
         scenes[-1]._keep = gpu_ctx._keep
     fo = c.FrameOut()
     got = []
-    for i in range(3):
-        assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
-    for i in range(3, 5):
-        assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
-        if i == 3:
-            assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[4])) == -1          # only four in flight
-        assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
-        cnt = np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()
-        got.append((int(fo.total_indices), cnt))
-    for _ in range(3):
+
+    def waited():
         assert c.lib.bq2_frame_wait(gpu_ctx._h, C.byref(fo)) == 0
         got.append((int(fo.total_indices), np.ctypeslib.as_array(c.lib.bq2_host_index_counts(gpu_ctx._h), (fo.n_pair_slots,)).copy()))
+    for i in range(depth):
+        assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[i])) == 0
+    assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[depth])) == -1      # only `depth` frames in flight
+    waited()                                                                      # the OLDEST frame
+    assert c.lib.bq2_world_submit(gpu_ctx._h, C.byref(scenes[depth])) == 0
+    for _ in range(depth):
+        waited()
+    assert len(got) == depth + 1
     for (ta, ca), (tb, cb) in zip(serial, got):
         assert ta == tb and np.array_equal(ca, cb)
 

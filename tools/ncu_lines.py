@@ -82,7 +82,7 @@ def main():
         if f not in src and os.path.exists(p):
             src[f] = open(p).read().splitlines()
     for (f, ln), (n, s, st) in sorted(per.items(), key=lambda kv: -kv[1][0]):
-        if n < tot_i * 0.003 and s < tot_s * 0.005:
+        if not os.environ.get("NCU_LINES_ALL") and n < tot_i * 0.003 and s < tot_s * 0.005:
             continue
         top = ",".join(f"{k}:{v}" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:3])
         text = src.get(f, [""] * (ln + 1))[ln - 1].strip()[:70] if ln else ""
