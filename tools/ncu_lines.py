@@ -47,7 +47,9 @@ def main():
     rep = sys.argv[1]
     sub = sys.argv[2] if len(sys.argv) > 2 and not sys.argv[2].startswith("--") else "kernel"
     so = sys.argv[sys.argv.index("--so") + 1] if "--so" in sys.argv else "berserkerquake2_b200/libbq2gpu.so"
-    m = sass_lines(so, sub)
+    # --sass <mangled substring>: which SASS function to map (template instantiations differ only in the mangled name)
+    sass_sub = sys.argv[sys.argv.index("--sass") + 1] if "--sass" in sys.argv else sub
+    m = sass_lines(so, sass_sub)
     txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     # first kernel block only
