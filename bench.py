@@ -213,15 +213,19 @@ def build_ring(ctx, n_ents, lights, first, total_ents, ring, own_results, thread
             "setup_s": time.time() - t0, "V": V, "T": T}
 
 
-def timed_regions(ctx, kept, steps, repeats, barrier, dev, dist):
-    """`repeats` device-timed regions of EXACTLY `steps` back-to-back launches each (bq2_resident_run: launched from
-    C between two CUDA events on the launching stream), a barrier + synchronize in front of each; every region's time
-    is the MAX over ranks.  Returns (median region ms, all region ms)."""
+def timed_regions(ctx, kept, steps, repeats, barrier, dev, dist, streams=1):
+    """`repeats` device-timed regions of EXACTLY `steps` back-to-back launches each (bq2_resident_run[_streams]:
+    launched from C between two CUDA events), a barrier + synchronize in front of each; every region's time is the MAX
+    over ranks.  streams > 1: the launches are dealt round-robin onto that many streams, as independent frames in
+    flight run (the events are on the first stream, the others are joined into it before the second event).
+    Returns (median region ms, all region ms)."""
     from berserkerquake2_b200 import shard
+    if len(kept) < 2:
+        streams = 1                                     # one resident frame: its launches share result arrays, one stream
     ms = []
     for r in range(repeats):
         barrier()
-        ms.append(ctx.run_ring(kept, (r * steps) % len(kept), steps, timed=True))
+        ms.append(ctx.run_ring(kept, (r * steps) % len(kept), steps, timed=True, streams=streams))
     barrier()
     ms = shard.max_over_ranks(ms, dev, dist)
     return float(np.median(ms)), [float(x) for x in ms]
@@ -261,7 +265,7 @@ def traffic_probe(args):
     R = build_ring(ctx, n_ents, lights, 0, n_ents, ring, own_results=ring > 1, threads=args.threads)
     ctx.run_ring(R["kept"], 0, max(args.warmup, 3) + ring)
     ctx.profiler_range(True)                            # range replay measures the range as one unit; application replay
-    ctx.run_ring(R["kept"], 0, args.steps)              # profiles the launches inside it one by one
+    ctx.run_ring(R["kept"], 0, args.steps, timed=True, streams=args.streams if ring > 1 else 1)   # profiles the launches one by one
     ctx.profiler_range(False)
     ctx.close()
 
@@ -278,7 +282,7 @@ def measure_traffic(args, log_dir):
         return None, "ncu not found"
     os.makedirs(log_dir, exist_ok=True)
     base = [sys.executable, os.path.abspath(__file__), "--_traffic_probe", "--workload", args.workload,
-            "--steps", str(args.steps), "--warmup", str(args.warmup), "--threads", str(args.threads)]
+            "--steps", str(args.steps), "--warmup", str(args.warmup), "--threads", str(args.threads), "--streams", str(args.streams)]
     metrics = "dram__bytes_read.sum,dram__bytes_write.sum"
     tries = [
         ("range", "ncu --replay-mode app-range over cudaProfilerStart/Stop around the K back-to-back launches",
@@ -392,8 +396,9 @@ def run_gpu(args):
     if clocks:
         clocks.mark()
     launches0 = ctx.kernel_launches
-    ms_total_max, region_ms = timed_regions(ctx, kept_frames, args.steps, args.repeats, barrier, dev, dist)
+    ms_total_max, region_ms = timed_regions(ctx, kept_frames, args.steps, args.repeats, barrier, dev, dist, streams=args.streams)
     launches = (ctx.kernel_launches - launches0) // args.repeats
+    ms_one_stream, region_ms_one = timed_regions(ctx, kept_frames, args.steps, args.repeats, barrier, dev, dist, streams=1)
     med_r = int(np.argsort(region_ms)[len(region_ms) // 2])               # the repeat that is reported
     total_indices = sum(ring_indices[(med_r * args.steps + i) % ring] for i in range(args.steps))   # over its K steps
     if clocks:                                         # the timed regions are shorter than nvidia-smi's period:
@@ -595,14 +600,20 @@ def run_gpu(args):
                       f" MB of results to {ring} different sets of arrays (L2: {l2_bytes / 1e6:.0f} MB)",
                 "resident_frames": ring, "input_bytes_per_step": step_input_bytes,
                 "result_array_bytes_owned_per_frame": result_bytes_per_frame,
-                "timed_regions_ms": region_ms, "repeats": args.repeats,
-                "timing": f"EXACTLY K = {args.steps} launches back to back from C (bq2_resident_run) between one pair of CUDA "
-                          f"events on the launching stream; the region is run {args.repeats} times with a barrier + "
-                          "synchronize in front of each, each region's time is the max over ranks, the MEDIAN region is "
-                          "reported (all of them in timed_regions_ms).  The launches carry programmatic stream "
-                          "serialization: all K steps run in stream order and complete inside the events, the read-only "
-                          "front of step N+1 (record load, TMA staging, lerp, triangle normals) overlaps the tail of step "
-                          "N; roofline.isolated_launch_ms = one launch alone between two events after an L2 flush"},
+                "timed_regions_ms": region_ms, "repeats": args.repeats, "streams": args.streams,
+                "ms_per_step_one_stream": ms_one_stream / args.steps, "timed_regions_ms_one_stream": region_ms_one,
+                "timing": f"EXACTLY K = {args.steps} launches back to back from C (bq2_resident_run_streams) between one pair of "
+                          f"CUDA events; the region is run {args.repeats} times with a barrier + synchronize in front of each, "
+                          "each region's time is the max over ranks, the MEDIAN region is reported (all of them in "
+                          f"timed_regions_ms).  The K steps are K INDEPENDENT frames (own inputs, own result arrays), dealt "
+                          f"round-robin onto {args.streams} streams as the library runs frames in flight (bq2_world_submit gives "
+                          "every frame in flight its own stream): the first event is recorded on stream 0, the other streams "
+                          "wait for it, and they are joined into stream 0 before the second event, so every launch starts after "
+                          "the first and ends before the second.  On each stream the launches also carry programmatic stream "
+                          "serialization.  ms_per_step_one_stream = all K launches on ONE stream (round 1's way): there step N+1 "
+                          "may only stage, lerp and build normals under the tail of step N and then waits for it "
+                          "(griddepcontrol.wait); on two streams nothing orders it behind step N (profiles/r02_c2_pdl_timeline.md). "
+                          "roofline.isolated_launch_ms = one launch alone between two events after an L2 flush"},
             "e2e": {"value": g_e2e_tris / args.steps / (e2e_ms_max * 1e-3 / args.steps), "unit": "tris/s",
                     "ms_per_step": e2e_ms_max / args.steps, "gpu_launches_per_step": launches_e2e / args.steps,
                     "repeats": e2e_repeats, "ms_per_step_min_max_rank0": e2e_spread,
@@ -742,7 +753,7 @@ def c3_strong_leg(args, local, rank, world, barrier, dev, dist, l2_bytes):
     n_pairs = R["scene0"][4]
     steps = args.steps
     ctx.run_ring(kept, 0, max(3, min(args.warmup, 5)))
-    ms_max, region_ms = timed_regions(ctx, kept, steps, max(3, min(args.repeats, 5)), barrier, dev, dist)
+    ms_max, region_ms = timed_regions(ctx, kept, steps, max(3, min(args.repeats, 5)), barrier, dev, dist, streams=args.streams)
     med_r = int(np.argsort(region_ms)[len(region_ms) // 2])
     idx = sum(R["indices"][(med_r * steps + i) % ring] for i in range(steps))
     per_rank = shard.gather_counters([n_pairs * steps, count * V * steps, idx // 3, idx, count], dev, dist)
@@ -760,7 +771,7 @@ def c3_strong_leg(args, local, rank, world, barrier, dev, dist, l2_bytes):
             "scaling": "strong", "n_gpus": world, "entities_total": g_ents, "lights_per_entity": Lt, "pairs_total": g_pairs // steps,
             "value": g_tris / (ms_max * 1e-3), "unit": "tris/s", "pairs_per_s": g_pairs / (ms_max * 1e-3),
             "lerped_verts_per_s": g_verts / (ms_max * 1e-3), "ms_per_step": ms_per_step, "steps": steps,
-            "timed_regions_ms": region_ms, "resident_frames": ring, "setup_s": R["setup_s"],
+            "timed_regions_ms": region_ms, "resident_frames": ring, "streams": args.streams if ring > 1 else 1, "setup_s": R["setup_s"],
             "roofline": rf}
 
 
@@ -903,6 +914,7 @@ def main():
     ap.add_argument("--cpu-pin", type=int, default=-1, help=argparse.SUPPRESS)
     ap.add_argument("--repeats", type=int, default=11, help="device-timed regions of K steps each; the median is reported")
     ap.add_argument("--threads", type=int, default=0, help="host threads generating the synthetic models (0 = this rank's cores)")
+    ap.add_argument("--streams", type=int, default=2, help="streams the K independent resident frames of the timed region are dealt onto")
     ap.add_argument("--no-c3", action="store_true", help="skip the strong-scaling leg (BASELINE configs[2])")
     ap.add_argument("--c3-entities", type=int, default=65536)
     ap.add_argument("--no-traffic", action="store_true", help="skip the in-run DRAM traffic measurement (ncu child)")

@@ -124,6 +124,7 @@ EXPORTS_GPU_H = [
     _sig("bq2_resident_result_bytes", u64, vp),
     _sig("bq2_resident_replay", C.c_int, vp, vp),
     _sig("bq2_resident_run", C.c_int, vp, C.POINTER(vp), i32, i32, i32, C.POINTER(f32)),
+    _sig("bq2_resident_run_streams", C.c_int, vp, C.POINTER(vp), i32, i32, i32, i32, C.POINTER(f32)),
     _sig("bq2_resident_download", C.c_int, vp, vp, C.c_int, u64, u64, vp),
     _sig("bq2_hash_results", C.c_int, vp, vp, vp, i32),
     _sig("bq2_profiler_range", C.c_int, vp, C.c_int),

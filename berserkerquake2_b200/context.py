@@ -262,11 +262,15 @@ class Context:
     def replay_kept(self, handle):
         self._check(c.lib.bq2_resident_replay(self._h, handle))
 
-    def run_ring(self, handles, start, k, timed=False):
+    def run_ring(self, handles, start, k, timed=False, streams=1):
         """bq2_resident_run: k replays launched from C, handles[(start + i) % len]; timed: returns the milliseconds
-        between two CUDA events on the stream around the k launches (the call waits for the second)."""
+        between two CUDA events on the stream around the k launches (the call waits for the second).  streams > 1:
+        bq2_resident_run_streams, the launches dealt round-robin onto that many streams."""
         arr = (C.c_void_p * len(handles))(*[h.value if isinstance(h, C.c_void_p) else h for h in handles])
         ms = C.c_float(0.0)
+        if streams > 1:
+            self._check(c.lib.bq2_resident_run_streams(self._h, arr, len(handles), int(start), int(k), int(streams), C.byref(ms)))
+            return float(ms.value) if timed else None
         self._check(c.lib.bq2_resident_run(self._h, arr, len(handles), int(start), int(k), C.byref(ms) if timed else None))
         return float(ms.value) if timed else None
 

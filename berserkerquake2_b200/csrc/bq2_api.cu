@@ -198,6 +198,8 @@ struct bq2_ctx {
     int cur = 0;                                                 /* state of the most recently submitted frame */
     uint64_t submit_seq = 0, wait_seq = 0;
     int last_waited = 0;
+    bool busy[BQ2_FRAME_STATES] = {};                            /* submitted, not yet waited for */
+    int  order[BQ2_FRAME_STATES] = {};                           /* states of the frames in flight, oldest first (ring) */
     bool use_graphs = getenv("BQ2_NO_GRAPH") == nullptr;
     bool submitted = false;
     struct HostRange { const unsigned char *base; size_t bytes; };
@@ -240,6 +242,18 @@ bq2_status guard_exception(bq2_ctx *ctx) noexcept
     catch (...) {}
     try { if (ctx) ctx->err = what; } catch (...) {}
     return s;
+}
+
+/* The state a submit takes: the one in use when nothing is in flight (a caller that never overlaps frames lives in one
+   state), else the lowest-numbered state that is neither in flight nor the one bq2_frame_wait returned last (its results
+   stay valid until the next wait).  A caller with d frames in flight thus touches d + 1 states, not the whole ring --
+   every state keeps result arrays of the largest frame it has seen. */
+int pick_state(const bq2_ctx *ctx)
+{
+    if (ctx->submit_seq == ctx->wait_seq) return ctx->cur;
+    for (int k = 0; k < BQ2_FRAME_STATES; k++)
+        if (!ctx->busy[k] && k != ctx->last_waited) return k;
+    return -1;                                                    /* cannot happen: at most BQ2_MAX_IN_FLIGHT are busy */
 }
 
 bq2_status arena_alloc(bq2_ctx *ctx, size_t bytes, unsigned char **out)
@@ -716,7 +730,8 @@ try {
         return fail(ctx, BQ2_E_INVALID, "bq2_frame: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: the maximum number of frames is already in flight (bq2_max_frames_in_flight), call bq2_frame_wait first");
-    const int slot_k = (ctx->submit_seq != ctx->wait_seq) ? (ctx->cur + 1) % BQ2_FRAME_STATES : ctx->cur;   /* ring */
+    const int slot_k = pick_state(ctx);
+    if (slot_k < 0) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: no free frame state");
     FrameState &F = ctx->fs[slot_k];
     PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
     const int nE = fd->n_ents, nP = fd->n_pairs;
@@ -922,6 +937,7 @@ try {
     ctx->submitted = true;
     { FrameState::Meta &m = F.meta; m.world = false; m.tables = false; m.n_ent_slots = nES; m.n_pair_slots = nPS;
       m.total_verts = total_verts; m.stride = stride; }
+    ctx->order[ctx->submit_seq % BQ2_FRAME_STATES] = slot_k; ctx->busy[slot_k] = true;
     ctx->submit_seq++; ctx->cur = slot_k;
     tr.lap(6);
     return BQ2_OK;
@@ -937,7 +953,8 @@ try {
         CK(cudaStreamSynchronize(ctx->fs[ctx->cur].stream), "cudaStreamSynchronize(frame)");
         k = ctx->last_waited;
     } else {                                                     /* the OLDEST frame in flight */
-        k = (ctx->cur + BQ2_FRAME_STATES - (int)(ctx->submit_seq - ctx->wait_seq - 1)) % BQ2_FRAME_STATES;
+        k = ctx->order[ctx->wait_seq % BQ2_FRAME_STATES];
+        ctx->busy[k] = false;
         ctx->wait_seq++; ctx->last_waited = k;                   /* the frame is consumed whatever happens below */
         { bq2_status js = worker_join_frame(ctx, ctx->fs[k]); if (js != BQ2_OK) return js; }   /* the submit worker has issued it */
         CK(cudaStreamSynchronize(ctx->fs[k].stream), "cudaStreamSynchronize(frame)");   /* one frame per state and stream */
@@ -1381,7 +1398,8 @@ try {
         return fail(ctx, BQ2_E_INVALID, "bq2_world: bad descriptor");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     if (ctx->submit_seq - ctx->wait_seq >= BQ2_MAX_IN_FLIGHT) return fail(ctx, BQ2_E_INVALID, "bq2_world_submit: the maximum number of frames is already in flight (bq2_max_frames_in_flight), call bq2_frame_wait first");
-    const int slot_k = (ctx->submit_seq != ctx->wait_seq) ? (ctx->cur + 1) % BQ2_FRAME_STATES : ctx->cur;   /* ring */
+    const int slot_k = pick_state(ctx);
+    if (slot_k < 0) return fail(ctx, BQ2_E_INVALID, "bq2_frame_submit: no free frame state");
     FrameState &F = ctx->fs[slot_k];
     PinBuf &h_records = F.hrec, &h_counts = F.hcnt;
     const int nE = wd->n_ents, nP = wd->n_pairs, nL = wd->n_lights;
@@ -1609,6 +1627,7 @@ try {
     ctx->submitted = true;
     { FrameState::Meta &m = F.meta; m.world = true; m.tables = tables; m.n_ent_slots = nE; m.n_pair_slots = nP;
       m.total_verts = total_verts; m.stride = stride; }
+    ctx->order[ctx->submit_seq % BQ2_FRAME_STATES] = slot_k; ctx->busy[slot_k] = true;
     ctx->submit_seq++; ctx->cur = slot_k;
     tr.lap(6);
     return BQ2_OK;
@@ -1673,9 +1692,10 @@ try { return frame_keep_impl(ctx, out, false); } catch (...) { return guard_exce
 bq2_status bq2_frame_keep_own(bq2_ctx *ctx, bq2_resident **out)
 try { return frame_keep_impl(ctx, out, true); } catch (...) { return guard_exception(ctx); }
 
-static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r)
+static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r, cudaStream_t on = nullptr)
 {
     FrameState &F = ctx->fs[r->state];
+    cudaStream_t stream = on ? on : F.stream;
     if (!r->own && (r->L.lerped != F.lerped.p || r->L.extruded != F.extruded.p || r->L.indices != F.indices.p ||
         r->L.index_count != F.index_count.p || r->L.facing_bits != F.facing_bits.p))
         return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the result arrays of that frame state were re-allocated");
@@ -1685,12 +1705,12 @@ static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r)
     L.seq = (uint32_t)ctx->launches;
     if (r->k_warp.n) {
         L.n_ent_slots = r->k_warp.n;
-        CK((cudaError_t)bq2_launch_frame_warp(&L, r->k_warp.max_V, r->k_warp.max_T, r->k_warp.any_md2, F.stream, /*overlap=*/1), "launch(bq2_frame_warp_kernel)");
+        CK((cudaError_t)bq2_launch_frame_warp(&L, r->k_warp.max_V, r->k_warp.max_T, r->k_warp.any_md2, stream, /*overlap=*/1), "launch(bq2_frame_warp_kernel)");
         ctx->launches++;
     }
     if (r->k_team.n) {
         L.ents = r->L.ents + r->k_warp.n; L.rec_base = (uint32_t)r->k_warp.n; L.n_ent_slots = r->k_team.n;
-        CK((cudaError_t)bq2_launch_frame(&L, r->k_team.max_V, r->k_team.max_T, r->k_team.any_md2, F.stream, /*overlap=*/1), "launch(bq2_frame_kernel)");
+        CK((cudaError_t)bq2_launch_frame(&L, r->k_team.max_V, r->k_team.max_T, r->k_team.any_md2, stream, /*overlap=*/1), "launch(bq2_frame_kernel)");
         ctx->launches++;
     }
     return BQ2_OK;
@@ -1733,6 +1753,43 @@ try {
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         if (st == BQ2_OK && ce != cudaSuccess) return fail_cuda(ctx, ce, "bq2_resident_run(events)");
     }
+    return st;
+} catch (...) { return guard_exception(ctx); }
+
+/* The same with the k launches dealt round-robin onto n_streams of the ctx's streams (frames in flight on different
+   streams, as bq2_world_submit runs them): the frames are independent -- each kept frame owns its result arrays -- so
+   nothing orders launch i + 1 behind launch i, and the tail of one overlaps the body of the next.  Needs frames kept
+   with bq2_frame_keep_own and no team-kernel records (their scratch rows belong to the frame state).  The events are
+   on the first stream; the others start after the first event and are joined before the second. */
+bq2_status bq2_resident_run_streams(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k,
+                                    int32_t n_streams, float *ms)
+try {
+    if (!ctx || !ring || n_ring <= 0 || k < 0 || start < 0 || n_streams < 1 || n_streams > BQ2_FRAME_STATES) return BQ2_E_INVALID;
+    worker_drain(ctx);
+    CK(cudaSetDevice(ctx->device), "cudaSetDevice");
+    for (int i = 0; i < n_ring; i++) {
+        if (!ring[i]) return fail(ctx, BQ2_E_INVALID, "bq2_resident_run_streams: NULL frame in the ring");
+        if (n_streams > 1 && (!ring[i]->own || ring[i]->k_team.n))
+            return fail(ctx, BQ2_E_INVALID, "bq2_resident_run_streams: frames on several streams must own their result arrays and use the warp kernel only");
+    }
+    cudaStream_t s0 = ctx->fs[ring[0]->state].stream;
+    std::vector<cudaStream_t> ss; ss.push_back(s0);
+    for (int j = 0; j < BQ2_FRAME_STATES && (int)ss.size() < n_streams; j++) if (ctx->fs[j].stream != s0) ss.push_back(ctx->fs[j].stream);
+    std::vector<cudaEvent_t> ev(ss.size() + 1, nullptr);
+    for (auto &e : ev) CK(cudaEventCreateWithFlags(&e, cudaEventDefault), "cudaEventCreate");
+    cudaEvent_t e0 = ev[0], e1 = ev[ss.size()];
+    CK(cudaEventRecord(e0, s0), "cudaEventRecord");
+    for (size_t j = 1; j < ss.size(); j++) CK(cudaStreamWaitEvent(ss[j], e0, 0), "cudaStreamWaitEvent");
+    bq2_status st = BQ2_OK;
+    for (int i = 0; i < k && st == BQ2_OK; i++) st = resident_launch(ctx, ring[(start + i) % n_ring], ss[(size_t)i % ss.size()]);
+    for (size_t j = 1; j < ss.size(); j++) { cudaEventRecord(ev[j], ss[j]); cudaStreamWaitEvent(s0, ev[j], 0); }
+    cudaError_t ce = cudaEventRecord(e1, s0);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(e1);
+    float t = 0.0f;
+    if (ce == cudaSuccess) ce = cudaEventElapsedTime(&t, e0, e1);
+    for (auto &e : ev) cudaEventDestroy(e);
+    if (ms) *ms = t;
+    if (st == BQ2_OK && ce != cudaSuccess) return fail_cuda(ctx, ce, "bq2_resident_run_streams(events)");
     return st;
 } catch (...) { return guard_exception(ctx); }
 

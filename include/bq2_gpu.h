@@ -21,6 +21,15 @@
  * launch does every pair.  integration/bq2_dropin.c shows the reference
  * signatures re-implemented on top of this header (batch of one).
  *
+ * Of the five signatures SURVEY 8(b) lists, THREE are exported as symbols by the shim (integration/bq2_dropin.c, linked
+ * in front of the engine): R_CalcAliasFrameLerp, R_CalcAliasFrameLerpShadow, R_CalcAliasFrameShadowVolume -- the engine's
+ * own, unmodified R_DrawAliasShadowVolume then runs on the GPU (tests/test_dropin.py, bench.py e2e.dropin).  The other
+ * TWO are NOT symbols of this project, on purpose: R_DrawAliasShadowVolume (M:63713) and R_DrawMD3AliasShadowVolume
+ * (M:63800) are mostly OpenGL state and draw calls, which stay the engine's; the first needs no change at all, the second
+ * is monolithic and takes the five-line patch of INTEGRATION.md section 1 that calls bq2_dropin_md3_mesh() for its
+ * per-mesh compute block (M:63885-63991).  Their filters and loops are available batched: bq2_render_opts /
+ * bq2_host_entity_casts (M:63722-63727, 64041-64133), bq2_build_records / bq2_world_submit.
+ *
  * Plain C, plain pointers and sizes; no torch / C++ types.  All functions return BQ2_OK (0) or a
  * negative bq2_status; bq2_last_error() gives text.  Nothing here ever longjmps or aborts and
  * there is NO CPU fallback: without a CUDA device bq2_create() fails with BQ2_E_NODEVICE.
@@ -269,6 +278,12 @@ bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r);
 /* k replays launched from C, ring[(start + i) % n_ring] for i = 0 .. k-1 (all kept on one frame state).  ms != NULL:
  * two CUDA events on the stream bracket the k launches; the call waits for the second and returns their distance. */
 bq2_status bq2_resident_run(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k, float *ms);
+/* The same with the k launches dealt round-robin onto n_streams of the ctx's streams, as frames in flight run: the
+ * kept frames are independent (bq2_frame_keep_own; warp-kernel records only), so the tail of one launch overlaps the
+ * body of the next instead of the next waiting for it (programmatic dependent launch orders them on ONE stream).  The
+ * two events are on the first stream; the other streams start after the first event and are joined before the second. */
+bq2_status bq2_resident_run_streams(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k,
+                                    int32_t n_streams, float *ms);
 void       bq2_resident_free(bq2_ctx *ctx, bq2_resident *r);
 /* cudaProfilerStart (on != 0) / cudaProfilerStop after a device synchronize: the range ncu's range replay measures */
 bq2_status bq2_profiler_range(bq2_ctx *ctx, int on);

@@ -103,17 +103,20 @@ def main():
         wd = ctx.world_desc(*pin, None, bq2.WANT_SHADOW, 0)
         fo = c.FrameOut()
         k = max(6, steps // 4)
-        depth = 4 if n_pairs <= (1 << 18) else 2            # frames in flight (each owns its result arrays: memory)
+        depth = 8 if n_pairs <= (1 << 16) else 4 if n_pairs <= (1 << 18) else 2   # frames in flight (each owns its result arrays: memory)
+        def ok(rc):
+            if rc != 0:
+                raise RuntimeError(f"rank {rank}, {n_pairs} pairs: status {rc}: {c.lib.bq2_last_error(ctx._h)}")
         for _ in range(depth - 1):
-            assert c.lib.bq2_world_submit(ctx._h, C.byref(wd)) == 0
-        for _ in range(3 * depth):                          # every frame state allocates and captures its graph
-            assert c.lib.bq2_world_submit(ctx._h, C.byref(wd)) == 0 and c.lib.bq2_frame_wait(ctx._h, C.byref(fo)) == 0
+            ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd)))
+        for _ in range(3 * depth + 18):                     # every frame state allocates and captures its graph
+            ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd))); ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
         t0 = time.perf_counter()
         for _ in range(k):
-            c.lib.bq2_world_submit(ctx._h, C.byref(wd)); c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+            ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd))); ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
         e2e_ms = (time.perf_counter() - t0) * 1e3 / k
         for _ in range(depth - 1):
-            c.lib.bq2_frame_wait(ctx._h, C.byref(fo))
+            ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
         assert fo.total_indices == tot
         for x in pin:
             c.lib.bq2_host_free(ctx._h, x.ctypes.data)
