@@ -12,6 +12,8 @@ ls -la gpurun_out/traffic_* 2>/dev/null
 if [ -f gpurun_variants/libbq2gpu_tl.so ]; then
   BQ2_LIB=gpurun_variants/libbq2gpu_tl.so timeout 200 python tools/timeline.py --out gpurun_out/timeline_$tag.md > gpurun_out/timeline_$tag.log 2>&1; echo timeline=$?
   tail -25 gpurun_out/timeline_$tag.log
+  BQ2_LIB=gpurun_variants/libbq2gpu_tl.so timeout 200 python tools/timeline.py --streams 2 --out gpurun_out/timeline2_$tag.md > gpurun_out/timeline2_$tag.log 2>&1; echo timeline2=$?
+  tail -22 gpurun_out/timeline2_$tag.log
 fi
 if [ "$2" != "quick" ]; then
   timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_ref_$tag.log 2> gpurun_out/bench_ref_$tag.err; echo ref=$?

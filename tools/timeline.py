@@ -74,8 +74,10 @@ starts = np.array([us(r[:, 0].min()) for r in rows]); ends = np.array([us(r[:, 7
 P(f"Start-to-start distance of consecutive launches: median {np.median(np.diff(starts)):.2f} us; one launch from its first CTA start "
   f"to its last CTA done: median {np.median(ends - starts):.2f} us.  The difference is what the overlap hides: the CTAs of launch n+1 "
   "become resident while launch n drains, stage their key frames and table, lerp and build the triangle normals (shared memory "
-  "only) and then sit in `griddepcontrol.wait` until launch n has completed and flushed -- no global write of launch n+1 is "
-  "issued before that (stamp 5 >= last CTA done of the launch in front, column 5 vs column 6 of the row above).")
+  "only) and then sit in `griddepcontrol.wait` until the launch in front of them ON THEIR STREAM has completed and flushed -- no "
+  "global write of a launch is issued before that." + (" On one stream that is launch n itself (column 5 >= column 6 of the row above)."
+  if a.streams == 1 else f" On {a.streams} streams it is launch n+1-{a.streams}, which finished long ago: launch n+1 does not wait for launch n at all, "
+  "the two run side by side and the SMs that launch n leaves idle in its tail are filled at once."))
 d = a.streams                                       # launch i follows launch i - streams on its stream
 chk = all(us(rows[i][:, 5].min()) >= ends[i - d] - 0.2 for i in range(d, K))
 P("")
