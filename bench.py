@@ -161,6 +161,30 @@ METRIC = ("shadow-volume tris/s (fused MD2 lerp + light-facing + silhouette/cap/
           "lerped verts/s alongside")
 
 
+def rank_cpus(local, world):
+    """The logical CPUs of the physical cores that belong to local rank `local` of `world`: the cores this process may
+    use are grouped by /sys/.../topology/thread_siblings_list and dealt out in contiguous blocks."""
+    cpus = sorted(os.sched_getaffinity(0))
+    cores = {}
+    for c in cpus:
+        key = (c,)
+        try:
+            with open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list") as f:
+                txt = f.read().strip()
+            sib = set()
+            for part in txt.split(","):
+                lo, _, hi = part.partition("-")
+                sib.update(range(int(lo), int(hi or lo) + 1))
+            key = tuple(sorted(x for x in sib if x in cpus)) or (c,)
+        except (OSError, ValueError):
+            pass
+        cores[key] = True
+    phys = sorted(cores)
+    per = max(1, len(phys) // max(world, 1))
+    mine = phys[local * per:(local + 1) * per] or phys
+    return sorted({c for core in mine for c in core})
+
+
 def workload_config(name):
     """The keys that define the workload -- identical on both arms (the driver compares them)."""
     n_ents, lights, desc = WORKLOADS[name]
@@ -352,11 +376,9 @@ def run_gpu(args):
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if hasattr(os, "sched_setaffinity"):               # one host core per rank for the launching thread's neighbourhood:
-        cpus = sorted(os.sched_getaffinity(0))         # ranks share the box, the clock sampler and torchrun too
-        per = max(1, len(cpus) // max(world, 1))
-        mine = cpus[local * per:(local + 1) * per] or cpus
-        try:
+    if hasattr(os, "sched_setaffinity"):               # every rank gets its own PHYSICAL cores (both hyper-threads of each):
+        mine = rank_cpus(local, world)                 # the frame loop's thread and the ctx's submit worker then do not
+        try:                                           # share a core with each other or with another rank
             os.sched_setaffinity(0, mine)
         except OSError:
             pass
