@@ -28,6 +28,9 @@
 #include "bq2_internal.h"
 
 #include <time.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
 namespace {
 
 /* BQ2_TRACE=1: host time per phase of bq2_frame_submit, printed by bq2_destroy (diagnostics only) */
@@ -1304,8 +1307,40 @@ static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F)
  * other entry point that touches frame states or CUDA objects of the ctx -- first waits for the worker to have
  * finished what was posted.  The worker spins for a short while between frames (a frame loop posts every few
  * microseconds) and then sleeps on a condition variable. */
-static void worker_main(bq2_ctx *ctx)
+/* Best effort, Linux: keep the worker off the physical core the caller's thread is running on (a spinning hyper-thread
+   sibling slows the caller's per-entity loop by a third).  caller_cpu = sched_getcpu() of the thread that started it. */
+static void worker_avoid_core(int caller_cpu)
 {
+#if defined(__linux__)
+    cpu_set_t allowed, mine;
+    if (caller_cpu < 0 || sched_getaffinity(0, sizeof allowed, &allowed) != 0) return;
+    char path[96], buf[128];
+    snprintf(path, sizeof path, "/sys/devices/system/cpu/cpu%d/topology/thread_siblings_list", caller_cpu);
+    mine = allowed;
+    CPU_CLR(caller_cpu, &mine);
+    FILE *f = fopen(path, "r");
+    if (f) {
+        if (fgets(buf, sizeof buf, f)) {
+            for (char *p = buf; *p;) {                       /* "a-b,c,..." */
+                char *end; long lo = strtol(p, &end, 10), hi = lo;
+                if (end == p) break;
+                if (*end == '-') { hi = strtol(end + 1, &end, 10); }
+                for (long c = lo; c <= hi && c < CPU_SETSIZE; c++) CPU_CLR((int)c, &mine);
+                p = (*end == ',') ? end + 1 : end;
+                if (*end != ',') break;
+            }
+        }
+        fclose(f);
+    }
+    if (CPU_COUNT(&mine) > 0) sched_setaffinity(0, sizeof mine, &mine);
+#else
+    (void)caller_cpu;
+#endif
+}
+
+static void worker_main(bq2_ctx *ctx, int caller_cpu)
+{
+    worker_avoid_core(caller_cpu);
     cudaSetDevice(ctx->device);
     uint64_t tail = 0;
     for (;;) {
@@ -1345,7 +1380,11 @@ static void worker_main(bq2_ctx *ctx)
 static void worker_wake(bq2_ctx *ctx)
 {
     if (!ctx->worker.joinable()) {
-        try { ctx->worker = std::thread(worker_main, ctx); } catch (...) { ctx->use_worker = false; }
+        int cpu = -1;
+#if defined(__linux__)
+        cpu = sched_getcpu();
+#endif
+        try { ctx->worker = std::thread(worker_main, ctx, cpu); } catch (...) { ctx->use_worker = false; }
         return;
     }
     std::lock_guard<std::mutex> lk(ctx->wmx);
