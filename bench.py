@@ -294,12 +294,36 @@ def traffic_probe(args):
     ctx.close()
 
 
+def parse_ncu_dram_csv(path):
+    """(dram bytes read, dram bytes written, rows) summed over an `ncu --csv --print-units base` log: one row pair for a
+    range replay, one per launch for an application replay."""
+    import csv
+    rd = wr = 0.0
+    rows = 0
+    with open(path, newline="") as f:
+        lines = [l for l in f if not l.startswith("==")]
+    hdr = None
+    for row in csv.reader(lines):
+        if hdr is None:
+            if "Metric Name" in row and "Metric Value" in row:
+                hdr = {k: i for i, k in enumerate(row)}
+            continue
+        try:
+            name, val = row[hdr["Metric Name"]], float(row[hdr["Metric Value"]].replace(",", ""))
+        except (IndexError, ValueError):
+            continue
+        if name == "dram__bytes_read.sum":
+            rd += val; rows += 1
+        elif name == "dram__bytes_write.sum":
+            wr += val
+    return rd, wr, rows
+
+
 def measure_traffic(args, log_dir):
     """dram__bytes_read.sum + dram__bytes_write.sum over the K back-to-back steps of the timed region, per step.
     A child process repeats the region under ncu (a number TIMED under a profiler is never reported; byte counters are
     not timings): first as one range (range replay over cudaProfilerStart/Stop: the launches overlap as they do in
     the timed region), else per kernel (application replay: launches serialised, cache state natural)."""
-    import csv
     import shutil
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu):
@@ -330,24 +354,7 @@ def measure_traffic(args, log_dir):
         if r.returncode != 0 or not os.path.exists(log):
             why.append(f"{mode}: rc={r.returncode} {r.stderr.strip()[-200:]}")
             continue
-        rd = wr = 0.0
-        rows = 0
-        with open(log, newline="") as f:
-            lines = [l for l in f if not l.startswith("==")]
-        hdr = None
-        for row in csv.reader(lines):
-            if hdr is None:
-                if "Metric Name" in row and "Metric Value" in row:
-                    hdr = {k: i for i, k in enumerate(row)}
-                continue
-            try:
-                name, val = row[hdr["Metric Name"]], float(row[hdr["Metric Value"]].replace(",", ""))
-            except (IndexError, ValueError):
-                continue
-            if name == "dram__bytes_read.sum":
-                rd += val; rows += 1
-            elif name == "dram__bytes_write.sum":
-                wr += val
+        rd, wr, rows = parse_ncu_dram_csv(log)
         if rows == 0:
             why.append(f"{mode}: no counter rows in {os.path.basename(log)}")
             continue

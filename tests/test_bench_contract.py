@@ -58,3 +58,25 @@ def test_byte_formulas_match_survey_8d():
     assert bench.min_traffic_bytes(1, 0, V, T, 0) == 2 * 4 * V + 128 + 12 * T + 12 * V
     assert bench.min_traffic_bytes(0, 1, V, T, I) == 48 + 12 * V + 64 + 4 + 4 * I
     assert bench.min_traffic_bytes(E, E * Lt, V, T, E * Lt * I) < bench.algorithmic_bytes(E, E * Lt, V, T, E * Lt * I)
+
+
+def test_traffic_probe_parser_and_rank_pinning():
+    """The in-run DRAM-traffic figure comes out of an ncu CSV log: the parser is checked on the committed round-2 capture
+    (100 back-to-back C2 steps in one range: 53.2 MB per step against 52.5 MB of unique bytes), and on a per-launch log;
+    every rank of an N-rank run gets its own CPUs."""
+    sys.path.insert(0, ROOT)
+    import bench
+    rd, wr, rows = bench.parse_ncu_dram_csv(os.path.join(ROOT, "profiles", "r02_c2_traffic_range.csv"))
+    assert rows == 1 and rd > 0 and wr > 0
+    per_step = (rd + wr) / 100
+    unique = bench.min_traffic_bytes(1024, 4096, 258, 512, 4096 * 1687.2)
+    assert 0.9 < per_step / unique < 1.1
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False) as f:
+        f.write('==PROF== Connected\n"ID","Kernel Name","Metric Name","Metric Unit","Metric Value"\n')
+        for i in range(3):
+            f.write(f'"{i}","k","dram__bytes_read.sum","byte","1,000"\n"{i}","k","dram__bytes_write.sum","byte","{2000 + i}"\n')
+    assert bench.parse_ncu_dram_csv(f.name) == (3000.0, 6003.0, 3)
+    os.unlink(f.name)
+    sets = [set(bench.rank_cpus(r, 4)) for r in range(4)]
+    assert all(sets) and (len(os.sched_getaffinity(0)) < 4 or all(not (sets[i] & sets[j]) for i in range(4) for j in range(i)))

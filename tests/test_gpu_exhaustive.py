@@ -62,12 +62,28 @@ def test_c2_every_pair_matches_the_reference(oracle):
         assert ms > 0
         for h in ring:
             assert np.array_equal(ctx.hash_results(len(want), h), want)
+        # the same frames dealt onto two and three streams (independent frames in flight): still every pair
+        for streams in (2, 3):
+            assert ctx.run_ring(ring, 0, 11, timed=True, streams=streams) > 0
+            for h in ring:
+                assert np.array_equal(ctx.hash_results(len(want), h), want), streams
+        # one strided copy brings the index rows of a frame back: equal to the per-pair downloads
+        res = ctx.frame(ents, pairs)
+        words = int(res.index_counts.max())
+        packed = np.zeros((len(want), words), np.uint32)
+        assert c_api.lib.bq2_download_indices(ctx._h, 0, len(want), words, c_api.ptr(packed)) == 0
+        for p in (0, 1, 777, len(want) - 1):
+            n = int(res.index_counts[p])
+            assert np.array_equal(packed[p, :n], res.indices(p))
+        assert c_api.lib.bq2_download_indices(ctx._h, 0, len(want) + 1, words, c_api.ptr(packed)) < 0      # outside the frame
         # a frame kept WITHOUT own arrays shares the state's: still the same results after the ring ran
         ctx.frame(ents, pairs)
         shared = ctx.keep()
         assert c_api.lib.bq2_resident_result_bytes(shared) == 0
         ctx.run_ring([shared], 0, 3)
         assert np.array_equal(ctx.hash_results(len(want), shared), want)
+        arr = (__import__("ctypes").c_void_p * 2)(shared.value, ring[0].value)                           # several streams need frames
+        assert c_api.lib.bq2_resident_run_streams(ctx._h, arr, 2, 0, 4, 2, None) < 0                      # that own their result arrays
         cnt = ctx.download_kept(ring[0], c_api.A_INDEX_COUNT, 0, len(want), np.uint32)
         assert int(cnt.sum()) > 0 and (cnt % 6 == 0).all()
         for h in ring + [shared]:
