@@ -157,11 +157,11 @@ struct bq2_resident {                   /* bq2_frame_keep: a frame's device reco
     /* bq2_frame_keep_own: the frame's result arrays are its own (a ring of such frames writes a different set of
        output lines on every step instead of overwriting one set that stays in L2) */
     bool own = false;
-    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh;
+    DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh, tri_normals;
     DevBuf<uint32_t> facing_bits, indices, index_count;
     size_t result_bytes = 0;
     void release() {
-        records.release(); lerped.release(); extruded.release(); normals.release(); tangents.release(); binormals.release();
+        records.release(); tri_normals.release(); lerped.release(); extruded.release(); normals.release(); tangents.release(); binormals.release();
         lightp.release(); tsh.release(); facing_bits.release(); indices.release(); index_count.release();
     }
 };
@@ -1719,6 +1719,8 @@ static bq2_status frame_keep_impl(bq2_ctx *ctx, bq2_resident **out, bool own)
         BQ2_OWN(lerped); BQ2_OWN(extruded); BQ2_OWN(facing_bits); BQ2_OWN(indices); BQ2_OWN(index_count);
         BQ2_OWN(normals); BQ2_OWN(tangents); BQ2_OWN(binormals); BQ2_OWN(lightp); BQ2_OWN(tsh);
         #undef BQ2_OWN
+        /* ... and its own scratch rows for the team kernel's triangle normals (not a result: not counted) */
+        if (e == cudaSuccess && F.tri_normals.p) { e = r->tri_normals.ensure(F.tri_normals.cap); r->L.tri_normals = r->tri_normals.p; }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(F.stream);
     if (e != cudaSuccess) { r->release(); delete r; return fail_cuda(ctx, e, "bq2_frame_keep"); }
@@ -1738,7 +1740,7 @@ static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r, cudaStrea
     if (!r->own && (r->L.lerped != F.lerped.p || r->L.extruded != F.extruded.p || r->L.indices != F.indices.p ||
         r->L.index_count != F.index_count.p || r->L.facing_bits != F.facing_bits.p))
         return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the result arrays of that frame state were re-allocated");
-    if (r->L.tri_normals != F.tri_normals.p || r->L.meshes != ctx->d_meshes.p)
+    if ((!r->own && r->L.tri_normals != F.tri_normals.p) || r->L.meshes != ctx->d_meshes.p)
         return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the mesh table or the scratch rows of that frame state were re-allocated");
     bq2_launch L = r->L;
     L.seq = (uint32_t)ctx->launches;
@@ -1798,7 +1800,7 @@ try {
 /* The same with the k launches dealt round-robin onto n_streams of the ctx's streams (frames in flight on different
    streams, as bq2_world_submit runs them): the frames are independent -- each kept frame owns its result arrays -- so
    nothing orders launch i + 1 behind launch i, and the tail of one overlaps the body of the next.  Needs frames kept
-   with bq2_frame_keep_own and no team-kernel records (their scratch rows belong to the frame state).  The events are
+   with bq2_frame_keep_own (result arrays and team-kernel scratch rows of their own).  The events are
    on the first stream; the others start after the first event and are joined before the second. */
 bq2_status bq2_resident_run_streams(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k,
                                     int32_t n_streams, float *ms)
@@ -1808,8 +1810,8 @@ try {
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     for (int i = 0; i < n_ring; i++) {
         if (!ring[i]) return fail(ctx, BQ2_E_INVALID, "bq2_resident_run_streams: NULL frame in the ring");
-        if (n_streams > 1 && (!ring[i]->own || ring[i]->k_team.n))
-            return fail(ctx, BQ2_E_INVALID, "bq2_resident_run_streams: frames on several streams must own their result arrays and use the warp kernel only");
+        if (n_streams > 1 && !ring[i]->own)
+            return fail(ctx, BQ2_E_INVALID, "bq2_resident_run_streams: frames on several streams must own their result arrays (bq2_frame_keep_own)");
     }
     cudaStream_t s0 = ctx->fs[ring[0]->state].stream;
     std::vector<cudaStream_t> ss; ss.push_back(s0);

@@ -279,7 +279,7 @@ bq2_status bq2_resident_replay(bq2_ctx *ctx, const bq2_resident *r);
  * two CUDA events on the stream bracket the k launches; the call waits for the second and returns their distance. */
 bq2_status bq2_resident_run(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k, float *ms);
 /* The same with the k launches dealt round-robin onto n_streams of the ctx's streams, as frames in flight run: the
- * kept frames are independent (bq2_frame_keep_own; warp-kernel records only), so the tail of one launch overlaps the
+ * kept frames are independent (bq2_frame_keep_own), so the tail of one launch overlaps the
  * body of the next instead of the next waiting for it (programmatic dependent launch orders them on ONE stream).  The
  * two events are on the first stream; the other streams start after the first event and are joined before the second. */
 bq2_status bq2_resident_run_streams(bq2_ctx *ctx, bq2_resident *const *ring, int32_t n_ring, int32_t start, int32_t k,

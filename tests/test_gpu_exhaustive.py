@@ -107,6 +107,15 @@ def test_c4_md3_every_slot_matches_the_reference(oracle, ref):
         res = ctx.frame(ents, pairs)
         assert res.n_pair_slots == 4 * len(pe)
         got = ctx.hash_results(res.n_pair_slots)
+        # team-kernel frames kept with their own result arrays AND scratch rows, dealt onto two streams: same hashes
+        ring = []
+        for _ in range(2):
+            ctx.frame(ents, pairs)
+            ring.append(ctx.keep(own_results=True))
+        assert ctx.run_ring(ring, 0, 6, timed=True, streams=2) > 0
+        for h in ring:
+            assert np.array_equal(ctx.hash_results(res.n_pair_slots, h), got)
+            ctx.free_kept(h)
         for p in range(len(pe)):
             W = we[int(pe[p])]
             drawn, out = ref.md3_shadow(md3.frame_translate, md3.meshes, int(W["frame"]), int(W["oldframe"]), float(W["backlerp"]),
