@@ -682,6 +682,14 @@ def run_gpu(args):
             "clocks": clock_info,
             "setup_s": setup_s,
         }
+        out["roofline"]["one_stream"] = {
+            "kernel_ms": ms_one_stream / args.steps,
+            "frac": out["roofline"]["bytes_per_launch"] / (ms_one_stream / args.steps * 1e-3) / 1e9 / out["roofline"]["peak"],
+            "what": "the same K launches on ONE stream (programmatic dependent launch only): each step waits for the step in "
+                    "front before its first global write"}
+        out["roofline"]["kernel_ms_definition"] = ("timed region / K: the K launches are independent frames dealt onto "
+                                                   f"{args.streams} streams, so consecutive launches overlap; one_stream and "
+                                                   "isolated_launch_ms are the same kernel without that overlap")
         out["roofline"]["isolated_launch_ms"] = {
             "l2_flushed_by_memset": iso["dirty"], "l2_flushed_then_read": iso["clean"],
             "what": "ONE launch between two events on an otherwise idle stream: adds the launch and completion latency "
