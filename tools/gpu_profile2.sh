@@ -1,17 +1,15 @@
 #!/usr/bin/env bash
-# ncu --set full captures of the frame kernels (C2 warp kernel, C4 team kernel, brush kernel) + the e2e host trace.
+# Round-2 profile pass on one B200 (under gpurun): the ncu launch list of the bench command and --set full captures of
+# both instantiations of the warp kernel that the bench line uses (<0,0>: the device-timed region, host-built records;
+# <1,0>: the end-to-end frames, device-built records), each only after the same command has run without ncu.
 tag=${1:-x}
 mkdir -p gpurun_out
-timeout 200 python tools/e2e_trace.py 2>&1 | tail -14
-CMD2="python bench.py --steps 3 --warmup 3 --no-cpu --spinup 0 --no-c3 --no-traffic --no-dropin --repeats 1"
-$CMD2 > gpurun_out/plain_c2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:bq2_frame_warp -s 20 -c 2 -o gpurun_out/prof_c2_$tag -f $CMD2 > gpurun_out/ncu_c2.log 2>&1
-echo c2full=$?
-CMD4="python tools/bench_c4.py --no-ntb --steps 3"
-$CMD4 > gpurun_out/plain_c4.log 2>&1; tail -1 gpurun_out/plain_c4.log | cut -c1-300
-ncu --set full --clock-control none --import-source on -k regex:bq2_frame_kernel -s 2 -c 1 -o gpurun_out/prof_c4_$tag -f $CMD4 > gpurun_out/ncu_c4.log 2>&1
-echo c4full=$?
-CMD5="python tools/bench_brush.py"
-$CMD5 > gpurun_out/plain_brush.log 2>&1; tail -4 gpurun_out/plain_brush.log
-ncu --set full --clock-control none --import-source on -k regex:bq2_brush -s 2 -c 1 -o gpurun_out/prof_brush_$tag -f $CMD5 > gpurun_out/ncu_brush.log 2>&1
-echo brushfull=$?
+CMD="python bench.py --steps 5 --warmup 3 --no-cpu --spinup 0 --no-c3 --no-traffic --no-dropin --repeats 3"
+$CMD > gpurun_out/plain_launches.log 2>&1; echo plain=$?
+ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches.log 2>&1
+echo launches=$?
+ncu --set full --clock-control none --import-source on -k regex:bq2_frame_warp_kernel -s 30 -c 1 -o gpurun_out/prof_c2_00_$tag -f $CMD > gpurun_out/ncu_c2_00.log 2>&1
+echo c2_00=$?
+ncu --set full --clock-control none --import-source on -k "regex:bq2_frame_warp_kernel<1, 0>|bq2_frame_warp_kernel<\(bool\)1, \(bool\)0>" -s 40 -c 1 -o gpurun_out/prof_c2_10_$tag -f $CMD > gpurun_out/ncu_c2_10.log 2>&1
+echo c2_10=$?
+ls -la gpurun_out/prof_c2_*_$tag.ncu-rep gpurun_out/launches_$tag.csv
