@@ -34,3 +34,16 @@ def test_brush_volumes_match_oracle(gpu_ctx, oracle):
         assert np.array_equal(bits(vc), bits(wv)), k
         assert np.array_equal(ic, wi), k
     assert sum(len(w[1]) for w in want) > 50000
+    # a call without the large brush, and brushes of a few hundred polygons
+    small = [k for k in range(40) if k % len(models) != 4]
+    got_s = gpu_ctx.brush_volumes(np.array([pairs[k] for k in small], c.BRUSH_PAIR_DTYPE), np.concatenate([lits[k] for k in small]))
+    for (vc, ic), k in zip(got_s, small):
+        assert np.array_equal(bits(vc), bits(want[k][0])) and np.array_equal(ic, want[k][1]), k
+    for slices, bands in ((16, 12), (20, 12), (28, 8), (36, 7)):
+        m = BrushModel(slices, bands, 11)
+        bid = gpu_ctx.upload_brush(m.numverts, m.verts, m.neighbours, m.fence)
+        lm = np.array([60.0, -45.0, 30.0], np.float32)
+        lit = m.lit(lm)
+        (vc, ic), = gpu_ctx.brush_volumes(np.array([(bid, tuple(lm), np.float32(9600.0))], c.BRUSH_PAIR_DTYPE), lit)
+        wv, wi = oracle.brush_volume(m, lit, lm, 300.0)
+        assert np.array_equal(bits(vc), bits(wv)) and np.array_equal(ic, wi), (slices, bands, m.n_polys, int(m.first[-1]))
