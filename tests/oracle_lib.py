@@ -517,13 +517,18 @@ def pair_hash(lerped, extruded, viss, tris_verts, lerped_out=True):
     return np.uint64(h)
 
 
-_HASH_JOB = {}
-
-
-def _hash_worker(rng):
+def _hash_worker_main(argv):
+    """child process of reference_pair_hashes: `python oracle_lib.py --hash-worker <job dir> <lo> <hi> <timed passes>`.
+    A fresh interpreter (no fork of a process that holds a CUDA context and helper threads); the job's arrays are
+    memory-mapped from the job directory."""
+    import json
     import time
-    lo, hi = rng
-    J = _HASH_JOB
+    job, lo, hi, passes = argv[0], int(argv[1]), int(argv[2]), int(argv[3])
+    ld = lambda n: np.load(os.path.join(job, n + ".npy"), mmap_mode="r")
+    blob_data, blob_off, nb_data, nb_off = ld("blob_data"), ld("blob_off"), ld("nb_data"), ld("nb_off")
+    we, wl = np.load(os.path.join(job, "we.npy")), np.load(os.path.join(job, "wl.npy"))
+    pe, pl = np.load(os.path.join(job, "pe.npy"))[lo:hi], np.load(os.path.join(job, "pl.npy"))[lo:hi]
+    n = hi - lo
     lib = C.CDLL(REF_SO)
     lib.bq2ref_init()
     fn = lib.bq2ref_md2_world_hash
@@ -532,46 +537,72 @@ def _hash_worker(rng):
     bench = lib.bq2ref_md2_world_bench
     bench.restype = C.c_longlong
     bench.argtypes = [vp] * 2 + [i32] + [vp] * 8
-    we, wl, pe, pl = J["we"], J["wl"], J["pe"][lo:hi], J["pl"][lo:hi]
-    n = hi - lo
-    if n == 0:
-        return np.zeros(0, np.uint64), 0
     model_of = we["model"][pe]
-    bp = (vp * n)(*[J["blobs"][int(m)].ctypes.data for m in model_of])
-    nbp = (vp * n)(*[J["nbs"][int(m)].ctypes.data for m in model_of])
+    used = {}
+    for m in np.unique(model_of):                       # private, writable copies of the models this slice touches
+        m = int(m)
+        used[m] = (np.array(blob_data[blob_off[m]:blob_off[m + 1]]), np.array(nb_data[nb_off[m]:nb_off[m + 1]]))
+    bp = (vp * n)(*[used[int(m)][0].ctypes.data for m in model_of])
+    nbp = (vp * n)(*[used[int(m)][1].ctypes.data for m in model_of])
     a = [np.ascontiguousarray(x) for x in (we["frame"][pe].astype(np.int32), we["oldframe"][pe].astype(np.int32),
                                            we["backlerp"][pe].astype(np.float32), we["origin"][pe], we["oldorigin"][pe],
                                            we["angles"][pe], wl["origin"][pl], wl["radius"][pl].astype(np.float32))]
     out = np.zeros(n, np.uint64)
-    tot = fn(bp, nbp, n, *[P(x) for x in a], P(out))
+    tot = fn(bp, nbp, n, *[P(x) for x in a], P(out)) if n else 0
     secs = 0.0
-    if J.get("timed_passes"):                            # the same slice again, without the hashing, timed
+    if passes and n:                                    # the same slice again, without the hashing, timed
         t0 = time.perf_counter()
-        for _ in range(J["timed_passes"]):
+        for _ in range(passes):
             bench(bp, nbp, n, *[P(x) for x in a])
-        secs = (time.perf_counter() - t0) / J["timed_passes"]
-    return out, int(tot), secs
+        secs = (time.perf_counter() - t0) / passes
+    np.save(os.path.join(job, f"out_{lo}.npy"), out)
+    print(json.dumps({"total": int(tot), "secs": secs}), flush=True)
 
 
 def reference_pair_hashes(blobs, nbs, we, wl, pe, pl, procs=None, timed_passes=0, want_seconds=False):
     """hash of every pair (pe[k], pl[k]) computed by the unmodified reference (whole R_DrawAliasShadowVolume per pair),
-    fanned out over forked processes (the engine keeps its state in globals).  blobs / nbs: per MODEL id (we["model"]
-    indexes them): MD2 images and int32 neighbour tables.  Returns (uint64 [n_pairs], total index count)."""
-    import multiprocessing as mp
+    fanned out over one child process per host core (the engine keeps its state in globals).  blobs / nbs: per MODEL id
+    (we["model"] indexes them): MD2 images and int32 neighbour tables.  The children are fresh interpreters started with
+    subprocess -- the caller usually holds a CUDA context and helper threads, which a fork() would not survive reliably --
+    and read the job from memory-mapped files.  Returns (uint64 [n_pairs], total index count)."""
+    import json
+    import shutil
+    import subprocess
+    import sys
+    import tempfile
     procs = procs or max(1, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else 4)
     n = len(pe)
     procs = max(1, min(procs, n))
-    _HASH_JOB.clear()
-    _HASH_JOB.update(blobs=[np.ascontiguousarray(b) for b in blobs], nbs=[np.ascontiguousarray(x, np.int32) for x in nbs],
-                     we=we, wl=wl, pe=np.ascontiguousarray(pe, np.int32), pl=np.ascontiguousarray(pl, np.int32),
-                     timed_passes=int(timed_passes))
-    ranges = [(n * w // procs, n * (w + 1) // procs) for w in range(procs)]
-    if procs == 1:
-        res = [_hash_worker(ranges[0])]
-    else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            res = pool.map(_hash_worker, ranges)
-    _HASH_JOB.clear()
+    job = tempfile.mkdtemp(prefix="bq2hash_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        bl = [np.ascontiguousarray(b, np.uint8).reshape(-1) for b in blobs]
+        nl = [np.ascontiguousarray(x, np.int32).reshape(-1) for x in nbs]
+        np.save(os.path.join(job, "blob_off.npy"), np.concatenate([[0], np.cumsum([len(b) for b in bl])]).astype(np.int64))
+        np.save(os.path.join(job, "nb_off.npy"), np.concatenate([[0], np.cumsum([len(x) for x in nl])]).astype(np.int64))
+        np.save(os.path.join(job, "blob_data.npy"), np.concatenate(bl) if bl else np.zeros(0, np.uint8))
+        np.save(os.path.join(job, "nb_data.npy"), np.concatenate(nl) if nl else np.zeros(0, np.int32))
+        del bl, nl
+        for name, arr in (("we", we), ("wl", wl), ("pe", np.ascontiguousarray(pe, np.int32)), ("pl", np.ascontiguousarray(pl, np.int32))):
+            np.save(os.path.join(job, name + ".npy"), np.ascontiguousarray(arr))
+        ranges = [(n * w // procs, n * (w + 1) // procs) for w in range(procs)]
+        here = os.path.abspath(__file__)
+        children = [subprocess.Popen([sys.executable, here, "--hash-worker", job, str(lo), str(hi), str(int(timed_passes))],
+                                     stdout=subprocess.PIPE, text=True) for lo, hi in ranges]
+        res = []
+        for (lo, hi), ch in zip(ranges, children):
+            so, _ = ch.communicate(timeout=1800)
+            if ch.returncode != 0:
+                raise RuntimeError(f"reference hash worker [{lo}, {hi}) failed with status {ch.returncode}")
+            meta = json.loads([l for l in so.splitlines() if l.startswith("{")][-1])
+            res.append((np.load(os.path.join(job, f"out_{lo}.npy")), meta["total"], meta["secs"]))
+    finally:
+        shutil.rmtree(job, ignore_errors=True)
     if want_seconds:        # seconds per pass over the whole list = the slowest process's (timed_passes > 0), and the process count
         return np.concatenate([r[0] for r in res]), sum(r[1] for r in res), max(r[2] for r in res), procs
     return np.concatenate([r[0] for r in res]), sum(r[1] for r in res)
+
+
+if __name__ == "__main__":
+    import sys
+    if len(sys.argv) >= 6 and sys.argv[1] == "--hash-worker":
+        _hash_worker_main(sys.argv[2:])
