@@ -20,7 +20,7 @@ One "step" = one pass of the path over the whole batch = ONE launch of the fused
             THIS RUN by a child process under ncu's range replay over the same K back-to-back steps.
   e2e       the same metric through the C ABI from HOST arrays: bq2_world_submit (host: validation, numbering,
             AngleVectors; H2D; record-building kernel + fused kernel; D2H of the per-pair counts) + bq2_frame_wait,
-            eight frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
+            sixteen frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
   c3_strong BASELINE configs[2] as written: 65,536 entities x 8 lights sharded entity-major over the N GPUs
             (strong scaling), same timing rules
   cpu_baseline  oracle/_ref (the unmodified reference, compiled headless) on the host cores, N=1 only
@@ -53,8 +53,8 @@ L2_FLUSH_BYTES = 256 << 20
 E2E_REPEATS = 9            # the K-frame wall-clock measurement is repeated at least this often, and for at least
 E2E_MIN_SECONDS = 0.5      # this long (nine 100-frame runs last 20 ms: one hiccup of the host would cover them all);
 E2E_MAX_REPEATS = 999      # the median run is reported, min/max alongside
-E2E_IN_FLIGHT = int(os.environ.get("BQ2_BENCH_IN_FLIGHT", "8"))   # frames the e2e leg keeps in flight (the library allows
-                           # eight, bq2_max_frames_in_flight; the results of each stay separate)
+E2E_IN_FLIGHT = int(os.environ.get("BQ2_BENCH_IN_FLIGHT", "16"))  # frames the e2e leg keeps in flight (the library allows
+                           # sixteen, bq2_max_frames_in_flight; the results of each stay separate); 8 / 4 / 2 / 1 beside it
 
 
 def peaks():
@@ -494,7 +494,7 @@ def run_gpu(args):
             e2e_wait()
         return (tot, dt) if timed else tot
 
-    e2e_run(max(args.warmup, 30))      # every frame state of the ring has captured its graph before the timed frames
+    e2e_run(max(args.warmup, 40))      # every frame state of the ring has captured its graph before the timed frames
     barrier()
     _, e2e_py_s = e2e_run(args.steps, timed=True)                  # the same loop driven from Python (ctypes per call)
     # the frame loop as an engine runs it: C on top of the public ABI (csrc/bq2_frame_loop.c), same calls, same depth
@@ -508,7 +508,7 @@ def run_gpu(args):
             raise RuntimeError(c.lib.bq2_last_error(ctx._h))
         return int(tot64.value), float(sec.value)
 
-    e2e_loop(max(args.warmup, 30))
+    e2e_loop(max(args.warmup, 40))
     barrier()
     launches_e2e0 = ctx.kernel_launches
     e2e_runs, t_e2e0 = [], time.perf_counter()                     # K frames each; the median run is reported
@@ -519,10 +519,10 @@ def run_gpu(args):
     e2e_indices, e2e_s = sorted(e2e_runs, key=lambda r: r[1])[e2e_repeats // 2]
     e2e_spread = [min(r[1] for r in e2e_runs) * 1e3 / args.steps, max(r[1] for r in e2e_runs) * 1e3 / args.steps]
     barrier()
-    e2e_loop(max(args.warmup, 30), wd_pageable)                    # the same from pageable arrays (staged by the library)
+    e2e_loop(max(args.warmup, 40), wd_pageable)                    # the same from pageable arrays (staged by the library)
     _, e2e_pageable_s = e2e_loop(args.steps, wd_pageable)
     e2e_by_depth = {}
-    for d in (2, 4):                                               # fewer frames in flight: less latency, lower rate
+    for d in (2, 4, 8):                                            # fewer frames in flight: less latency, lower rate
         e2e_loop(20, None, d)
         e2e_by_depth[d] = float(np.median([e2e_loop(args.steps, None, d)[1] for _ in range(9)]))
     t0 = time.perf_counter()                                      # one frame at a time (latency of a frame)
@@ -652,6 +652,7 @@ def run_gpu(args):
                     "frames_in_flight": E2E_IN_FLIGHT,
                     "ms_per_step_2_in_flight": e2e_by_depth[2] * 1e3 / args.steps,
                     "ms_per_step_4_in_flight": e2e_by_depth[4] * 1e3 / args.steps,
+                    "ms_per_step_8_in_flight": e2e_by_depth[8] * 1e3 / args.steps,
                     "ms_per_step_host_built_records": e2e_host_s * 1e3 / args.steps,
                     "geometry_d2h": {"ms_per_step": e2e_geo_s * 1e3, "tris_per_s": e2e_indices / args.steps / 3 / e2e_geo_s,
                                      "d2h_bytes_per_step": geo_bytes, "d2h_gb_per_s": geo_bytes / e2e_geo_s / 1e9,

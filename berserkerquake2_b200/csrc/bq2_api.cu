@@ -88,13 +88,14 @@ struct PinBuf {
 
 /* everything that belongs to ONE frame */
 #define BQ2_DIRECT_MIN_BYTES (1u << 20)
-/* Eight frames in flight: a world frame is a chain of five dependent stream operations (copy in, clear, two kernels,
-   copy out) whose END-TO-END LATENCY is 50-60 us on a B200 even when the kernels are trivial (copy-engine and graph-node
-   latencies), so the frame rate of a pipelined caller is latency / frames in flight until the host or the SMs become the
-   limit: C2 measured 21.3 / 17.1 / 14.8 us per frame with 4 / 6 / 8 in flight (profiles/r02_history.md). */
+/* Up to sixteen frames in flight: a world frame is a chain of five dependent stream operations (copy in, clear, two
+   kernels, copy out) whose END-TO-END LATENCY is 50-60 us on a B200 even when the kernels are trivial (copy-engine and
+   graph-node latencies), so the frame rate of a pipelined caller is latency / frames in flight until the host or the SMs
+   become the limit: C2 measured 21.3 / 17.1 / 14.7 / 13.1 / 12.6 us per frame with 4 / 6 / 8 / 12 / 16 in flight
+   (profiles/r02_history.md).  States are taken on demand: a caller pays for the depth it uses. */
 #ifndef BQ2_FRAME_STATES        /* (overridable for experiments: make EXTRA="-DBQ2_FRAME_STATES=5 -DBQ2_MAX_IN_FLIGHT=4") */
-#define BQ2_FRAME_STATES   9
-#define BQ2_MAX_IN_FLIGHT  8
+#define BQ2_FRAME_STATES   17
+#define BQ2_MAX_IN_FLIGHT  16
 #endif
 static_assert(BQ2_MAX_IN_FLIGHT < BQ2_FRAME_STATES, "the state bq2_frame_wait returned last must not be the one taken next");
 struct FrameState {
@@ -196,7 +197,7 @@ struct bq2_ctx {
     /* Complete frame states (host tables, pinned buffers, device records AND device result arrays, stream, event,
        graph) used as a ring: frames i+1, i+2 are packed, copied and computed while frame i is still on the GPU or
        being consumed.  A submit takes the next state of the ring when a frame is in flight, the same one otherwise;
-       with at most BQ2_MAX_IN_FLIGHT (eight) in flight the state bq2_frame_wait returned last is never the one taken next. */
+       with at most BQ2_MAX_IN_FLIGHT (sixteen) in flight the state bq2_frame_wait returned last is never the one taken next. */
     FrameState fs[BQ2_FRAME_STATES];
     int cur = 0;                                                 /* state of the most recently submitted frame */
     uint64_t submit_seq = 0, wait_seq = 0;

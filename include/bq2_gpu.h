@@ -199,7 +199,7 @@ bq2_status   bq2_create(int device, bq2_ctx **out);
 void         bq2_destroy(bq2_ctx *ctx);
 const char  *bq2_last_error(const bq2_ctx *ctx);          /* ctx may be NULL: last create error   */
 void        *bq2_stream(bq2_ctx *ctx);                     /* cudaStream_t of the most recently submitted frame (each of
-                                                              the nine frame states has its own -- up to eight frames in
+                                                              the frame states has its own -- up to sixteen frames in
                                                               flight; fixed for callers that never overlap frames) */
 int          bq2_device(const bq2_ctx *ctx);
 uint64_t     bq2_kernel_launches(const bq2_ctx *ctx);      /* kernels launched by this ctx so far  */
@@ -242,11 +242,11 @@ bq2_status bq2_model_info(const bq2_ctx *ctx, int32_t model_id, int32_t *is_md3,
 /* Host records in, one fused launch per model family, per-slot counts back.  Equivalent to
  * bq2_frame_submit + bq2_frame_wait. */
 bq2_status bq2_frame(bq2_ctx *ctx, const bq2_frame_desc *desc, bq2_frame_out *out);
-/* Up to EIGHT frames may be in flight (bq2_max_frames_in_flight): bq2_frame_submit (or bq2_world_submit) for frames
- * i+1 .. i+7 may be called before bq2_frame_wait for frame i, so the host packs the next frames while the GPU works;
+/* Up to SIXTEEN frames may be in flight (bq2_max_frames_in_flight): bq2_frame_submit (or bq2_world_submit) for frames
+ * i+1 .. i+15 may be called before bq2_frame_wait for frame i, so the host packs the next frames while the GPU works;
  * bq2_frame_wait always completes the OLDEST submitted frame.  (A frame is a chain of dependent stream operations with
  * 50-60 us of latency end to end; a pipelined caller's frame rate is that latency / frames in flight until the host or
- * the SMs become the limit.)  The ctx holds a ring of nine complete frame states -- pinned host
+ * the SMs become the limit.)  The ctx holds seventeen complete frame states, taken on demand -- pinned host
  * buffers, device records, device RESULT arrays, host offset tables, stream, CUDA graph -- and a submit takes the
  * next one when a frame is in flight: the copies and kernels of consecutive frames overlap on the GPU, and what
  * bq2_frame_wait returned for frame i (device pointers, offset tables, bq2_download / bq2_expand_trisverts) stays

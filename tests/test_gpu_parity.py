@@ -465,7 +465,7 @@ def test_two_frames_in_flight(gpu_ctx, oracle):
     from berserkerquake2_b200 import _capi as c
     scenes, serial = [], []
     depth = c.lib.bq2_max_frames_in_flight()
-    assert depth == 8
+    assert depth == 16
     for i in range(depth + 1):
         we, wl, pe, pl = world_scene(40 + 7 * i, 3, 6, n_models=4, seed=500 + i)
         we["model"] = np.array(mids)[we["model"]]

@@ -45,10 +45,10 @@ def test_ring_soak(oracle):
         kept = None
         for step in range(700):
             action = rng.rand()
-            if action < 0.55 and len(in_flight) < 8:                 # submit (world path)
+            if action < 0.55 and len(in_flight) < 16:                 # submit (world path)
                 k = int(rng.randint(0, len(scenes)))
                 ctx.world_submit(scenes[k][0]); in_flight.append(k)
-            elif action < 0.62 and len(in_flight) < 8:               # submit (host-built records)
+            elif action < 0.62 and len(in_flight) < 16:               # submit (host-built records)
                 k = int(rng.randint(0, len(scenes)))
                 ctx.submit(scenes[k][2], scenes[k][3]); in_flight.append(k)
             elif action < 0.90 and in_flight:                        # wait for the oldest
