@@ -125,7 +125,7 @@ struct FrameState {
         const void *lights = nullptr, *pair_ent = nullptr, *pair_light = nullptr;   /* caller arrays the worker still reads */
         bool direct = false, stage = false, use_key = false;
         size_t off_xf = 0, off_lights = 0, off_pe = 0, off_pl = 0, off_b = 0, basis_bytes = 0, copy_end = 0, tot_word = 0, cnt_word = 0;
-        int nE = 0, nL = 0, nP = 0; uint32_t want = 0;
+        int nE = 0, nL = 0, nP = 0, n_rot = 0; uint32_t want = 0;
         GraphKey key{};
         bq2_status status = BQ2_OK; std::string err;
     } job;
@@ -418,6 +418,7 @@ static bq2_status worker_post(bq2_ctx *ctx, int k);
 static void worker_wake(bq2_ctx *ctx);
 static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F);
 static void stage_caller_arrays(FrameState &F);
+static void finish_bases(FrameState &F);
 
 int bq2_abi_version(void) { return BQ2_ABI_VERSION; }
 int bq2_max_frames_in_flight(void) { return BQ2_MAX_IN_FLIGHT; }
@@ -1255,6 +1256,13 @@ static bool host_pinned(const bq2_ctx *ctx, const void *p, size_t bytes)
 }
 
 /* ---- the stream operations of a world frame, from what bq2_world_submit left in F.job ---------------------- */
+/* the AngleVectors of the frame's rotated entities (their rows hold the angles until now) */
+static void finish_bases(FrameState &F)
+{
+    FrameState::WorldJob &J = F.job;
+    if (J.n_rot) { bq2_host_bases_from_angles((float *)(F.hrec.p + J.off_b), J.n_rot); J.n_rot = 0; }
+}
+
 static void stage_caller_arrays(FrameState &F)
 {
     const FrameState::WorldJob &J = F.job;
@@ -1366,6 +1374,7 @@ static void worker_main(bq2_ctx *ctx, int caller_cpu)
         tl_err_sink = &F.job.err;
         bq2_status st = BQ2_OK;
         try {
+            finish_bases(F);
             if (F.job.stage) stage_caller_arrays(F);
             st = world_enqueue(ctx, F);
         } catch (...) { st = BQ2_E_NOMEM; F.job.err = "submit worker: out of host memory"; }
@@ -1620,7 +1629,7 @@ try {
         J.direct = direct; J.lights = wd->lights; J.pair_ent = wd->pair_ent; J.pair_light = wd->pair_light;
         J.off_xf = off_xf; J.off_lights = off_lights; J.off_pe = off_pe; J.off_pl = off_pl; J.off_b = off_b;
         J.basis_bytes = basis_bytes; J.copy_end = copy_end; J.tot_word = tot_word; J.cnt_word = cnt_word;
-        J.nE = nE; J.nL = nL; J.nP = nP; J.want = want; J.status = BQ2_OK;
+        J.nE = nE; J.nL = nL; J.nP = nP; J.want = want; J.status = BQ2_OK; J.n_rot = ws.n_rotated;
         J.use_key = !(tr.gpu || tables);
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, (int32_t)basis_bytes, 0, 0, 0, 0};
@@ -1649,6 +1658,7 @@ try {
             bq2_status ws_ = worker_post(ctx, slot_k);
             if (ws_ != BQ2_OK) return ws_;
         } else {
+            finish_bases(F);
             if (J.stage) { stage_caller_arrays(F); J.stage = false; }
             bq2_status es = world_enqueue(ctx, F);
             if (es != BQ2_OK) return es;

@@ -323,8 +323,10 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         /* AngleVectors once per entity: the reference evaluates them again for the move delta and for every light
            (same inputs, same libm, same values) */
         if (W->angles[0] || W->angles[1] || W->angles[2]) {
+            /* the row holds the ANGLES until bq2_host_bases_from_angles turns it into forward / right / up: the trigonometry
+               (libm, ~20 ns per sincosf) can then run on the ctx's submit worker instead of the caller's thread */
             float *b = bases + 9 * (size_t)n_rot;
-            bq2_host_angle_vectors(W->angles, b, b + 3, b + 6);
+            b[0] = W->angles[0]; b[1] = W->angles[1]; b[2] = W->angles[2];
             x->basis = n_rot++;
         } else
             x->basis = -1;
@@ -349,6 +351,17 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
     st->lerped_verts_padded = (uint32_t)voff; st->team_normal_rows = (uint32_t)team_rows; st->n_rotated = n_rot;
     st->total_verts = total_verts;
     return 0;
+}
+
+/* rows of bases[] written by the loop above: angles -> forward, right, up (AngleVectors M:37566, the engine's libm) */
+void bq2_host_bases_from_angles(float *bases, int32_t n_rot)
+{
+    int32_t r;
+    for (r = 0; r < n_rot; r++) {
+        float *b = bases + 9 * (size_t)r;
+        const float ang[3] = { b[0], b[1], b[2] };
+        bq2_host_angle_vectors(ang, b, b + 3, b + 6);
+    }
 }
 
 /* ---- load-time neighbour tables, host C ------------------------------------- */

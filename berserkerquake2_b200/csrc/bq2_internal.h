@@ -164,6 +164,9 @@ struct bq2_world_entity;
  * -4 the frame's rows do not fit 32-bit row numbers. */
 void bq2_model_row_derive(bq2_model_row *row);
 struct bq2_render_opts;
+/* bases[] as bq2_host_world_entities leaves it holds each rotated entity's ANGLES in the first three floats of its row;
+   this turns the rows into forward / right / up (libm).  Run by the submit worker, or inline. */
+void bq2_host_bases_from_angles(float *bases, int32_t n_rot);
 void bq2_host_filter_masks(const struct bq2_render_opts *opts, int *off, uint32_t *ent_mask, uint32_t *model_mask, uint32_t *model_xor, int *brush);
 int  bq2_host_world_entities(const struct bq2_world_entity *ents, int32_t n, const bq2_model_row *models, int32_t n_models,
                              const struct bq2_render_opts *opts, bq2_dev_went *rows, float *bases /* [n][9] */, int32_t *rec_of_ent, uint32_t *ent_vert_off,

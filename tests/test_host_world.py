@@ -33,6 +33,16 @@ def run(we, rows, opts=None):
             bases.ctypes.data, rec.ctypes.data, voff.ctypes.data, st.ctypes.data)
     if rc == 0:
         assert np.isnan(bases[st[0]["n_rotated"]:]).all()
+        # the loop leaves each rotated entity's ANGLES in its row (the trigonometry runs afterwards, on the submit worker
+        # when the ctx has one): rows [0, n_rotated) hold angles in [0..3) and nothing else yet
+        nr = int(st[0]["n_rotated"])
+        rot = [e for e in range(n) if we["angles"][e][0] or we["angles"][e][1] or we["angles"][e][2]]
+        assert len(rot) == nr
+        for r, e in enumerate(rot):
+            assert np.array_equal(bases[r, :3].view(np.uint32), we["angles"][e].view(np.uint32)) and np.isnan(bases[r, 3:]).all()
+        conv = c.lib.bq2_host_bases_from_angles
+        conv.restype = None; conv.argtypes = [C.c_void_p, C.c_int32]
+        conv(bases.ctypes.data, nr)
         for f in ("model", "frame", "oldframe", "rf_flags", "backlerp", "origin", "oldorigin"):      # copied bit for bit
             assert np.array_equal(hx[f].view(np.uint32), we[f].view(np.uint32)), f
     run.bases = bases
