@@ -660,16 +660,16 @@ def run_gpu(args):
                                              f"(the first {cnt_max} words of each pair's row, one strided copy) copied to "
                                              "page-locked host memory: the route for a renderer that draws from host arrays"},
                     "h2d_bytes_per_step": n_ents * 64 + 16 + len(wl_c) * 16 + n_pairs * 8 + h2d_basis_bytes, "d2h_bytes_per_step": 4 * n_pairs + 24,
-                    "what": "per frame: bq2_world_submit (host: per-entity validation, numbering and AngleVectors into one 64-byte "
-                            "row per entity that also carries the caller's entity fields; H2D of those rows, the bases of the "
-                            "rotated entities and the caller's lights and pairs from the library's pinned buffer (the caller's "
-                            "own arrays are page-locked memory from bq2_host_alloc); the record-building kernel + the "
-                            "fused kernel; D2H of per-pair index counts + totals) + "
-                            "bq2_frame_wait, wall clock over K frames (median of %d such runs) with %d frames in flight (each has its own records, "
-                            "result arrays and stream; the clock runs over K submit+wait iterations of the full pipeline, K "
-                            "frames in and K frames out); the loop itself is C on the public ABI (csrc/bq2_frame_loop.c), as "
-                            "an engine would run it; ms_per_step_python_driver = the same calls made from Python; "
-                            "ms_per_step_serial = one at a time; " % (e2e_repeats, E2E_IN_FLIGHT) +
+                    "what": "per frame: bq2_world_submit (caller's thread: per-entity validation and numbering into one 64-byte row per "
+                            "entity that also carries the caller's entity fields; the ctx's submit worker: AngleVectors of the rotated "
+                            "entities (libm), staging of the caller's page-locked light and pair lists, the frame's graph launch; H2D of "
+                            "the rows, bases, lights and pairs; the record-building kernel + the fused kernel; D2H of per-pair index "
+                            "counts + totals) + bq2_frame_wait, wall clock over K frames (median of %d such runs) with %d frames in "
+                            "flight (each has its own records, result arrays and stream; the clock runs over K submit+wait iterations "
+                            "of the full pipeline, K frames in and K frames out); the loop itself is C on the public ABI "
+                            "(csrc/bq2_frame_loop.c), as an engine would run it; ms_per_step_python_driver = the same calls made from "
+                            "Python; ms_per_step_N_in_flight = fewer frames in flight; ms_per_step_serial = one at a time; "
+                            % (e2e_repeats, E2E_IN_FLIGHT) +
                             "vertex/index buffers stay in HBM for the draw"},
             "shared_model_variant": {
                 "what": "SURVEY 8(d): the same frame with every entity instantiating ONE model (one launch alone after an "
