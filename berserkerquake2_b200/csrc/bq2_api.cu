@@ -119,11 +119,17 @@ struct FrameState {
     DevBuf<unsigned char> d_world;                               /* world path: dpairs | buckets | overflow chain */
     bq2_world_launch wlaunch{};
     bool world_mode = false, world_tables = false;
+    /* The last kernel of a world frame hands the counts to the host and clears what the next frame accumulates into
+       (totals, pairs per record, chain heads): as long as the frames on this state keep their shape and buffer, no
+       clear is needed in front of them.  tail_clean: that holds for (clean_ptr, clean_nP, clean_nE). */
+    bool tail_clean = false; const void *clean_ptr = nullptr; int clean_nP = -1, clean_nE = -1;
+    uint32_t *hcnt_dev = nullptr; const void *hcnt_dev_of = nullptr;     /* device alias of hcnt (mapped page-locked memory) */
+    uint32_t *keep_cnt = nullptr;                                /* pairs per record of the finished frame (replay, hash) */
     /* what the stream operations of a world frame need, so that they can be enqueued by the ctx's submit worker
        (bq2_world_submit returns after the per-entity loop; bq2_frame_wait meets the worker before it meets the GPU) */
     struct WorldJob {
         const void *lights = nullptr, *pair_ent = nullptr, *pair_light = nullptr;   /* caller arrays the worker still reads */
-        bool direct = false, stage = false, use_key = false;
+        bool direct = false, stage = false, use_key = false, clean = false;
         size_t off_xf = 0, off_lights = 0, off_pe = 0, off_pl = 0, off_b = 0, basis_bytes = 0, copy_end = 0, tot_word = 0, cnt_word = 0;
         int nE = 0, nL = 0, nP = 0, n_rot = 0; uint32_t want = 0;
         GraphKey key{};
@@ -205,6 +211,7 @@ struct bq2_ctx {
     bool busy[BQ2_FRAME_STATES] = {};                            /* submitted, not yet waited for */
     int  order[BQ2_FRAME_STATES] = {};                           /* states of the frames in flight, oldest first (ring) */
     bool use_graphs = getenv("BQ2_NO_GRAPH") == nullptr;
+    bool pdl_world = getenv("BQ2_PDL_WORLD") != nullptr && atoi(getenv("BQ2_PDL_WORLD")) != 0;
     bool submitted = false;
     struct HostRange { const unsigned char *base; size_t bytes; };
     std::vector<HostRange> host_ranges;                          /* page-locked memory handed out by bq2_host_alloc */
@@ -402,7 +409,7 @@ struct StageTimer {
         cudaEventSynchronize(ev[4]);
         for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms * 1e3; }
         if (++frames % 100 == 0)
-            fprintf(stderr, "bq2 trace (GPU, us/frame): H2D %.1f  record-building kernel %.1f  frame kernel(s) %.1f  D2H %.1f\n",
+            fprintf(stderr, "bq2 trace (GPU, us/frame): H2D %.1f  clear + record-building kernel %.1f  frame kernel(s) %.1f  counts to host %.1f\n",
                     acc[0] / frames, acc[1] / frames, acc[2] / frames, acc[3] / frames);
     }
 };
@@ -915,6 +922,7 @@ try {
 
     /* ---- go -------------------------------------------------------------------------------------- */
     tr.lap(5);
+    F.tail_clean = false;                                        /* this frame's counts overwrite what a world frame left cleared */
     if (rec_bytes)
         CK(cudaMemcpyAsync(F.d_records.p, h_records.p, rec_bytes, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(records)");
     /* slots of non-casting MD3 meshes are never written by a kernel, and a frame without BQ2_WANT_SHADOW writes no
@@ -1290,23 +1298,32 @@ static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F)
             CK(cudaMemcpyAsync(F.d_records.p + J.off_xf, h_records.p + J.off_xf, J.copy_end - J.off_xf, cudaMemcpyHostToDevice, F.stream), "cudaMemcpy(world records)");
         if (st) st->mark(1, F.stream);
         Wl.n_pairs = (J.want & BQ2_WANT_SHADOW) ? J.nP : 0;         /* the entity records are always built */
-        if (Wl.n_pairs)
+        /* totals, pairs per record and chain heads were left cleared by the frame in front (J.clean), else clear them */
+        if (!Wl.n_pairs) {  /* no pair thread runs: nothing writes the per-pair counts, clear them too */
+            const size_t words = J.clean ? J.tot_word : J.cnt_word + 2 * (size_t)J.nE;
+            if (words) CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * words, F.stream), "cudaMemset(counts, totals, pair lists)");
+        } else if (!J.clean)
             CK(cudaMemsetAsync(Wl.totals, 0, sizeof(uint32_t) * (8 + 2 * (size_t)J.nE), F.stream), "cudaMemset(totals, pair lists)");
-        else        /* no pair thread runs: nothing writes the per-pair counts, clear them with the rest */
-            CK(cudaMemsetAsync(F.index_count.p, 0, sizeof(uint32_t) * (J.cnt_word + 2 * (size_t)J.nE), F.stream), "cudaMemset(counts, totals, pair lists)");
         if (J.nP || J.nE) {
             CK((cudaError_t)bq2_launch_world_setup(&Wl, F.stream), "launch(bq2_world_link_kernel)");
             COUNT_LAUNCH(ctx, bq2_world_setup_launches(&Wl));
         }
         if (st) st->mark(2, F.stream);
-        bq2_status ls = launch_kernels(ctx, F);
+        const int pdl = ctx->pdl_world && !st;
+        bq2_status ls = launch_kernels(ctx, F, pdl);
         if (ls != BQ2_OK) return ls;
         if (st) st->mark(3, F.stream);
-        CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * (J.tot_word + 6), cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts + totals)");
+        (void)h_counts;
+        CK((cudaError_t)bq2_launch_frame_tail(F.index_count.p, F.hcnt_dev, F.keep_cnt, (uint32_t)J.tot_word + 8u, (uint32_t)J.tot_word,
+                                              (uint32_t)J.cnt_word, (uint32_t)(J.cnt_word + (size_t)J.nE), F.stream, pdl),
+           "launch(bq2_frame_tail_kernel)");
+        COUNT_LAUNCH(ctx, 1);
         if (st) { st->mark(4, F.stream); st->finish(); }
         return BQ2_OK;
     };
-    return enqueue_frame(ctx, F, J.use_key ? &J.key : nullptr, enqueue);
+    const bq2_status es = enqueue_frame(ctx, F, J.use_key ? &J.key : nullptr, enqueue);
+    if (es != BQ2_OK) F.tail_clean = false;
+    return es;
 }
 
 /* ---- submit worker ------------------------------------------------------------------------------------------
@@ -1556,12 +1573,19 @@ try {
         CK(F.indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
     if (ws.team_normal_rows) CK(F.tri_normals.ensure(4 * (size_t)ws.team_normal_rows + 4), "cudaMalloc(triangle normals)");
-    /* one buffer: index counts | 8-byte aligned, three 64-bit totals (one D2H copy brings both) | pairs per record |
-       overflow-chain heads.  One memset clears totals .. heads (heads to 0: a chain is only walked for as many nodes
-       as were pushed). */
+    /* one buffer: index counts | 8-byte aligned, three 64-bit totals | pairs per record | overflow-chain heads | the
+       finished frame's pairs per record.  The frame's last kernel hands counts + totals to the host and clears totals
+       and pairs per record for the next frame; a frame that does not find them cleared clears totals .. heads itself
+       (heads to 0: a chain is only walked for as many nodes as were pushed). */
     const size_t tot_word = ((size_t)nP + 1) & ~(size_t)1, cnt_word = tot_word + 8;
-    CK(F.index_count.ensure(cnt_word + 2 * (size_t)nE + 8), "cudaMalloc(index_count)");
+    CK(F.index_count.ensure(cnt_word + 3 * (size_t)nE + 8), "cudaMalloc(index_count)");
     CK(h_counts.ensure(sizeof(uint32_t) * (tot_word + 8)), "cudaMallocHost(counts)");
+    if (F.hcnt_dev_of != h_counts.p) {
+        void *dp = nullptr;
+        CK(cudaHostGetDevicePointer(&dp, h_counts.p, 0), "cudaHostGetDevicePointer(counts)");
+        F.hcnt_dev = (uint32_t *)dp; F.hcnt_dev_of = h_counts.p;
+    }
+    const bool clean = F.tail_clean && F.clean_ptr == F.index_count.p && F.clean_nP == nP && F.clean_nE == nE;
     const size_t w_pairs = ((size_t)nP * sizeof(bq2_dev_pair) + 15) & ~(size_t)15, w_bucket = (size_t)nE * BQ2_BUCKET * 4,
                  w_next = (size_t)nP * 4;
     CK(F.d_world.ensure(w_pairs + w_bucket + w_next + 64), "cudaMalloc(world scratch)");
@@ -1601,6 +1625,7 @@ try {
     Wl.bucket = (uint32_t *)(dw + w_pairs); Wl.onext = (uint32_t *)(dw + w_pairs + w_bucket);
     Wl.totals = (unsigned long long *)(F.index_count.p + tot_word);
     Wl.bucket_cnt = F.index_count.p + cnt_word; Wl.ohead = Wl.bucket_cnt + nE;
+    F.keep_cnt = Wl.ohead + nE;
     Wl.vert_stride = maxVpad; Wl.bits_stride = maxBitw;
     Wl.index_count = F.index_count.p;
     Wl.view = (const float *)(rb + off_view);
@@ -1631,8 +1656,10 @@ try {
         J.basis_bytes = basis_bytes; J.copy_end = copy_end; J.tot_word = tot_word; J.cnt_word = cnt_word;
         J.nE = nE; J.nL = nL; J.nP = nP; J.want = want; J.status = BQ2_OK; J.n_rot = ws.n_rotated;
         J.use_key = !(tr.gpu || tables);
+        J.clean = clean;
+        F.tail_clean = true; F.clean_ptr = F.index_count.p; F.clean_nP = nP; F.clean_nE = nE;    /* (world_enqueue takes it back if it fails) */
         const int32_t kv[20] = {nE, nP, nL, (int32_t)want, (int32_t)stride, ws.n_warp, ws.n_team, ws.warp_max_V, ws.warp_max_T, ws.warp_md2,
-                                ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, (int32_t)basis_bytes, 0, 0, 0, 0};
+                                ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, (int32_t)basis_bytes, clean ? 1 : 0, 0, 0, 0};
         memset(&J.key, 0, sizeof J.key);
         memcpy(J.key.v, kv, sizeof kv);
         const void *kp[16] = {direct ? wd->ents : nullptr, direct ? wd->lights : nullptr, direct ? wd->pair_ent : nullptr,
@@ -1698,8 +1725,11 @@ try {
     FrameState &F = ctx->fs[ctx->cur];
     if (!ctx->submitted || !F.n_ent_slots) return fail(ctx, BQ2_E_INVALID, "bq2_frame_replay: nothing submitted");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    if (F.world_mode)                                            /* the kernels add to the totals: start from zero */
+    F.tail_clean = false;
+    if (F.world_mode) {                                          /* the kernels add to the totals: start from zero */
         CK(cudaMemsetAsync(F.wlaunch.totals, 0, 2 * sizeof(unsigned long long), F.stream), "cudaMemset(totals)");
+        F.launch.bucket_cnt = F.keep_cnt;                        /* where the frame's last kernel left the pairs per record */
+    }
     return launch_kernels(ctx, F, /*overlap=*/1);
 } catch (...) { return guard_exception(ctx); }
 
@@ -1753,6 +1783,7 @@ static bq2_status resident_launch(bq2_ctx *ctx, const bq2_resident *r, cudaStrea
         return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the result arrays of that frame state were re-allocated");
     if ((!r->own && r->L.tri_normals != F.tri_normals.p) || r->L.meshes != ctx->d_meshes.p)
         return fail(ctx, BQ2_E_INVALID, "bq2_resident_replay: the mesh table or the scratch rows of that frame state were re-allocated");
+    if (!r->own) F.tail_clean = false;                           /* writes counts into the state's buffer */
     bq2_launch L = r->L;
     L.seq = (uint32_t)ctx->launches;
     if (r->k_warp.n) {
@@ -1873,6 +1904,7 @@ try {
     CK(cudaMalloc(&d, sizeof(unsigned long long) * (size_t)n_pair_slots), "cudaMalloc(hashes)");
     cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long) * (size_t)n_pair_slots, F.stream);
     bq2_launch L = r ? r->L : F.launch;
+    if (!r && F.world_mode) L.bucket_cnt = F.keep_cnt;          /* where the frame's last kernel left the pairs per record */
     const FrameState::KLaunch &kw = r ? r->k_warp : F.k_warp, &kt = r ? r->k_team : F.k_team;
     const bq2_dev_ent *ents0 = L.ents;
     if (e == cudaSuccess && kw.n) { L.n_ent_slots = kw.n; L.rec_base = 0; e = (cudaError_t)bq2_launch_hash(&L, d, F.stream); ctx->launches++; }
