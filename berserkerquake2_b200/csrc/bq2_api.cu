@@ -1151,17 +1151,19 @@ try {
     }
     first[n_polys] = ns;
     if (ns > BQ2_BRUSH_MAX_SLOTS) return fail(ctx, BQ2_E_LIMIT, "bq2_upload_brush: too many polygon vertices");
-    std::vector<uint32_t> slot_poly(ns);
-    for (int p = 0; p < n_polys; p++) for (uint32_t k = first[p]; k < first[p + 1]; k++) slot_poly[k] = (uint32_t)p;
+    /* per slot: owning polygon | fence << 31, position in the polygon | numverts << 16 */
+    std::vector<uint32_t> slot_info(2 * (size_t)ns);
+    for (int p = 0; p < n_polys; p++)
+        for (uint32_t k = first[p]; k < first[p + 1]; k++) {
+            slot_info[2 * (size_t)k] = (uint32_t)p | ((fence && fence[p]) ? 0x80000000u : 0u);
+            slot_info[2 * (size_t)k + 1] = (k - first[p]) | ((uint32_t)numverts[p] << 16);
+        }
     for (uint32_t k = 0; k < ns; k++) if (neighbours[k] < -1 || neighbours[k] >= n_polys) return fail(ctx, BQ2_E_INVALID, "bq2_upload_brush: neighbour out of range");
-    const size_t o_first = 0, o_nbr = 4 * ((size_t)n_polys + 1), o_sp = o_nbr + 4 * (size_t)ns, o_v = o_sp + 4 * (size_t)ns,
-                 o_f = o_v + 12 * (size_t)ns, total = o_f + (size_t)n_polys;
+    const size_t o_v = 0, o_si = 16 * (size_t)ns, o_nbr = o_si + 8 * (size_t)ns, total = o_nbr + 4 * (size_t)ns;
     std::vector<unsigned char> img(total, 0);
-    memcpy(&img[o_first], first.data(), 4 * ((size_t)n_polys + 1));
+    for (uint32_t k = 0; k < ns; k++) memcpy(&img[o_v + 16 * (size_t)k], verts + 3 * (size_t)k, 12);     /* xyz, w = 0 */
+    memcpy(&img[o_si], slot_info.data(), 8 * (size_t)ns);
     memcpy(&img[o_nbr], neighbours, 4 * (size_t)ns);
-    memcpy(&img[o_sp], slot_poly.data(), 4 * (size_t)ns);
-    memcpy(&img[o_v], verts, 12 * (size_t)ns);
-    if (fence) memcpy(&img[o_f], fence, (size_t)n_polys);
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
     unsigned char *d = nullptr;
     bq2_status st = arena_alloc(ctx, total, &d);
@@ -1169,8 +1171,7 @@ try {
     CK(cudaMemcpyAsync(d, img.data(), total, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(brush)");
     CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(brush)");
     bq2_brush_dev_h bd{};
-    bd.first = (const uint32_t *)(d + o_first); bd.nbr = (const int32_t *)(d + o_nbr); bd.slot_poly = (const uint32_t *)(d + o_sp);
-    bd.verts = (const float *)(d + o_v); bd.fence = d + o_f; bd.n_polys = n_polys; bd.n_slots = (int32_t)ns;
+    bd.slot_info = d + o_si; bd.nbr = (const int32_t *)(d + o_nbr); bd.verts = d + o_v; bd.n_polys = n_polys; bd.n_slots = (int32_t)ns;
     ctx->brush_dev.push_back(bd);
     bq2_ctx::Brush b; b.n_polys = n_polys; b.n_slots = (int)ns; b.worst_indices = worst;
     ctx->brushes.push_back(b);

@@ -200,11 +200,10 @@ int  bq2_launch_tangents(const uint16_t *idx_xyz, int xyz_stride, const uint16_t
                          uint8_t *out_n, uint8_t *out_t, uint8_t *out_b, size_t out_stride, void *stream);
 size_t bq2_tangents_smem_bytes(int T, int V, int num_st, int mode);
 /* brush-model volumes (8f.4): device mirrors of the records the kernel reads */
-typedef struct bq2_brush_dev_h { const uint32_t *first; const int32_t *nbr; const uint32_t *slot_poly; const float *verts;
-                                 const uint8_t *fence; int32_t n_polys, n_slots; } bq2_brush_dev_h;
+typedef struct bq2_brush_dev_h { const void *slot_info; const int32_t *nbr; const void *verts; int32_t n_polys, n_slots; } bq2_brush_dev_h;
 typedef struct bq2_brush_pair_dev_h { int32_t brush; float light[3]; float scale; uint32_t lit_off; } bq2_brush_pair_dev_h;
-#define BQ2_BRUSH_MAX_POLYS 4096        /* 10 bytes per polygon + 3 per polygon vertex of shared memory          */
-#define BQ2_BRUSH_MAX_SLOTS 24576       /* a polygon has at most 255 shadow edges in front of an edge (u8 rank)  */
+#define BQ2_BRUSH_MAX_POLYS 4096        /* 1 byte per polygon + 2.75 per polygon vertex of shared memory         */
+#define BQ2_BRUSH_MAX_SLOTS 24576       /* slot numbers and running sums are kept in 16 bits                     */
 int  bq2_launch_brush(const void *brushes, const void *pairs, const uint8_t *lit, float *vcache, uint32_t *icache,
                       uint32_t *counts, uint32_t vert_stride, uint32_t index_stride, int n_pairs, int max_polys, int max_slots,
                       void *stream);
