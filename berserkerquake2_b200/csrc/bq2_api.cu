@@ -220,7 +220,8 @@ struct bq2_ctx {
     struct Brush { int n_polys = 0, n_slots = 0, worst_indices = 0; };
     std::vector<Brush> brushes; std::vector<bq2_brush_dev_h> brush_dev; DevBuf<bq2_brush_dev_h> d_brushes;
     DevBuf<unsigned char> d_brush_in; DevBuf<float> brush_vcache; DevBuf<uint32_t> brush_icache, brush_counts;
-    std::vector<uint32_t> h_brush_counts; uint32_t brush_vstride = 0, brush_istride = 0; int brush_pairs = 0;
+    PinBuf h_brush, h_brush_lit;                                 /* page-locked: pair records | counts; staged lit bytes */
+    const uint32_t *h_brush_counts = nullptr; uint32_t brush_vstride = 0, brush_istride = 0; int brush_pairs = 0;
 };
 
 namespace {
@@ -426,6 +427,7 @@ static void worker_wake(bq2_ctx *ctx);
 static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F);
 static void stage_caller_arrays(FrameState &F);
 static void finish_bases(FrameState &F);
+static bool host_pinned(const bq2_ctx *ctx, const void *p, size_t bytes);
 
 int bq2_abi_version(void) { return BQ2_ABI_VERSION; }
 int bq2_max_frames_in_flight(void) { return BQ2_MAX_IN_FLIGHT; }
@@ -487,7 +489,7 @@ void bq2_destroy(bq2_ctx *ctx)
     for (Slab &s : ctx->slabs) cudaFree(s.base);
     ctx->d_meshes.release(); ctx->d_models.release();
     ctx->d_brushes.release(); ctx->d_brush_in.release(); ctx->brush_vcache.release();
-    ctx->brush_icache.release(); ctx->brush_counts.release();
+    ctx->brush_icache.release(); ctx->brush_counts.release(); ctx->h_brush.release(); ctx->h_brush_lit.release();
     for (FrameState &f : ctx->fs) f.release();                   /* streams included */
     for (const bq2_ctx::HostRange &r : ctx->host_ranges) cudaFreeHost((void *)r.base);
     delete ctx;
@@ -1187,7 +1189,11 @@ try {
     worker_drain(ctx);
     if (n_pairs < 0 || (n_pairs && (!pairs || !lit)) || !out) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: bad arguments");
     CK(cudaSetDevice(ctx->device), "cudaSetDevice");
-    std::vector<bq2_brush_pair_dev_h> hp((size_t)n_pairs + 1);
+    /* pair records and the returned counts live in page-locked memory of the ctx: the copies are DMA, not staged by the driver */
+    const size_t o_lit = (((size_t)n_pairs * sizeof(bq2_brush_pair_dev_h)) + 15) & ~(size_t)15;
+    CK(ctx->h_brush.ensure(o_lit + 8 * (size_t)n_pairs + 16), "cudaMallocHost(brush pairs)");
+    bq2_brush_pair_dev_h *hp = (bq2_brush_pair_dev_h *)ctx->h_brush.p;
+    uint32_t *h_counts = (uint32_t *)(ctx->h_brush.p + o_lit);
     uint32_t lit_bytes = 0, vstride = 4, istride = 4; int max_polys = 1, max_slots = 1;
     for (int k = 0; k < n_pairs; k++) {
         if (pairs[k].brush < 0 || pairs[k].brush >= (int32_t)ctx->brushes.size()) return fail(ctx, BQ2_E_INVALID, "bq2_brush_volumes: unknown brush");
@@ -1198,24 +1204,31 @@ try {
         vstride = std::max(vstride, (uint32_t)b.n_slots); istride = std::max(istride, (uint32_t)b.worst_indices);
         max_polys = std::max(max_polys, b.n_polys); max_slots = std::max(max_slots, b.n_slots);
     }
-    const size_t o_lit = (((size_t)n_pairs * sizeof(bq2_brush_pair_dev_h)) + 15) & ~(size_t)15;
     CK(ctx->d_brush_in.ensure(o_lit + lit_bytes + 16), "cudaMalloc(brush pairs)");
     istride = (istride + 1u) & ~1u;                      /* index rows start 8-byte aligned (the kernel stores index pairs) */
     CK(ctx->brush_vcache.ensure(6 * (size_t)n_pairs * vstride + 4), "cudaMalloc(brush vcache)");
     CK(ctx->brush_icache.ensure((size_t)n_pairs * istride + 4), "cudaMalloc(brush icache)");
     CK(ctx->brush_counts.ensure(2 * (size_t)n_pairs + 2), "cudaMalloc(brush counts)");
-    ctx->h_brush_counts.assign(2 * (size_t)n_pairs + 2, 0u);
+    ctx->h_brush_counts = h_counts;
     if (n_pairs) {
-        CK(cudaMemcpyAsync(ctx->d_brush_in.p, hp.data(), (size_t)n_pairs * sizeof(bq2_brush_pair_dev_h), cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(brush pairs)");
-        CK(cudaMemcpyAsync(ctx->d_brush_in.p + o_lit, lit, lit_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(lit)");
+        /* the lit bytes: straight from the caller's array when that is page-locked memory of this ctx (bq2_host_alloc),
+           else through a page-locked staging buffer */
+        const unsigned char *lit_src = lit;
+        if (!host_pinned(ctx, lit, lit_bytes)) {
+            CK(ctx->h_brush_lit.ensure((size_t)lit_bytes + 16), "cudaMallocHost(lit)");
+            memcpy(ctx->h_brush_lit.p, lit, lit_bytes);
+            lit_src = ctx->h_brush_lit.p;
+        }
+        CK(cudaMemcpyAsync(ctx->d_brush_in.p, hp, (size_t)n_pairs * sizeof(bq2_brush_pair_dev_h), cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(brush pairs)");
+        CK(cudaMemcpyAsync(ctx->d_brush_in.p + o_lit, lit_src, lit_bytes, cudaMemcpyHostToDevice, ctx->stream), "cudaMemcpy(lit)");
         CK((cudaError_t)bq2_launch_brush(ctx->d_brushes.p, ctx->d_brush_in.p, ctx->d_brush_in.p + o_lit, ctx->brush_vcache.p, ctx->brush_icache.p,
                                          ctx->brush_counts.p, vstride, istride, n_pairs, max_polys, max_slots, ctx->stream), "launch(bq2_brush_kernel)");
         ctx->launches++;
-        CK(cudaMemcpyAsync(ctx->h_brush_counts.data(), ctx->brush_counts.p, 8 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(brush counts)");
+        CK(cudaMemcpyAsync(h_counts, ctx->brush_counts.p, 8 * (size_t)n_pairs, cudaMemcpyDeviceToHost, ctx->stream), "cudaMemcpy(brush counts)");
     }
     CK(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize(brush)");
     ctx->brush_vstride = vstride; ctx->brush_istride = istride; ctx->brush_pairs = n_pairs;
-    out->vcache = ctx->brush_vcache.p; out->icache = ctx->brush_icache.p; out->counts = ctx->h_brush_counts.data();
+    out->vcache = ctx->brush_vcache.p; out->icache = ctx->brush_icache.p; out->counts = ctx->h_brush_counts;
     out->vert_stride = vstride; out->index_stride = istride;
     return BQ2_OK;
 } catch (...) { return guard_exception(ctx); }
