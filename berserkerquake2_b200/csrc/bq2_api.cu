@@ -88,11 +88,11 @@ struct PinBuf {
 
 /* everything that belongs to ONE frame */
 #define BQ2_DIRECT_MIN_BYTES (1u << 20)
-/* Up to sixteen frames in flight: a world frame is a chain of five dependent stream operations (copy in, clear, two
-   kernels, copy out) whose END-TO-END LATENCY is 50-60 us on a B200 even when the kernels are trivial (copy-engine and
-   graph-node latencies), so the frame rate of a pipelined caller is latency / frames in flight until the host or the SMs
-   become the limit: C2 measured 21.3 / 17.1 / 14.7 / 13.1 / 12.6 us per frame with 4 / 6 / 8 / 12 / 16 in flight
-   (profiles/r02_history.md).  States are taken on demand: a caller pays for the depth it uses. */
+/* Up to sixteen frames in flight: a world frame is a chain of four dependent stream operations (copy in, record-building
+   kernel, frame kernel, a last kernel that hands the counts to the host) whose END-TO-END LATENCY is ~40 us on a B200
+   (profiles/r02_chain_latency.md), so the frame rate of a pipelined caller is latency / frames in flight until the host
+   or the SMs become the limit: C2 measured 30.0 / 16.9 / 12.7 / 12.0 us per frame with 2 / 4 / 8 / 16 in flight.
+   States are taken on demand: a caller pays for the depth it uses. */
 #ifndef BQ2_FRAME_STATES        /* (overridable for experiments: make EXTRA="-DBQ2_FRAME_STATES=5 -DBQ2_MAX_IN_FLIGHT=4") */
 #define BQ2_FRAME_STATES   17
 #define BQ2_MAX_IN_FLIGHT  16
@@ -1660,7 +1660,8 @@ try {
     /* per-slot host tables used by bq2_expand_trisverts */
     F.slot_mesh_V.resize((size_t)nP); F.slot_mesh_T.resize((size_t)nP); F.pair_slot_entslot.resize((size_t)nP);
 
-    /* the frame's stream operations: H2D, record building, the fused kernel(s), D2H of counts + totals -- issued by the
+    /* the frame's stream operations: H2D, record building, the fused kernel(s), the kernel that stores counts + totals
+       to the page-locked result buffer -- issued by the
        submit worker when the ctx has one and the caller's arrays may be read after this call returns (page-locked
        memory from bq2_host_alloc: the contract already says they stay unchanged until bq2_frame_wait), else here */
     {
