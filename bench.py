@@ -19,7 +19,8 @@ One "step" = one pass of the path over the whole batch = ONE launch of the fused
             bytes charged per pair) beside it; traffic = dram__bytes_read + dram__bytes_write per step, MEASURED IN
             THIS RUN by a child process under ncu's range replay over the same K back-to-back steps.
   e2e       the same metric through the C ABI from HOST arrays: bq2_world_submit (host: validation, numbering,
-            AngleVectors; H2D; record-building kernel + fused kernel; D2H of the per-pair counts) + bq2_frame_wait,
+            AngleVectors; H2D; record-building kernel + fused kernel; a last kernel that stores the per-pair counts and
+            totals to the page-locked result buffer) + bq2_frame_wait,
             sixteen frames in flight, the loop itself in C (csrc/bq2_frame_loop.c), wall clock over K iterations
   c3_strong BASELINE configs[2] as written: 65,536 entities x 8 lights sharded entity-major over the N GPUs
             (strong scaling), same timing rules
@@ -659,12 +660,13 @@ def run_gpu(args):
                                      "what": "the same frames, and every frame's lerped rows, extruded rows and index buffers "
                                              f"(the first {cnt_max} words of each pair's row, one strided copy) copied to "
                                              "page-locked host memory: the route for a renderer that draws from host arrays"},
-                    "h2d_bytes_per_step": n_ents * 64 + 16 + len(wl_c) * 16 + n_pairs * 8 + h2d_basis_bytes, "d2h_bytes_per_step": 4 * n_pairs + 24,
+                    "h2d_bytes_per_step": n_ents * 64 + 16 + len(wl_c) * 16 + n_pairs * 8 + h2d_basis_bytes, "d2h_bytes_per_step": 4 * ((n_pairs + 1) // 2 * 2 + 8),
                     "what": "per frame: bq2_world_submit (caller's thread: per-entity validation and numbering into one 64-byte row per "
                             "entity that also carries the caller's entity fields; the ctx's submit worker: AngleVectors of the rotated "
                             "entities (libm), staging of the caller's page-locked light and pair lists, the frame's graph launch; H2D of "
-                            "the rows, bases, lights and pairs; the record-building kernel + the fused kernel; D2H of per-pair index "
-                            "counts + totals) + bq2_frame_wait, wall clock over K frames (median of %d such runs) with %d frames in "
+                            "the rows, bases, lights and pairs; the record-building kernel + the fused kernel; per-pair index counts + "
+                            "totals stored to the page-locked result buffer by the frame's last kernel -- d2h_bytes_per_step, over "
+                            "PCIe like a copy) + bq2_frame_wait, wall clock over K frames (median of %d such runs) with %d frames in "
                             "flight (each has its own records, result arrays and stream; the clock runs over K submit+wait iterations "
                             "of the full pipeline, K frames in and K frames out); the loop itself is C on the public ABI "
                             "(csrc/bq2_frame_loop.c), as an engine would run it; ms_per_step_python_driver = the same calls made from "
