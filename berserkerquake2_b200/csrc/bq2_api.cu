@@ -88,6 +88,7 @@ struct PinBuf {
 
 /* everything that belongs to ONE frame */
 #define BQ2_DIRECT_MIN_BYTES (1u << 20)
+#define BQ2_TAIL_STORE_MAX_WORDS 16384u      /* per-pair counts beyond 64 KB go through the copy engine */
 /* Up to sixteen frames in flight: a world frame is a chain of four dependent stream operations (copy in, record-building
    kernel, frame kernel, a last kernel that hands the counts to the host) whose END-TO-END LATENCY is ~40 us on a B200
    (profiles/r02_chain_latency.md), so the frame rate of a pipelined caller is latency / frames in flight until the host
@@ -1327,10 +1328,15 @@ static bq2_status world_enqueue(bq2_ctx *ctx, FrameState &F)
         bq2_status ls = launch_kernels(ctx, F, pdl);
         if (ls != BQ2_OK) return ls;
         if (st) st->mark(3, F.stream);
-        (void)h_counts;
-        CK((cudaError_t)bq2_launch_frame_tail(F.index_count.p, F.hcnt_dev, F.keep_cnt, (uint32_t)J.tot_word + 8u, (uint32_t)J.tot_word,
+        /* counts of a small frame are stored to the result buffer by the last kernel itself (5.4 us behind a kernel
+           against 7.2 us for a copy node); beyond 64 KB the copy engine is the faster way over PCIe (a kernel's stores to
+           host memory run at about a third of its rate) and the last kernel hands over the totals only */
+        const uint32_t copy_from = J.tot_word > BQ2_TAIL_STORE_MAX_WORDS ? (uint32_t)J.tot_word : 0u;
+        CK((cudaError_t)bq2_launch_frame_tail(F.index_count.p, F.hcnt_dev, F.keep_cnt, copy_from, (uint32_t)J.tot_word + 8u, (uint32_t)J.tot_word,
                                               (uint32_t)J.cnt_word, (uint32_t)(J.cnt_word + (size_t)J.nE), F.stream, pdl),
            "launch(bq2_frame_tail_kernel)");
+        if (copy_from)
+            CK(cudaMemcpyAsync(h_counts.p, F.index_count.p, sizeof(uint32_t) * J.tot_word, cudaMemcpyDeviceToHost, F.stream), "cudaMemcpy(counts)");
         COUNT_LAUNCH(ctx, 1);
         if (st) { st->mark(4, F.stream); st->finish(); }
         return BQ2_OK;

@@ -184,9 +184,9 @@ int  bq2_launch_frame(const bq2_launch *L, int max_V, int max_T, int any_md2, vo
 int  bq2_launch_frame_warp(const bq2_launch *L, int max_V, int max_T, int any_md2, void *stream, int overlap);  /* warp */
 int  bq2_launch_world_setup(const bq2_world_launch *W, void *stream);   /* returns cudaError_t; one kernel */
 int  bq2_world_setup_launches(const bq2_world_launch *W);
-/* counts + totals [0, n_copy) to mapped host memory; words [keep_from, n_all) saved to keep[]; words [zero_from, n_all)
-   cleared for the next frame */
-int  bq2_launch_frame_tail(uint32_t *cnt, uint32_t *host, uint32_t *keep, uint32_t n_copy, uint32_t zero_from,
+/* words [copy_from, n_copy) of the counts + totals to mapped host memory; words [keep_from, n_all) saved to keep[]; words
+   [zero_from, n_all) cleared for the next frame (copy_from <= zero_from <= keep_from) */
+int  bq2_launch_frame_tail(uint32_t *cnt, uint32_t *host, uint32_t *keep, uint32_t copy_from, uint32_t n_copy, uint32_t zero_from,
                            uint32_t keep_from, uint32_t n_all, void *stream, int overlap);
 /* neighbour tables of one mesh on the device: idx = u16 vertex indices, in_stride u16s per triangle (6 for
    dtriangle_t, 3 for WORD indexes); out = int32[3*T] (device) */

@@ -111,10 +111,14 @@ def main():
             ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd)))
         for _ in range(3 * depth + 18):                     # every frame state allocates and captures its graph
             ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd))); ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
-        t0 = time.perf_counter()
-        for _ in range(k):
-            ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd))); ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / k
+        k = max(k, 4 * depth, 24)                           # a window much longer than the pipeline is deep, three of them
+        wins = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            for _ in range(k):
+                ok(c.lib.bq2_world_submit(ctx._h, C.byref(wd))); ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
+            wins.append((time.perf_counter() - t0) * 1e3 / k)
+        e2e_ms = float(np.median(wins))
         for _ in range(depth - 1):
             ok(c.lib.bq2_frame_wait(ctx._h, C.byref(fo)))
         assert fo.total_indices == tot
