@@ -922,3 +922,59 @@ def test_back_to_back_replays_keep_stream_order(gpu_ctx, oracle, want):
             assert np.array_equal(bits(r.extruded(p, m.V)), e), (last, p)
     for h, *_ in kept:
         gpu_ctx.free_kept(h)
+
+
+def test_world_frame_counters_survive_whatever_ran_on_the_state_before(gpu_ctx, oracle):
+    """A world frame's last kernel hands the counts to the host and clears what the NEXT frame of the same shape
+    accumulates into, so a steady-state frame has no clear in front.  Whatever else used the frame state in between --
+    a frame of another shape, a host-built frame, a replay, a frame without shadow volumes, frames in flight -- the
+    next world frame must still count from zero: counts, totals and the per-pair hash of every frame are compared with
+    the first one's (graph route: no BQ2_WANT_TABLES)."""
+    models = [Md2Model(oracle, s, r, frames=6, seed=300 + i) for i, (s, r) in enumerate([(8, 5), (16, 9)])]
+    mids = [m.upload(gpu_ctx) for m in models]
+    want = bq2.WANT_SHADOW
+
+    def scene(n_ents, lights, seed):
+        we, wl, pe, pl = world_scene(n_ents, lights, 6, n_models=2, seed=seed)
+        we["model"] = np.array(mids)[we["model"]]
+        return we, wl, pe, pl
+
+    A, B = scene(90, 3, 41), scene(57, 5, 42)
+
+    def run(s, w=want):
+        r = gpu_ctx.world_frame(*s, want=w)
+        return r.index_counts.copy(), int(r.total_indices), (gpu_ctx.hash_results(len(s[2])) if w & bq2.WANT_SHADOW else None)
+
+    cnt_a, tot_a, h_a = run(A)
+    cnt_b, tot_b, h_b = run(B)
+    assert tot_a > 0 and tot_b > 0 and tot_a == int(cnt_a.sum()) and tot_b == int(cnt_b.sum())
+
+    def same(got, ref):
+        return np.array_equal(got[0], ref[0]) and got[1] == ref[1] and np.array_equal(got[2], ref[2])
+
+    ref_a, ref_b = (cnt_a, tot_a, h_a), (cnt_b, tot_b, h_b)
+    for _ in range(4):                                            # same shape again and again: the graph, no clear
+        assert same(run(A), ref_a)
+    assert same(run(B), ref_b) and same(run(A), ref_a) and same(run(A), ref_a)       # another shape in between
+    ents, pairs = gpu_ctx.build_records(*A)                        # a host-built frame on the same state
+    hb = gpu_ctx.frame(ents, pairs)
+    assert int(hb.total_indices) == tot_a
+    assert same(run(A), ref_a) and same(run(A), ref_a)
+    gpu_ctx.replay(); r = gpu_ctx.wait()                           # a replay adds to the totals it cleared itself ...
+    assert int(r.total_indices) == tot_a
+    assert np.array_equal(gpu_ctx.hash_results(len(A[2])), h_a)    # ... and still finds the frame's pair lists
+    assert same(run(A), ref_a) and same(run(A), ref_a)
+    c0, t0, _ = run(A, 0)                                          # no shadow volumes: every count reads zero
+    assert t0 == 0 and not c0.any()
+    assert same(run(A), ref_a) and same(run(A), ref_a)
+    d = gpu_ctx.world_desc(*A, None, want, 0); d._keep = gpu_ctx._keep
+    for _ in range(3):
+        gpu_ctx.world_submit(d)                                    # three in flight on three states, then the same again
+    for _ in range(9):
+        r = gpu_ctx.wait()
+        assert int(r.total_indices) == tot_a and np.array_equal(r.index_counts, cnt_a)
+        gpu_ctx.world_submit(d)
+    for _ in range(3):
+        r = gpu_ctx.wait()
+        assert int(r.total_indices) == tot_a and np.array_equal(r.index_counts, cnt_a)
+    assert same(run(B), ref_b) and same(run(A), ref_a)
