@@ -13,7 +13,9 @@ for line in sys.stdin:
         d["config"]["workload"][:28], d["ms_per_step"] * 1e3, iso.get("l2_flushed_by_memset", 0) * 1e3, r["frac"],
         r["survey_8d_per_pair_form"]["frac"], d["e2e"]["ms_per_step"] * 1e3, d["value"], d.get("setup_s", 0)))
     m = d["measurement"]
-    print("  regions_ms", [round(x, 4) for x in m["timed_regions_ms"]], "streams", m.get("streams"), "one-stream us/step", round(m.get("ms_per_step_one_stream", 0) * 1e3, 2))
+    print("  regions_ms", [round(x, 4) for x in m["timed_regions_ms"]], "streams", m.get("streams"), "one-stream us/step", round(m.get("ms_per_step_one_stream", 0) * 1e3, 2),
+          "long region (K=%s) us/step %.2f frac %.3f" % ((r.get("long_region") or {}).get("steps"), (r.get("long_region") or {}).get("kernel_ms", 0) * 1e3,
+                                                         (r.get("long_region") or {}).get("frac", 0)))
     print("  traffic/step", r.get("traffic"), "unique bytes", r.get("bytes_per_launch"), r.get("traffic_unmeasured", ""),
           (r.get("traffic_detail") or {}).get("how", ""))
     e = d["e2e"]
