@@ -1704,7 +1704,7 @@ try {
         }
         if (to_worker) {
             bq2_status ws_ = worker_post(ctx, slot_k);
-            if (ws_ != BQ2_OK) return ws_;
+            if (ws_ != BQ2_OK) { F.tail_clean = false; return ws_; }      /* nothing was enqueued: assume nothing about the counters */
         } else {
             finish_bases(F);
             if (J.stage) { stage_caller_arrays(F); J.stage = false; }
