@@ -112,7 +112,7 @@ struct FrameState {
     struct Meta { bool world = false, tables = false; int32_t n_ent_slots = 0, n_pair_slots = 0; uint64_t total_verts = 0; uint32_t stride = 0; } meta;
     /* A frame is ~6 stream operations.  When two consecutive frames on the same state have the same shape
        and buffers, the operations are captured once into a CUDA graph and replayed with one call. */
-    struct GraphKey { int32_t v[20]; const void *p[16]; };
+    struct GraphKey { int32_t v[20]; const void *p[24]; };
     struct GraphCache { GraphKey key{}; bool have_key = false; cudaGraphExec_t exec = nullptr; uint64_t kernels = 0; } gcache;
     DevBuf<unsigned char> d_records;
     DevBuf<float> lerped, extruded, normals, tangents, binormals, lightp, tsh, tri_normals;
@@ -994,8 +994,8 @@ try {
         const unsigned long long *t = (const unsigned long long *)((const uint32_t *)F.hcnt.p + (((size_t)m.n_pair_slots + 1) & ~(size_t)1));
         o.total_indices = t[0]; o.overflow_pairs = (int32_t)t[1];
         o.pair_slot_first = nullptr;                             /* slot p is caller pair p */
-        o.pair_ts_offset = nullptr;
         o.pair_vert_offset = m.tables ? F.world_pvoff.data() : nullptr;
+        o.pair_ts_offset = o.pair_vert_offset;                   /* LightP / tsH rows of a pair are numbered like its extruded row */
         o.pair_bits_offset = m.tables ? F.world_pboff.data() : nullptr;
         if (t[2]) { o.total_pairs = (uint64_t)m.n_pair_slots; if (out) *out = o; return fail(ctx, BQ2_E_INVALID, "bq2_world: a pair refers to an entity or light out of range (it was skipped)"); }
     } else {
@@ -1514,7 +1514,8 @@ try {
     Trace &tr = ctx->trace; tr.start(); tr.n++;
     bq2_world_stats ws{};
     int er = -3;
-    if (!(want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT))) {
+    const bool want_tb = (want & (BQ2_WANT_NTB | BQ2_WANT_TSLIGHT)) != 0;
+    if (!want_tb || (want & BQ2_WANT_NTB)) {                     /* (TSLIGHT without NTB: the host-built route reports it) */
         CK(h_records.ensure(std::max<size_t>(rec_bytes, 16)), "cudaMallocHost(records)");
         F.ent_slot_first.resize((size_t)nE + 1); F.ent_vert_off.resize((size_t)nE + 1); F.ent_tb_off.assign((size_t)nE + 1, 0u);
         F.slot_record.resize((size_t)nE + 1);
@@ -1523,9 +1524,14 @@ try {
         if (er == -1) return fail(ctx, BQ2_E_INVALID, "bq2_world: entity refers to an unknown model");
         if (er == -2) return fail(ctx, BQ2_E_INVALID, "bq2_world: frame out of range");
         if (er == -4) return fail(ctx, BQ2_E_LIMIT, "bq2_world: more than 2^32 output rows, split the frame");
+        /* tangent-space outputs on this route: every model with per-VERTEX N/T/B rows (MD3, smooth MD2 with tangent /
+           binormal bytes), so that an entity's N/T/B rows and a pair's LightP / tsH rows are numbered like its vertex rows */
+        if (er == 0 && want_tb && (ws.and_mflags & (BQ2_MESH_SMOOTH | BQ2_MESH_HAS_TB)) != (BQ2_MESH_SMOOTH | BQ2_MESH_HAS_TB)) er = -3;
+        if (er == 0 && want_tb) F.ent_tb_off = F.ent_vert_off;
     }
     if (er != 0) {
-        /* multi-mesh models or tangent-space outputs: host-built records, same slot numbering (filtered pairs
+        /* multi-mesh models, or tangent-space outputs for models with per-triangle rows (non-smooth MD2) or without
+           tangent / binormal bytes: host-built records, same slot numbering (filtered pairs
            keep their slot) */
         ctx->tmp_ents.resize((size_t)nE + 1); ctx->tmp_pairs.resize((size_t)nP + 1);
         int32_t kept = 0;
@@ -1593,6 +1599,15 @@ try {
         CK(F.indices.ensure((size_t)nP * stride + 4), "cudaMalloc(indices)");
     }
     if (ws.team_normal_rows) CK(F.tri_normals.ensure(4 * (size_t)ws.team_normal_rows + 4), "cudaMalloc(triangle normals)");
+    if (want & BQ2_WANT_NTB) {
+        CK(F.normals.ensure(3 * (size_t)voff + 4), "cudaMalloc(normals)");
+        CK(F.tangents.ensure(3 * (size_t)voff + 4), "cudaMalloc(tangents)");
+        CK(F.binormals.ensure(3 * (size_t)voff + 4), "cudaMalloc(binormals)");
+    }
+    if (want & BQ2_WANT_TSLIGHT) {
+        CK(F.lightp.ensure(3 * (size_t)nP * maxVpad + 4), "cudaMalloc(lightp)");
+        CK(F.tsh.ensure(3 * (size_t)nP * maxVpad + 4), "cudaMalloc(tsh)");
+    }
     /* one buffer: index counts | 8-byte aligned, three 64-bit totals | pairs per record | overflow-chain heads | the
        finished frame's pairs per record.  The frame's last kernel hands counts + totals to the host and clears totals
        and pairs per record for the next frame; a frame that does not find them cleared clears totals .. heads itself
@@ -1657,7 +1672,9 @@ try {
     L.n_ent_slots = nE; L.want = want & ~BQ2_WANT_TABLES; L.index_stride = stride;
     L.lerped = F.lerped.p; L.extruded = F.extruded.p; L.facing_bits = F.facing_bits.p;
     L.indices = F.indices.p; L.index_count = F.index_count.p;
-    L.normals = nullptr; L.tangents = nullptr; L.binormals = nullptr; L.lightp = nullptr; L.tsh = nullptr;
+    const bool w_ntb = (want & BQ2_WANT_NTB) != 0, w_ts = (want & BQ2_WANT_TSLIGHT) != 0;
+    L.normals = w_ntb ? F.normals.p : nullptr; L.tangents = w_ntb ? F.tangents.p : nullptr; L.binormals = w_ntb ? F.binormals.p : nullptr;
+    L.lightp = w_ts ? F.lightp.p : nullptr; L.tsh = w_ts ? F.tsh.p : nullptr;
     L.totals = Wl.totals; L.tri_normals = F.tri_normals.p;
     L.bucket_cnt = Wl.bucket_cnt; L.bucket = Wl.bucket; L.ohead = Wl.ohead; L.onext = Wl.onext; L.rec_base = 0;
     F.n_ent_slots = nE; F.n_pair_slots = nP; F.n_ents = nE; F.n_pairs = nP;
@@ -1683,10 +1700,11 @@ try {
                                 ws.team_max_V, ws.team_max_T, ws.team_md2, (int32_t)maxVpad, (int32_t)maxBitw, (int32_t)basis_bytes, clean ? 1 : 0, 0, 0, 0};
         memset(&J.key, 0, sizeof J.key);
         memcpy(J.key.v, kv, sizeof kv);
-        const void *kp[16] = {direct ? wd->ents : nullptr, direct ? wd->lights : nullptr, direct ? wd->pair_ent : nullptr,
+        const void *kp[24] = {direct ? wd->ents : nullptr, direct ? wd->lights : nullptr, direct ? wd->pair_ent : nullptr,
                               direct ? wd->pair_light : nullptr,
                               F.d_records.p, F.d_world.p, h_records.p, h_counts.p, F.lerped.p, F.extruded.p, F.facing_bits.p,
-                              F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, ctx->d_models.p};
+                              F.indices.p, F.index_count.p, ctx->d_meshes.p, F.tri_normals.p, ctx->d_models.p,
+                              L.normals, L.tangents, L.binormals, L.lightp, L.tsh, nullptr, nullptr, nullptr};
         memcpy(J.key.p, kp, sizeof kp);
         /* to the worker unless it is asleep (an engine that submits once per 16 ms frame would pay the wake-up latency on
            every frame: it is woken for the frames that follow only when submits come in quick succession) */

@@ -286,6 +286,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
     int32_t n_warp = 0, n_team = 0, n_rot = 0;
     uint64_t voff = 0, team_rows = 0;          /* stored as 32-bit row numbers; checked after the loop */
     uint64_t total_verts = 0;
+    uint32_t and_flags = 0xffffffffu;
     int16_t m[8];
     int32_t e;
 #if defined(__SSE2__)
@@ -306,6 +307,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         if ((uint32_t)W->model >= (uint32_t)n_models) return -1;
         mo = &models[W->model];
         if (mo->n_mesh != 1) return -3;
+        and_flags &= mo->mflags;
         if ((uint32_t)W->frame >= (uint32_t)mo->F || (uint32_t)W->oldframe >= (uint32_t)mo->F) return -2;
 #if defined(__SSE2__)
         mx = _mm_max_epi16(mx, _mm_loadu_si128((const __m128i *)mo->cmax));
@@ -349,7 +351,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         st->max_vpad = (uint32_t)(mV + 3) & ~3u; st->max_bitw = (uint32_t)(mT + 31) >> 5; st->max_T = mT;
     }
     st->lerped_verts_padded = (uint32_t)voff; st->team_normal_rows = (uint32_t)team_rows; st->n_rotated = n_rot;
-    st->total_verts = total_verts;
+    st->total_verts = total_verts; st->and_mflags = and_flags;
     return 0;
 }
 

@@ -151,6 +151,7 @@ typedef struct bq2_world_stats {
     uint32_t team_normal_rows;              /* sum of Tp over team-kernel records */
     int32_t  n_rotated;                     /* rows of bases[] written */
     uint64_t total_verts;
+    uint32_t and_mflags;                    /* AND of the mesh flags of every entity's model (BQ2_MESH_*; all ones for no entity) */
 } bq2_world_stats;
 
 #ifdef __cplusplus

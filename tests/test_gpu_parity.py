@@ -978,3 +978,51 @@ def test_world_frame_counters_survive_whatever_ran_on_the_state_before(gpu_ctx, 
         r = gpu_ctx.wait()
         assert int(r.total_indices) == tot_a and np.array_equal(r.index_counts, cnt_a)
     assert same(run(B), ref_b) and same(run(A), ref_a)
+
+
+def test_world_route_tangent_space_outputs_match_the_host_built_route(gpu_ctx, oracle):
+    """N/T/B rows and LightP / tsH through the device-built route (bq2_world_frame with BQ2_WANT_NTB | BQ2_WANT_TSLIGHT:
+    every model single-mesh with per-vertex rows) are bit-identical to the host-built route, which the oracle and the
+    golden vectors check -- smooth MD2 of the warp-kernel and the team-kernel class and a one-surface MD3, rotated entities,
+    a view origin; a frame that mixes in a NON-smooth MD2 takes the host-built route and returns its tables."""
+    from scenes import Md3Model
+    md2 = [Md2Model(oracle, 8, 5, frames=4, seed=21, tangent_space=True), Md2Model(oracle, 40, 30, frames=3, seed=22, tangent_space=True)]
+    md3 = Md3Model(oracle, slices=12, rings=9, frames=4, num_meshes=1, seed=23)
+    assert md2[1].T > 1024                                           # team-kernel class
+    mids = [m.upload(gpu_ctx) for m in md2] + [md3.upload(gpu_ctx)]
+    we, wl, pe, pl = world_scene(24, 3, 3, n_models=3, seed=77)
+    we["model"] = np.array(mids)[we["model"]]
+    view = np.array([31.0, -17.0, 55.0], np.float32)
+    want = bq2.WANT_SHADOW | bq2.WANT_NTB | bq2.WANT_TSLIGHT
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl, view_world=view)
+    rh = gpu_ctx.frame(ents, pairs, want=want)
+    # rows are padded to four: the last three of a padded row may be padding (never written), they are left out
+    Vs = [int(rh.ent_vert_offset[e + 1] - rh.ent_vert_offset[e]) for e in range(len(we))]
+    host_ntb = [[x.copy() for x in rh.ntb(e, Vs[e])] for e in range(len(we))]
+    host_ts = [[x.copy() for x in rh.tslight(p, Vs[pe[p]])] for p in range(len(pe))]
+    host_ext = [rh.extruded(p, Vs[pe[p]]).copy() for p in range(len(pe))]
+    host_idx = [rh.indices(p).copy() for p in range(len(pe))]
+    for rnd in range(3):                                          # the third frame replays the captured graph
+        rw = gpu_ctx.world_frame(we, wl, pe, pl, view_world=view, want=want | (bq2.WANT_TABLES if rnd == 0 else 0))
+        if rnd:                                                   # without tables: rows of pair p start at p * stride
+            stride_v = int(max(Vs))
+            rw.pair_vert_offset = rw.pair_ts_offset = np.arange(len(pe) + 1, dtype=np.uint32) * stride_v
+        assert np.array_equal(rw.index_counts, rh.index_counts)
+        for e in range(len(we)):
+            for x, y in zip(rw.ntb(e, Vs[e]), host_ntb[e]):
+                assert np.array_equal(bits(x).reshape(-1)[:3 * Vs[e] - 9], bits(y).reshape(-1)[:3 * Vs[e] - 9]), (rnd, e)
+        for p in range(len(pe)):
+            v = Vs[pe[p]]
+            for x, y in zip(rw.tslight(p, v), host_ts[p]):
+                assert np.array_equal(bits(x).reshape(-1)[:3 * v - 9], bits(y).reshape(-1)[:3 * v - 9]), (rnd, p)
+            assert np.array_equal(bits(rw.extruded(p, v)).reshape(-1)[:3 * v - 9], bits(host_ext[p]).reshape(-1)[:3 * v - 9])
+            assert np.array_equal(rw.indices(p), host_idx[p])
+    # a non-smooth MD2 in the frame: per-triangle rows, the host-built route takes over (its tables come back)
+    flat = Md2Model(oracle, 6, 5, frames=3, seed=24, tangent_space=True, smooth=False)
+    fid = flat.upload(gpu_ctx)
+    we2 = we.copy(); we2["model"][0] = fid; we2["frame"][0] %= 3; we2["oldframe"][0] %= 3
+    r2 = gpu_ctx.world_frame(we2, wl, pe, pl, view_world=view, want=want | bq2.WANT_TABLES)
+    e2, p2 = gpu_ctx.build_records(we2, wl, pe, pl, view_world=view)
+    r2h = gpu_ctx.frame(e2, p2, want=want)
+    assert np.array_equal(r2.index_counts, r2h.index_counts) and np.array_equal(r2.ent_tb_offset, r2h.ent_tb_offset)
+    assert int(r2.ent_tb_offset[1] - r2.ent_tb_offset[0]) == ((flat.T + 3) & ~3)
