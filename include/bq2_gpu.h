@@ -469,8 +469,12 @@ bq2_status bq2_build_records_opts(bq2_ctx *ctx, const bq2_world_entity *ents, in
  *   - pair slot p IS caller pair p (a pair whose entity casts no volume keeps its slot, index_count 0);
  *   - the pair offset tables of bq2_frame_out are produced only with BQ2_WANT_TABLES (tests, the shim);
  *   - an out-of-range pair_ent / pair_light is reported by bq2_frame_wait (BQ2_E_INVALID), not up front.
- * Frames that use a multi-mesh MD3 model or ask for BQ2_WANT_NTB / BQ2_WANT_TSLIGHT take the host-built
- * route internally, with the same slot numbering. */
+ * BQ2_WANT_NTB / BQ2_WANT_TSLIGHT: when every model of the frame has per-VERTEX N/T/B rows (MD3; MD2 uploaded smooth
+ * with tangent / binormal bytes) an entity's N/T/B rows are numbered like its lerped row (ent_tb_offset ==
+ * ent_vert_offset) and a pair's LightP / tsH rows like its extruded row (pair_ts_offset == pair_vert_offset).
+ * Frames that use a multi-mesh MD3 model, or ask for tangent-space outputs of a non-smooth MD2 (per-triangle rows) or of
+ * a model without tangent / binormal bytes, take the host-built route internally, with the same slot numbering and the
+ * host-built route's tables (an order of magnitude slower end to end: 154 against 16-22 us per C2 frame). */
 #define BQ2_WANT_TABLES  0x10u
 typedef struct bq2_world_desc {
     const bq2_world_entity *ents;    int32_t n_ents;

@@ -58,8 +58,28 @@ def main():
             if i >= 5:
                 ts.append(e0.elapsed_time(e1))
         out[name] = float(np.median(ts)) * 1e3
+    # end to end from host arrays (bq2_world_submit + bq2_frame_wait, the C frame loop of bench.py's e2e leg): frames with
+    # per-vertex rows go through the device-built route, a non-smooth MD2 falls back to host-built records
+    import ctypes as C
+    from berserkerquake2_b200 import _capi as c
+    loop = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(bq2.__file__)), "libbq2loop.so"))
+    loop.bq2_frame_loop.restype = C.c_int
+    loop.bq2_frame_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    pin = [ctx.host_array(x) for x in (we, wl, pe, pl)]
+    e2e = {}
+    for name, want in (("shadow", bq2.WANT_SHADOW), ("shadow+ntb", bq2.WANT_SHADOW | bq2.WANT_NTB),
+                       ("shadow+ntb+tslight", bq2.WANT_SHADOW | bq2.WANT_NTB | bq2.WANT_TSLIGHT)):
+        wd = ctx.world_desc(*pin, view, want, 0)
+        sec, tot = C.c_double(0), C.c_uint64(0)
+        for depth in (16, 1):
+            assert loop.bq2_frame_loop(ctx._h, C.byref(wd), 100, depth, C.byref(sec), C.byref(tot)) == 0, c.lib.bq2_last_error(ctx._h)
+            rs = []
+            for _ in range(9):
+                assert loop.bq2_frame_loop(ctx._h, C.byref(wd), 200, depth, C.byref(sec), C.byref(tot)) == 0
+                rs.append(sec.value / 200 * 1e6)
+            e2e[f"{name}, {depth} in flight"] = float(np.median(rs))
     print(json.dumps({"workload": f"{a.entities} MD2 entities x {a.lights} lights (V={V}, T={T}), {'flat' if a.flat else 'smooth'} basis",
-                      "kernel_us": out}))
+                      "kernel_us": out, "e2e_us_per_frame": e2e}))
     ctx.close()
 
 
