@@ -1498,10 +1498,11 @@ try {
         for (size_t i = 0; i < ctx->models.size(); i++) {
             const Model &mo = ctx->models[i];
             const bq2_dev_mesh &me = ctx->meshes[mo.first_mesh];
-            ctx->model_rows[i] = bq2_model_row{mo.F, mo.md3 ? 1 : 0, mo.first_mesh, (mo.n_mesh == 1 && mo.casts[0]) ? 1 : 2,
+            ctx->model_rows[i] = bq2_model_row{mo.F, mo.md3 ? 1 : 0, mo.first_mesh, mo.n_mesh == 1 ? 1 : 2,
                                                me.V, me.T, me.Tp, me.flags};
             bq2_model_row_derive(&ctx->model_rows[i]);
             ctx->model_rows[i].pad[0] = (int32_t)mo.rf_flags;
+            ctx->model_rows[i].pad[1] = mo.casts[0] ? 0 : 1;     /* a mesh whose skin casts no shadow (M:63811-63816): lerp, no volume */
         }
     }
     const size_t off_xf = (size_t)nE * sizeof(bq2_dev_ent), off_view = off_xf + (size_t)nE * sizeof(bq2_dev_went),

@@ -333,7 +333,7 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
         } else
             x->basis = -1;
         x->rec = rec;
-        x->pair_rec = (f_off | (W->rf_flags & f_em) | (((uint32_t)mo->pad[0] ^ f_mx) & f_mm)) ? -1 : rec;   /* M:63722-63727, 64041-64089 */
+        x->pair_rec = (f_off | (W->rf_flags & f_em) | (((uint32_t)mo->pad[0] ^ f_mx) & f_mm) | (uint32_t)mo->pad[1]) ? -1 : rec;   /* M:63722-63727, 64041-64089; pad[1]: the model's one mesh casts nothing */
         x->vert_off = (uint32_t)voff; x->nrm_off = nrm_off;
         ent_vert_off[e] = (uint32_t)voff;
         voff += mo->vpad; total_verts += (uint64_t)mo->V;

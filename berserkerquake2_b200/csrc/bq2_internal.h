@@ -139,7 +139,8 @@ typedef struct bq2_model_row {      /* host mirror of a model for the C entity l
     /* derived by bq2_model_row_derive, so that the loop has nothing to decide per entity: */
     uint32_t vpad;                  /* lerped row length, V rounded up to 4                                    */
     int32_t  team;                  /* 0: warp-kernel mesh (V <= BQ2_WARP_MAX_V and T <= BQ2_WARP_MAX_T), 1: team kernel */
-    int32_t  pad[2];                /* [0] = model_t.flags bits of the caller loop's filter (bq2_model_set_rf_flags) */
+    int32_t  pad[2];                /* [0] = model_t.flags bits of the caller loop's filter (bq2_model_set_rf_flags),
+                                       [1] != 0: the model's one mesh casts no shadow (its skin's flag, M:63811-63816) */
     int16_t  cmax[8];               /* the mesh's contribution to {warp max V, warp max T, team max V, team max T,
                                        warp has an MD2, team has an MD2, 0, 0}: the frame's values are the
                                        lane-wise maxima over its entities (V <= 4,096 and T <= 8,192 fit 16 bits) */

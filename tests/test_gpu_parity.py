@@ -1026,3 +1026,28 @@ def test_world_route_tangent_space_outputs_match_the_host_built_route(gpu_ctx, o
     r2h = gpu_ctx.frame(e2, p2, want=want)
     assert np.array_equal(r2.index_counts, r2h.index_counts) and np.array_equal(r2.ent_tb_offset, r2h.ent_tb_offset)
     assert int(r2.ent_tb_offset[1] - r2.ent_tb_offset[0]) == ((flat.T + 3) & ~3)
+
+
+def test_world_route_keeps_a_model_whose_one_mesh_casts_no_shadow(gpu_ctx, oracle):
+    """A one-surface MD3 whose skin says "no shadow" (M:63811-63816) is lerped but casts no volume.  It does not push the
+    frame onto the host-built route (device-built frames return no pair_slot_first table): its pairs keep their slots
+    with index_count 0, everything else equals the host-built route."""
+    quiet = Md3Model(oracle, 10, 7, frames=4, num_meshes=1, seed=31, casts=[0])
+    m2 = Md2Model(oracle, 10, 7, frames=4, seed=32)
+    idq, id2 = quiet.upload(gpu_ctx), m2.upload(gpu_ctx)
+    we, wl, pe, pl = world_scene(8, 3, 4, seed=63)
+    we["model"] = [idq, id2, id2, idq, id2, idq, id2, id2]
+    rw = gpu_ctx.world_frame(we, wl, pe, pl)
+    assert not rw.out.pair_slot_first                                # the device-built route
+    ents, pairs = gpu_ctx.build_records(we, wl, pe, pl)
+    rh = gpu_ctx.frame(ents, pairs)
+    assert np.array_equal(rw.index_counts, rh.index_counts) and int(rw.total_indices) == int(rh.total_indices) > 0
+    Vq = quiet.meshes[0]["verts"].shape[1]
+    for p in range(len(pe)):
+        e = int(pe[p])
+        if int(we["model"][e]) == idq:
+            assert rw.index_counts[p] == 0
+            assert np.array_equal(bits(rw.lerped(e, Vq)), bits(rh.lerped(e, Vq)))
+        else:
+            assert rw.index_counts[p] > 0 and np.array_equal(rw.indices(p), rh.indices(p))
+            assert np.array_equal(bits(rw.extruded(p, m2.V)), bits(rh.extruded(p, m2.V)))
