@@ -355,6 +355,10 @@ int bq2_host_world_entities(const bq2_world_entity *ents, int32_t n, const bq2_m
     return 0;
 }
 
+/* sizes of the three structs the entity loop exchanges with its caller, for harnesses that mirror them (tests/test_host_world.py) */
+void bq2_host_world_struct_sizes(int32_t out[3])
+{ out[0] = (int32_t)sizeof(bq2_model_row); out[1] = (int32_t)sizeof(bq2_dev_went); out[2] = (int32_t)sizeof(bq2_world_stats); }
+
 /* rows of bases[] written by the loop above: angles -> forward, right, up (AngleVectors M:37566, the engine's libm) */
 void bq2_host_bases_from_angles(float *bases, int32_t n_rot)
 {

@@ -165,6 +165,7 @@ struct bq2_world_entity;
  * entities and these rows.  Returns 0, -1 unknown model, -2 frame out of range, -3 a model is not single-mesh,
  * -4 the frame's rows do not fit 32-bit row numbers. */
 void bq2_model_row_derive(bq2_model_row *row);
+void bq2_host_world_struct_sizes(int32_t out[3]);   /* sizeof model row, entity row, stats: for harnesses that mirror them */
 struct bq2_render_opts;
 /* bases[] as bq2_host_world_entities leaves it holds each rotated entity's ANGLES in the first three floats of its row;
    this turns the rows into forward / right / up (libm).  Run by the submit worker, or inline. */

@@ -17,8 +17,8 @@ XFORM = np.dtype([("model", "<i4"), ("frame", "<i4"), ("oldframe", "<i4"), ("rf_
 STATS = np.dtype([("n_warp", "<i4"), ("n_team", "<i4"), ("warp_max_V", "<i4"), ("warp_max_T", "<i4"), ("warp_md2", "<i4"),
                   ("team_max_V", "<i4"), ("team_max_T", "<i4"), ("team_md2", "<i4"), ("lerped_verts_padded", "<u4"),
                   ("max_vpad", "<u4"), ("max_bitw", "<u4"), ("max_T", "<i4"), ("team_normal_rows", "<u4"), ("n_rotated", "<i4"),
-                  ("total_verts", "<u8")])
-assert MODEL_ROW.itemsize == 64 and XFORM.itemsize == 64 and STATS.itemsize == 64
+                  ("total_verts", "<u8"), ("and_mflags", "<u4"), ("_tail", "<u4")])
+assert MODEL_ROW.itemsize == 64 and XFORM.itemsize == 64 and STATS.itemsize == 72        # sizeof(bq2_world_stats): checked by test_struct_sizes
 MESH_MD3 = 0x1
 
 
@@ -47,6 +47,13 @@ def run(we, rows, opts=None):
             assert np.array_equal(hx[f].view(np.uint32), we[f].view(np.uint32)), f
     run.bases = bases
     return rc, hx, rec[:n], voff, st[0]
+
+
+def test_struct_mirrors_have_the_librarys_sizes():
+    """The numpy mirrors above are written into by C: a mirror shorter than its struct would be overrun silently."""
+    sizes = (C.c_int32 * 3)()
+    c.lib.bq2_host_world_struct_sizes(sizes)
+    assert list(sizes) == [MODEL_ROW.itemsize, XFORM.itemsize, STATS.itemsize]
 
 
 def rows_of(shapes):
@@ -90,6 +97,9 @@ def test_numbering_classes_and_stats():
     assert st["lerped_verts_padded"] == vpad.sum() and st["max_vpad"] == vpad.max() and st["max_T"] == T.max()
     assert st["max_bitw"] == ((T + 31) >> 5).max() and st["team_normal_rows"] == Tp[~small].sum()
     assert st["total_verts"] == V.sum()
+    assert st["and_mflags"] == 0                                     # MD2 and MD3 models together: no mesh flag common to all
+    rc, _, _, _, st3 = run(we[rows["md3"][we["model"]] == 1], rows)
+    assert rc == 0 and st3["and_mflags"] == MESH_MD3                 # what the tangent-space route decides on (per-vertex rows)
 
 
 def test_validation_codes():
@@ -142,6 +152,10 @@ def test_flag_filter_and_basis():
             assert np.array_equal(got, np.concatenate([fwd, right, up]).astype(np.float32).view(np.uint32)), e
             n_rot += 1
     assert st["n_rotated"] == n_rot == 4
+    # a model whose one mesh casts no shadow (pad[1]): lerped like the others, never a pair record
+    rows["pad"][0][1] = 1
+    rc, hx2, rec2, _, _ = run(we, rows)
+    assert rc == 0 and (hx2["pair_rec"] == -1).all() and np.array_equal(hx2["rec"], rec2) and sorted(rec2) == list(range(len(flags)))
 
 
 def test_rows_and_bases_carry_what_the_record_kernel_needs():
